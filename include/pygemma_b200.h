@@ -1,0 +1,149 @@
+/*
+ * pygemma_b200.h -- C ABI of the B200-native per-SNP LMM association scan.
+ *
+ * This is the drop-in boundary for the hot path of rlangefe/pygemma:
+ *
+ *   lmm.pygemma(Y, X, W, K, ...)                      reference lmm/lmm.py:87
+ *     eigh(K), clip d >= 0                            lmm/lmm.py:151-162   -> pg_set_kinship / pg_set_eigen
+ *     U.T @ Y, U.T @ W                                lmm/lmm.py:245-246   -> pg_set_design
+ *     U.T @ X                                         lmm/lmm.py:244       -> pg_scan (rotation stage)
+ *     Pool.imap(calculate, SampleIter(...))           lmm/lmm.py:378-403   -> pg_scan (REML stage)
+ *       calc_lambda_restricted                        pygemma_model.pyx:64
+ *       precompute_mat                                pygemma_model.pyx:880
+ *       newton, brentq, derivative/likelihood formulas  pyx:1349, :176, :1656-1698, :1813
+ *       calc_beta_vg_ve_restricted_overload           pyx:1514
+ *       F_wald, stats.f.sf                            lmm/lmm.py:471,:482
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative pg_status on failure;
+ *     pg_last_error() gives the message (CUDA / cuSOLVER / cuBLAS text included).
+ *   - all pointers are caller-owned; host entry points are synchronous at return.
+ *   - a handle is bound to one CUDA device and is not thread-safe.
+ *   - there is no CPU fallback: without a usable CUDA device pg_create fails.
+ *   - per-SNP failure (status[g] != 0) yields a NaN row, never an error return,
+ *     like the reference's LinAlgError branch (lmm/lmm.py:484-493).
+ */
+#ifndef PYGEMMA_B200_H
+#define PYGEMMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+typedef struct pg_handle pg_handle;
+
+typedef enum {
+    PG_OK = 0,
+    PG_ERR_ARG = -1,      /* bad argument / call order */
+    PG_ERR_CUDA = -2,     /* CUDA runtime error */
+    PG_ERR_CUSOLVER = -3, /* eigendecomposition failed */
+    PG_ERR_CUBLAS = -4,
+    PG_ERR_NO_DEVICE = -5,
+    PG_ERR_ALLOC = -6
+} pg_status;
+
+/* element type of the genotype matrix handed to pg_scan */
+typedef enum { PG_X_I8 = 0, PG_X_F32 = 1, PG_X_F64 = 2 } pg_xdtype;
+
+/* memory layout of the genotype matrix */
+typedef enum {
+    PG_X_SAMPLE_MAJOR = 0, /* (n, m) C-order as NumPy passes it: element (j, g) at X[j*ld + g], ld >= m */
+    PG_X_SNP_MAJOR = 1     /* (m, n): element (j, g) at X[g*ld + j], ld >= n */
+} pg_xlayout;
+
+/* rotation engine (stage 1 of pg_scan) */
+typedef enum {
+    PG_ROT_AUTO = 0,  /* integer dosages -> exact int8-split tensor-core path when available, else FP64 */
+    PG_ROT_FP64 = 1,  /* FP64 GEMM */
+    PG_ROT_I8SPLIT = 2
+} pg_rotation;
+
+/* device-side timings of the last pg_scan call, milliseconds (CUDA events) */
+typedef struct {
+    float total_ms;   /* whole call, first H2D to last D2H */
+    float h2d_ms;     /* genotype uploads (overlapped with compute after the first block) */
+    float convert_ms; /* dosage -> fp64 / layout change */
+    float rotate_ms;  /* U^T X */
+    float reml_ms;    /* per-SNP REML kernel */
+    float d2h_ms;     /* result download */
+    int32_t n_blocks; /* SNP blocks processed */
+    int32_t block_snps;
+    int32_t reml_launches, rotate_launches, convert_launches;
+    int32_t reserved;
+} pg_timing;
+
+int pg_abi_version(void);
+int pg_device_count(int* count);
+
+/* last error text of a handle (or of the failed pg_create when h == NULL) */
+const char* pg_last_error(const pg_handle* h);
+
+/* n samples, c0 covariate columns of W (intercept included by the caller, lmm/lmm.py:94) */
+int pg_create(int n, int c0, int device, pg_handle** out);
+int pg_destroy(pg_handle* h);
+
+/*
+ * Eigendecomposition K = U diag(d) U^T on the device (cuSOLVER syevd, FP64), eigenvalues clipped at 0.
+ * Replaces scipy.linalg.eigh + np.maximum(0, .) of lmm/lmm.py:151-157.  K_host is n*n doubles
+ * (symmetric, so row/column order is immaterial).  d_out_host (nullable) receives the n eigenvalues;
+ * eig_ms (nullable) the device time.  This is setup: it is not part of the scan metric.
+ */
+int pg_set_kinship(pg_handle* h, const double* K_host, double* d_out_host, float* eig_ms);
+
+/*
+ * Supply an eigendecomposition computed elsewhere.  u_row_major = 1: U[j*n + i] is component j of
+ * eigenvector i (NumPy C-order result of eigh); 0: column-major (LAPACK / cuSOLVER order).
+ * U may be NULL when the inputs of pg_set_design / pg_scan are already rotated (eigen=False,
+ * lmm/lmm.py:164-167,:243): then d is the eigenvalue vector and is clipped at 0 like the reference does.
+ */
+int pg_set_eigen(pg_handle* h, const double* U_host, int u_row_major, const double* d_host);
+int pg_set_eigen_device(pg_handle* h, const double* U_dev, int u_row_major, const double* d_dev);
+/* copy the handle's U (column-major) and d into caller-provided device buffers (multi-GPU broadcast) */
+int pg_get_eigen_device(pg_handle* h, double* U_dev_out, double* d_dev_out);
+
+/*
+ * Covariates and phenotype: W_host is (n, c0) C-order, y_host is n doubles.  Computes U^T W and U^T y
+ * (lmm/lmm.py:245-246) unless already_rotated, and builds the SNP-independent lambda tables.
+ */
+int pg_set_design(pg_handle* h, const double* W_host, const double* y_host, int already_rotated, float* ms);
+
+/* rotation engine selection and block size (0 = automatic) */
+int pg_set_options(pg_handle* h, int rotation, int64_t block_snps);
+
+/*
+ * The scan: for each of the m genotype columns, rotate (unless the handle holds rotated inputs),
+ * find the REML lambda (grid != 0: 12-point grid search, pyx:99-132; else bracket scan + Brent +
+ * Newton, pyx:135-194) and compute the Wald statistics.  Outputs are m doubles each, in input
+ * column order, no filtering (lmm/lmm.py:401-411).  status / n_eval2 / n_eval3 are nullable:
+ * n_eval2 / n_eval3 count the passes over the rotated genotype vector with 2 / 3 powers of H^-1.
+ * pg_scan takes host pointers; pg_scan_device takes device pointers for X and for every output.
+ */
+int pg_scan(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+            double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
+            int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing);
+int pg_scan_device(pg_handle* h, const void* X_dev, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+                   double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
+                   int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing);
+
+/*
+ * Unit-level probes used by the parity tests (mirrors of the reference's Python-callable cpdefs).
+ * pg_probe_precompute: one precompute_mat(lam, ...) (pyx:880) for one rotated genotype vector x (host,
+ * n doubles): out9 = {yPy, yPPy, yPPPy, trP, trPP, logdet_H, logdet_WtHinvW, xPx, yPx}.
+ * fixed_index >= 0 evaluates the exact table row of lambda = 10^(fixed_index-5) instead of `lam`.
+ */
+int pg_probe_precompute(pg_handle* h, const double* x_rot_host, double lam, int fixed_index, int full,
+                        double* out9);
+/* F(1, nu) survival function evaluated on the device for k values (scipy.stats.f.sf, lmm/lmm.py:482) */
+int pg_probe_f_sf(pg_handle* h, const double* F_host, double nu, int64_t k, double* p_host);
+/* rotated genotypes of the last SNP block pg_scan processed: copies min(count, block) * n doubles
+ * (SNP-major) and reports the global index of the block's first SNP in *row0 (nullable) */
+int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, int64_t* row0);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYGEMMA_B200_H */

@@ -1,0 +1,236 @@
+"""ctypes binding of libpygemma_b200.so (include/pygemma_b200.h).
+
+The shared library is the product: if it is missing or does not load this
+module raises -- there is no Python or CPU fallback for the scan.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpygemma_b200.so")
+
+PG_X_I8, PG_X_F32, PG_X_F64 = 0, 1, 2
+PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1
+PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT = 0, 1, 2
+
+# every symbol include/pygemma_b200.h declares (tests check the library exports each one)
+SYMBOLS = [
+    "pg_abi_version", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
+    "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_options",
+    "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
+]
+
+
+class PgTiming(ctypes.Structure):
+    _fields_ = [("total_ms", ctypes.c_float), ("h2d_ms", ctypes.c_float), ("convert_ms", ctypes.c_float),
+                ("rotate_ms", ctypes.c_float), ("reml_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
+                ("n_blocks", ctypes.c_int32), ("block_snps", ctypes.c_int32), ("reml_launches", ctypes.c_int32),
+                ("rotate_launches", ctypes.c_int32), ("convert_launches", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class PgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pygemma_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library (building it is __graft_entry__.build()'s / pygemma_b200.build's job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m pygemma_b200.build` (nvcc, sm_100a). "
+            "pygemma_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    L.pg_abi_version.restype = i32
+    L.pg_device_count.argtypes = [ctypes.POINTER(i32)]
+    L.pg_last_error.restype = ctypes.c_char_p
+    L.pg_last_error.argtypes = [vp]
+    L.pg_create.argtypes = [i32, i32, i32, ctypes.POINTER(vp)]
+    L.pg_destroy.argtypes = [vp]
+    L.pg_set_kinship.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_float)]
+    L.pg_set_eigen.argtypes = [vp, vp, i32, vp]
+    L.pg_set_eigen_device.argtypes = [vp, vp, i32, vp]
+    L.pg_get_eigen_device.argtypes = [vp, vp, vp]
+    L.pg_set_design.argtypes = [vp, vp, vp, i32, ctypes.POINTER(ctypes.c_float)]
+    L.pg_set_options.argtypes = [vp, i32, i64]
+    scan_args = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 9 + [ctypes.POINTER(PgTiming)]
+    L.pg_scan.argtypes = scan_args
+    L.pg_scan_device.argtypes = scan_args
+    L.pg_probe_precompute.argtypes = [vp, vp, dbl, i32, i32, vp]
+    L.pg_probe_f_sf.argtypes = [vp, vp, dbl, i64, vp]
+    L.pg_probe_rotated.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
+    for name in SYMBOLS:
+        if name not in ("pg_last_error",):
+            getattr(L, name).restype = i32
+    L.pg_last_error.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+_XDT = {np.dtype(np.int8): PG_X_I8, np.dtype(np.float32): PG_X_F32, np.dtype(np.float64): PG_X_F64}
+
+
+def xdtype_of(a) -> int:
+    try:
+        return _XDT[np.dtype(a.dtype)]
+    except KeyError:
+        raise TypeError(f"genotype dtype {a.dtype} not supported by the C ABI (int8, float32, float64)")
+
+
+class Handle:
+    """Owns one pg_handle (one GPU).  Thin, 1:1 with the C ABI."""
+
+    def __init__(self, n: int, c0: int, device: int = 0):
+        self.L = load()
+        self.n, self.c0, self.device = int(n), int(c0), int(device)
+        h = ctypes.c_void_p()
+        rc = self.L.pg_create(self.n, self.c0, self.device, ctypes.byref(h))
+        if rc != 0:
+            raise PgError(rc, self.L.pg_last_error(None).decode())
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PgError(rc, self.L.pg_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # --- setup -------------------------------------------------------------------------------
+    def set_kinship(self, K):
+        K = np.ascontiguousarray(K, dtype=np.float64)
+        assert K.shape == (self.n, self.n)
+        d = np.empty(self.n)
+        ms = ctypes.c_float(0)
+        self._ck(self.L.pg_set_kinship(self.h, _ptr(K), _ptr(d), ctypes.byref(ms)))
+        return d, float(ms.value)
+
+    def set_eigen(self, U, d):
+        d = np.ascontiguousarray(d, dtype=np.float64).reshape(-1)
+        assert d.shape[0] == self.n
+        if U is None:
+            self._ck(self.L.pg_set_eigen(self.h, None, 0, _ptr(d)))
+            return
+        U = np.asarray(U, dtype=np.float64)
+        assert U.shape == (self.n, self.n)
+        if U.flags.f_contiguous and not U.flags.c_contiguous:
+            self._ck(self.L.pg_set_eigen(self.h, _ptr(U), 0, _ptr(d)))
+        else:
+            U = np.ascontiguousarray(U)
+            self._ck(self.L.pg_set_eigen(self.h, _ptr(U), 1, _ptr(d)))
+
+    def set_eigen_device(self, U_ptr: int, u_row_major: bool, d_ptr: int):
+        self._ck(self.L.pg_set_eigen_device(self.h, ctypes.c_void_p(U_ptr), int(u_row_major), ctypes.c_void_p(d_ptr)))
+
+    def get_eigen_device(self, U_ptr: int, d_ptr: int):
+        self._ck(self.L.pg_get_eigen_device(self.h, ctypes.c_void_p(U_ptr), ctypes.c_void_p(d_ptr)))
+
+    def set_design(self, W, y, already_rotated=False):
+        W = np.ascontiguousarray(W, dtype=np.float64).reshape(self.n, self.c0)
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        assert y.shape[0] == self.n
+        ms = ctypes.c_float(0)
+        self._ck(self.L.pg_set_design(self.h, _ptr(W) if self.c0 else None, _ptr(y), int(already_rotated),
+                                      ctypes.byref(ms)))
+        return float(ms.value)
+
+    def set_options(self, rotation=PG_ROT_AUTO, block_snps=0):
+        self._ck(self.L.pg_set_options(self.h, int(rotation), int(block_snps)))
+
+    # --- scan --------------------------------------------------------------------------------
+    def scan(self, X, grid=False, layout=PG_X_SAMPLE_MAJOR, with_counts=True):
+        """Host-buffer scan.  X: (n, m) sample-major or (m, n) SNP-major ndarray, any stride along rows."""
+        if X.ndim != 2:
+            raise ValueError("X must be 2-D")
+        if layout == PG_X_SAMPLE_MAJOR:
+            n, m = X.shape
+        else:
+            m, n = X.shape
+        if n != self.n:
+            raise ValueError(f"X has {n} samples, handle was created for {self.n}")
+        if X.strides[1] != X.itemsize or (X.shape[0] > 1 and X.strides[0] % X.itemsize) or X.strides[0] < 0:
+            X = np.ascontiguousarray(X)
+        ld = X.strides[0] // X.itemsize if X.shape[0] > 1 else X.shape[1]
+        ld = max(ld, X.shape[1])
+        out = {k: np.empty(m) for k in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald")}
+        st = np.zeros(m, dtype=np.int32)
+        e2 = np.zeros(m, dtype=np.int32) if with_counts else None
+        e3 = np.zeros(m, dtype=np.int32) if with_counts else None
+        tm = PgTiming()
+        self._ck(self.L.pg_scan(self.h, _ptr(X), xdtype_of(X), ld, layout, m, int(bool(grid)),
+                                _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
+                                _ptr(out["F_wald"]), _ptr(out["p_wald"]), _ptr(st), _ptr(e2), _ptr(e3),
+                                ctypes.byref(tm)))
+        out["status"] = st
+        if with_counts:
+            out["n_eval2"], out["n_eval3"] = e2, e3
+        out["timing"] = tm.as_dict()
+        return out
+
+    def scan_device(self, x_ptr: int, xdtype: int, ld: int, layout: int, m: int, grid: bool, out_ptrs, status_ptr=0,
+                    e2_ptr=0, e3_ptr=0):
+        """Device-buffer scan: x_ptr and the six out_ptrs are raw CUDA device pointers."""
+        tm = PgTiming()
+        vp = ctypes.c_void_p
+        self._ck(self.L.pg_scan_device(self.h, vp(x_ptr), xdtype, ld, layout, m, int(bool(grid)),
+                                       *[vp(p) for p in out_ptrs], vp(status_ptr or None), vp(e2_ptr or None),
+                                       vp(e3_ptr or None), ctypes.byref(tm)))
+        return tm.as_dict()
+
+    # --- probes ------------------------------------------------------------------------------
+    def probe_precompute(self, x_rot, lam, fixed_index=-1, full=True):
+        x = np.ascontiguousarray(x_rot, dtype=np.float64).reshape(-1)
+        out = np.empty(9)
+        self._ck(self.L.pg_probe_precompute(self.h, _ptr(x), float(lam), int(fixed_index), int(bool(full)), _ptr(out)))
+        return out
+
+    def probe_f_sf(self, F, nu):
+        F = np.ascontiguousarray(F, dtype=np.float64).reshape(-1)
+        p = np.empty_like(F)
+        self._ck(self.L.pg_probe_f_sf(self.h, _ptr(F), float(nu), F.shape[0], _ptr(p)))
+        return p
+
+    def probe_rotated(self, count):
+        xr = np.empty((count, self.n))
+        row0 = ctypes.c_int64(0)
+        self._ck(self.L.pg_probe_rotated(self.h, _ptr(xr), count, ctypes.byref(row0)))
+        return xr, int(row0.value)
+
+
+def device_count() -> int:
+    c = ctypes.c_int(0)
+    load().pg_device_count(ctypes.byref(c))
+    return int(c.value)

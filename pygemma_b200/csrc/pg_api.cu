@@ -1,0 +1,656 @@
+// pg_api.cu -- C-ABI implementation (include/pygemma_b200.h): handle, eigendecomposition, design
+// rotation, table building and the blocked scan pipeline (upload -> stage -> rotate -> REML -> download).
+//
+// Host-side mirror of the reference driver lmm/lmm.py:87-411; the reference's multiprocessing chunking
+// (SampleIter, lmm/lmm.py:413-436) becomes SNP blocks streamed through one GPU.
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pygemma_b200.h"
+#include "reml_kernels.cuh"
+#include "rotate_kernels.cuh"
+
+using namespace pg;
+
+static thread_local std::string g_create_error;
+
+struct pg_handle {
+    int n = 0, c0 = 0, device = 0;
+    int sm_count = 148;
+    std::string err;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cublasHandle_t blas = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    // eigen
+    double* U = nullptr;  // n x n
+    int u_op_t = 1;       // 1: stored column-major U (rotation uses U^T = op T); 0: stored buffer is U^T column-major
+    bool have_U = false, have_d = false, have_design = false;
+    double* d = nullptr;  // n
+    // design
+    double* wy = nullptr;  // n x (c0+1) column-major, rotated
+    bool rotated_inputs = false;
+    // tables
+    double *fixtab = nullptr, *itab = nullptr, *basis = nullptr, *lambdas = nullptr;
+    TriAB* tri_ab = nullptr;
+    Tables tab{};
+    // scan workspace
+    int rotation = PG_ROT_AUTO;
+    long long block_snps_opt = 0;
+    long long blk = 0;  // allocated block size (SNPs)
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    double *xf = nullptr, *xr = nullptr;
+    size_t xbuf_elems = 0;
+    unsigned long long* counter = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    RotWorkspace rot;
+    long long last_block_count = 0, last_block_row0 = 0;
+};
+
+static int fail(pg_handle* h, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(h, PG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CKB(call)                                                                                     \
+    do {                                                                                              \
+        cublasStatus_t s_ = (call);                                                                   \
+        if (s_ != CUBLAS_STATUS_SUCCESS)                                                              \
+            return fail(h, PG_ERR_CUBLAS, "%s:%d %s -> cublas status %d", __FILE__, __LINE__, #call, (int)s_); \
+    } while (0)
+#define CKS(call)                                                                                     \
+    do {                                                                                              \
+        cusolverStatus_t s_ = (call);                                                                 \
+        if (s_ != CUSOLVER_STATUS_SUCCESS)                                                            \
+            return fail(h, PG_ERR_CUSOLVER, "%s:%d %s -> cusolver status %d", __FILE__, __LINE__, #call, (int)s_); \
+    } while (0)
+
+extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
+
+extern "C" int pg_device_count(int* count)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (count) *count = (e == cudaSuccess) ? c : 0;
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        return PG_ERR_NO_DEVICE;
+    }
+    return PG_OK;
+}
+
+extern "C" const char* pg_last_error(const pg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int free_all(pg_handle* h)
+{
+    cudaSetDevice(h->device);
+    rot_free(&h->rot);
+    for (int s = 0; s < 2; ++s) {
+        if (h->stage[s]) cudaFree(h->stage[s]);
+        if (h->ev_ready[s]) cudaEventDestroy(h->ev_ready[s]);
+        if (h->ev_free[s]) cudaEventDestroy(h->ev_free[s]);
+    }
+    void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr, h->counter};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (h->blas) cublasDestroy(h->blas);
+    if (h->solver) cusolverDnDestroy(h->solver);
+    if (h->compute) cudaStreamDestroy(h->compute);
+    if (h->copy) cudaStreamDestroy(h->copy);
+    return 0;
+}
+
+extern "C" int pg_destroy(pg_handle* h)
+{
+    if (!h) return PG_OK;
+    free_all(h);
+    delete h;
+    return PG_OK;
+}
+
+extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
+{
+    if (!out) return fail(nullptr, PG_ERR_ARG, "pg_create: out is NULL");
+    *out = nullptr;
+    if (n < 2 || c0 < 0 || c0 + 2 > kMaxCols || n - c0 - 1 < 1)
+        return fail(nullptr, PG_ERR_ARG, "pg_create: need n >= 2, 0 <= c0 <= %d, n - c0 - 1 >= 1 (got n=%d c0=%d)",
+                    kMaxCols - 2, n, c0);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, PG_ERR_NO_DEVICE, "pg_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, PG_ERR_ARG, "pg_create: device %d of %d", device, count);
+    pg_handle* h = new pg_handle;
+    h->n = n; h->c0 = c0; h->device = device;
+    int rc = [&]() -> int {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(h, PG_ERR_NO_DEVICE, "pg_create: device %d is sm_%d%d; this build targets sm_100a only", device,
+                        prop.major, prop.minor);
+        h->sm_count = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+        CKB(cublasCreate(&h->blas));
+        CKB(cublasSetStream(h->blas, h->compute));
+        CKS(cusolverDnCreate(&h->solver));
+        CKS(cusolverDnSetStream(h->solver, h->compute));
+        for (int s = 0; s < 2; ++s) {
+            CK(cudaEventCreateWithFlags(&h->ev_ready[s], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_free[s], cudaEventDisableTiming));
+        }
+        const int k0 = c0 + 1, T0 = k0 * (k0 + 1) / 2, NF = 3 * T0 + 3;
+        CK(cudaMalloc(&h->d, sizeof(double) * n));
+        CK(cudaMalloc(&h->wy, sizeof(double) * (size_t)n * k0));
+        CK(cudaMalloc(&h->fixtab, sizeof(double) * (size_t)kNumFixed * NF));
+        CK(cudaMalloc(&h->itab, sizeof(double) * (size_t)kNumIntervals * kNodes * NF));
+        CK(cudaMalloc(&h->basis, sizeof(double) * kNodes * kNodes));
+        CK(cudaMalloc(&h->lambdas, sizeof(double) * kNumTableRows));
+        CK(cudaMalloc(&h->tri_ab, sizeof(TriAB) * kMaxTri));
+        CK(cudaMalloc(&h->counter, sizeof(unsigned long long)));
+        std::vector<TriAB> tab(kMaxTri);
+        fill_tri_ab(tab.data());
+        CK(cudaMemcpy(h->tri_ab, tab.data(), sizeof(TriAB) * kMaxTri, cudaMemcpyHostToDevice));
+        std::vector<double> basis(kNodes * kNodes), lams(kNumTableRows);
+        fill_basis(basis.data());
+        for (int r = 0; r < kNumTableRows; ++r) lams[r] = table_lambda(r);
+        CK(cudaMemcpy(h->basis, basis.data(), sizeof(double) * basis.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->lambdas, lams.data(), sizeof(double) * lams.size(), cudaMemcpyHostToDevice));
+        h->tab.c0 = c0; h->tab.k0 = k0; h->tab.T0 = T0; h->tab.NF = NF;
+        h->tab.fixtab = h->fixtab; h->tab.itab = h->itab; h->tab.basis = h->basis; h->tab.tri_ab = h->tri_ab;
+        return PG_OK;
+    }();
+    if (rc != PG_OK) {
+        g_create_error = h->err;
+        free_all(h);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return PG_OK;
+}
+
+static int ensure_U(pg_handle* h)
+{
+    if (!h->U) CK(cudaMalloc(&h->U, sizeof(double) * (size_t)h->n * h->n));
+    return PG_OK;
+}
+
+extern "C" int pg_set_kinship(pg_handle* h, const double* K_host, double* d_out_host, float* eig_ms)
+{
+    if (!h || !K_host) return fail(h, PG_ERR_ARG, "pg_set_kinship: NULL argument");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n;
+    int rc = ensure_U(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->U, K_host, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, h->compute));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    cusolverDnParams_t params;
+    CKS(cusolverDnCreateParams(&params));
+    size_t wdev = 0, whost = 0;
+    CKS(cusolverDnXsyevd_bufferSize(h->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F,
+                                    h->U, n, CUDA_R_64F, h->d, CUDA_R_64F, &wdev, &whost));
+    void* dwork = nullptr;
+    int* info = nullptr;
+    CK(cudaMalloc(&dwork, wdev ? wdev : 8));
+    CK(cudaMalloc(&info, sizeof(int)));
+    std::vector<char> hwork(whost ? whost : 8);
+    CK(cudaEventRecord(e0, h->compute));
+    cusolverStatus_t st = cusolverDnXsyevd(h->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                           CUDA_R_64F, h->U, n, CUDA_R_64F, h->d, CUDA_R_64F, dwork, wdev,
+                                           hwork.data(), whost, info);
+    CK(cudaEventRecord(e1, h->compute));
+    int hinfo = -1;
+    cudaError_t ce = cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->compute);
+    cudaError_t se = cudaStreamSynchronize(h->compute);
+    cudaFree(dwork);
+    cudaFree(info);
+    cusolverDnDestroyParams(params);
+    if (st != CUSOLVER_STATUS_SUCCESS) return fail(h, PG_ERR_CUSOLVER, "cusolverDnXsyevd status %d", (int)st);
+    if (ce != cudaSuccess || se != cudaSuccess)
+        return fail(h, PG_ERR_CUDA, "syevd: %s", cudaGetErrorString(ce != cudaSuccess ? ce : se));
+    if (hinfo != 0) return fail(h, PG_ERR_CUSOLVER, "syevd did not converge (info=%d)", hinfo);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (eig_ms) *eig_ms = ms;
+    clip_nonneg_kernel<<<(n + 255) / 256, 256, 0, h->compute>>>(h->d, n);
+    CK(cudaGetLastError());
+    if (d_out_host) CK(cudaMemcpyAsync(d_out_host, h->d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->compute));
+    CK(cudaStreamSynchronize(h->compute));
+    h->u_op_t = 1; h->have_U = true; h->have_d = true; h->rotated_inputs = false; h->have_design = false;
+    rot_invalidate(&h->rot);
+    return PG_OK;
+}
+
+static int set_eigen_common(pg_handle* h, const double* U, int u_row_major, const double* d, cudaMemcpyKind kind)
+{
+    if (!h || !d) return fail(h, PG_ERR_ARG, "pg_set_eigen: NULL argument");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n;
+    if (U) {
+        int rc = ensure_U(h);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->U, U, sizeof(double) * (size_t)n * n, kind, h->compute));
+        // a row-major U buffer read as column-major is U^T: the rotation then uses it untransposed
+        h->u_op_t = u_row_major ? 0 : 1;
+        h->have_U = true;
+    } else {
+        h->have_U = false;
+    }
+    CK(cudaMemcpyAsync(h->d, d, sizeof(double) * n, kind, h->compute));
+    clip_nonneg_kernel<<<(n + 255) / 256, 256, 0, h->compute>>>(h->d, n);  // lmm/lmm.py:157 / :166
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->compute));
+    h->have_d = true; h->have_design = false;
+    rot_invalidate(&h->rot);
+    return PG_OK;
+}
+
+extern "C" int pg_set_eigen(pg_handle* h, const double* U_host, int u_row_major, const double* d_host)
+{
+    return set_eigen_common(h, U_host, u_row_major, d_host, cudaMemcpyHostToDevice);
+}
+
+extern "C" int pg_set_eigen_device(pg_handle* h, const double* U_dev, int u_row_major, const double* d_dev)
+{
+    return set_eigen_common(h, U_dev, u_row_major, d_dev, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int pg_get_eigen_device(pg_handle* h, double* U_dev_out, double* d_dev_out)
+{
+    if (!h || !h->have_U || !h->have_d) return fail(h, PG_ERR_ARG, "pg_get_eigen_device: no eigendecomposition held");
+    if (!h->u_op_t) return fail(h, PG_ERR_ARG, "pg_get_eigen_device: U is held transposed");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n;
+    if (U_dev_out)
+        CK(cudaMemcpyAsync(U_dev_out, h->U, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, h->compute));
+    if (d_dev_out) CK(cudaMemcpyAsync(d_dev_out, h->d, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->compute));
+    CK(cudaStreamSynchronize(h->compute));
+    return PG_OK;
+}
+
+static int build_tables(pg_handle* h)
+{
+    const int T0 = h->tab.T0;
+    const int nchunks = (T0 + kTablePairs - 1) / kTablePairs;
+    dim3 grid(nchunks + 1, kNumTableRows);
+    build_tables_kernel<<<grid, 256, 0, h->compute>>>(h->n, h->c0, h->d, h->wy, h->lambdas, h->fixtab, h->itab,
+                                                      h->tri_ab);
+    CK(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y_host, int already_rotated, float* ms)
+{
+    if (!h || !y_host || (!W_host && h->c0 > 0)) return fail(h, PG_ERR_ARG, "pg_set_design: NULL argument");
+    if (!h->have_d) return fail(h, PG_ERR_ARG, "pg_set_design: call pg_set_kinship / pg_set_eigen first");
+    if (!already_rotated && !h->have_U) return fail(h, PG_ERR_ARG, "pg_set_design: no U held and inputs are not rotated");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n, c0 = h->c0, k0 = c0 + 1;
+    // (n, c0) C-order + y -> column-major n x (c0+1)
+    std::vector<double> col((size_t)n * k0);
+    for (int j = 0; j < c0; ++j)
+        for (int l = 0; l < n; ++l) col[(size_t)j * n + l] = W_host[(size_t)l * c0 + j];
+    for (int l = 0; l < n; ++l) col[(size_t)c0 * n + l] = y_host[l];
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->compute));
+    if (already_rotated) {
+        CK(cudaMemcpyAsync(h->wy, col.data(), sizeof(double) * col.size(), cudaMemcpyHostToDevice, h->compute));
+    } else {
+        double* raw = nullptr;
+        CK(cudaMalloc(&raw, sizeof(double) * col.size()));
+        CK(cudaMemcpyAsync(raw, col.data(), sizeof(double) * col.size(), cudaMemcpyHostToDevice, h->compute));
+        const double one = 1.0, zero = 0.0;
+        // wy = U^T [W, y]  (lmm/lmm.py:245-246)
+        cublasStatus_t s = cublasDgemm(h->blas, h->u_op_t ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, n, k0, n, &one, h->U,
+                                       n, raw, n, &zero, h->wy, n);
+        cudaStreamSynchronize(h->compute);
+        cudaFree(raw);
+        if (s != CUBLAS_STATUS_SUCCESS) return fail(h, PG_ERR_CUBLAS, "pg_set_design: dgemm status %d", (int)s);
+    }
+    h->rotated_inputs = already_rotated != 0;
+    int rc = build_tables(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(e1, h->compute));
+    CK(cudaStreamSynchronize(h->compute));
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = t;
+    h->have_design = true;
+    return PG_OK;
+}
+
+extern "C" int pg_set_options(pg_handle* h, int rotation, int64_t block_snps)
+{
+    if (!h) return PG_ERR_ARG;
+    if (rotation < PG_ROT_AUTO || rotation > PG_ROT_I8SPLIT) return fail(h, PG_ERR_ARG, "pg_set_options: rotation %d", rotation);
+    if (block_snps < 0) return fail(h, PG_ERR_ARG, "pg_set_options: block_snps %lld", (long long)block_snps);
+    h->rotation = rotation;
+    h->block_snps_opt = block_snps;
+    return PG_OK;
+}
+
+static size_t xdtype_size(int t) { return t == PG_X_I8 ? 1 : (t == PG_X_F32 ? 4 : 8); }
+
+static int ensure_workspace(pg_handle* h, long long m, int xdtype)
+{
+    const int n = h->n;
+    long long blk = h->block_snps_opt;
+    if (blk <= 0) {
+        blk = (long long)((size_t(1) << 29) / (sizeof(double) * (size_t)n));  // ~512 MB of fp64 per buffer
+        blk = std::max<long long>(256, (blk / 256) * 256);
+        blk = std::min<long long>(blk, 16384);
+    }
+    blk = std::min(blk, std::max<long long>(m, 1));
+    blk = ((blk + 31) / 32) * 32;
+    const size_t need = (size_t)blk * n;
+    if (need > h->xbuf_elems) {
+        if (h->xf) cudaFree(h->xf);
+        if (h->xr) cudaFree(h->xr);
+        h->xf = h->xr = nullptr;
+        h->xbuf_elems = 0;
+        CK(cudaMalloc(&h->xf, sizeof(double) * need));
+        CK(cudaMalloc(&h->xr, sizeof(double) * need));
+        h->xbuf_elems = need;
+    }
+    const size_t sbytes = need * xdtype_size(xdtype);
+    if (sbytes > h->stage_bytes) {
+        for (int s = 0; s < 2; ++s) {
+            if (h->stage[s]) cudaFree(h->stage[s]);
+            h->stage[s] = nullptr;
+        }
+        h->stage_bytes = 0;
+        for (int s = 0; s < 2; ++s) CK(cudaMalloc(&h->stage[s], sbytes));
+        h->stage_bytes = sbytes;
+    }
+    h->blk = blk;
+    return PG_OK;
+}
+
+static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld, int layout, long long mb, double* dst)
+{
+    if (stage_to_snp_major(h->compute, h->n, src, xdtype, ld, layout, mb, dst)) {
+        cudaError_t e_ = cudaGetLastError();
+        return fail(h, PG_ERR_CUDA, "staging kernel: %s", cudaGetErrorString(e_));
+    }
+    return PG_OK;
+}
+
+static int launch_reml(pg_handle* h, const double* xr, long long mb, long long row0, int grid_mode, double* const out[6],
+                       int* status, int* e2, int* e3)
+{
+    ScanArgs a;
+    a.n = h->n; a.c0 = h->c0; a.grid = grid_mode; a.m = mb; a.row0 = row0;
+    a.d = h->d; a.wy = h->wy; a.xr = xr; a.ldx = h->n; a.tab = h->tab;
+    for (int i = 0; i < 6; ++i) a.out[i] = out[i];
+    a.status = status; a.n_eval2 = e2; a.n_eval3 = e3; a.counter = h->counter;
+    const int k = h->c0 + 2, TT = k * (k + 1) / 2;
+    const size_t per_warp = sizeof(double) * 3 * TT;
+    int warps = 8;
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    const size_t smem = per_warp * warps;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(reml_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
+    long long want = (mb + warps - 1) / warps;
+    int grid = (int)std::min<long long>(want, (long long)h->sm_count * ctas_per_sm);
+    grid = std::max(grid, 1);
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), h->compute));
+    reml_scan_kernel<<<grid, warps * 32, smem, h->compute>>>(a);
+    CK(cudaGetLastError());
+    return PG_OK;
+}
+
+struct EvPair {
+    cudaEvent_t a, b;
+};
+
+static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int layout, long long m, int grid_mode,
+                     double* const out_user[6], int32_t* status, int32_t* e2, int32_t* e3, pg_timing* timing,
+                     bool on_device)
+{
+    if (!h) return PG_ERR_ARG;
+    if (!X || m < 0) return fail(h, PG_ERR_ARG, "pg_scan: NULL X or negative m");
+    for (int i = 0; i < 6; ++i)
+        if (!out_user[i] && m > 0) return fail(h, PG_ERR_ARG, "pg_scan: NULL output %d", i);
+    if (xdtype < PG_X_I8 || xdtype > PG_X_F64) return fail(h, PG_ERR_ARG, "pg_scan: xdtype %d", xdtype);
+    if (layout != PG_X_SAMPLE_MAJOR && layout != PG_X_SNP_MAJOR) return fail(h, PG_ERR_ARG, "pg_scan: layout %d", layout);
+    if (!h->have_design) return fail(h, PG_ERR_ARG, "pg_scan: call pg_set_design first");
+    const int n = h->n;
+    if ((layout == PG_X_SAMPLE_MAJOR && ld < m) || (layout == PG_X_SNP_MAJOR && ld < n))
+        return fail(h, PG_ERR_ARG, "pg_scan: ld %lld too small", ld);
+    if (timing) memset(timing, 0, sizeof *timing);
+    if (m == 0) return PG_OK;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_workspace(h, m, xdtype);
+    if (rc) return rc;
+    const long long blk = h->blk;
+    const long long nblocks = (m + blk - 1) / blk;
+    const size_t esz = xdtype_size(xdtype);
+    const bool rotate = !h->rotated_inputs;
+
+    // outputs: device arrays (user's when on_device, temporaries otherwise)
+    double* dout[6];
+    int *dstatus = nullptr, *de2 = nullptr, *de3 = nullptr;
+    double* dtmp = nullptr;
+    int* itmp = nullptr;
+    if (on_device) {
+        for (int i = 0; i < 6; ++i) dout[i] = out_user[i];
+        dstatus = status; de2 = e2; de3 = e3;
+    } else {
+        CK(cudaMalloc(&dtmp, sizeof(double) * 6 * (size_t)m));
+        CK(cudaMalloc(&itmp, sizeof(int) * 3 * (size_t)m));
+        for (int i = 0; i < 6; ++i) dout[i] = dtmp + (size_t)i * m;
+        dstatus = itmp; de2 = itmp + m; de3 = itmp + 2 * (size_t)m;
+    }
+
+    std::vector<EvPair> ev_conv(nblocks), ev_rot(nblocks), ev_reml(nblocks), ev_h2d(nblocks);
+    auto mk = [&](EvPair& p) { cudaEventCreate(&p.a); cudaEventCreate(&p.b); };
+    for (long long b = 0; b < nblocks; ++b) { mk(ev_conv[b]); mk(ev_rot[b]); mk(ev_reml[b]); if (!on_device) mk(ev_h2d[b]); }
+    cudaEvent_t t0, t1, t2;
+    cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+    int n_rot_launch = 0;
+
+    rc = [&]() -> int {
+        CK(cudaEventRecord(t0, h->compute));
+        CK(cudaStreamWaitEvent(h->copy, t0, 0));
+        for (long long b = 0; b < nblocks; ++b) {
+            const long long g0 = b * blk, mb = std::min(blk, m - g0);
+            const int s = (int)(b & 1);
+            const void* src_dev;
+            long long ld_dev;
+            if (on_device) {
+                src_dev = (layout == PG_X_SAMPLE_MAJOR) ? (const char*)X + (size_t)g0 * esz
+                                                        : (const char*)X + (size_t)g0 * ld * esz;
+                ld_dev = ld;
+            } else {
+                if (b >= 2) CK(cudaStreamWaitEvent(h->copy, h->ev_free[s], 0));
+                CK(cudaEventRecord(ev_h2d[b].a, h->copy));
+                if (layout == PG_X_SAMPLE_MAJOR) {
+                    // n rows of mb elements, host pitch ld
+                    CK(cudaMemcpy2DAsync(h->stage[s], (size_t)mb * esz, (const char*)X + (size_t)g0 * esz,
+                                         (size_t)ld * esz, (size_t)mb * esz, (size_t)n, cudaMemcpyHostToDevice, h->copy));
+                    ld_dev = mb;
+                } else {
+                    CK(cudaMemcpy2DAsync(h->stage[s], (size_t)n * esz, (const char*)X + (size_t)g0 * ld * esz,
+                                         (size_t)ld * esz, (size_t)n * esz, (size_t)mb, cudaMemcpyHostToDevice, h->copy));
+                    ld_dev = n;
+                }
+                CK(cudaEventRecord(ev_h2d[b].b, h->copy));
+                CK(cudaEventRecord(h->ev_ready[s], h->copy));
+                CK(cudaStreamWaitEvent(h->compute, h->ev_ready[s], 0));
+                src_dev = h->stage[s];
+            }
+            const double* xr_block = nullptr;
+            CK(cudaEventRecord(ev_conv[b].a, h->compute));
+            bool staged = false;
+            int used_i8 = 0;
+            if (rotate) {
+                // try the fused-conversion rotation engines first (they read the raw block directly)
+                int r2 = rot_run(&h->rot, h->blas, h->compute, h->rotation, h->U, h->u_op_t, n, src_dev, xdtype, ld_dev,
+                                 layout, mb, h->xf, h->xr, &staged, &used_i8, &n_rot_launch, ev_conv[b].b, ev_rot[b].a,
+                                 ev_rot[b].b, h->sm_count);
+                if (r2 != 0) return fail(h, r2, "rotation failed: %s", rot_error(&h->rot));
+                xr_block = h->xr;
+            } else {
+                int r2 = launch_stage(h, src_dev, xdtype, ld_dev, layout, mb, h->xr);
+                if (r2) return r2;
+                CK(cudaEventRecord(ev_conv[b].b, h->compute));
+                CK(cudaEventRecord(ev_rot[b].a, h->compute));
+                CK(cudaEventRecord(ev_rot[b].b, h->compute));
+                xr_block = h->xr;
+            }
+            if (!on_device) CK(cudaEventRecord(h->ev_free[s], h->compute));
+            CK(cudaEventRecord(ev_reml[b].a, h->compute));
+            int r3 = launch_reml(h, xr_block, mb, g0, grid_mode, dout, dstatus, de2, de3);
+            if (r3) return r3;
+            CK(cudaEventRecord(ev_reml[b].b, h->compute));
+            h->last_block_count = mb;
+            h->last_block_row0 = g0;
+        }
+        CK(cudaEventRecord(t1, h->compute));
+        if (!on_device) {
+            for (int i = 0; i < 6; ++i)
+                CK(cudaMemcpyAsync(out_user[i], dout[i], sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
+            if (status) CK(cudaMemcpyAsync(status, dstatus, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
+            if (e2) CK(cudaMemcpyAsync(e2, de2, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
+            if (e3) CK(cudaMemcpyAsync(e3, de3, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
+        }
+        CK(cudaEventRecord(t2, h->compute));
+        CK(cudaStreamSynchronize(h->compute));
+        CK(cudaStreamSynchronize(h->copy));
+        return PG_OK;
+    }();
+
+    if (rc == PG_OK && timing) {
+        float v = 0;
+        cudaEventElapsedTime(&timing->total_ms, t0, t2);
+        cudaEventElapsedTime(&timing->d2h_ms, t1, t2);
+        for (long long b = 0; b < nblocks; ++b) {
+            cudaEventElapsedTime(&v, ev_conv[b].a, ev_conv[b].b); timing->convert_ms += v;
+            cudaEventElapsedTime(&v, ev_rot[b].a, ev_rot[b].b); timing->rotate_ms += v;
+            cudaEventElapsedTime(&v, ev_reml[b].a, ev_reml[b].b); timing->reml_ms += v;
+            if (!on_device) { cudaEventElapsedTime(&v, ev_h2d[b].a, ev_h2d[b].b); timing->h2d_ms += v; }
+        }
+        timing->n_blocks = (int32_t)nblocks;
+        timing->block_snps = (int32_t)blk;
+        timing->reml_launches = (int32_t)nblocks;
+        timing->rotate_launches = n_rot_launch;
+        timing->convert_launches = (int32_t)nblocks;
+    }
+    for (long long b = 0; b < nblocks; ++b) {
+        cudaEventDestroy(ev_conv[b].a); cudaEventDestroy(ev_conv[b].b);
+        cudaEventDestroy(ev_rot[b].a); cudaEventDestroy(ev_rot[b].b);
+        cudaEventDestroy(ev_reml[b].a); cudaEventDestroy(ev_reml[b].b);
+        if (!on_device) { cudaEventDestroy(ev_h2d[b].a); cudaEventDestroy(ev_h2d[b].b); }
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+    if (dtmp) cudaFree(dtmp);
+    if (itmp) cudaFree(itmp);
+    if (rc != PG_OK) {
+        cudaStreamSynchronize(h->compute);
+        cudaStreamSynchronize(h->copy);
+    }
+    return rc;
+}
+
+extern "C" int pg_scan(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+                       double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
+                       int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing)
+{
+    double* out[6] = {beta, se_beta, tau, lambda, F_wald, p_wald};
+    return scan_impl(h, X, xdtype, ld, layout, m, grid, out, status, n_eval2, n_eval3, timing, false);
+}
+
+extern "C" int pg_scan_device(pg_handle* h, const void* X_dev, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+                              double* beta, double* se_beta, double* tau, double* lambda, double* F_wald,
+                              double* p_wald, int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing)
+{
+    double* out[6] = {beta, se_beta, tau, lambda, F_wald, p_wald};
+    return scan_impl(h, X_dev, xdtype, ld, layout, m, grid, out, status, n_eval2, n_eval3, timing, true);
+}
+
+extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, double lam, int fixed_index, int full,
+                                   double* out9)
+{
+    if (!h || !x_rot_host || !out9) return fail(h, PG_ERR_ARG, "pg_probe_precompute: NULL argument");
+    if (!h->have_design) return fail(h, PG_ERR_ARG, "pg_probe_precompute: call pg_set_design first");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n;
+    double *dx = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&dx, sizeof(double) * n));
+    CK(cudaMalloc(&dout, sizeof(double) * 9));
+    CK(cudaMemcpyAsync(dx, x_rot_host, sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
+    ScanArgs a{};
+    a.n = n; a.c0 = h->c0; a.grid = 0; a.m = 1; a.row0 = 0; a.d = h->d; a.wy = h->wy; a.xr = dx; a.ldx = n; a.tab = h->tab;
+    const int k = h->c0 + 2, TT = k * (k + 1) / 2;
+    const size_t smem = sizeof(double) * 3 * TT;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(probe_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_precompute_kernel<<<1, 32, smem, h->compute>>>(a, lam, fixed_index, full, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out9, dout, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->compute));
+    CK(cudaStreamSynchronize(h->compute));
+    cudaFree(dx);
+    cudaFree(dout);
+    return PG_OK;
+}
+
+extern "C" int pg_probe_f_sf(pg_handle* h, const double* F_host, double nu, int64_t k, double* p_host)
+{
+    if (!h || !F_host || !p_host || k < 0) return fail(h, PG_ERR_ARG, "pg_probe_f_sf: bad argument");
+    if (k == 0) return PG_OK;
+    CK(cudaSetDevice(h->device));
+    double *dF = nullptr, *dp = nullptr;
+    CK(cudaMalloc(&dF, sizeof(double) * k));
+    CK(cudaMalloc(&dp, sizeof(double) * k));
+    CK(cudaMemcpyAsync(dF, F_host, sizeof(double) * k, cudaMemcpyHostToDevice, h->compute));
+    probe_f_sf_kernel<<<(unsigned)((k + 127) / 128), 128, 0, h->compute>>>(dF, nu, k, dp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(p_host, dp, sizeof(double) * k, cudaMemcpyDeviceToHost, h->compute));
+    CK(cudaStreamSynchronize(h->compute));
+    cudaFree(dF);
+    cudaFree(dp);
+    return PG_OK;
+}
+
+extern "C" int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, int64_t* row0)
+{
+    if (!h || !xr_host || count < 0) return fail(h, PG_ERR_ARG, "pg_probe_rotated: bad argument");
+    if (!h->xr || h->last_block_count == 0) return fail(h, PG_ERR_ARG, "pg_probe_rotated: no scan has run");
+    CK(cudaSetDevice(h->device));
+    const long long c = std::min<long long>(count, h->last_block_count);
+    CK(cudaMemcpy(xr_host, h->xr, sizeof(double) * (size_t)c * h->n, cudaMemcpyDeviceToHost));
+    if (row0) *row0 = h->last_block_row0;
+    return PG_OK;
+}

@@ -1,0 +1,217 @@
+// pg_eval.cuh -- assembling and reducing the (c0+2)x(c0+2) "Pab" matrices of one likelihood evaluation.
+//
+// The reference rebuilds the full Gram matrices [W0,x,y]^T H^-k [W0,x,y] from scratch for every SNP
+// and every lambda (pygemma_model.pyx:938,:943,:1002).  Only the x row/column depends on the SNP; the
+// [W0,y] block is a function of lambda alone.  Here that block comes from tables:
+//   * exact tables at the 11 fixed lambdas 10^-5..10^5 (every grid-mode evaluation, the bracket scan),
+//   * Chebyshev interpolation in log10(lambda) for the SNP-specific lambdas Brent/Newton visit
+//     (8 sub-intervals per decade, 12 nodes each: interpolation error < 1e-14 of the Cauchy-Schwarz
+//     scale of each entry, i.e. below the rounding error of summing n terms directly).
+// The x row is produced by the caller (a warp-collective pass over the rotated genotype vector).
+//
+// The same source runs warp-parallel on the device (32 lanes, __syncwarp between pivots) and serially on
+// the host (tests/host_shim.cpp) so indexing and arithmetic are unit-tested without a GPU.
+#pragma once
+
+#include "pg_math.cuh"
+
+namespace pg {
+
+#if defined(__CUDA_ARCH__)
+#define PG_LANE ((int)(threadIdx.x & 31))
+#define PG_NLANES 32
+#define PG_SYNCWARP() __syncwarp()
+#else
+#define PG_LANE 0
+#define PG_NLANES 1
+#define PG_SYNCWARP() ((void)0)
+#endif
+
+constexpr int kMaxCols = 64;  // c0 + 2 <= 64
+constexpr int kMaxTri = kMaxCols * (kMaxCols + 1) / 2;
+
+PG_HD int tri(int r, int s) { return r * (r + 1) / 2 + s; }  // r >= s
+
+struct TriAB {
+    unsigned char a, b;
+};
+
+// SNP-independent tables for one (W0, y, d): see file header.
+struct Tables {
+    int c0, k0, T0, NF;     // k0 = c0+1 columns [W0, y]; T0 = k0(k0+1)/2; NF = 3*T0 + 3
+    const double* fixtab;   // [kNumFixed][NF]
+    const double* itab;     // [kNumIntervals][kNodes][NF]
+    const double* basis;    // [kNodes][kNodes]: basis[k*kNodes + j] = eps_j cos(j*pi*(k+1/2)/N) / N
+    const TriAB* tri_ab;    // [kMaxTri]: idx -> (a, b) with idx = a(a+1)/2 + b
+};
+
+// function index layout inside a table row
+PG_HD int fn_pair(const Tables& t, int power /*0,1,2*/, int q) { return power * t.T0 + q; }
+PG_HD int fn_trP(const Tables& t) { return 3 * t.T0; }
+PG_HD int fn_trPP(const Tables& t) { return 3 * t.T0 + 1; }
+PG_HD int fn_logdetH(const Tables& t) { return 3 * t.T0 + 2; }
+
+struct Level0 {
+    double trP, trPP, logdetH;
+};
+
+// Fill the [W0,y] block of the packed lower triangles A, B (and C when full) for `lam`.
+//   fixed_t >= 0 : exact row of the fixed table; otherwise Chebyshev interpolation.
+// Full index space: 0..c0-1 = W0 columns, c0 = x, c0+1 = y.
+template <bool FULL>
+PG_HD_NOINLINE void assemble_w0y(const Tables& t, double lam, int fixed_t, double* A, double* B, double* C,
+                                 Level0* l0)
+{
+    const int c0 = t.c0, NF = t.NF, T0 = t.T0;
+    const int npow = FULL ? 3 : 2;
+    if (fixed_t >= 0) {
+        const double* row = t.fixtab + (size_t)fixed_t * NF;
+        for (int q = PG_LANE; q < T0; q += PG_NLANES) {
+            const TriAB ab = t.tri_ab[q];
+            const int r = (ab.a == c0) ? c0 + 1 : ab.a, s = (ab.b == c0) ? c0 + 1 : ab.b;
+            const int dst = tri(r, s);
+            A[dst] = row[q];
+            B[dst] = row[T0 + q];
+            if (FULL) C[dst] = row[2 * T0 + q];
+        }
+        l0->trP = row[3 * T0]; l0->trPP = row[3 * T0 + 1]; l0->logdetH = row[3 * T0 + 2];
+        (void)npow;
+        return;
+    }
+    int iv;
+    double xloc;
+    interval_of(lam, &iv, &xloc);
+    double L[kNodes];
+    {
+        double T[kNodes];
+        T[0] = 1.0; T[1] = xloc;
+        for (int j = 2; j < kNodes; ++j) T[j] = 2.0 * xloc * T[j - 1] - T[j - 2];
+        for (int k = 0; k < kNodes; ++k) {
+            double s = 0.0;
+            for (int j = 0; j < kNodes; ++j) s += t.basis[k * kNodes + j] * T[j];
+            L[k] = s;
+        }
+    }
+    const double* base = t.itab + (size_t)iv * kNodes * NF;
+    for (int q = PG_LANE; q < T0; q += PG_NLANES) {
+        const TriAB ab = t.tri_ab[q];
+        const int r = (ab.a == c0) ? c0 + 1 : ab.a, s = (ab.b == c0) ? c0 + 1 : ab.b;
+        const int dst = tri(r, s);
+        double va = 0.0, vb = 0.0, vc = 0.0;
+        for (int k = 0; k < kNodes; ++k) {
+            const double* row = base + (size_t)k * NF;
+            va += L[k] * row[q];
+            vb += L[k] * row[T0 + q];
+            if (FULL) vc += L[k] * row[2 * T0 + q];
+        }
+        A[dst] = va;
+        B[dst] = vb;
+        if (FULL) C[dst] = vc;
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < kNodes; ++k) {
+        const double* row = base + (size_t)k * NF + 3 * T0;
+        s0 += L[k] * row[0];
+        s1 += L[k] * row[1];
+        s2 += L[k] * row[2];
+    }
+    l0->trP = s0; l0->trPP = s1; l0->logdetH = s2;
+}
+
+// The Pab recursion over covariates (pygemma_model.pyx:936-963 / :989-1036) on packed lower triangles.
+// On entry A, B, (C) hold the level-0 Gram matrices; on exit they hold level c_f = c0+1.
+// Order inside a level follows the reference: tr_Pi_Pi, C, tr_Pi, B, logdet, A (all read level i-1 values
+// of the pivot column, which no update of level i touches).
+template <bool FULL>
+PG_HD_NOINLINE void pab_recursion(const Tables& t, double* A, double* B, double* C, const Level0& l0,
+                                  bool need_logdet, EvalOut* out)
+{
+    const int c0 = t.c0, k = c0 + 2, cf = c0 + 1;
+    if (PG_LANE == 0) A[0] = cy_max(A[0], kMinVal);  // pyx:939 / :993
+    PG_SYNCWARP();
+    double trP = l0.trP, trPP = l0.trPP, logdetWHW = 0.0;
+    for (int i = 1; i <= cf; ++i) {
+        const int p = i - 1;
+        const int pp = tri(p, p);
+        const double app = A[pp], bpp = B[pp];
+        const double cpp = FULL ? C[pp] : 0.0;
+        if (i == cf) {  // level c0 complete: Wald scalars (pyx:1529-1533)
+            out->xPx = app;
+            out->yPx = A[tri(c0 + 1, c0)];
+        }
+        const double inv = 1.0 / app;
+        const double al2 = -inv;                  // -1/a_pp
+        const double al4 = bpp / (app * app);     // b_pp/a_pp^2
+        double alc = 0.0;
+        if (FULL) {
+            trPP = trPP + (bpp / app) * (bpp / app) - 2 * (cpp / app);          // pyx:1008-1009
+            alc = (cpp / (app * app)) - ((bpp * bpp) / (app * app * app));      // pyx:1011
+        }
+        trP = trP - bpp / app;                                                  // pyx:948 / :1020
+        if (need_logdet) logdetWHW += log(app);                                 // pyx:957 / :1029
+        const int q = k - i, T = q * (q + 1) / 2;
+        for (int idx = PG_LANE; idx < T; idx += PG_NLANES) {
+            const TriAB ab = t.tri_ab[idx];
+            const int r = i + ab.a, s = i + ab.b;
+            const int rs = tri(r, s), rp = tri(r, p), sp = tri(s, p);
+            const double ar = A[rp], as = A[sp], br = B[rp], bs = B[sp];
+            if (FULL) {
+                const double cr = C[rp], cs = C[sp];
+                double v = (C[rs] + alc * ar * as) + al2 * (ar * cs + cr * as) + al2 * (br * bs)
+                           + al4 * (ar * bs + br * as);                         // pyx:1011-1014
+                if (idx == 0) v = cy_max(v, kMinVal);                           // pyx:1016
+                C[rs] = v;
+            }
+            {
+                double v = (B[rs] + al4 * ar * as) + al2 * (ar * bs + br * as);  // pyx:950-951 / :1022-1023
+                if (idx == 0) v = cy_max(v, kMinVal);                           // pyx:953 / :1025
+                B[rs] = v;
+            }
+            {
+                double v = A[rs] + al2 * ar * as;                               // pyx:959 / :1031
+                if (idx == 0) v = cy_max(v, kMinVal);                           // pyx:961 / :1034
+                A[rs] = v;
+            }
+        }
+        PG_SYNCWARP();
+    }
+    const int yy = tri(k - 1, k - 1);
+    out->yPy = A[yy];
+    out->yPPy = B[yy];
+    out->yPPPy = FULL ? C[yy] : NAN;
+    out->trP = trP;
+    out->trPP = FULL ? trPP : NAN;
+    out->logdetH = l0.logdetH;
+    out->logdetWHW = logdetWHW;
+    PG_SYNCWARP();
+}
+
+// Host-side helpers shared by the C-ABI implementation and the CPU shim -------------------------------
+
+inline void fill_tri_ab(TriAB* tab)
+{
+    for (int a = 0; a < kMaxCols; ++a)
+        for (int b = 0; b <= a; ++b) {
+            tab[tri(a, b)].a = (unsigned char)a;
+            tab[tri(a, b)].b = (unsigned char)b;
+        }
+}
+
+inline void fill_basis(double* basis /* kNodes*kNodes */)
+{
+    for (int k = 0; k < kNodes; ++k)
+        for (int j = 0; j < kNodes; ++j)
+            basis[k * kNodes + j] =
+                (j == 0 ? 1.0 : 2.0) * cos(j * 3.14159265358979323846 * (k + 0.5) / kNodes) / kNodes;
+}
+
+// lambda of table row: rows 0..kNumFixed-1 are the fixed lambdas, then interval-major nodes
+inline double table_lambda(int row)
+{
+    if (row < kNumFixed) return fixed_lambda(row);
+    const int r = row - kNumFixed;
+    return node_lambda(r / kNodes, r % kNodes);
+}
+constexpr int kNumTableRows = kNumFixed + kNumIntervals * kNodes;
+
+}  // namespace pg

@@ -1,0 +1,147 @@
+"""Drop-in for the reference's `pygemma.lmm.pygemma` (reference lmm/lmm.py:87-411), B200-native.
+
+    from pygemma_b200 import lmm
+    df = lmm.pygemma(Y, X, W, K, snps=snps, verbose=1)
+
+Same call, same argument meaning, same DataFrame (`beta, se_beta, tau, lambda, F_wald, p_wald[, SNPs]`,
+one row per genotype column in input order, nothing filtered).  The work happens in
+libpygemma_b200.so (CUDA, sm_100a) through the C ABI of include/pygemma_b200.h:
+
+    eigh(K)                 lmm/lmm.py:151-162  -> cuSOLVER syevd on the GPU (timed separately)
+    U.T @ {X, Y, W}         lmm/lmm.py:243-246  -> device GEMMs, X in SNP blocks
+    Pool.imap(calculate)    lmm/lmm.py:378-403  -> per-SNP REML kernel
+
+Differences from the reference, all documented in DESIGN.md: arithmetic is float64 throughout (the
+reference mixes float32 storage into a float64 core), so every returned column is float64; `nproc` is
+accepted and ignored (parallelism is the GPU, or several GPUs under torch.distributed); `de=True`
+raises (it raises in the reference too: lmm/lmm.py:499 unpacks a 5-tuple into 4 names).
+There is no CPU fallback: without the CUDA library or a GPU the call raises.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import pandas as pd
+
+from . import _capi
+
+COLUMNS = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
+
+# timings of the most recent call (seconds / milliseconds), for callers that want them without verbose
+last_timing: dict = {}
+
+
+class DifferentialExpressionUnsupported(NotImplementedError, ValueError):
+    """de=True: broken in the reference (ValueError from lmm/lmm.py:499), not provided here."""
+
+
+def _as_genotypes(X):
+    X = np.asarray(X)
+    if X.ndim != 2:
+        raise ValueError("X must have shape (n, m)")
+    dt = X.dtype
+    if dt == np.int8 or dt == np.float32 or dt == np.float64:
+        return X
+    if dt == np.bool_:
+        return X.astype(np.int8)
+    if np.issubdtype(dt, np.integer):
+        if X.size == 0 or (X.min() >= -128 and X.max() <= 127):
+            return X.astype(np.int8)
+        return X.astype(np.float64)
+    if dt == np.float16:
+        return X.astype(np.float32)
+    return X.astype(np.float64)
+
+
+def _log(verbose, msg):
+    if verbose > 0:
+        print(f"[pygemma_b200] {msg}", flush=True)
+
+
+def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=False, grid=False, eigen=True,
+            nproc=1, device=None):
+    """Per-SNP LMM association scan (GEMMA Wald test) on a B200.
+
+    Args mirror the reference (lmm/lmm.py:87-103): Y (n,) or (n, 1) phenotype; X (n, m) genotypes
+    (int8 dosages, float32 or float64; other dtypes are converted); W (n, c) covariates, intercept
+    column supplied by the caller; K (n, n) relatedness matrix, or the (n,) eigenvalue vector when
+    eigen=False (then Y, X, W are taken as already rotated, lmm/lmm.py:164-167); Z: K <- Z K Z^T;
+    snps: labels for the 'SNPs' column; grid: 12-point grid search for lambda instead of
+    Brent + Newton.  `device` (extension) selects the CUDA device; default 0 or the
+    torch.distributed local rank.
+    """
+    global last_timing
+    t_start = time.time()
+    if de:
+        raise DifferentialExpressionUnsupported(
+            "de=True is not supported (the reference's calculate_de raises ValueError at lmm/lmm.py:499)")
+
+    from . import multi  # torch.distributed plumbing, only active when a process group exists
+
+    X = _as_genotypes(X)
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)  # lmm/lmm.py:115-116
+    W = np.asarray(W, dtype=np.float64)
+    if W.ndim == 1:
+        W = W.reshape(-1, 1)
+    n, m = X.shape
+    c0 = W.shape[1]
+    if Y.shape[0] != n or W.shape[0] != n:
+        raise ValueError(f"shape mismatch: X {X.shape}, Y {Y.shape}, W {W.shape}")
+    K = np.asarray(K, dtype=np.float64)
+    if Z is not None:
+        Z = np.asarray(Z, dtype=np.float64)
+        K = Z @ K @ Z.T  # lmm/lmm.py:124-125
+    if eigen and K.shape != (n, n):
+        raise ValueError(f"K must be ({n}, {n}) when eigen=True, got {K.shape}")
+    if not eigen and K.reshape(-1).shape[0] != n:
+        raise ValueError(f"with eigen=False K must be the ({n},) eigenvalue vector, got {K.shape}")
+
+    if not disable_checks:
+        # lmm/lmm.py:253-256 tests the rotated arrays; a NaN survives (and only arises from) the rotation
+        # of a NaN input, so the inputs are tested instead of downloading U^T X
+        if (X.dtype.kind == "f" and np.isnan(X).any()) or np.isnan(Y).any() or np.isnan(W).any():
+            raise ValueError("NaNs present in data")
+
+    ctx = multi.context(device)
+    timing = {"n": n, "m": m, "c0": c0, "world_size": ctx.world_size}
+    h = _capi.Handle(n, c0, ctx.device)
+    try:
+        t0 = time.time()
+        if eigen:
+            _log(verbose, "Starting eigendecomposition...")
+            timing["eig_ms"] = multi.setup_eigen(ctx, h, K)
+            _log(verbose, f"Eigendecomposition computed - {round(time.time() - t0, 3)} s")
+        else:
+            h.set_eigen(None, K.reshape(-1))
+        t0 = time.time()
+        timing["design_ms"] = h.set_design(W, Y.reshape(-1), already_rotated=not eigen)
+        _log(verbose, f"Rotated Y, W and built lambda tables - {round(time.time() - t0, 3)} s")
+        _log(verbose, f"Running {m} SNPs with {n} individuals...")
+        t0 = time.time()
+        a, b = ctx.shard(m)  # contiguous SNP range of this rank (SampleIter, lmm/lmm.py:427-434)
+        res = h.scan(X[:, a:b], grid=grid)
+        timing["scan"] = res["timing"]
+        out = multi.gather_results(ctx, res, m)
+        timing["scan_wall_s"] = time.time() - t0
+        _log(verbose, f"Finished testing {m} SNPs in {round(time.time() - t0, 3)} s "
+                      f"(device: rotate {res['timing']['rotate_ms']:.1f} ms, REML {res['timing']['reml_ms']:.1f} ms)")
+    finally:
+        h.close()
+
+    bad = out["status"] != 0
+    data = {}
+    for c in COLUMNS:
+        col = out[c]
+        if bad.any():
+            col = col.copy()
+            col[bad] = np.nan  # lmm/lmm.py:484-493
+        data[c] = col
+    results_df = pd.DataFrame(data, columns=COLUMNS)
+    if snps is not None:
+        results_df["SNPs"] = snps  # lmm/lmm.py:408-409 (same statement: pandas alignment semantics preserved)
+    timing["total_s"] = time.time() - t_start
+    timing["n_eval2_mean"] = float(out["n_eval2"].mean()) if m else 0.0
+    timing["n_eval3_mean"] = float(out["n_eval3"].mean()) if m else 0.0
+    last_timing = timing
+    return results_df

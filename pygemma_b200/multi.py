@@ -1,0 +1,128 @@
+"""Multi-GPU plumbing for the scan: one process per GPU under torch.distributed.
+
+The path shards by SNP exactly like the reference shards across processes
+(SampleIter, reference lmm/lmm.py:413-436: `nproc` contiguous chunks of ceil(m/nproc) columns,
+results concatenated in chunk order).  Collectives:
+  * once per call: broadcast of U (n*n doubles) and d (n doubles) from the rank that ran the
+    eigendecomposition (NCCL over NVLink when the backend is nccl);
+  * at the end: all-gather of the per-SNP result rows (9 numbers per SNP).
+There is no exchange inside the data path.  With no process group (or world_size 1) every function
+here degenerates to the single-GPU behaviour.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+RESULT_KEYS = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald", "status", "n_eval2", "n_eval3"]
+
+
+@dataclass
+class Context:
+    rank: int = 0
+    world_size: int = 1
+    device: int = 0
+    backend: str = ""
+
+    def shard(self, m: int):
+        """Contiguous column range [a, b) of this rank: ceil(m / world) columns per rank (lmm/lmm.py:429-431)."""
+        return shard_range(m, self.rank, self.world_size)
+
+
+def shard_range(m: int, rank: int, world: int):
+    per = -(-m // world) if world > 0 else m
+    a = min(rank * per, m)
+    b = min((rank + 1) * per, m)
+    return a, b
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def context(device=None) -> Context:
+    dist = _dist()
+    if dist is None:
+        return Context(0, 1, int(device) if device is not None else int(os.environ.get("PYGEMMA_B200_DEVICE", 0)), "")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    return Context(rank, world, int(device), dist.get_backend())
+
+
+def _coll_device(ctx: Context):
+    import torch
+
+    return torch.device(f"cuda:{ctx.device}") if ctx.backend == "nccl" else torch.device("cpu")
+
+
+def setup_eigen(ctx: Context, handle, K) -> float:
+    """Eigendecomposition on rank 0, broadcast of U and d to the other ranks' handles.  Returns syevd ms."""
+    if ctx.world_size == 1:
+        _, ms = handle.set_kinship(K)
+        return ms
+    import torch
+    import torch.distributed as dist
+
+    n = handle.n
+    if ctx.backend != "nccl":
+        raise RuntimeError("multi-GPU eigen broadcast needs the nccl backend (device buffers)")
+    dev = _coll_device(ctx)
+    U_t = torch.empty(n * n, dtype=torch.float64, device=dev)
+    d_t = torch.empty(n, dtype=torch.float64, device=dev)
+    ms = 0.0
+    if ctx.rank == 0:
+        _, ms = handle.set_kinship(K)
+        handle.get_eigen_device(U_t.data_ptr(), d_t.data_ptr())
+    torch.cuda.synchronize(dev)
+    dist.broadcast(U_t, src=0)
+    dist.broadcast(d_t, src=0)
+    torch.cuda.synchronize(dev)
+    if ctx.rank != 0:
+        handle.set_eigen_device(U_t.data_ptr(), False, d_t.data_ptr())
+    del U_t, d_t
+    return ms
+
+
+def pack_results(res: dict, per: int) -> np.ndarray:
+    """(9, per) float64 block of one rank's rows, NaN / 0 padded to the common shard length."""
+    k = res["beta"].shape[0]
+    blk = np.full((len(RESULT_KEYS), per), np.nan)
+    for i, key in enumerate(RESULT_KEYS):
+        blk[i, :k] = res[key] if key in res else 0
+    return blk
+
+
+def unpack_results(blocks, m: int, world: int) -> dict:
+    """Concatenate rank blocks in rank order (= input column order) and trim the padding."""
+    out = {key: np.empty(m, dtype=np.float64 if i < 6 else np.int32) for i, key in enumerate(RESULT_KEYS)}
+    for r, blk in enumerate(blocks):
+        a, b = shard_range(m, r, world)
+        for i, key in enumerate(RESULT_KEYS):
+            vals = blk[i, : b - a]
+            out[key][a:b] = vals if i < 6 else np.nan_to_num(vals).astype(np.int32)
+    return out
+
+
+def gather_results(ctx: Context, res: dict, m: int) -> dict:
+    """All ranks end up with all m rows, in input order."""
+    if ctx.world_size == 1:
+        return res
+    import torch
+    import torch.distributed as dist
+
+    per = -(-m // ctx.world_size)
+    dev = _coll_device(ctx)
+    mine = torch.from_numpy(pack_results(res, per)).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(ctx.world_size)]
+    dist.all_gather(parts, mine)
+    blocks = [p.cpu().numpy() for p in parts]
+    return unpack_results(blocks, m, ctx.world_size)

@@ -1,0 +1,172 @@
+// tests/host_shim.cpp -- compiles the product's host/device scalar headers (pygemma_b200/csrc/pg_math.cuh,
+// pg_eval.cuh) with g++ so that the optimiser state machine, the table interpolation, the Pab recursion
+// and the F-distribution tail are unit-tested on the CPU box.  TEST CODE: never shipped, never used by
+// the product path; the genotype-dependent dot products that the GPU does warp-collectively are plain
+// loops here.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "../pygemma_b200/csrc/pg_eval.cuh"
+
+using namespace pg;
+
+namespace {
+
+struct HostTables {
+    std::vector<double> fixtab, itab, basis;
+    std::vector<TriAB> tri_ab;
+    Tables t;
+};
+
+// exact table rows: Gram of [W0, y] weighted by h^p, plus sum h, sum h^2, sum log(lam d + 1)
+void build_tables(HostTables& H, int n, int c0, const double* d, const double* wy /* col-major n x (c0+1) */)
+{
+    const int k0 = c0 + 1, T0 = k0 * (k0 + 1) / 2, NF = 3 * T0 + 3;
+    H.fixtab.assign((size_t)kNumFixed * NF, 0.0);
+    H.itab.assign((size_t)kNumIntervals * kNodes * NF, 0.0);
+    H.basis.resize(kNodes * kNodes);
+    H.tri_ab.resize(kMaxTri);
+    fill_tri_ab(H.tri_ab.data());
+    fill_basis(H.basis.data());
+    std::vector<long double> acc(NF);
+    for (int row = 0; row < kNumTableRows; ++row) {
+        const double lam = table_lambda(row);
+        std::fill(acc.begin(), acc.end(), 0.0L);
+        for (int l = 0; l < n; ++l) {
+            const double tt = lam * d[l] + 1.0, h = 1.0 / tt;
+            const long double h1 = h, h2 = (long double)h * h, h3 = h2 * h;
+            for (int r = 0; r < k0; ++r)
+                for (int s = 0; s <= r; ++s) {
+                    const long double p = (long double)wy[(size_t)r * n + l] * wy[(size_t)s * n + l];
+                    const int q = tri(r, s);
+                    acc[q] += p * h1; acc[T0 + q] += p * h2; acc[2 * T0 + q] += p * h3;
+                }
+            acc[3 * T0] += h1; acc[3 * T0 + 1] += h2; acc[3 * T0 + 2] += logl((long double)tt);
+        }
+        double* dst = row < kNumFixed ? &H.fixtab[(size_t)row * NF] : &H.itab[(size_t)(row - kNumFixed) * NF];
+        for (int f = 0; f < NF; ++f) dst[f] = (double)acc[f];
+    }
+    H.t.c0 = c0; H.t.k0 = k0; H.t.T0 = T0; H.t.NF = NF;
+    H.t.fixtab = H.fixtab.data(); H.t.itab = H.itab.data(); H.t.basis = H.basis.data();
+    H.t.tri_ab = H.tri_ab.data();
+}
+
+void eval_snp(const HostTables& H, int n, const double* d, const double* wy, const double* x, double lam,
+              int fixed_t, int full, int need_ll, bool exact_w0y, EvalOut* out)
+{
+    const int c0 = H.t.c0, k = c0 + 2, k0 = c0 + 1;
+    const int TT = k * (k + 1) / 2;
+    std::vector<double> A(TT, 0.0), B(TT, 0.0), C(TT, 0.0);
+    Level0 l0;
+    if (full) assemble_w0y<true>(H.t, lam, fixed_t, A.data(), B.data(), C.data(), &l0);
+    else assemble_w0y<false>(H.t, lam, fixed_t, A.data(), B.data(), C.data(), &l0);
+    std::vector<long double> a1(k0 + 1, 0.0L), a2(k0 + 1, 0.0L), a3(k0 + 1, 0.0L);
+    for (int l = 0; l < n; ++l) {
+        const double h = 1.0 / (lam * d[l] + 1.0);
+        const long double xh = (long double)x[l] * h, xh2 = xh * h, xh3 = xh2 * h;
+        for (int j = 0; j < k0; ++j) {
+            const double w = wy[(size_t)j * n + l];
+            a1[j] += xh * w; a2[j] += xh2 * w; a3[j] += xh3 * w;
+        }
+        a1[k0] += xh * x[l]; a2[k0] += xh2 * x[l]; a3[k0] += xh3 * x[l];
+    }
+    for (int j = 0; j < c0; ++j) {
+        A[tri(c0, j)] = (double)a1[j]; B[tri(c0, j)] = (double)a2[j]; C[tri(c0, j)] = (double)a3[j];
+    }
+    A[tri(c0, c0)] = (double)a1[k0]; B[tri(c0, c0)] = (double)a2[k0]; C[tri(c0, c0)] = (double)a3[k0];
+    A[tri(c0 + 1, c0)] = (double)a1[c0]; B[tri(c0 + 1, c0)] = (double)a2[c0]; C[tri(c0 + 1, c0)] = (double)a3[c0];
+    if (exact_w0y && fixed_t < 0) {  // bypass the interpolation: exact [W0,y] block at this lambda
+        long double s0 = 0, s1 = 0, s2 = 0;
+        for (int r = 0; r < k0; ++r)
+            for (int s = 0; s <= r; ++s) {
+                long double p1 = 0, p2 = 0, p3 = 0;
+                for (int l = 0; l < n; ++l) {
+                    const double h = 1.0 / (lam * d[l] + 1.0);
+                    const long double p = (long double)wy[(size_t)r * n + l] * wy[(size_t)s * n + l];
+                    p1 += p * h; p2 += p * h * h; p3 += p * h * h * h;
+                }
+                const int rr = r == c0 ? c0 + 1 : r, ss = s == c0 ? c0 + 1 : s;
+                A[tri(rr, ss)] = (double)p1; B[tri(rr, ss)] = (double)p2; C[tri(rr, ss)] = (double)p3;
+            }
+        for (int l = 0; l < n; ++l) {
+            const double tt = lam * d[l] + 1.0, h = 1.0 / tt;
+            s0 += h; s1 += (long double)h * h; s2 += logl((long double)tt);
+        }
+        l0.trP = (double)s0; l0.trPP = (double)s1; l0.logdetH = (double)s2;
+    }
+    if (full) pab_recursion<true>(H.t, A.data(), B.data(), C.data(), l0, need_ll, out);
+    else pab_recursion<false>(H.t, A.data(), B.data(), C.data(), l0, need_ll, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+// SnpSolver + table/interpolation evaluator over a block of rotated SNPs (SNP-major xr)
+void pgh_scan(int n, int c0, long m, const double* d, const double* wy, const double* xr, int grid,
+              int exact_w0y, double* out6 /* m x 6 */, int32_t* status, int32_t* evals /* m x 2 */)
+{
+    HostTables H;
+    build_tables(H, n, c0, d, wy);
+    for (long g = 0; g < m; ++g) {
+        SnpSolver s;
+        s.init(n, c0, grid);
+        while (s.pending()) {
+            EvalOut e;
+            eval_snp(H, n, d, wy, xr + (size_t)g * n, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(),
+                     exact_w0y != 0, &e);
+            s.feed(e);
+        }
+        double* o = out6 + g * 6;
+        o[0] = s.beta; o[1] = s.se; o[2] = s.tau; o[3] = s.lambda; o[4] = s.F; o[5] = s.p;
+        status[g] = s.status; evals[2 * g] = s.n_eval2; evals[2 * g + 1] = s.n_eval3;
+    }
+}
+
+double pgh_f_sf(double F, double nu) { return f_sf_1(F, nu); }
+
+// drive pg::Brent on f(x) = p0 + p1 x + p2 x^2 + p3 x^3 + p4 exp(-x); returns root, fills the query sequence
+double pgh_brent(const double* p, double a, double b, double xtol, double rtol, int maxiter, double* xs, int cap,
+                 int* ncalls)
+{
+    auto f = [&](double x) { return p[0] + x * (p[1] + x * (p[2] + x * p[3])) + p[4] * exp(-x); };
+    int nc = 0;
+    auto rec = [&](double x) { if (nc < cap) xs[nc] = x; nc++; return f(x); };
+    Brent br;
+    const double fa = rec(a), fb = rec(b);
+    br.start(a, fa, b, fb, xtol, rtol, maxiter);
+    while (!br.done) br.feed(rec(br.query()));
+    *ncalls = nc;
+    return br.root;
+}
+
+double pgh_interp_error(int n, int c0, const double* d, const double* wy, double lam, int power)
+{
+    // max over [W0,y] pairs of |interp - exact| / sqrt(G_rr G_ss) at this lambda
+    HostTables H;
+    build_tables(H, n, c0, d, wy);
+    const int k = c0 + 2, TT = k * (k + 1) / 2, k0 = c0 + 1;
+    std::vector<double> A(TT), B(TT), C(TT);
+    Level0 l0;
+    assemble_w0y<true>(H.t, lam, -1, A.data(), B.data(), C.data(), &l0);
+    const double* M = power == 1 ? A.data() : (power == 2 ? B.data() : C.data());
+    std::vector<long double> ex(k0 * k0, 0.0L);
+    for (int r = 0; r < k0; ++r)
+        for (int s = 0; s <= r; ++s)
+            for (int l = 0; l < n; ++l) {
+                const double h = 1.0 / (lam * d[l] + 1.0);
+                ex[r * k0 + s] += (long double)wy[(size_t)r * n + l] * wy[(size_t)s * n + l] * powl(h, power);
+            }
+    double worst = 0;
+    for (int r = 0; r < k0; ++r)
+        for (int s = 0; s <= r; ++s) {
+            const int rr = r == c0 ? c0 + 1 : r, ss = s == c0 ? c0 + 1 : s;
+            const double e = fabs((double)((long double)M[tri(rr, ss)] - ex[r * k0 + s])) /
+                             sqrt((double)(ex[r * k0 + r] * ex[s * k0 + s]));
+            if (e > worst) worst = e;
+        }
+    return worst;
+}
+}

@@ -1,0 +1,66 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/pygemma_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from pygemma_b200 import _capi, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _capi.load()
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "pygemma_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/pygemma_b200.h but not exported"
+    assert sorted(_capi.SYMBOLS) == names
+
+
+def test_abi_version(lib):
+    txt = open(os.path.join(ROOT, "include", "pygemma_b200.h")).read()
+    assert lib.pg_abi_version() == int(re.search(r"#define PG_ABI_VERSION (\d+)", txt).group(1))
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU pg_create must fail loudly (PG_ERR_NO_DEVICE), never compute on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_capi.PgError) as ei:
+        _capi.Handle(100, 2, 0)
+    assert ei.value.code == -5 and "no CPU fallback" in str(ei.value)
+
+
+def test_create_rejects_bad_shapes(lib):
+    h = ctypes.c_void_p()
+    assert lib.pg_create(1, 0, 0, ctypes.byref(h)) == -1
+    assert lib.pg_create(100, 63, 0, ctypes.byref(h)) == -1
+    assert b"c0" in lib.pg_last_error(None)
+
+
+def test_timing_struct_matches_header():
+    assert ctypes.sizeof(_capi.PgTiming) == 6 * 4 + 6 * 4
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under pygemma_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "pygemma_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no CPU or oracle", ""), os.path.join(dirpath, f)

@@ -1,0 +1,155 @@
+"""CPU tests of the product's host/device scalar code (compiled for the host by tests/host_shim.cpp)
+and of the Python host layer.  The optimiser state machine, the lambda tables + Chebyshev interpolation,
+the Pab recursion and the F-tail are the same source the CUDA kernels compile."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import hostshim
+from conftest import COLS, GOLDEN
+from oracle import oracle
+from pygemma_b200 import multi
+
+
+def rel(a, b):
+    a = np.asarray(a, float)
+    b = np.asarray(b, float)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+SCANS = sorted(glob.glob(os.path.join(GOLDEN, "scan_*.npz")))
+
+
+@pytest.mark.parametrize("path", SCANS, ids=[os.path.basename(p)[5:-4] for p in SCANS])
+def test_solver_with_tables_matches_ref64(path):
+    g = np.load(path)
+    xt = np.ascontiguousarray(g["xr"].T)
+    o = hostshim.scan(g["d"], g["yr"], g["wr"], xt, grid=bool(g["grid"]))
+    assert (o["status"] == 0).all()
+    ok = np.array([0, 2, 4, 5, 6, 7]) if "degenerate" in path else np.arange(xt.shape[0])
+    for c in COLS:
+        tol = 1e-6 if c == "lambda" else 1e-8
+        assert rel(o[c][ok], g[f"r64_{c}"][ok]).max() < tol, (c, rel(o[c][ok], g[f"r64_{c}"][ok]).max())
+
+
+def test_interpolated_tables_equal_exact_tables():
+    g = np.load(os.path.join(GOLDEN, "scan_interior.npz"))
+    xt = np.ascontiguousarray(g["xr"].T)
+    a = hostshim.scan(g["d"], g["yr"], g["wr"], xt, exact_w0y=False)
+    b = hostshim.scan(g["d"], g["yr"], g["wr"], xt, exact_w0y=True)
+    for c in COLS:
+        assert rel(a[c], b[c]).max() < 1e-10, c
+    assert np.array_equal(a["n_eval2"], b["n_eval2"]) and np.array_equal(a["n_eval3"], b["n_eval3"])
+
+
+def test_interpolation_error_bound():
+    rng = np.random.default_rng(3)
+    n, c0 = 600, 4
+    L = hostshim.lib()
+    for spectrum in ("mp", "wide"):
+        d = rng.chisquare(4, n) / 4 if spectrum == "mp" else 10.0 ** rng.uniform(-8, 4, n)
+        wy = np.asfortranarray(np.c_[np.ones(n), rng.standard_normal((n, c0))])
+        for lam in 10.0 ** rng.uniform(-5, 5, 12):
+            for p in (1, 2, 3):
+                e = L.pgh_interp_error(n, c0, hostshim._p(np.ascontiguousarray(d)), hostshim._p(wy), float(lam), p)
+                assert e < 2e-13, (spectrum, lam, p, e)
+
+
+def test_f_sf_matches_scipy():
+    from scipy import stats
+
+    L = hostshim.lib()
+    rng = np.random.default_rng(1)
+    for nu in (3, 17, 443, 1929, 9989, 49989):
+        F = np.concatenate([10.0 ** rng.uniform(-12, 3.3, 300), [0.0, 1e-300, 1.0, 50.0, 1400.0]])
+        ref = stats.f.sf(F, 1, nu)
+        got = np.array([L.pgh_f_sf(float(f), float(nu)) for f in F])
+        m = ref > 1e-300
+        assert rel(got[m], ref[m]).max() < 1e-9, (nu, rel(got[m], ref[m]).max())
+    assert np.isnan(L.pgh_f_sf(float("nan"), 10.0))
+    assert L.pgh_f_sf(float("inf"), 10.0) == 0.0
+
+
+def test_brent_state_machine_is_scipy_brentq():
+    import ctypes
+
+    from scipy import optimize
+
+    L = hostshim.lib()
+    rng = np.random.default_rng(9)
+    checked = 0
+    for _ in range(6000):
+        p = np.ascontiguousarray(rng.standard_normal(5) * rng.choice([0.0, 1.0], size=5, p=[0.3, 0.7]))
+        a = 10.0 ** rng.integers(-5, 5)
+        b = a * 10.0
+        f = lambda x: oracle.poly_eval(p, x)
+        fa, fb = f(a), f(b)
+        if fa == 0 or fb == 0 or np.signbit(fa) == np.signbit(fb):
+            continue
+        xs_ref = []
+
+        def g(x):
+            xs_ref.append(x)
+            return f(x)
+
+        r_sp = optimize.brentq(g, a, b, rtol=0.1, maxiter=100, disp=False)
+        xs = np.empty(256)
+        nc = ctypes.c_int(0)
+        r = L.pgh_brent(hostshim._p(p), a, b, 2e-12, 0.1, 100, hostshim._p(xs), 256, ctypes.byref(nc))
+        # the shim evaluates the same polynomial with its own exp(): compare roots to rounding, counts exactly
+        assert nc.value == len(xs_ref)
+        assert abs(r - r_sp) <= 1e-12 * abs(r_sp)
+        checked += 1
+    assert checked > 300
+
+
+def test_shard_range_is_sampleiter():
+    """multi.shard_range reproduces SampleIter's chunking (reference lmm/lmm.py:427-434)."""
+    for m in (1, 7, 100, 101, 12226):
+        for world in (1, 2, 3, 8):
+            per = int(np.ceil(m / world))
+            cover = []
+            for r in range(world):
+                a, b = multi.shard_range(m, r, world)
+                assert a == min(r * per, m) and b == min((r + 1) * per, m)
+                cover += list(range(a, b))
+            assert cover == list(range(m))
+
+
+def test_pack_unpack_roundtrip():
+    rng = np.random.default_rng(0)
+    m, world = 11, 3
+    full = {k: rng.standard_normal(m) for k in multi.RESULT_KEYS[:6]}
+    full.update({k: rng.integers(0, 30, m).astype(np.int32) for k in multi.RESULT_KEYS[6:]})
+    per = -(-m // world)
+    blocks = []
+    for r in range(world):
+        a, b = multi.shard_range(m, r, world)
+        blocks.append(multi.pack_results({k: v[a:b] for k, v in full.items()}, per))
+    out = multi.unpack_results(blocks, m, world)
+    for k in multi.RESULT_KEYS:
+        assert np.array_equal(out[k], full[k]), k
+
+
+def test_pygemma_argument_contract():
+    from pygemma_b200 import lmm
+
+    n, m = 20, 5
+    Y, X, W, K = np.zeros(n), np.zeros((n, m), dtype=np.int8), np.ones((n, 1)), np.eye(n)
+    with pytest.raises(ValueError):
+        lmm.pygemma(Y, X, W, K, de=True)
+    with pytest.raises(NotImplementedError):
+        lmm.pygemma(Y, X, W, K, de=True)
+    with pytest.raises(ValueError):
+        lmm.pygemma(Y[:-1], X, W, K)
+    with pytest.raises(ValueError):
+        lmm.pygemma(Y, X, W, np.eye(n + 1))
+    Xf = X.astype(np.float64)
+    Xf[0, 0] = np.nan
+    with pytest.raises(ValueError, match="NaNs present in data"):
+        lmm.pygemma(Y, Xf, W, K, disable_checks=False)
+    assert lmm._as_genotypes(np.zeros((2, 2), dtype=np.int64)).dtype == np.int8
+    assert lmm._as_genotypes(np.full((2, 2), 300)).dtype == np.float64
+    assert lmm._as_genotypes(np.zeros((2, 2), dtype=np.float16)).dtype == np.float32
