@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- SNPs/sec of the per-SNP LMM association scan at n = 10 000 samples (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--snps M] [--grid]
+
+A "step" is one pass of the hot path (rotation U^T X + per-SNP REML/Wald scan) over one batch of
+M synthetic SNPs (default: BASELINE.json configs[2], n = 10 000, M = 100 000, c0 = 10 covariates).
+The one-time eigendecomposition (cuSOLVER syevd) is setup: timed separately, excluded from the metric.
+
+  value     whole-job SNPs/s with the genotypes already resident in HBM (pg_scan_device), CUDA events
+  e2e       the same metric through the host-buffer C-ABI call pg_scan (what lmm.pygemma calls): pinned
+            host genotypes in, host result arrays out, copies inside the timed region
+  roofline  dominant kernel: achieved algorithmic FLOP/s over the measured peak
+  cpu_baseline / --impl reference: the reference's own Cython path (oracle/_ref, built from
+            /root/reference by oracle/build_ref.py) timed on this box's host cores on a bounded sample
+
+N > 1: one process per GPU (torchrun); U and d are broadcast once over NCCL, every rank scans its own
+M SNPs (weak scaling), no collective in the data path; time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES = 10000
+C0 = 10
+METRIC = "SNPs/sec at n=10k samples"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU-baseline worker (separate interpreter: no CUDA context, BLAS threads pinned to 1)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(path: str) -> None:
+    """Times the reference's scan (lmm.calculate through multiprocessing.Pool, reference lmm/lmm.py:378-401)
+    and its fp32 rotation (lmm/lmm.py:244) on the sample stored in `path`."""
+    import multiprocessing
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    z = np.load(path)
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    kind = "reference"
+    try:
+        from pygemma import lmm as ref  # literal reference build (fp32 storage)
+    except Exception as e:  # pragma: no cover - the reference did not build in this container
+        ref = None
+        kind = "port"
+        err = str(e)
+    d, y, w, x = z["d"], z["y"], z["w"], z["x"]  # rotated, x is (n, m_s)
+    steps, warmup, nproc = int(z["steps"]), int(z["warmup"]), int(z["nproc"])
+    n, m_s = x.shape
+    times = []
+    rot_times = []
+    u = z["u"] if "u" in z.files else None
+    if ref is not None:
+        f32 = np.float32
+        d32, y32, w32, x32 = d.astype(f32), y.astype(f32).reshape(-1, 1), np.ascontiguousarray(w.astype(f32)), \
+            np.ascontiguousarray(x.astype(f32))
+        with multiprocessing.Pool(nproc) as pool:
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                rows = []
+                with np.errstate(all="ignore"):
+                    for r in pool.imap(ref.calculate, ref.SampleIter(x32, y32, w32, d32, bool(z["grid"]), nproc)):
+                        rows = rows + r
+                dt = time.perf_counter() - t0
+                assert len(rows) == m_s
+                if it >= warmup:
+                    times.append(dt)
+        if u is not None:
+            xs = np.ascontiguousarray(z["xraw"].astype(f32))
+            for it in range(3):
+                t0 = time.perf_counter()
+                _ = u.T @ xs
+                rot_times.append(time.perf_counter() - t0)
+    else:
+        from oracle import oracle
+
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            oracle.scan_rotated(d, y, w, np.ascontiguousarray(x.T), grid=bool(z["grid"]), fast=True)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    t_scan = float(np.mean(times))
+    t_rot = float(np.min(rot_times)) * (m_s / z["xraw"].shape[1]) if rot_times else 0.0
+    print(json.dumps({"kind": kind, "cores": nproc, "m_sample": int(m_s), "scan_s": t_scan, "rotate_s": t_rot,
+                      "snps_per_s": m_s / (t_scan + t_rot), "snps_per_s_scan_only": m_s / t_scan,
+                      "ms_per_step": 1e3 * (t_scan + t_rot)}))
+
+
+def run_cpu_reference(n, c0, grid, steps, warmup, m_sample=None, seed=5):
+    """Builds a rotated-space synthetic sample and times the reference on it in a fresh interpreter."""
+    from pygemma_b200.synth import make_spectral_problem
+
+    cores = os.cpu_count() or 1
+    nproc = max(1, cores)
+    if m_sample is None:
+        m_sample = max(64, 24 * nproc)
+    p = make_spectral_problem(n, m_sample, c0, seed=seed, xdtype=np.float64)
+    rng = np.random.default_rng(seed)
+    m_rot = min(m_sample, 256)
+    u = rng.standard_normal((n, n), dtype=np.float32)  # timing of the fp32 sgemm only
+    xraw = rng.integers(0, 3, size=(n, m_rot)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "sample.npz")
+        np.savez(path, d=p["d"], y=p["Y"].reshape(-1), w=p["W"], x=p["X"].astype(np.float32), u=u, xraw=xraw, grid=np.array(grid),
+                 steps=steps, warmup=warmup, nproc=nproc)
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1",
+                   CUDA_VISIBLE_DEVICES="")
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--_cpu_worker", path], env=env,
+                           capture_output=True, text=True, timeout=3000)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError(f"cpu reference worker failed: {r.stdout[-2000:]} {r.stderr[-2000:]}")
+    out = json.loads(lines[-1])
+    out["sample"] = (f"{out['m_sample']} synthetic SNPs at n={n}, c0={c0}, {'grid' if grid else 'Brent+Newton'} mode, "
+                     f"reference lmm.calculate over multiprocessing.Pool({nproc}) with 1 BLAS thread per process "
+                     f"+ fp32 U.T@X rotation on all cores; mean of {steps} runs after {warmup} warm-ups")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.dev)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "source_hbm": "fallback"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        peaks["hbm_gbs"] = float(j.get("hbm_gbs", peaks["hbm_gbs"]))
+        peaks["source_hbm"] = "measured (MEASURED_PEAKS.json)"
+    q = os.path.join(ROOT, "profiles", "peaks_fp64_int8.json")
+    if os.path.exists(q):
+        j = json.load(open(q))
+        peaks.update({k: float(v) for k, v in j.items() if isinstance(v, (int, float))})
+        peaks["source_fp64"] = "measured on this pool by tools/peak_fp64 (profiles/peaks_fp64_int8.json)"
+    else:
+        peaks.update({"fp64_fma_tflops": 34.0, "fp64_dmma_tflops": 37.0, "dgemm_tflops": 36.0, "int8_gemm_tops": 3600.0})
+        peaks["source_fp64"] = "fallback"
+    return peaks
+
+
+def make_gpu_problem(torch, dev, n, m, c0, seed, rank):
+    """Synthetic UKB-shape inputs generated on the device: binomial dosages (int8, sample-major), kinship
+    from an independent standardised panel (+1e-3 I), intercept + gaussian covariates, polygenic phenotype."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    m_k = 2 * n
+    maf = torch.rand(m_k, generator=g, device=dev) * 0.45 + 0.05
+    G = ((torch.rand(n, m_k, generator=g, device=dev) < maf).to(torch.float64)
+         + (torch.rand(n, m_k, generator=g, device=dev) < maf).to(torch.float64))
+    sd = G.std(dim=0)
+    sd[sd == 0] = 1.0
+    G = (G - G.mean(dim=0)) / sd
+    K = G @ G.T / m_k
+    K.diagonal().add_(1e-3)
+    b = torch.randn(m_k, generator=g, device=dev, dtype=torch.float64)
+    u = G @ b / (m_k ** 0.5)
+    u = u / u.std()
+    W = torch.cat([torch.ones(n, 1, device=dev, dtype=torch.float64),
+                   torch.randn(n, c0 - 1, generator=g, device=dev, dtype=torch.float64)], dim=1)
+    y = (0.5 ** 0.5) * u + (0.5 ** 0.5) * torch.randn(n, generator=g, device=dev, dtype=torch.float64)
+    y = y + 0.05 * W[:, 1:].sum(dim=1)
+    del G
+    # genotypes of this rank (different SNPs per rank: weak scaling)
+    gx = torch.Generator(device=dev)
+    gx.manual_seed(seed * 1000 + 17 + rank)
+    X = torch.empty((n, m), dtype=torch.int8, device=dev)
+    step = 8192
+    for a in range(0, m, step):
+        bnd = min(m, a + step)
+        mf = torch.rand(bnd - a, generator=gx, device=dev) * 0.45 + 0.05
+        X[:, a:bnd] = ((torch.rand(n, bnd - a, generator=gx, device=dev) < mf).to(torch.int8)
+                       + (torch.rand(n, bnd - a, generator=gx, device=dev) < mf).to(torch.int8))
+    return K, W, y, X
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from pygemma_b200 import _capi, multi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pygemma_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n, m, c0, grid = args.n, args.snps, args.c0, bool(args.grid)
+    ctx = multi.context(local)
+
+    K, W, y, X = make_gpu_problem(torch, dev, n, m, c0, seed=20240 + 2, rank=rank)
+    h = _capi.Handle(n, c0, local)
+    stream = torch.cuda.current_stream(dev)
+    h.set_stream(stream.cuda_stream)
+
+    # ---- setup (excluded from the metric): eigendecomposition on rank 0, NCCL broadcast of U and d
+    t0 = time.perf_counter()
+    K_host = K.cpu().numpy() if rank == 0 else None
+    del K
+    eig_ms = multi.setup_eigen(ctx, h, K_host)
+    del K_host
+    setup_s = time.perf_counter() - t0
+    W_host, y_host = W.cpu().numpy(), y.cpu().numpy()
+    design_ms = h.set_design(W_host, y_host)
+
+    out_dev = torch.empty((6, m), dtype=torch.float64, device=dev)
+    st_dev = torch.zeros((3, m), dtype=torch.int32, device=dev)
+    out_ptrs = [out_dev[i].data_ptr() for i in range(6)]
+
+    def step_resident():
+        return h.scan_device(X.data_ptr(), _capi.PG_X_I8, m, _capi.PG_X_SAMPLE_MAJOR, m, grid, out_ptrs,
+                             st_dev[0].data_ptr(), st_dev[1].data_ptr(), st_dev[2].data_ptr())
+
+    X_host = torch.empty((n, m), dtype=torch.int8, pin_memory=True)
+    X_host.copy_(X)
+    X_np = X_host.numpy()
+
+    def step_e2e():
+        return h.scan(X_np, grid=grid)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        sampler = ClockSampler(local) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        tms = []
+        for _ in range(steps):
+            tms.append(fn())
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        dev_ms = e0.elapsed_time(e1)
+        ms = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1]), tms, clocks
+
+    dev_ms, wall_ms, tms, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    res_tm = tms[-1]
+    ms_per_step = dev_ms / args.steps
+    value = world * m / (ms_per_step * 1e-3)
+    e2e_dev_ms, e2e_wall_ms, e2e_tms, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    e2e_ms = e2e_wall_ms / args.steps  # host-visible time of the synchronous call (>= device time)
+    e2e_value = world * m / (e2e_ms * 1e-3)
+    counts = st_dev.cpu().numpy()
+    bad = int((counts[0] != 0).sum())
+    ev2, ev3 = float(counts[1].mean()), float(counts[2].mean())
+
+    peaks = load_peaks()
+    # ---- roofline of the dominant kernel (per launch = per SNP block; times are CUDA-event sums of the last step)
+    nb = res_tm["n_blocks"]
+    rot_ms, reml_ms = res_tm["rotate_ms"], res_tm["reml_ms"]
+    k0 = c0 + 2
+    reml_flops = m * (n * (ev2 * 2 * 2 * (c0 + 3) + ev3 * 2 * 3 * (c0 + 3)))  # 2 n K (c0+3) per pass
+    if rot_ms >= reml_ms:
+        rot_engine = res_tm.get("rot_engine", "fp64")
+        flops = 2.0 * n * n * m
+        ach = flops / (rot_ms * 1e-3) / 1e12
+        peak = peaks["fp64_dmma_tflops"]
+        roofline = {"kernel": "rotation U^T X (cuBLAS DGEMM, FP64 tensor pipe)", "bound": "tensor", "achieved": ach,
+                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": "FP64 DMMA rate " + peaks["source_fp64"],
+                    "algorithmic_flops_per_snp": 2.0 * n * n, "share_of_step": rot_ms / (rot_ms + reml_ms + res_tm["convert_ms"])}
+    else:
+        ach = reml_flops / (reml_ms * 1e-3) / 1e12
+        peak = peaks["fp64_fma_tflops"]
+        roofline = {"kernel": "reml_scan_kernel", "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": "FP64 FMA rate " + peaks["source_fp64"],
+                    "algorithmic_flops_per_snp": reml_flops / m,
+                    "share_of_step": reml_ms / (rot_ms + reml_ms + res_tm["convert_ms"])}
+    roofline["per_kernel_ms_last_step"] = {"convert": res_tm["convert_ms"], "rotate": rot_ms, "reml": reml_ms}
+    roofline["reml_tflops"] = reml_flops / (reml_ms * 1e-3) / 1e12
+    roofline["reml_hbm_gbs"] = 8.0 * n * m / (reml_ms * 1e-3) / 1e9
+    roofline["rotate_tflops_fp64_equiv"] = 2.0 * n * n * m / (rot_ms * 1e-3) / 1e12
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "SNPs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "ours",
+        "config": {"workload": f"synthetic UKB-shape n={n} samples x {m} SNPs per GPU, c0={c0} covariates, "
+                               f"{'grid-search' if grid else 'Brent+Newton'} lambda, int8 dosages (BASELINE.json configs[2])",
+                   "n": n, "snps_per_gpu": m, "c0": c0, "grid": grid, "parallelism": f"snp-shard x{world}",
+                   "l2": "inputs_larger_than_l2 (1 GB int8 genotypes + 80 KB/SNP rotated fp64 per step)"},
+        "e2e": {"value": e2e_value, "unit": "SNPs/s", "h2d_bytes_per_step": int(n) * int(m) * world,
+                "d2h_bytes_per_step": int(m) * (6 * 8 + 3 * 4) * world, "ms_per_step": e2e_ms,
+                "device_ms_per_step": e2e_dev_ms / args.steps,
+                "api": "pg_scan (C ABI, host buffers) as called by pygemma_b200.lmm.pygemma"},
+        "gpu_launches": int(sum(t["convert_launches"] + t["reml_launches"] + t["rotate_launches"] for t in tms)),
+        "clocks": clocks, "roofline": roofline,
+        "setup": {"syevd_ms": eig_ms, "eigen_setup_s": setup_s, "design_tables_ms": design_ms},
+        "evals_per_snp": {"two_power_passes": ev2, "three_power_passes": ev3}, "nan_rows": bad,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = run_cpu_reference(n, c0, grid, steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": cb["snps_per_s"], "unit": "SNPs/s", "cores": cb["cores"], "kind": cb["kind"],
+                                    "sample": cb["sample"], "scan_only_snps_per_s": cb["snps_per_s_scan_only"]}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "SNPs/s", "cores": os.cpu_count(), "kind": "reference",
+                                    "sample": f"failed: {e}"}
+    h.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = run_cpu_reference(args.n, args.c0, bool(args.grid), steps=args.steps, warmup=args.warmup)
+    line = {
+        "metric": METRIC, "value": cb["snps_per_s"], "unit": "SNPs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (reference mix)", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"synthetic UKB-shape n={args.n} samples, c0={args.c0} covariates, "
+                               f"{'grid-search' if args.grid else 'Brent+Newton'} lambda; bounded sample of "
+                               f"{cb['m_sample']} SNPs per step (BASELINE.json configs[2])",
+                   "n": args.n, "c0": args.c0, "grid": bool(args.grid)},
+        "cpu_baseline": {"value": cb["snps_per_s"], "unit": "SNPs/s", "cores": cb["cores"], "kind": cb["kind"],
+                         "sample": cb["sample"]},
+        "e2e": {"value": cb["snps_per_s"], "unit": "SNPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--snps", type=int, default=100000, help="SNPs per GPU per step")
+    ap.add_argument("--n", type=int, default=N_SAMPLES)
+    ap.add_argument("--c0", type=int, default=C0)
+    ap.add_argument("--grid", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--_cpu_worker", default=None)
+    args = ap.parse_args()
+    if args._cpu_worker:
+        _cpu_worker(args._cpu_worker)
+        return
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

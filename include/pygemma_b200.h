@@ -111,6 +111,13 @@ int pg_get_eigen_device(pg_handle* h, double* U_dev_out, double* d_dev_out);
  */
 int pg_set_design(pg_handle* h, const double* W_host, const double* y_host, int already_rotated, float* ms);
 
+/*
+ * Run all device work of this handle on a caller-owned CUDA stream (a cudaStream_t passed as void*),
+ * e.g. torch's current stream, so the caller can bracket calls with its own CUDA events.  NULL restores
+ * the handle's private stream.  Genotype uploads still use a private copy stream, ordered by events.
+ */
+int pg_set_stream(pg_handle* h, void* stream);
+
 /* rotation engine selection and block size (0 = automatic) */
 int pg_set_options(pg_handle* h, int rotation, int64_t block_snps);
 

@@ -20,7 +20,7 @@ PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT = 0, 1, 2
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)
 SYMBOLS = [
     "pg_abi_version", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
-    "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_options",
+    "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_stream", "pg_set_options",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
 
@@ -68,6 +68,7 @@ def load():
     L.pg_get_eigen_device.argtypes = [vp, vp, vp]
     L.pg_set_design.argtypes = [vp, vp, vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.pg_set_options.argtypes = [vp, i32, i64]
+    L.pg_set_stream.argtypes = [vp, vp]
     scan_args = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 9 + [ctypes.POINTER(PgTiming)]
     L.pg_scan.argtypes = scan_args
     L.pg_scan_device.argtypes = scan_args
@@ -166,6 +167,10 @@ class Handle:
         self._ck(self.L.pg_set_design(self.h, _ptr(W) if self.c0 else None, _ptr(y), int(already_rotated),
                                       ctypes.byref(ms)))
         return float(ms.value)
+
+    def set_stream(self, stream_ptr: int):
+        """Run the handle's device work on a caller stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self.L.pg_set_stream(self.h, ctypes.c_void_p(stream_ptr or None)))
 
     def set_options(self, rotation=PG_ROT_AUTO, block_snps=0):
         self._ck(self.L.pg_set_options(self.h, int(rotation), int(block_snps)))

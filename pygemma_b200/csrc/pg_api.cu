@@ -27,6 +27,7 @@ struct pg_handle {
     int sm_count = 148;
     std::string err;
     cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t own_compute = nullptr;  // compute defaults to this; pg_set_stream can point it at a caller stream
     cublasHandle_t blas = nullptr;
     cusolverDnHandle_t solver = nullptr;
     // eigen
@@ -115,7 +116,7 @@ static int free_all(pg_handle* h)
         if (b) cudaFree(b);
     if (h->blas) cublasDestroy(h->blas);
     if (h->solver) cusolverDnDestroy(h->solver);
-    if (h->compute) cudaStreamDestroy(h->compute);
+    if (h->own_compute) cudaStreamDestroy(h->own_compute);
     if (h->copy) cudaStreamDestroy(h->copy);
     return 0;
 }
@@ -151,7 +152,8 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
             return fail(h, PG_ERR_NO_DEVICE, "pg_create: device %d is sm_%d%d; this build targets sm_100a only", device,
                         prop.major, prop.minor);
         h->sm_count = prop.multiProcessorCount;
-        CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->own_compute, cudaStreamNonBlocking));
+        h->compute = h->own_compute;
         CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
         CKB(cublasCreate(&h->blas));
         CKB(cublasSetStream(h->blas, h->compute));
@@ -347,6 +349,17 @@ extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y
     cudaEventDestroy(e1);
     if (ms) *ms = t;
     h->have_design = true;
+    return PG_OK;
+}
+
+extern "C" int pg_set_stream(pg_handle* h, void* stream)
+{
+    if (!h) return PG_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->compute));
+    h->compute = stream ? (cudaStream_t)stream : h->own_compute;
+    CKB(cublasSetStream(h->blas, h->compute));
+    CKS(cusolverDnSetStream(h->solver, h->compute));
     return PG_OK;
 }
 

@@ -173,7 +173,7 @@ def test_rotation_matches_lapack_rotation():
     from pygemma_b200.synth import make_problem
 
     capi = _capi()
-    p = make_problem(300, 64, 2, seed=5, m_k=150)
+    p = make_problem(300, 64, 2, seed=5, m_k=900)  # m_k > n: no degenerate eigenspace
     with capi.Handle(300, 2) as h:
         d, _ = h.set_kinship(p["K"])
         h.set_design(p["W"], p["Y"])
