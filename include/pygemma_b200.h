@@ -73,7 +73,7 @@ typedef struct {
     int32_t n_blocks; /* SNP blocks processed */
     int32_t block_snps;
     int32_t reml_launches, rotate_launches, convert_launches;
-    int32_t reserved;
+    int32_t rot_engine; /* engine the rotation used: PG_ROT_FP64 / PG_ROT_I8SPLIT, 0 when no rotation ran */
 } pg_timing;
 
 int pg_abi_version(void);

@@ -30,10 +30,10 @@ class PgTiming(ctypes.Structure):
                 ("rotate_ms", ctypes.c_float), ("reml_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
                 ("n_blocks", ctypes.c_int32), ("block_snps", ctypes.c_int32), ("reml_launches", ctypes.c_int32),
                 ("rotate_launches", ctypes.c_int32), ("convert_launches", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("rot_engine", ctypes.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
 class PgError(RuntimeError):

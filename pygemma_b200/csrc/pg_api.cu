@@ -16,6 +16,7 @@
 
 #include "../../include/pygemma_b200.h"
 #include "reml_kernels.cuh"
+#include "reml_stream.cuh"
 #include "rotate_kernels.cuh"
 
 using namespace pg;
@@ -24,6 +25,9 @@ static thread_local std::string g_create_error;
 
 struct pg_handle {
     int n = 0, c0 = 0, device = 0;
+    long long ldw = 0;  // padded leading dimension of d / wy (multiple of kTile, zero-filled)
+    long long ldx = 0;  // padded row length of the rotated genotype block (multiple of 16, zero-filled)
+    bool use_v1 = false;
     int sm_count = 148;
     std::string err;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -144,6 +148,9 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
     if (device < 0 || device >= count) return fail(nullptr, PG_ERR_ARG, "pg_create: device %d of %d", device, count);
     pg_handle* h = new pg_handle;
     h->n = n; h->c0 = c0; h->device = device;
+    h->ldw = ((long long)n + kTile - 1) / kTile * kTile;
+    h->ldx = ((long long)n + 15) / 16 * 16;
+    h->use_v1 = getenv("PG_REML_V1") != nullptr;
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -164,8 +171,10 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
             CK(cudaEventCreateWithFlags(&h->ev_free[s], cudaEventDisableTiming));
         }
         const int k0 = c0 + 1, T0 = k0 * (k0 + 1) / 2, NF = 3 * T0 + 3;
-        CK(cudaMalloc(&h->d, sizeof(double) * n));
-        CK(cudaMalloc(&h->wy, sizeof(double) * (size_t)n * k0));
+        CK(cudaMalloc(&h->d, sizeof(double) * h->ldw));
+        CK(cudaMalloc(&h->wy, sizeof(double) * (size_t)h->ldw * k0));
+        CK(cudaMemset(h->d, 0, sizeof(double) * h->ldw));
+        CK(cudaMemset(h->wy, 0, sizeof(double) * (size_t)h->ldw * k0));
         CK(cudaMalloc(&h->fixtab, sizeof(double) * (size_t)kNumFixed * NF));
         CK(cudaMalloc(&h->itab, sizeof(double) * (size_t)kNumIntervals * kNodes * NF));
         CK(cudaMalloc(&h->basis, sizeof(double) * kNodes * kNodes));
@@ -302,7 +311,7 @@ static int build_tables(pg_handle* h)
     const int T0 = h->tab.T0;
     const int nchunks = (T0 + kTablePairs - 1) / kTablePairs;
     dim3 grid(nchunks + 1, kNumTableRows);
-    build_tables_kernel<<<grid, 256, 0, h->compute>>>(h->n, h->c0, h->d, h->wy, h->lambdas, h->fixtab, h->itab,
+    build_tables_kernel<<<grid, 256, 0, h->compute>>>(h->n, h->c0, h->d, h->wy, h->ldw, h->lambdas, h->fixtab, h->itab,
                                                       h->tri_ab);
     CK(cudaGetLastError());
     return PG_OK;
@@ -325,7 +334,8 @@ extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, h->compute));
     if (already_rotated) {
-        CK(cudaMemcpyAsync(h->wy, col.data(), sizeof(double) * col.size(), cudaMemcpyHostToDevice, h->compute));
+        CK(cudaMemcpy2DAsync(h->wy, sizeof(double) * h->ldw, col.data(), sizeof(double) * n, sizeof(double) * n, k0,
+                             cudaMemcpyHostToDevice, h->compute));
     } else {
         double* raw = nullptr;
         CK(cudaMalloc(&raw, sizeof(double) * col.size()));
@@ -333,7 +343,7 @@ extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y
         const double one = 1.0, zero = 0.0;
         // wy = U^T [W, y]  (lmm/lmm.py:245-246)
         cublasStatus_t s = cublasDgemm(h->blas, h->u_op_t ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, n, k0, n, &one, h->U,
-                                       n, raw, n, &zero, h->wy, n);
+                                       n, raw, n, &zero, h->wy, (int)h->ldw);
         cudaStreamSynchronize(h->compute);
         cudaFree(raw);
         if (s != CUBLAS_STATUS_SUCCESS) return fail(h, PG_ERR_CUBLAS, "pg_set_design: dgemm status %d", (int)s);
@@ -386,7 +396,7 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
     }
     blk = std::min(blk, std::max<long long>(m, 1));
     blk = ((blk + 31) / 32) * 32;
-    const size_t need = (size_t)blk * n;
+    const size_t need = (size_t)blk * h->ldx;
     if (need > h->xbuf_elems) {
         if (h->xf) cudaFree(h->xf);
         if (h->xr) cudaFree(h->xr);
@@ -394,6 +404,7 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         h->xbuf_elems = 0;
         CK(cudaMalloc(&h->xf, sizeof(double) * need));
         CK(cudaMalloc(&h->xr, sizeof(double) * need));
+        CK(cudaMemset(h->xr, 0, sizeof(double) * need));
         h->xbuf_elems = need;
     }
     const size_t sbytes = need * xdtype_size(xdtype);
@@ -412,7 +423,7 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
 
 static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld, int layout, long long mb, double* dst)
 {
-    if (stage_to_snp_major(h->compute, h->n, src, xdtype, ld, layout, mb, dst)) {
+    if (stage_to_snp_major(h->compute, h->n, src, xdtype, ld, layout, mb, dst, h->ldx)) {
         cudaError_t e_ = cudaGetLastError();
         return fail(h, PG_ERR_CUDA, "staging kernel: %s", cudaGetErrorString(e_));
     }
@@ -424,9 +435,21 @@ static int launch_reml(pg_handle* h, const double* xr, long long mb, long long r
 {
     ScanArgs a;
     a.n = h->n; a.c0 = h->c0; a.grid = grid_mode; a.m = mb; a.row0 = row0;
-    a.d = h->d; a.wy = h->wy; a.xr = xr; a.ldx = h->n; a.tab = h->tab;
+    a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = xr; a.ldx = h->ldx; a.tab = h->tab;
     for (int i = 0; i < 6; ++i) a.out[i] = out[i];
     a.status = status; a.n_eval2 = e2; a.n_eval3 = e3; a.counter = h->counter;
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), h->compute));
+    if (!h->use_v1) {
+        const StreamCfg cfg = stream_config(h->c0);
+        const int ncmax = std::min(h->c0 + 1, (int)kChunkCols);
+        CK(cudaFuncSetAttribute(reml_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+        const int ctas_per_sm = cfg.smem <= 110 * 1024 ? 2 : 1;
+        long long want = (mb + cfg.nw - 1) / cfg.nw;
+        int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
+        reml_stream_kernel<<<grid, cfg.nw * 32, cfg.smem, h->compute>>>(a, cfg.nw, ncmax);
+        CK(cudaGetLastError());
+        return PG_OK;
+    }
     const int k = h->c0 + 2, TT = k * (k + 1) / 2;
     const size_t per_warp = sizeof(double) * 3 * TT;
     int warps = 8;
@@ -438,7 +461,6 @@ static int launch_reml(pg_handle* h, const double* xr, long long mb, long long r
     long long want = (mb + warps - 1) / warps;
     int grid = (int)std::min<long long>(want, (long long)h->sm_count * ctas_per_sm);
     grid = std::max(grid, 1);
-    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), h->compute));
     reml_scan_kernel<<<grid, warps * 32, smem, h->compute>>>(a);
     CK(cudaGetLastError());
     return PG_OK;
@@ -492,7 +514,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     for (long long b = 0; b < nblocks; ++b) { mk(ev_conv[b]); mk(ev_rot[b]); mk(ev_reml[b]); if (!on_device) mk(ev_h2d[b]); }
     cudaEvent_t t0, t1, t2;
     cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
-    int n_rot_launch = 0;
+    int n_rot_launch = 0, last_engine = 0;
 
     rc = [&]() -> int {
         CK(cudaEventRecord(t0, h->compute));
@@ -526,15 +548,15 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             }
             const double* xr_block = nullptr;
             CK(cudaEventRecord(ev_conv[b].a, h->compute));
-            bool staged = false;
             int used_i8 = 0;
             if (rotate) {
                 // try the fused-conversion rotation engines first (they read the raw block directly)
                 int r2 = rot_run(&h->rot, h->blas, h->compute, h->rotation, h->U, h->u_op_t, n, src_dev, xdtype, ld_dev,
-                                 layout, mb, h->xf, h->xr, &staged, &used_i8, &n_rot_launch, ev_conv[b].b, ev_rot[b].a,
-                                 ev_rot[b].b, h->sm_count);
+                                 layout, mb, blk, h->xf, h->xr, h->ldx, &used_i8, &n_rot_launch, ev_conv[b].b, ev_rot[b].a,
+                                 ev_rot[b].b);
                 if (r2 != 0) return fail(h, r2, "rotation failed: %s", rot_error(&h->rot));
                 xr_block = h->xr;
+                last_engine = used_i8 ? PG_ROT_I8SPLIT : PG_ROT_FP64;
             } else {
                 int r2 = launch_stage(h, src_dev, xdtype, ld_dev, layout, mb, h->xr);
                 if (r2) return r2;
@@ -580,6 +602,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->reml_launches = (int32_t)nblocks;
         timing->rotate_launches = n_rot_launch;
         timing->convert_launches = (int32_t)nblocks;
+        timing->rot_engine = last_engine;
     }
     for (long long b = 0; b < nblocks; ++b) {
         cudaEventDestroy(ev_conv[b].a); cudaEventDestroy(ev_conv[b].b);
@@ -621,11 +644,12 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     CK(cudaSetDevice(h->device));
     const int n = h->n;
     double *dx = nullptr, *dout = nullptr;
-    CK(cudaMalloc(&dx, sizeof(double) * n));
+    CK(cudaMalloc(&dx, sizeof(double) * h->ldx));
     CK(cudaMalloc(&dout, sizeof(double) * 9));
+    CK(cudaMemsetAsync(dx, 0, sizeof(double) * h->ldx, h->compute));
     CK(cudaMemcpyAsync(dx, x_rot_host, sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
     ScanArgs a{};
-    a.n = n; a.c0 = h->c0; a.grid = 0; a.m = 1; a.row0 = 0; a.d = h->d; a.wy = h->wy; a.xr = dx; a.ldx = n; a.tab = h->tab;
+    a.n = n; a.c0 = h->c0; a.grid = 0; a.m = 1; a.row0 = 0; a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = dx; a.ldx = h->ldx; a.tab = h->tab;
     const int k = h->c0 + 2, TT = k * (k + 1) / 2;
     const size_t smem = sizeof(double) * 3 * TT;
     if (smem > 48 * 1024)
@@ -663,7 +687,8 @@ extern "C" int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, in
     if (!h->xr || h->last_block_count == 0) return fail(h, PG_ERR_ARG, "pg_probe_rotated: no scan has run");
     CK(cudaSetDevice(h->device));
     const long long c = std::min<long long>(count, h->last_block_count);
-    CK(cudaMemcpy(xr_host, h->xr, sizeof(double) * (size_t)c * h->n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2D(xr_host, sizeof(double) * h->n, h->xr, sizeof(double) * h->ldx, sizeof(double) * h->n, (size_t)c,
+                    cudaMemcpyDeviceToHost));
     if (row0) *row0 = h->last_block_row0;
     return PG_OK;
 }

@@ -24,7 +24,8 @@ struct ScanArgs {
     long long m;          // SNPs in this block
     long long row0;       // global row of the block's first SNP
     const double* d;      // eigenvalues (clipped), n
-    const double* wy;     // rotated [W0, y], column-major n x (c0+1)
+    const double* wy;     // rotated [W0, y], column-major, column j at wy + j*ldw (zero-padded)
+    long long ldw;
     const double* xr;     // rotated genotypes, SNP-major: SNP g at xr + g*ldx
     long long ldx;
     Tables tab;
@@ -50,7 +51,8 @@ __device__ __forceinline__ void xrow_pass(const ScanArgs& a, const double* __res
 {
     const int n = a.n, lane = threadIdx.x & 31;
     const double* __restrict__ d = a.d;
-    const double* __restrict__ w = a.wy + (size_t)jb * n;
+    const double* __restrict__ w = a.wy + (size_t)jb * a.ldw;
+    const size_t ldw = (size_t)a.ldw;
     double a1[NC], a2[NC], a3[NC];
     double xx1 = 0.0, xx2 = 0.0, xx3 = 0.0;
 #pragma unroll
@@ -68,7 +70,7 @@ __device__ __forceinline__ void xrow_pass(const ScanArgs& a, const double* __res
         }
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-            const double wv = w[(size_t)j * n + l];
+            const double wv = w[(size_t)j * ldw + l];
             a1[j] = fma(xh, wv, a1[j]);
             a2[j] = fma(xh2, wv, a2[j]);
             if (FULL) a3[j] = fma(xh3, wv, a3[j]);
@@ -201,7 +203,7 @@ __global__ void probe_f_sf_kernel(const double* F, double nu, long long k, doubl
 // (three powers each) or, for the last chunk, the three scalar functions, over all n eigenvalues.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_tables_kernel(int n, int c0, const double* __restrict__ d,
-                                                            const double* __restrict__ wy,
+                                                            const double* __restrict__ wy, long long ldw,
                                                             const double* __restrict__ lambdas,
                                                             double* fixtab, double* itab, const TriAB* tri_ab)
 {
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(int n, int c0, const 
             const double h2 = h * h, h3 = h2 * h;
 #pragma unroll
             for (int i = 0; i < kTablePairs; ++i) {
-                const double p = wy[(size_t)ra[i] * n + l] * wy[(size_t)sa[i] * n + l];
+                const double p = wy[(size_t)ra[i] * ldw + l] * wy[(size_t)sa[i] * ldw + l];
                 acc[3 * i] = fma(p, h, acc[3 * i]);
                 acc[3 * i + 1] = fma(p, h2, acc[3 * i + 1]);
                 acc[3 * i + 2] = fma(p, h3, acc[3 * i + 2]);
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(int n, int c0, const 
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void to_snp_major_kernel(const T* __restrict__ src, long long ld, int layout, int n, long long mb,
-                                    double* __restrict__ dst)
+                                    double* __restrict__ dst, long long ldd)
 {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -289,14 +291,14 @@ __global__ void to_snp_major_kernel(const T* __restrict__ src, long long ld, int
         for (int r = ty; r < 32; r += 8) {
             const long long g = g0 + r;
             const int j = j0 + tx;
-            if (g < mb && j < n) dst[(size_t)g * n + j] = tile[tx][r];
+            if (g < mb && j < n) dst[(size_t)g * ldd + j] = tile[tx][r];
         }
     } else {
 #pragma unroll
         for (int r = ty; r < 32; r += 8) {
             const long long g = g0 + r;
             const int j = j0 + tx;
-            if (g < mb && j < n) dst[(size_t)g * n + j] = (double)src[(size_t)g * ld + j];
+            if (g < mb && j < n) dst[(size_t)g * ldd + j] = (double)src[(size_t)g * ld + j];
         }
     }
 }

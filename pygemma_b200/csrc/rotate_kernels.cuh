@@ -4,8 +4,10 @@
 // device GEMM whose output layout is what the REML kernel streams (SNP g at xr + g*n).
 //
 // Engines
-//   PG_ROT_FP64     FP64 GEMM (cuBLAS DGEMM on the staged fp64 block): any genotype dtype.
-//   PG_ROT_I8SPLIT  exact integer path for int8 dosages (see rotate_i8.cuh when built in).
+//   PG_ROT_FP64     FP64 GEMM on the staged fp64 block: any genotype dtype.
+//   PG_ROT_I8SPLIT  exact integer-split path for int8 dosages (rotate_i8.cuh): eight int8 tensor-core
+//                   GEMMs against the digit planes of U^T, recombined exactly.
+//   PG_ROT_AUTO     int8 genotypes -> I8SPLIT, everything else -> FP64.
 #pragma once
 
 #include <cublas_v2.h>
@@ -15,55 +17,154 @@
 
 #include "../../include/pygemma_b200.h"
 #include "reml_kernels.cuh"
+#include "rotate_i8.cuh"
 
 namespace pg {
 
 struct RotWorkspace {
     std::string err;
-    bool valid = false;
+    // int8-split state
+    bool planes_valid = false;
+    int n = 0, npad = 0, ldk = 0;
+    int8_t* planes = nullptr;  // [8][npad][ldk]
+    int* exps = nullptr;       // [n]
+    int8_t* x8 = nullptr;      // [cap_snps][ldk]
+    long long cap_snps = 0;
+    int32_t* P = nullptr;      // [(8*npad) x sub] column-major
+    long long sub = 0;
+    float slice_ms = 0.f;
 };
 
-inline void rot_free(RotWorkspace* w) { w->valid = false; }
-inline void rot_invalidate(RotWorkspace* w) { w->valid = false; }
+inline void rot_free(RotWorkspace* w)
+{
+    if (w->planes) cudaFree(w->planes);
+    if (w->exps) cudaFree(w->exps);
+    if (w->x8) cudaFree(w->x8);
+    if (w->P) cudaFree(w->P);
+    w->planes = nullptr; w->exps = nullptr; w->x8 = nullptr; w->P = nullptr;
+    w->planes_valid = false; w->cap_snps = 0; w->sub = 0;
+}
+inline void rot_invalidate(RotWorkspace* w) { w->planes_valid = false; }
 inline const char* rot_error(RotWorkspace* w) { return w->err.c_str(); }
 
 inline int stage_to_snp_major(cudaStream_t stream, int n, const void* src, int xdtype, long long ld, int layout,
-                              long long mb, double* dst)
+                              long long mb, double* dst, long long ldd)
 {
     dim3 block(32, 8), grid((unsigned)((mb + 31) / 32), (unsigned)((n + 31) / 32));
     switch (xdtype) {
     case PG_X_I8:
-        to_snp_major_kernel<int8_t><<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, dst);
+        to_snp_major_kernel<int8_t><<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, dst, ldd);
         break;
     case PG_X_F32:
-        to_snp_major_kernel<float><<<grid, block, 0, stream>>>((const float*)src, ld, layout, n, mb, dst);
+        to_snp_major_kernel<float><<<grid, block, 0, stream>>>((const float*)src, ld, layout, n, mb, dst, ldd);
         break;
     default:
-        to_snp_major_kernel<double><<<grid, block, 0, stream>>>((const double*)src, ld, layout, n, mb, dst);
+        to_snp_major_kernel<double><<<grid, block, 0, stream>>>((const double*)src, ld, layout, n, mb, dst, ldd);
         break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : PG_ERR_CUDA;
 }
 
+#define PG_ROT_CK(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            w->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            return PG_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U, int u_op_t, int n, long long blk)
+{
+    const int npad = (n + 15) / 16 * 16, ldk = npad;
+    if (w->n != n || !w->planes) {
+        rot_free(w);
+        w->n = n; w->npad = npad; w->ldk = ldk;
+        PG_ROT_CK(cudaMalloc(&w->planes, (size_t)kSlices * npad * ldk));
+        PG_ROT_CK(cudaMalloc(&w->exps, sizeof(int) * n));
+    }
+    const long long cap = (blk + 63) / 64 * 64;
+    if (cap > w->cap_snps) {
+        if (w->x8) cudaFree(w->x8);
+        w->x8 = nullptr;
+        PG_ROT_CK(cudaMalloc(&w->x8, (size_t)cap * ldk));
+        PG_ROT_CK(cudaMemsetAsync(w->x8, 0, (size_t)cap * ldk, stream));
+        w->cap_snps = cap;
+    }
+    // int32 partial products: 8*npad x sub; keep the buffer near 1 GiB
+    long long sub = (long long)((size_t(1) << 30) / ((size_t)kSlices * npad * 4));
+    sub = std::max<long long>(64, std::min<long long>((sub / 64) * 64, cap));
+    if (sub > w->sub) {
+        if (w->P) cudaFree(w->P);
+        w->P = nullptr;
+        PG_ROT_CK(cudaMalloc(&w->P, (size_t)kSlices * npad * sub * sizeof(int32_t)));
+        w->sub = sub;
+    }
+    if (!w->planes_valid) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+        slice_u_kernel<<<npad, 256, 0, stream>>>(U, u_op_t ? 1 : 0, n, npad, ldk, w->planes, w->exps);
+        PG_ROT_CK(cudaGetLastError());
+        cudaEventRecord(e1, stream);
+        PG_ROT_CK(cudaStreamSynchronize(stream));
+        cudaEventElapsedTime(&w->slice_ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        w->planes_valid = true;
+    }
+    return 0;
+}
+
 // Rotates one block.  xf: staging buffer (mb x n fp64), xr: output (mb x n fp64, SNP-major).
 inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, int rotation, const double* U, int u_op_t,
-                   int n, const void* src, int xdtype, long long ld, int layout, long long mb, double* xf, double* xr,
-                   bool* staged, int* used_i8, int* n_launch, cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin,
-                   cudaEvent_t ev_rot_end, int sm_count)
+                   int n, const void* src, int xdtype, long long ld, int layout, long long mb, long long blk, double* xf,
+                   double* xr, long long ldx, int* used_i8, int* n_launch, cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin,
+                   cudaEvent_t ev_rot_end)
 {
-    (void)rotation; (void)sm_count;
-    *used_i8 = 0;
-    int rc = stage_to_snp_major(stream, n, src, xdtype, ld, layout, mb, xf);
-    if (rc) { w->err = "staging kernel launch failed"; return rc; }
-    *staged = true;
+    const bool i8 = (xdtype == PG_X_I8) && (rotation == PG_ROT_AUTO || rotation == PG_ROT_I8SPLIT);
+    if (rotation == PG_ROT_I8SPLIT && xdtype != PG_X_I8) {
+        w->err = "PG_ROT_I8SPLIT needs int8 genotypes";
+        return PG_ERR_ARG;
+    }
+    *used_i8 = i8 ? 1 : 0;
+    if (!i8) {
+        int rc = stage_to_snp_major(stream, n, src, xdtype, ld, layout, mb, xf, n);
+        if (rc) { w->err = "staging kernel launch failed"; return rc; }
+        (*n_launch)++;
+        cudaEventRecord(ev_conv_end, stream);
+        cudaEventRecord(ev_rot_begin, stream);
+        const double one = 1.0, zero = 0.0;
+        // column-major view: Xr (n x mb, ld n) = op(U) (n x n) * Xf (n x mb, ld n)
+        cublasStatus_t s = cublasDgemm(blas, u_op_t ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, n, (int)mb, n, &one, U, n,
+                                       xf, n, &zero, xr, (int)ldx);
+        if (s != CUBLAS_STATUS_SUCCESS) { w->err = "cublasDgemm failed, status " + std::to_string((int)s); return PG_ERR_CUBLAS; }
+        cudaEventRecord(ev_rot_end, stream);
+        return 0;
+    }
+    int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
+    if (rc) return rc;
+    {
+        dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
+        stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch)++;
+    }
     cudaEventRecord(ev_conv_end, stream);
     cudaEventRecord(ev_rot_begin, stream);
-    const double one = 1.0, zero = 0.0;
-    // column-major view: Xr (n x mb, ld n) = op(U) (n x n) * Xf (n x mb, ld n)
-    cublasStatus_t s = cublasDgemm(blas, u_op_t ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, n, (int)mb, n, &one, U, n, xf,
-                                   n, &zero, xr, n);
-    if (s != CUBLAS_STATUS_SUCCESS) { w->err = "cublasDgemm failed, status " + std::to_string((int)s); return PG_ERR_CUBLAS; }
-    (*n_launch)++;
+    const int32_t ione = 1, izero = 0;
+    const int M = kSlices * w->npad;
+    for (long long g0 = 0; g0 < mb; g0 += w->sub) {
+        const long long cnt = std::min(w->sub, mb - g0);
+        const long long cnt_pad = (cnt + 15) / 16 * 16;  // x8 rows beyond mb are zero / stale: ignored downstream
+        cublasStatus_t s = cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_N, M, (int)cnt_pad, w->ldk, &ione, w->planes,
+                                        CUDA_R_8I, w->ldk, w->x8 + (size_t)g0 * w->ldk, CUDA_R_8I, w->ldk, &izero, w->P,
+                                        CUDA_R_32I, M, CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
+        if (s != CUBLAS_STATUS_SUCCESS) { w->err = "cublasGemmEx(int8) failed, status " + std::to_string((int)s); return PG_ERR_CUBLAS; }
+        dim3 grid((unsigned)((n + 255) / 256), (unsigned)cnt);
+        combine_i8_kernel<<<grid, 256, 0, stream>>>(w->P, w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch)++;
+    }
     cudaEventRecord(ev_rot_end, stream);
     return 0;
 }

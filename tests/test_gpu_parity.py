@@ -236,3 +236,56 @@ def test_full_size_properties():
     # first 24 SNPs against the oracle at full n
     ref = oracle.scan_rotated(p["d"], p["Y"], p["W"], np.ascontiguousarray(X[:, :24].T))
     _check(o, ref, idx=np.arange(24), tag="n=10000")
+
+
+def test_i8split_rotation_equals_fp64_rotation():
+    """The exact integer-split tensor-core rotation against the FP64 GEMM rotation on the same int8 dosages:
+    rotated vectors agree to fp64 rounding of the FP64 path, scan outputs to 1e-9."""
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    n, m = 777, 203  # odd sizes: exercises every padding path
+    p = make_problem(n, m, 3, seed=9, m_k=2000)
+    res = {}
+    with capi.Handle(n, 3) as h:
+        h.set_kinship(p["K"])
+        h.set_design(p["W"], p["Y"])
+        for eng in (capi.PG_ROT_FP64, capi.PG_ROT_I8SPLIT):
+            h.set_options(rotation=eng, block_snps=128)
+            o = h.scan(p["X"])
+            assert o["timing"]["rot_engine"] == eng
+            xr, row0 = h.probe_rotated(64)
+            assert row0 == 128
+            res[eng] = (o, xr)
+        h.set_options(rotation=capi.PG_ROT_I8SPLIT)
+        with pytest.raises(capi.PgError):
+            h.scan(p["X"].astype(np.float32))
+    (o64, x64), (o8, x8) = res[capi.PG_ROT_FP64], res[capi.PG_ROT_I8SPLIT]
+    scale = np.sqrt((p["X"].astype(np.float64) ** 2).sum(0))[128:192, None]
+    assert (np.abs(x64 - x8) / scale).max() < 1e-13
+    for c in COLS:
+        assert rel(o8[c], o64[c]).max() < 1e-9, c
+
+
+def test_v1_and_stream_kernels_agree():
+    """The CTA-lock-step streaming kernel against the simple warp-per-SNP kernel (PG_REML_V1=1)."""
+    import subprocess
+    import sys
+
+    code = ("import numpy as np, sys; sys.path.insert(0, '.');"
+            "from pygemma_b200 import _capi; from pygemma_b200.synth import make_spectral_problem;"
+            "p = make_spectral_problem(1300, 160, 14, seed=4, xdtype=np.float64);"
+            "h = _capi.Handle(1300, 14); h.set_eigen(None, p['d']); h.set_design(p['W'], p['Y'], already_rotated=True);"
+            "o = h.scan(p['X']); np.save(sys.argv[1], np.stack([o[c] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]))")
+    import tempfile
+
+    outs = []
+    for v1 in (False, True):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            env = dict(os.environ)
+            env.pop("PG_REML_V1", None)
+            if v1:
+                env["PG_REML_V1"] = "1"
+            subprocess.check_call([sys.executable, "-c", code, f.name], env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+            outs.append(np.load(f.name))
+    assert rel(outs[0], outs[1]).max() < 1e-9
