@@ -390,9 +390,11 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
     const int n = h->n;
     long long blk = h->block_snps_opt;
     if (blk <= 0) {
-        blk = (long long)((size_t(1) << 29) / (sizeof(double) * (size_t)n));  // ~512 MB of fp64 per buffer
+        blk = (long long)((size_t(1) << 31) / (sizeof(double) * (size_t)n));  // ~2 GiB of fp64 per buffer
         blk = std::max<long long>(256, (blk / 256) * 256);
-        blk = std::min<long long>(blk, 16384);
+        blk = std::min<long long>(blk, 32768);
+        // keep at least four blocks in flight on large inputs so uploads overlap compute
+        if (m >= 4 * 8192) blk = std::min<long long>(blk, std::max<long long>(8192, ((m + 3) / 4 + 255) / 256 * 256));
     }
     blk = std::min(blk, std::max<long long>(m, 1));
     blk = ((blk + 31) / 32) * 32;

@@ -263,17 +263,20 @@ PG_HD void lagrange_basis(double x, double* L /* kNodes */)
 // Per-SNP optimiser as a resumable state machine.  Usage:
 //   SnpSolver s; s.init(n, c0, grid);
 //   while (s.pending()) { EvalOut e = evaluate(s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll()); s.feed(e); }
-//   s.beta ... s.p_wald
-// Fixed-lambda requests come first (index t = 0..10 <-> lambda = 10^(t-5)), so a caller that has
-// the fixed-lambda scalars precomputed can serve them without touching the genotype vector.
+//   s.beta ... s.p
+// The 11 fixed-lambda evaluations (index t <-> lambda = 10^(t-5)) are requested first, in order; they do
+// not depend on anything the optimiser decides, so a caller can serve them from precomputed dot products
+// (phase F of the GPU scan) and hand the machine over to the streaming kernel only when the first
+// SNP-specific lambda is requested (Brent / Newton / root likelihood).  The reference interleaves the same
+// evaluations with the bracket handling (pyx:154-192); the values, comparisons and their order are the same.
 // ------------------------------------------------------------------------------------------------
 struct SnpSolver {
     enum Phase { kFixed = 0, kBrent = 1, kNewton = 2, kRootLL = 3, kDone = 4 };
     int n, c0, cf, grid;
     int phase;
-    int t_req;  // fixed index being requested in kFixed; order is 0, 10, 1, 2, ..., 9
+    int t_req;  // fixed index being requested in kFixed
     int idx;    // current bracket [10^(idx-5), 10^(idx-4)], idx = 0..9
-    double f_prev, f_cur, f_hi;  // d1 at the bracket ends / at lambda = 1e5
+    double d1_fixed[kNumFixed];
     // best candidate so far (pyx:144-152,:186-192) with its Wald scalars
     double best_lambda, best_ll, best_xPx, best_yPx, best_yPy;
     Brent br;
@@ -305,11 +308,13 @@ struct SnpSolver {
     {
         n = n_; c0 = c0_; cf = c0_ + 1; grid = grid_;
         idx = 0; status = 0; n_eval2 = 0; n_eval3 = 0;
-        f_prev = f_cur = f_hi = 0;
         best_lambda = 0; best_ll = 0; best_xPx = best_yPx = best_yPy = 0;
         nt_root = 0; nt_iter = 0;
         lambda = beta = se = tau = F = p = NAN;
         br.done = 0;
+        grid_ll0 = 0; grid_in_ll = -INFINITY; grid_in_lam = 0;
+        grid_w0[0] = grid_w0[1] = grid_w0[2] = 0; grid_in_w[0] = grid_in_w[1] = grid_in_w[2] = 0;
+        for (int k = 0; k < kNumFixed; ++k) d1_fixed[k] = 0;
         request_fixed(0);
     }
 
@@ -340,73 +345,77 @@ struct SnpSolver {
         request(nt_root, 1, 0);
     }
 
-    // bracket idx is [lambda_idx, lambda_idx+1] with d1 values f_prev, f_cur (pyx:154-174)
-    PG_HD void try_bracket()
+    // scan brackets idx.. for a sign change of d1 (pyx:154-174); issue the first Brent request or finish
+    PG_HD void next_bracket()
     {
-        for (;;) {
-            if (copysign(1.0, f_prev) * copysign(1.0, f_cur) < 0) {  // pyx:174
-                if (isnan(f_prev) || isnan(f_cur)) {
-                    status = 1;  // SciPy's brentq raises on a NaN function value: the row becomes NaN
-                } else {
-                    br.start(fixed_lambda(idx), f_prev, fixed_lambda(idx + 1), f_cur, 2e-12, 0.1, 100);
-                    if (br.done) { start_newton(br.root); return; }
-                    phase = kBrent;
-                    request(br.query(), 0, 0);
-                    return;
-                }
+        for (; idx < kNumFixed - 1; ++idx) {
+            const double f0 = d1_fixed[idx], f1 = d1_fixed[idx + 1];
+            if (copysign(1.0, f0) * copysign(1.0, f1) < 0) {  // pyx:174
+                if (isnan(f0) || isnan(f1)) { status = 1; continue; }  // SciPy's brentq raises on NaN: row -> NaN
+                br.start(fixed_lambda(idx), f0, fixed_lambda(idx + 1), f1, 2e-12, 0.1, 100);
+                if (br.done) { start_newton(br.root); return; }
+                phase = kBrent;
+                request(br.query(), 0, 0);
+                return;
             }
-            if (!advance()) return;
         }
+        finish();
     }
 
-    // move to the next bracket; returns true when f_cur is already known (last bracket) and the
-    // caller should test it, false when a request is pending or the SNP is finished
-    PG_HD bool advance()
+    // number of brackets with a sign change (valid once the fixed phase is complete)
+    PG_HD int count_brackets() const
     {
-        f_prev = f_cur;
-        idx++;
-        if (idx <= kNumFixed - 3) { request_fixed(idx + 1); return false; }
-        if (idx == kNumFixed - 2) { f_cur = f_hi; return true; }
-        finish();
-        return false;
+        int c = 0;
+        for (int k = 0; k < kNumFixed - 1; ++k)
+            if (copysign(1.0, d1_fixed[k]) * copysign(1.0, d1_fixed[k + 1]) < 0) c++;
+        return c;
     }
 
     PG_HD void feed(const EvalOut& e)
     {
         if (rq_full) n_eval3++; else n_eval2++;
         if (phase == kFixed) {
-            const double d1 = reml_d1(rq_lambda, n, cf, e.yPy, e.yPPy, e.trP);
-            const double ll = rq_ll ? reml_loglik(n, cf, e.yPy, e.logdetH, e.logdetWHW) : 0.0;
-            if (t_req == 0) {  // pyx:144 / :109
-                f_prev = d1;
-                set_best(ll, rq_lambda, e);
-                request_fixed(kNumFixed - 1);
-                return;
+            const int t = t_req;
+            d1_fixed[t] = reml_d1(rq_lambda, n, cf, e.yPy, e.yPPy, e.trP);
+            if (rq_ll) {
+                const double ll = reml_loglik(n, cf, e.yPy, e.logdetH, e.logdetWHW);
+                if (t == 0) {
+                    set_best(ll, rq_lambda, e);  // pyx:144 / :109
+                } else if (t == kNumFixed - 1) {
+                    // the upper boundary beats the lower one on '<' (pyx:148 / :113); in grid mode the interior
+                    // points were compared with '>' against the running best, which started at the lower
+                    // boundary, so the upper boundary enters with the reference's boundary rule below
+                    if (grid) {
+                        // grid: best so far = argmax over {lo} U {10^-4..10^4} with strict '>' in lambda order;
+                        // reference order is {lo, hi} first, then 10^-5..10^4.  Reproduce it exactly:
+                        // hi wins over lo iff ll_lo < ll_hi; an interior point wins iff strictly greater than that.
+                        const double ll_lo = grid_ll0;
+                        double b_ll = ll_lo, b_lam = fixed_lambda(0);
+                        double b_w[3] = {grid_w0[0], grid_w0[1], grid_w0[2]};
+                        if (b_ll < ll) { b_ll = ll; b_lam = rq_lambda; b_w[0] = e.xPx; b_w[1] = e.yPx; b_w[2] = e.yPy; }
+                        if (grid_in_ll > b_ll) { b_ll = grid_in_ll; b_lam = grid_in_lam; b_w[0] = grid_in_w[0]; b_w[1] = grid_in_w[1]; b_w[2] = grid_in_w[2]; }
+                        best_ll = b_ll; best_lambda = b_lam; best_xPx = b_w[0]; best_yPx = b_w[1]; best_yPy = b_w[2];
+                    } else if (best_ll < ll) {
+                        set_best(ll, rq_lambda, e);
+                    }
+                } else if (grid) {
+                    // running argmax over the interior grid points in increasing lambda, strict '>' (pyx:128)
+                    if (ll > grid_in_ll) {
+                        grid_in_ll = ll; grid_in_lam = rq_lambda;
+                        grid_in_w[0] = e.xPx; grid_in_w[1] = e.yPx; grid_in_w[2] = e.yPy;
+                    }
+                }
+                if (t == 0 && grid) { grid_ll0 = ll; grid_w0[0] = e.xPx; grid_w0[1] = e.yPx; grid_w0[2] = e.yPy; }
             }
-            if (t_req == kNumFixed - 1) {  // pyx:146-152 / :111-117
-                f_hi = d1;
-                if (best_ll < ll) set_best(ll, rq_lambda, e);
-                idx = 0;
-                request_fixed(1);
-                return;
-            }
-            if (grid) {  // pyx:119-130 (the k = -5 candidate repeats the lower boundary and can never win)
-                if (ll > best_ll) set_best(ll, rq_lambda, e);
-                if (t_req < kNumFixed - 2) request_fixed(t_req + 1);
-                else finish();
-                return;
-            }
-            f_cur = d1;
-            try_bracket();
+            if (t + 1 < kNumFixed) { request_fixed(t + 1); return; }
+            if (grid) { finish(); return; }
+            idx = 0;
+            next_bracket();
             return;
         }
         if (phase == kBrent) {
             const double f = reml_d1(rq_lambda, n, cf, e.yPy, e.yPPy, e.trP);
-            if (isnan(f)) {
-                status = 1;
-                if (advance()) try_bracket();
-                return;
-            }
+            if (isnan(f)) { status = 1; idx++; next_bracket(); return; }
             br.feed(f);
             if (br.done) { start_newton(br.root); return; }
             request(br.query(), 0, 0);
@@ -438,10 +447,15 @@ struct SnpSolver {
         if (phase == kRootLL) {
             const double ll = reml_loglik(n, cf, e.yPy, e.logdetH, e.logdetWHW);
             if (ll > best_ll) set_best(ll, rq_lambda, e);  // pyx:190
-            if (advance()) try_bracket();
+            idx++;
+            next_bracket();
             return;
         }
     }
+
+    // grid-mode bookkeeping (lower boundary and running interior argmax)
+    double grid_ll0, grid_in_ll, grid_in_lam;
+    double grid_w0[3], grid_in_w[3];
 };
 
 }  // namespace pg

@@ -70,27 +70,36 @@ __device__ __forceinline__ void tile_compute(const double* __restrict__ sd, cons
                                              double (&a2)[NC], double (&a3)[NC], double& xx1, double& xx2,
                                              double& xx3)
 {
-#pragma unroll 1
-    for (int it = 0; it < kTile / 32; ++it) {
+    constexpr int kIt = kTile / 32;
+    // phase 1: the serial chain d -> 1/(lam d + 1) -> x h^p for all steps of the tile at once (independent
+    // chains overlap their latencies)
+    double xh[kIt], xh2[kIt], xh3[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
         const int l = it * 32 + lane;
-        // issue every shared-memory load of this step before the dependent arithmetic
+        const double xv = sx[l];
+        const double h = fast_rcp(fma(lam, sd[l], 1.0));
+        xh[it] = xv * h;
+        xh2[it] = xh[it] * h;
+        xh3[it] = FULL ? xh2[it] * h : 0.0;
+        if (FIRST) {
+            xx1 = fma(xh[it], xv, xx1);
+            xx2 = fma(xh2[it], xv, xx2);
+            if (FULL) xx3 = fma(xh3[it], xv, xx3);
+        }
+    }
+    // phase 2: rank-1 accumulation against the [W0, y] columns
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int l = it * 32 + lane;
         double wv[NC];
 #pragma unroll
         for (int j = 0; j < NC; ++j) wv[j] = sw[j * kTile + l];
-        const double xv = sx[l];
-        const double h = fast_rcp(fma(lam, sd[l], 1.0));
-        const double xh = xv * h, xh2 = xh * h;
-        const double xh3 = FULL ? xh2 * h : 0.0;
-        if (FIRST) {
-            xx1 = fma(xh, xv, xx1);
-            xx2 = fma(xh2, xv, xx2);
-            if (FULL) xx3 = fma(xh3, xv, xx3);
-        }
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-            a1[j] = fma(xh, wv[j], a1[j]);
-            a2[j] = fma(xh2, wv[j], a2[j]);
-            if (FULL) a3[j] = fma(xh3, wv[j], a3[j]);
+            a1[j] = fma(xh[it], wv[j], a1[j]);
+            a2[j] = fma(xh2[it], wv[j], a2[j]);
+            if (FULL) a3[j] = fma(xh3[it], wv[j], a3[j]);
         }
     }
 }

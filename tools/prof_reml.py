@@ -13,6 +13,7 @@ p = make_spectral_problem(n, m, c0, seed=1, xdtype=np.float64)
 with _capi.Handle(n, c0) as h:
     h.set_eigen(None, p["d"])
     h.set_design(p["W"], p["Y"], already_rotated=True)
+    h.set_options(block_snps=m)
     for rep in range(2):
         o = h.scan(p["X"], grid=grid)
     print(o["timing"], float(o["n_eval2"].mean()), float(o["n_eval3"].mean()))
