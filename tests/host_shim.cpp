@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "../pygemma_b200/csrc/compress_plan.h"
 #include "../pygemma_b200/csrc/pg_eval.cuh"
 
 using namespace pg;
@@ -101,6 +102,112 @@ void eval_snp(const HostTables& H, int n, const double* d, const double* wy, con
 }
 
 }  // namespace
+
+// one evaluation from the compressed moments z[j][k] (j = 0..c0-1: x.w_j, c0: x.y, c0+1: x.x) of one SNP
+namespace {
+void eval_snp_compressed(const HostTables& H, const CompressPlan& P, const double* z, double lam, int fixed_t,
+                                int full, int need_ll, EvalOut* out)
+{
+    const int c0 = H.t.c0, k = c0 + 2, k1 = c0 + 2, Kc = P.Kc;
+    const int TT = k * (k + 1) / 2;
+    std::vector<double> A(TT, 0.0), B(TT, 0.0), C(TT, 0.0);
+    Level0 l0;
+    if (full) assemble_w0y<true>(H.t, lam, fixed_t, A.data(), B.data(), C.data(), &l0);
+    else assemble_w0y<false>(H.t, lam, fixed_t, A.data(), B.data(), C.data(), &l0);
+    for (int j = 0; j < k1; ++j) {
+        double a1 = 0, a2 = 0, a3 = 0;
+        for (int q = 0; q < Kc; ++q) {
+            const double h = 1.0 / (lam * P.nodes[q] + 1.0), zz = z[(size_t)j * Kc + q];
+            a1 += h * zz; a2 += h * h * zz; a3 += h * h * h * zz;
+        }
+        const int dst = j < c0 ? tri(c0, j) : (j == c0 ? tri(c0 + 1, c0) : tri(c0, c0));
+        A[dst] = a1; B[dst] = a2; C[dst] = a3;
+    }
+    if (full) pab_recursion<true>(H.t, A.data(), B.data(), C.data(), l0, need_ll, out);
+    else pab_recursion<false>(H.t, A.data(), B.data(), C.data(), l0, need_ll, out);
+}
+}  // namespace
+
+extern "C" {
+
+// number of nodes the compression plan gives for the (ascending) eigenvalues d
+int pgh_plan_nodes(int n, const double* d_sorted)
+{
+    CompressPlan P;
+    build_compress_plan(d_sorted, n, &P);
+    return P.Kc;
+}
+
+// worst |compressed - direct| / sum_l |a_l| h_l^p over a lambda sweep, for a_l given (sorted order)
+double pgh_compress_error(int n, const double* d_sorted, const double* a, int power)
+{
+    CompressPlan P;
+    build_compress_plan(d_sorted, n, &P);
+    std::vector<long double> z(P.Kc, 0.0L);
+    for (const Segment& s : P.segs)
+        for (int l = s.l0; l < s.l1; ++l) {
+            if (s.type == kSegCopy) z[s.kb + (l - s.l0)] += a[l];
+            else for (int q = 0; q < s.kq; ++q) z[s.kb + q] += (long double)P.Lw[(size_t)l * kCq + q] * a[l];
+        }
+    double worst = 0;
+    for (int i = 0; i <= 400; ++i) {
+        const double lam = pow(10.0, -5.0 + i / 40.0);
+        long double ex = 0, ab = 0, cp = 0;
+        for (int l = 0; l < n; ++l) {
+            const long double h = powl(1.0L / ((long double)lam * d_sorted[l] + 1.0L), power);
+            ex += a[l] * h; ab += fabsl((long double)a[l]) * h;
+        }
+        for (int q = 0; q < P.Kc; ++q) cp += z[q] * powl(1.0L / ((long double)lam * P.nodes[q] + 1.0L), power);
+        const double e = (double)(fabsl(cp - ex) / ab);
+        if (e > worst) worst = e;
+    }
+    return worst;
+}
+
+// the scan on compressed moments: d / wy / xr in any eigenvalue order (sorted here)
+void pgh_scan_compressed(int n, int c0, long m, const double* d, const double* wy, const double* xr, int grid,
+                         double* out6, int32_t* status, int32_t* evals, int32_t* kc_out)
+{
+    std::vector<int> perm(n);
+    for (int l = 0; l < n; ++l) perm[l] = l;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return d[a] < d[b]; });
+    const int k0 = c0 + 1, k1 = c0 + 2;
+    std::vector<double> ds(n), wys((size_t)n * k0);
+    for (int l = 0; l < n; ++l) {
+        ds[l] = d[perm[l]];
+        for (int j = 0; j < k0; ++j) wys[(size_t)j * n + l] = wy[(size_t)j * n + perm[l]];
+    }
+    HostTables H;
+    build_tables(H, n, c0, ds.data(), wys.data());
+    CompressPlan P;
+    build_compress_plan(ds.data(), n, &P);
+    if (kc_out) *kc_out = P.Kc;
+    std::vector<double> z((size_t)k1 * P.Kc);
+    for (long g = 0; g < m; ++g) {
+        std::fill(z.begin(), z.end(), 0.0);
+        const double* x = xr + (size_t)g * n;
+        for (const Segment& s : P.segs)
+            for (int l = s.l0; l < s.l1; ++l) {
+                const double xv = x[perm[l]];
+                for (int j = 0; j < k1; ++j) {
+                    const double a = j < k0 ? xv * wys[(size_t)j * n + l] : xv * xv;
+                    if (s.type == kSegCopy) z[(size_t)j * P.Kc + s.kb + (l - s.l0)] += a;
+                    else for (int q = 0; q < s.kq; ++q) z[(size_t)j * P.Kc + s.kb + q] += P.Lw[(size_t)l * kCq + q] * a;
+                }
+            }
+        SnpSolver s;
+        s.init(n, c0, grid);
+        while (s.pending()) {
+            EvalOut e;
+            eval_snp_compressed(H, P, z.data(), s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), &e);
+            s.feed(e);
+        }
+        double* o = out6 + g * 6;
+        o[0] = s.beta; o[1] = s.se; o[2] = s.tau; o[3] = s.lambda; o[4] = s.F; o[5] = s.p;
+        status[g] = s.status; evals[2 * g] = s.n_eval2; evals[2 * g + 1] = s.n_eval3;
+    }
+}
+}
 
 extern "C" {
 

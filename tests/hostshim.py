@@ -20,7 +20,8 @@ def lib():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libpg_host_shim.so")
     srcs = [os.path.join(HERE, "host_shim.cpp"), os.path.join(ROOT, "pygemma_b200", "csrc", "pg_math.cuh"),
-            os.path.join(ROOT, "pygemma_b200", "csrc", "pg_eval.cuh")]
+            os.path.join(ROOT, "pygemma_b200", "csrc", "pg_eval.cuh"),
+            os.path.join(ROOT, "pygemma_b200", "csrc", "compress_plan.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so, "-lm"])
     L = ctypes.CDLL(so)
@@ -34,6 +35,13 @@ def lib():
                             _dp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.pgh_interp_error.restype = ctypes.c_double
     L.pgh_interp_error.argtypes = [ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_int]
+    L.pgh_plan_nodes.restype = ctypes.c_int
+    L.pgh_plan_nodes.argtypes = [ctypes.c_int, _dp]
+    L.pgh_compress_error.restype = ctypes.c_double
+    L.pgh_compress_error.argtypes = [ctypes.c_int, _dp, _dp, ctypes.c_int]
+    L.pgh_scan_compressed.restype = None
+    L.pgh_scan_compressed.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long, _dp, _dp, _dp, ctypes.c_int, _dp, _ip,
+                                      _ip, _ip]
     _lib = L
     return L
 
@@ -58,4 +66,26 @@ def scan(d, y, w0, xr_snp_major, grid=False, exact_w0y=False):
     r["status"] = st
     r["n_eval2"] = ev[:, 0].copy()
     r["n_eval3"] = ev[:, 1].copy()
+    return r
+
+
+def scan_compressed(d, y, w0, xr_snp_major, grid=False):
+    """The scan evaluated from the eigenvalue-space compressed moments (compress_plan.h)."""
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    w0 = np.asarray(w0, dtype=np.float64)
+    wy = np.asfortranarray(np.concatenate([w0, np.asarray(y, dtype=np.float64).reshape(-1, 1)], axis=1))
+    xr = np.ascontiguousarray(xr_snp_major, dtype=np.float64)
+    n, c0, m = d.shape[0], w0.shape[1], xr.shape[0]
+    out = np.empty((m, 6))
+    st = np.zeros(m, dtype=np.int32)
+    ev = np.zeros((m, 2), dtype=np.int32)
+    kc = np.zeros(1, dtype=np.int32)
+    lib().pgh_scan_compressed(n, c0, m, _p(d), _p(wy), _p(xr), int(grid), _p(out), st.ctypes.data_as(_ip),
+                              ev.ctypes.data_as(_ip), kc.ctypes.data_as(_ip))
+    cols = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
+    r = {c: out[:, i].copy() for i, c in enumerate(cols)}
+    r["status"] = st
+    r["n_eval2"] = ev[:, 0].copy()
+    r["n_eval3"] = ev[:, 1].copy()
+    r["nodes"] = int(kc[0])
     return r

@@ -153,3 +153,57 @@ def test_pygemma_argument_contract():
     assert lmm._as_genotypes(np.zeros((2, 2), dtype=np.int64)).dtype == np.int8
     assert lmm._as_genotypes(np.full((2, 2), 300)).dtype == np.float64
     assert lmm._as_genotypes(np.zeros((2, 2), dtype=np.float16)).dtype == np.float32
+
+
+# ---- eigenvalue-space compression (pygemma_b200/csrc/compress_plan.h) ----------------------------------
+
+def _spectra(rng, n):
+    mk = 2 * n
+    g = rng.standard_normal((n, mk))
+    mp = np.linalg.eigvalsh(g @ g.T / mk + 1e-3 * np.eye(n))
+    lowrank = np.concatenate([np.zeros(n // 3), rng.chisquare(3, n - n // 3)])
+    wide = 10.0 ** rng.uniform(-9, 4, n)
+    clustered = np.concatenate([np.full(n // 2, 0.37), 0.37 * (1 + 1e-9 * rng.random(n - n // 2 - 5)), [1e-30, 5.0, 6.0, 7e3, 1e-12]])
+    return {"mp": mp, "lowrank": lowrank, "wide": wide, "clustered": clustered}
+
+
+def test_compression_error_bound():
+    """sum_l a_l h_l^p from the compressed nodes agrees with the direct sum to rounding, for every lambda."""
+    rng = np.random.default_rng(5)
+    n = 1500
+    L = hostshim.lib()
+    for name, d in _spectra(rng, n).items():
+        d = np.sort(np.maximum(d, 0.0))
+        kc = L.pgh_plan_nodes(n, hostshim._p(d))
+        assert kc <= n
+        if name in ("mp", "lowrank", "clustered"):
+            assert kc < n // 4, (name, kc)
+        for a in (rng.standard_normal(n), rng.standard_normal(n) ** 2):
+            a = np.ascontiguousarray(a)
+            for p in (1, 2, 3):
+                e = L.pgh_compress_error(n, hostshim._p(d), hostshim._p(a), p)
+                assert e < (5e-14 if p == 3 else 2e-15), (name, p, e)
+
+
+@pytest.mark.parametrize("path", SCANS, ids=[os.path.basename(p)[5:-4] for p in SCANS])
+def test_compressed_scan_matches_ref64(path):
+    g = np.load(path)
+    xt = np.ascontiguousarray(g["xr"].T)
+    o = hostshim.scan_compressed(g["d"], g["yr"], g["wr"], xt, grid=bool(g["grid"]))
+    assert (o["status"] == 0).all()
+    ok = np.array([0, 2, 4, 5, 6, 7]) if "degenerate" in path else np.arange(xt.shape[0])
+    for c in COLS:
+        tol = 1e-6 if c == "lambda" else 1e-8
+        assert rel(o[c][ok], g[f"r64_{c}"][ok]).max() < tol, (c, rel(o[c][ok], g[f"r64_{c}"][ok]).max())
+
+
+def test_compressed_scan_equals_direct_scan():
+    """Same optimiser path (evaluation counts) and results to 1e-9 with and without the compression."""
+    g = np.load(os.path.join(GOLDEN, "scan_interior.npz"))
+    xt = np.ascontiguousarray(g["xr"].T)
+    a = hostshim.scan(g["d"], g["yr"], g["wr"], xt)
+    b = hostshim.scan_compressed(g["d"], g["yr"], g["wr"], xt)
+    assert b["nodes"] < g["d"].shape[0]
+    for c in COLS:
+        assert rel(a[c], b[c]).max() < 1e-9, (c, rel(a[c], b[c]).max())
+    assert np.array_equal(a["n_eval2"], b["n_eval2"]) and np.array_equal(a["n_eval3"], b["n_eval3"])
