@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 
 typedef struct pg_handle pg_handle;
 
@@ -62,6 +62,14 @@ typedef enum {
     PG_ROT_I8SPLIT = 2
 } pg_rotation;
 
+/* REML stage engine (stage 2 of pg_scan) */
+typedef enum {
+    PG_REML_AUTO = 0,       /* = PG_REML_COMPRESSED */
+    PG_REML_COMPRESSED = 1, /* eigenvalue-space compression (FP64 tensor-pipe contraction) + optimiser on the moments */
+    PG_REML_STREAM = 2,     /* optimiser streams the full rotated genotype vector on every evaluation (CTA lock step) */
+    PG_REML_WARP = 3        /* as STREAM, one independent warp per SNP (cross-check engine) */
+} pg_reml_engine;
+
 /* device-side timings of the last pg_scan call, milliseconds (CUDA events) */
 typedef struct {
     float total_ms;   /* whole call, first H2D to last D2H */
@@ -74,6 +82,9 @@ typedef struct {
     int32_t block_snps;
     int32_t reml_launches, rotate_launches, convert_launches;
     int32_t rot_engine; /* engine the rotation used: PG_ROT_FP64 / PG_ROT_I8SPLIT, 0 when no rotation ran */
+    float compress_ms;  /* part of reml_ms spent collapsing genotype vectors onto the compression nodes */
+    int32_t reml_engine; /* engine the REML stage used */
+    int32_t n_nodes;    /* compression nodes per SNP (n when the engine streams full vectors) */
 } pg_timing;
 
 int pg_abi_version(void);
@@ -120,6 +131,8 @@ int pg_set_stream(pg_handle* h, void* stream);
 
 /* rotation engine selection and block size (0 = automatic) */
 int pg_set_options(pg_handle* h, int rotation, int64_t block_snps);
+/* REML stage engine selection (default PG_REML_AUTO); all engines give the same results to rounding */
+int pg_set_reml_engine(pg_handle* h, int engine);
 
 /*
  * The scan: for each of the m genotype columns, rotate (unless the handle holds rotated inputs),

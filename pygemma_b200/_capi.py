@@ -16,11 +16,13 @@ LIB_PATH = os.path.join(_HERE, "libpygemma_b200.so")
 PG_X_I8, PG_X_F32, PG_X_F64 = 0, 1, 2
 PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1
 PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT = 0, 1, 2
+PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
 
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)
 SYMBOLS = [
     "pg_abi_version", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_stream", "pg_set_options",
+    "pg_set_reml_engine",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
 
@@ -30,7 +32,8 @@ class PgTiming(ctypes.Structure):
                 ("rotate_ms", ctypes.c_float), ("reml_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
                 ("n_blocks", ctypes.c_int32), ("block_snps", ctypes.c_int32), ("reml_launches", ctypes.c_int32),
                 ("rotate_launches", ctypes.c_int32), ("convert_launches", ctypes.c_int32),
-                ("rot_engine", ctypes.c_int32)]
+                ("rot_engine", ctypes.c_int32), ("compress_ms", ctypes.c_float), ("reml_engine", ctypes.c_int32),
+                ("n_nodes", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ }
@@ -69,6 +72,7 @@ def load():
     L.pg_set_design.argtypes = [vp, vp, vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.pg_set_options.argtypes = [vp, i32, i64]
     L.pg_set_stream.argtypes = [vp, vp]
+    L.pg_set_reml_engine.argtypes = [vp, i32]
     scan_args = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 9 + [ctypes.POINTER(PgTiming)]
     L.pg_scan.argtypes = scan_args
     L.pg_scan_device.argtypes = scan_args
@@ -174,6 +178,9 @@ class Handle:
 
     def set_options(self, rotation=PG_ROT_AUTO, block_snps=0):
         self._ck(self.L.pg_set_options(self.h, int(rotation), int(block_snps)))
+
+    def set_reml_engine(self, engine=PG_REML_AUTO):
+        self._ck(self.L.pg_set_reml_engine(self.h, int(engine)))
 
     # --- scan --------------------------------------------------------------------------------
     def scan(self, X, grid=False, layout=PG_X_SAMPLE_MAJOR, with_counts=True):

@@ -15,7 +15,9 @@
 #include <vector>
 
 #include "../../include/pygemma_b200.h"
+#include "compress.cuh"
 #include "reml_kernels.cuh"
+#include "reml_solve.cuh"
 #include "reml_stream.cuh"
 #include "rotate_kernels.cuh"
 
@@ -27,7 +29,7 @@ struct pg_handle {
     int n = 0, c0 = 0, device = 0;
     long long ldw = 0;  // padded leading dimension of d / wy (multiple of kTile, zero-filled)
     long long ldx = 0;  // padded row length of the rotated genotype block (multiple of 16, zero-filled)
-    bool use_v1 = false;
+    int engine = PG_REML_AUTO;  // REML stage engine (pg_set_reml_engine / env PG_REML_ENGINE)
     int sm_count = 148;
     std::string err;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -58,7 +60,27 @@ struct pg_handle {
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     RotWorkspace rot;
     long long last_block_count = 0, last_block_row0 = 0;
+    // internal eigen order: ascending d.  perm[l] = caller's index of the l-th smallest eigenvalue
+    std::vector<int> perm;
+    bool perm_identity = true;
+    int* perm_dev = nullptr;
+    // eigenvalue-space compression (compress_plan.h / compress.cuh)
+    CompressPlan hplan;
+    DevPlan plan;
+    double* Z = nullptr;  // [blk][c0+2][Kcp]
+    size_t z_elems = 0;
 };
+
+static void free_plan(pg_handle* h)
+{
+    DevPlan& P = h->plan;
+    void* bufs[] = {P.nodes, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    P = DevPlan{};
+    h->Z = nullptr;
+    h->z_elems = 0;
+}
 
 static int fail(pg_handle* h, int code, const char* fmt, ...)
 {
@@ -115,7 +137,9 @@ static int free_all(pg_handle* h)
         if (h->ev_ready[s]) cudaEventDestroy(h->ev_ready[s]);
         if (h->ev_free[s]) cudaEventDestroy(h->ev_free[s]);
     }
-    void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr, h->counter};
+    free_plan(h);
+    void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr, h->counter,
+                    h->perm_dev};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->blas) cublasDestroy(h->blas);
@@ -150,7 +174,11 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
     h->n = n; h->c0 = c0; h->device = device;
     h->ldw = ((long long)n + kTile - 1) / kTile * kTile;
     h->ldx = ((long long)n + 15) / 16 * 16;
-    h->use_v1 = getenv("PG_REML_V1") != nullptr;
+    if (const char* e = getenv("PG_REML_ENGINE")) {
+        if (!strcmp(e, "stream")) h->engine = PG_REML_STREAM;
+        else if (!strcmp(e, "warp")) h->engine = PG_REML_WARP;
+        else if (!strcmp(e, "compressed")) h->engine = PG_REML_COMPRESSED;
+    }
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -209,6 +237,115 @@ static int ensure_U(pg_handle* h)
     return PG_OK;
 }
 
+
+// U columns (eigenvectors) into ascending-eigenvalue order.  cols_contig: eigenvector i at src + i*n.
+__global__ void permute_u_kernel(const double* __restrict__ src, double* __restrict__ dst, int n,
+                                 const int* __restrict__ perm, int cols_contig)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int a = (int)(idx / n), b = (int)(idx % n);
+    // cols_contig: dst[i*n + j] = src[perm[i]*n + j] (a = i, b = j); else dst[j*n + i] = src[j*n + perm[i]] (a = j, b = i)
+    dst[idx] = cols_contig ? src[(size_t)perm[a] * n + b] : src[(size_t)a * n + perm[b]];
+}
+
+// Builds the compression plan for the handle's (ascending, clipped) eigenvalues and uploads it.
+static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
+{
+    const int n = h->n, c0 = h->c0, k0 = c0 + 1;
+    free_plan(h);
+    build_compress_plan(d_sorted.data(), n, &h->hplan);
+    const CompressPlan& H = h->hplan;
+    DevPlan& P = h->plan;
+    P.Kc = H.Kc;
+    P.Kcp = std::max(32, (H.Kc + 31) / 32 * 32);
+    std::vector<double> nodes(P.Kcp, 0.0);
+    std::copy(H.nodes.begin(), H.nodes.end(), nodes.begin());
+    CK(cudaMalloc(&P.nodes, sizeof(double) * P.Kcp));
+    CK(cudaMemcpy(P.nodes, nodes.data(), sizeof(double) * P.Kcp, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&P.Lw, sizeof(double) * (size_t)n * kCq));
+    CK(cudaMemcpy(P.Lw, H.Lw.data(), sizeof(double) * (size_t)n * kCq, cudaMemcpyHostToDevice));
+    std::vector<int> seg_kq(n, 0), copy_l, copy_node;
+    std::vector<CompItem> items;
+    P.ngroups = (k0 + kJGroup - 1) / kJGroup;
+    P.vpitch = P.ngroups * kGroupCols;
+    P.npad16 = (n + 15) / 16 * 16;
+    std::vector<int> order;
+    for (int si = 0; si < (int)H.segs.size(); ++si) {
+        const Segment& sg = H.segs[si];
+        if (sg.type == kSegCompress) {
+            for (int l = sg.l0; l < sg.l1; ++l) seg_kq[l] = sg.kq;
+            order.push_back(si);
+        } else {
+            for (int l = sg.l0; l < sg.l1; ++l) { copy_l.push_back(l); copy_node.push_back(sg.kb + (l - sg.l0)); }
+        }
+    }
+    // longest segments first: the tail of the grid is made of short work items
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (H.segs[a].l1 - H.segs[a].l0) > (H.segs[b].l1 - H.segs[b].l0);
+    });
+    for (int si : order) {
+        const Segment& sg = H.segs[si];
+        for (int g = 0; g < P.ngroups; ++g) {
+            CompItem it;
+            it.l0 = sg.l0; it.l1 = sg.l1; it.kb = sg.kb; it.kq = sg.kq;
+            it.j0 = g * kJGroup; it.nj = std::min<int>(kJGroup, k0 - it.j0); it.vcol0 = g * kGroupCols; it.pad = 0;
+            items.push_back(it);
+        }
+    }
+    CK(cudaMalloc(&P.seg_kq, sizeof(int) * n));
+    CK(cudaMemcpy(P.seg_kq, seg_kq.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    P.nitems = (int)items.size();
+    if (P.nitems) {
+        CK(cudaMalloc(&P.items, sizeof(CompItem) * items.size()));
+        CK(cudaMemcpy(P.items, items.data(), sizeof(CompItem) * items.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&P.V, sizeof(double) * (size_t)P.npad16 * P.vpitch));
+        CK(cudaMemset(P.V, 0, sizeof(double) * (size_t)P.npad16 * P.vpitch));
+    }
+    P.ncopy = (int)copy_l.size();
+    if (P.ncopy) {
+        CK(cudaMalloc(&P.copy_l, sizeof(int) * P.ncopy));
+        CK(cudaMalloc(&P.copy_node, sizeof(int) * P.ncopy));
+        CK(cudaMemcpy(P.copy_l, copy_l.data(), sizeof(int) * P.ncopy, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(P.copy_node, copy_node.data(), sizeof(int) * P.ncopy, cudaMemcpyHostToDevice));
+    }
+    return PG_OK;
+}
+
+// Brings the handle's eigen-system into ascending-eigenvalue order (h->d holds the clipped eigenvalues in the
+// caller's order, h->U the eigenvectors when have_U) and builds the compression plan.
+static int canonicalise_eigen(pg_handle* h)
+{
+    const int n = h->n;
+    std::vector<double> dh(n);
+    CK(cudaMemcpyAsync(dh.data(), h->d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->compute));
+    CK(cudaStreamSynchronize(h->compute));
+    h->perm.resize(n);
+    for (int l = 0; l < n; ++l) h->perm[l] = l;
+    std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) { return dh[a] < dh[b]; });
+    h->perm_identity = true;
+    for (int l = 0; l < n; ++l)
+        if (h->perm[l] != l) { h->perm_identity = false; break; }
+    std::vector<double> ds(n);
+    for (int l = 0; l < n; ++l) ds[l] = dh[h->perm[l]];
+    if (!h->perm_dev) CK(cudaMalloc(&h->perm_dev, sizeof(int) * n));
+    CK(cudaMemcpy(h->perm_dev, h->perm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    if (!h->perm_identity) {
+        CK(cudaMemcpy(h->d, ds.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+        if (h->have_U) {
+            double* tmp = nullptr;
+            CK(cudaMalloc(&tmp, sizeof(double) * (size_t)n * n));
+            const size_t total = (size_t)n * n;
+            permute_u_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->compute>>>(h->U, tmp, n, h->perm_dev, h->u_op_t);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(h->compute));
+            cudaFree(h->U);
+            h->U = tmp;
+        }
+    }
+    return upload_plan(h, ds);
+}
+
 extern "C" int pg_set_kinship(pg_handle* h, const double* K_host, double* d_out_host, float* eig_ms)
 {
     if (!h || !K_host) return fail(h, PG_ERR_ARG, "pg_set_kinship: NULL argument");
@@ -256,7 +393,7 @@ extern "C" int pg_set_kinship(pg_handle* h, const double* K_host, double* d_out_
     CK(cudaStreamSynchronize(h->compute));
     h->u_op_t = 1; h->have_U = true; h->have_d = true; h->rotated_inputs = false; h->have_design = false;
     rot_invalidate(&h->rot);
-    return PG_OK;
+    return canonicalise_eigen(h);
 }
 
 static int set_eigen_common(pg_handle* h, const double* U, int u_row_major, const double* d, cudaMemcpyKind kind)
@@ -280,7 +417,7 @@ static int set_eigen_common(pg_handle* h, const double* U, int u_row_major, cons
     CK(cudaStreamSynchronize(h->compute));
     h->have_d = true; h->have_design = false;
     rot_invalidate(&h->rot);
-    return PG_OK;
+    return canonicalise_eigen(h);
 }
 
 extern "C" int pg_set_eigen(pg_handle* h, const double* U_host, int u_row_major, const double* d_host)
@@ -325,10 +462,12 @@ extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y
     CK(cudaSetDevice(h->device));
     const int n = h->n, c0 = h->c0, k0 = c0 + 1;
     // (n, c0) C-order + y -> column-major n x (c0+1)
+    // rotated inputs arrive in the caller's eigen order: bring them into the handle's ascending order
     std::vector<double> col((size_t)n * k0);
+    const bool gather = already_rotated && !h->perm_identity;
     for (int j = 0; j < c0; ++j)
-        for (int l = 0; l < n; ++l) col[(size_t)j * n + l] = W_host[(size_t)l * c0 + j];
-    for (int l = 0; l < n; ++l) col[(size_t)c0 * n + l] = y_host[l];
+        for (int l = 0; l < n; ++l) col[(size_t)j * n + l] = W_host[(size_t)(gather ? h->perm[l] : l) * c0 + j];
+    for (int l = 0; l < n; ++l) col[(size_t)c0 * n + l] = y_host[gather ? h->perm[l] : l];
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -351,6 +490,11 @@ extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y
     h->rotated_inputs = already_rotated != 0;
     int rc = build_tables(h);
     if (rc) return rc;
+    if (h->plan.nitems) {
+        build_v_kernel<<<n, 128, 0, h->compute>>>(n, c0, h->plan.Lw, h->plan.seg_kq, h->wy, h->ldw, h->plan.V,
+                                                  h->plan.vpitch, h->plan.ngroups);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(e1, h->compute));
     CK(cudaStreamSynchronize(h->compute));
     float t = 0;
@@ -383,6 +527,14 @@ extern "C" int pg_set_options(pg_handle* h, int rotation, int64_t block_snps)
     return PG_OK;
 }
 
+extern "C" int pg_set_reml_engine(pg_handle* h, int engine)
+{
+    if (!h) return PG_ERR_ARG;
+    if (engine < PG_REML_AUTO || engine > PG_REML_WARP) return fail(h, PG_ERR_ARG, "pg_set_reml_engine: engine %d", engine);
+    h->engine = engine;
+    return PG_OK;
+}
+
 static size_t xdtype_size(int t) { return t == PG_X_I8 ? 1 : (t == PG_X_F32 ? 4 : 8); }
 
 static int ensure_workspace(pg_handle* h, long long m, int xdtype)
@@ -395,6 +547,9 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         blk = std::min<long long>(blk, 32768);
         // keep at least four blocks in flight on large inputs so uploads overlap compute
         if (m >= 4 * 8192) blk = std::min<long long>(blk, std::max<long long>(8192, ((m + 3) / 4 + 255) / 256 * 256));
+        // compressed moments of a block: at most 2 GiB
+        const size_t zrow = sizeof(double) * (size_t)(h->c0 + 2) * std::max(h->plan.Kcp, 32);
+        blk = std::min<long long>(blk, std::max<long long>(256, (long long)((size_t(1) << 31) / zrow) / 256 * 256));
     }
     blk = std::min(blk, std::max<long long>(m, 1));
     blk = ((blk + 31) / 32) * 32;
@@ -408,6 +563,17 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         CK(cudaMalloc(&h->xr, sizeof(double) * need));
         CK(cudaMemset(h->xr, 0, sizeof(double) * need));
         h->xbuf_elems = need;
+    }
+    if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
+        const size_t zneed = (size_t)blk * (h->c0 + 2) * h->plan.Kcp;
+        if (zneed > h->z_elems) {
+            if (h->Z) cudaFree(h->Z);
+            h->Z = nullptr;
+            h->z_elems = 0;
+            CK(cudaMalloc(&h->Z, sizeof(double) * zneed));
+            CK(cudaMemset(h->Z, 0, sizeof(double) * zneed));  // padding nodes stay zero for ever
+            h->z_elems = zneed;
+        }
     }
     const size_t sbytes = need * xdtype_size(xdtype);
     if (sbytes > h->stage_bytes) {
@@ -425,7 +591,8 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
 
 static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld, int layout, long long mb, double* dst)
 {
-    if (stage_to_snp_major(h->compute, h->n, src, xdtype, ld, layout, mb, dst, h->ldx)) {
+    if (stage_to_snp_major(h->compute, h->n, src, xdtype, ld, layout, mb, dst, h->ldx,
+                           h->perm_identity ? nullptr : h->perm_dev)) {
         cudaError_t e_ = cudaGetLastError();
         return fail(h, PG_ERR_CUDA, "staging kernel: %s", cudaGetErrorString(e_));
     }
@@ -433,7 +600,7 @@ static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld,
 }
 
 static int launch_reml(pg_handle* h, const double* xr, long long mb, long long row0, int grid_mode, double* const out[6],
-                       int* status, int* e2, int* e3)
+                       int* status, int* e2, int* e3, cudaEvent_t* ev_mid = nullptr)
 {
     ScanArgs a;
     a.n = h->n; a.c0 = h->c0; a.grid = grid_mode; a.m = mb; a.row0 = row0;
@@ -441,7 +608,43 @@ static int launch_reml(pg_handle* h, const double* xr, long long mb, long long r
     for (int i = 0; i < 6; ++i) a.out[i] = out[i];
     a.status = status; a.n_eval2 = e2; a.n_eval3 = e3; a.counter = h->counter;
     CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), h->compute));
-    if (!h->use_v1) {
+    if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
+        const DevPlan& P = h->plan;
+        const int ntiles = (int)((mb + kCtSnps - 1) / kCtSnps);
+        if (ev_mid) CK(cudaEventRecord(ev_mid[0], h->compute));
+        if (P.nitems) {
+            CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
+            compress_dmma_kernel<<<(unsigned)((long long)P.nitems * ntiles), 256, kCtSmemBytes, h->compute>>>(
+                xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, P.Kcp, h->Z, ntiles);
+            CK(cudaGetLastError());
+        }
+        if (P.ncopy) {
+            dim3 grid((unsigned)((P.ncopy + 127) / 128), (unsigned)((mb + 7) / 8));
+            compress_copy_kernel<<<grid, 128, 0, h->compute>>>(xr, h->ldx, mb, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw,
+                                                             h->c0, P.Kcp, h->Z);
+            CK(cudaGetLastError());
+        }
+        if (ev_mid) CK(cudaEventRecord(ev_mid[1], h->compute));
+        SolveArgs sa;
+        sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
+        sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = h->Z; sa.tab = h->tab;
+        for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
+        sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = h->counter;
+        const int k = h->c0 + 2, TT = k * (k + 1) / 2;
+        const size_t per_warp = sizeof(double) * 3 * TT;
+        int warps = 8;
+        while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
+        const size_t smem = per_warp * warps;
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(reml_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / std::max<size_t>(smem, 1)));
+        long long want = (mb + warps - 1) / warps;
+        int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
+        reml_solve_kernel<<<grid, warps * 32, smem, h->compute>>>(sa);
+        CK(cudaGetLastError());
+        return PG_OK;
+    }
+    if (h->engine == PG_REML_STREAM) {
         const StreamCfg cfg = stream_config(h->c0);
         const int ncmax = std::min(h->c0 + 1, (int)kChunkCols);
         CK(cudaFuncSetAttribute(reml_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
@@ -511,9 +714,10 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         dstatus = itmp; de2 = itmp + m; de3 = itmp + 2 * (size_t)m;
     }
 
-    std::vector<EvPair> ev_conv(nblocks), ev_rot(nblocks), ev_reml(nblocks), ev_h2d(nblocks);
+    std::vector<EvPair> ev_conv(nblocks), ev_rot(nblocks), ev_reml(nblocks), ev_h2d(nblocks), ev_cmp(nblocks);
     auto mk = [&](EvPair& p) { cudaEventCreate(&p.a); cudaEventCreate(&p.b); };
-    for (long long b = 0; b < nblocks; ++b) { mk(ev_conv[b]); mk(ev_rot[b]); mk(ev_reml[b]); if (!on_device) mk(ev_h2d[b]); }
+    for (long long b = 0; b < nblocks; ++b) { mk(ev_conv[b]); mk(ev_rot[b]); mk(ev_reml[b]); mk(ev_cmp[b]); if (!on_device) mk(ev_h2d[b]); }
+    const bool compressed = (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED);
     cudaEvent_t t0, t1, t2;
     cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
     int n_rot_launch = 0, last_engine = 0;
@@ -569,7 +773,8 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             }
             if (!on_device) CK(cudaEventRecord(h->ev_free[s], h->compute));
             CK(cudaEventRecord(ev_reml[b].a, h->compute));
-            int r3 = launch_reml(h, xr_block, mb, g0, grid_mode, dout, dstatus, de2, de3);
+            cudaEvent_t mid[2] = {ev_cmp[b].a, ev_cmp[b].b};
+            int r3 = launch_reml(h, xr_block, mb, g0, grid_mode, dout, dstatus, de2, de3, mid);
             if (r3) return r3;
             CK(cudaEventRecord(ev_reml[b].b, h->compute));
             h->last_block_count = mb;
@@ -597,6 +802,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             cudaEventElapsedTime(&v, ev_conv[b].a, ev_conv[b].b); timing->convert_ms += v;
             cudaEventElapsedTime(&v, ev_rot[b].a, ev_rot[b].b); timing->rotate_ms += v;
             cudaEventElapsedTime(&v, ev_reml[b].a, ev_reml[b].b); timing->reml_ms += v;
+            if (compressed) { cudaEventElapsedTime(&v, ev_cmp[b].a, ev_cmp[b].b); timing->compress_ms += v; }
             if (!on_device) { cudaEventElapsedTime(&v, ev_h2d[b].a, ev_h2d[b].b); timing->h2d_ms += v; }
         }
         timing->n_blocks = (int32_t)nblocks;
@@ -605,11 +811,15 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->rotate_launches = n_rot_launch;
         timing->convert_launches = (int32_t)nblocks;
         timing->rot_engine = last_engine;
+        timing->reml_engine = compressed ? PG_REML_COMPRESSED : h->engine;
+        timing->n_nodes = compressed ? h->plan.Kc : h->n;
+        if (compressed) timing->reml_launches = (int32_t)(nblocks * (1 + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)));
     }
     for (long long b = 0; b < nblocks; ++b) {
         cudaEventDestroy(ev_conv[b].a); cudaEventDestroy(ev_conv[b].b);
         cudaEventDestroy(ev_rot[b].a); cudaEventDestroy(ev_rot[b].b);
         cudaEventDestroy(ev_reml[b].a); cudaEventDestroy(ev_reml[b].b);
+        cudaEventDestroy(ev_cmp[b].a); cudaEventDestroy(ev_cmp[b].b);
         if (!on_device) { cudaEventDestroy(ev_h2d[b].a); cudaEventDestroy(ev_h2d[b].b); }
     }
     cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
@@ -649,7 +859,38 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     CK(cudaMalloc(&dx, sizeof(double) * h->ldx));
     CK(cudaMalloc(&dout, sizeof(double) * 9));
     CK(cudaMemsetAsync(dx, 0, sizeof(double) * h->ldx, h->compute));
-    CK(cudaMemcpyAsync(dx, x_rot_host, sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
+    std::vector<double> xs(n);
+    for (int l = 0; l < n; ++l) xs[l] = x_rot_host[h->perm_identity ? l : h->perm[l]];
+    CK(cudaMemcpyAsync(dx, xs.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
+    if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
+        const DevPlan& P = h->plan;
+        const int k1 = h->c0 + 2, TTc = k1 * (k1 + 1) / 2;
+        double* dz = nullptr;
+        CK(cudaMalloc(&dz, sizeof(double) * (size_t)k1 * P.Kcp));
+        CK(cudaMemsetAsync(dz, 0, sizeof(double) * (size_t)k1 * P.Kcp, h->compute));
+        if (P.nitems) {
+            CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
+            compress_dmma_kernel<<<(unsigned)P.nitems, 256, kCtSmemBytes, h->compute>>>(dx, h->ldx, 1, P.items, P.V, P.vpitch,
+                                                                                     h->c0, P.Kcp, dz, 1);
+            CK(cudaGetLastError());
+        }
+        if (P.ncopy) {
+            compress_copy_kernel<<<dim3((unsigned)((P.ncopy + 127) / 128), 1), 128, 0, h->compute>>>(
+                dx, h->ldx, 1, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw, h->c0, P.Kcp, dz);
+            CK(cudaGetLastError());
+        }
+        SolveArgs sa{};
+        sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz; sa.tab = h->tab;
+        const size_t smemc = sizeof(double) * 3 * TTc;
+        if (smemc > 48 * 1024)
+            CK(cudaFuncSetAttribute(probe_precompute_compressed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
+        probe_precompute_compressed_kernel<<<1, 32, smemc, h->compute>>>(sa, lam, fixed_index, full, dout);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out9, dout, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->compute));
+        CK(cudaStreamSynchronize(h->compute));
+        cudaFree(dx); cudaFree(dout); cudaFree(dz);
+        return PG_OK;
+    }
     ScanArgs a{};
     a.n = n; a.c0 = h->c0; a.grid = 0; a.m = 1; a.row0 = 0; a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = dx; a.ldx = h->ldx; a.tab = h->tab;
     const int k = h->c0 + 2, TT = k * (k + 1) / 2;
@@ -691,6 +932,14 @@ extern "C" int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, in
     const long long c = std::min<long long>(count, h->last_block_count);
     CK(cudaMemcpy2D(xr_host, sizeof(double) * h->n, h->xr, sizeof(double) * h->ldx, sizeof(double) * h->n, (size_t)c,
                     cudaMemcpyDeviceToHost));
+    if (!h->perm_identity) {  // report in the caller's eigen order
+        std::vector<double> row(h->n);
+        for (long long g = 0; g < c; ++g) {
+            double* r = xr_host + (size_t)g * h->n;
+            for (int l = 0; l < h->n; ++l) row[h->perm[l]] = r[l];
+            std::copy(row.begin(), row.end(), r);
+        }
+    }
     if (row0) *row0 = h->last_block_row0;
     return PG_OK;
 }

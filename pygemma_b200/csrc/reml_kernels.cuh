@@ -272,8 +272,10 @@ __global__ void __launch_bounds__(256) build_tables_kernel(int n, int c0, const 
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void to_snp_major_kernel(const T* __restrict__ src, long long ld, int layout, int n, long long mb,
-                                    double* __restrict__ dst, long long ldd)
+                                    double* __restrict__ dst, long long ldd, const int* __restrict__ perm)
 {
+    // perm (nullable): destination sample index j reads source sample perm[j] (pre-rotated inputs arriving in the
+    // caller's eigen order are brought into the handle's ascending-eigenvalue order)
     __shared__ double tile[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
     const long long g0 = (long long)blockIdx.x * 32;
@@ -284,7 +286,7 @@ __global__ void to_snp_major_kernel(const T* __restrict__ src, long long ld, int
         for (int r = ty; r < 32; r += 8) {
             const int j = j0 + r;
             const long long g = g0 + tx;
-            tile[r][tx] = (j < n && g < mb) ? (double)src[(size_t)j * ld + g] : 0.0;
+            tile[r][tx] = (j < n && g < mb) ? (double)src[(size_t)(perm ? perm[j] : j) * ld + g] : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -298,7 +300,7 @@ __global__ void to_snp_major_kernel(const T* __restrict__ src, long long ld, int
         for (int r = ty; r < 32; r += 8) {
             const long long g = g0 + r;
             const int j = j0 + tx;
-            if (g < mb && j < n) dst[(size_t)g * ldd + j] = (double)src[(size_t)g * ld + j];
+            if (g < mb && j < n) dst[(size_t)g * ldd + j] = (double)src[(size_t)g * ld + (perm ? perm[j] : j)];
         }
     }
 }

@@ -48,18 +48,18 @@ inline void rot_invalidate(RotWorkspace* w) { w->planes_valid = false; }
 inline const char* rot_error(RotWorkspace* w) { return w->err.c_str(); }
 
 inline int stage_to_snp_major(cudaStream_t stream, int n, const void* src, int xdtype, long long ld, int layout,
-                              long long mb, double* dst, long long ldd)
+                              long long mb, double* dst, long long ldd, const int* perm = nullptr)
 {
     dim3 block(32, 8), grid((unsigned)((mb + 31) / 32), (unsigned)((n + 31) / 32));
     switch (xdtype) {
     case PG_X_I8:
-        to_snp_major_kernel<int8_t><<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, dst, ldd);
+        to_snp_major_kernel<int8_t><<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, dst, ldd, perm);
         break;
     case PG_X_F32:
-        to_snp_major_kernel<float><<<grid, block, 0, stream>>>((const float*)src, ld, layout, n, mb, dst, ldd);
+        to_snp_major_kernel<float><<<grid, block, 0, stream>>>((const float*)src, ld, layout, n, mb, dst, ldd, perm);
         break;
     default:
-        to_snp_major_kernel<double><<<grid, block, 0, stream>>>((const double*)src, ld, layout, n, mb, dst, ldd);
+        to_snp_major_kernel<double><<<grid, block, 0, stream>>>((const double*)src, ld, layout, n, mb, dst, ldd, perm);
         break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : PG_ERR_CUDA;

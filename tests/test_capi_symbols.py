@@ -53,7 +53,7 @@ def test_create_rejects_bad_shapes(lib):
 
 
 def test_timing_struct_matches_header():
-    assert ctypes.sizeof(_capi.PgTiming) == 6 * 4 + 6 * 4
+    assert ctypes.sizeof(_capi.PgTiming) == 6 * 4 + 6 * 4 + 3 * 4
 
 
 def test_product_never_imports_oracle():

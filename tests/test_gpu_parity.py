@@ -267,25 +267,53 @@ def test_i8split_rotation_equals_fp64_rotation():
         assert rel(o8[c], o64[c]).max() < 1e-9, c
 
 
-def test_v1_and_stream_kernels_agree():
-    """The CTA-lock-step streaming kernel against the simple warp-per-SNP kernel (PG_REML_V1=1)."""
-    import subprocess
-    import sys
+def test_reml_engines_agree():
+    """The three REML engines -- compressed moments (default), CTA-lock-step streaming, warp-per-SNP -- on the same
+    rotated inputs: identical optimiser paths (evaluation counts) and results to 1e-9."""
+    from pygemma_b200.synth import make_spectral_problem
 
-    code = ("import numpy as np, sys; sys.path.insert(0, '.');"
-            "from pygemma_b200 import _capi; from pygemma_b200.synth import make_spectral_problem;"
-            "p = make_spectral_problem(1300, 160, 14, seed=4, xdtype=np.float64);"
-            "h = _capi.Handle(1300, 14); h.set_eigen(None, p['d']); h.set_design(p['W'], p['Y'], already_rotated=True);"
-            "o = h.scan(p['X']); np.save(sys.argv[1], np.stack([o[c] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]))")
-    import tempfile
+    capi = _capi()
+    for (n, m, c0, grid) in ((1300, 160, 14, False), (2500, 300, 3, False), (640, 100, 25, True)):
+        p = make_spectral_problem(n, m, c0, seed=4 + c0, xdtype=np.float64)
+        outs = {}
+        with capi.Handle(n, c0) as h:
+            h.set_eigen(None, p["d"])
+            h.set_design(p["W"], p["Y"], already_rotated=True)
+            for eng in (capi.PG_REML_COMPRESSED, capi.PG_REML_STREAM, capi.PG_REML_WARP):
+                h.set_reml_engine(eng)
+                outs[eng] = h.scan(p["X"], grid=grid)
+                assert outs[eng]["timing"]["reml_engine"] == eng
+        a = outs[capi.PG_REML_COMPRESSED]
+        assert a["timing"]["n_nodes"] < n
+        for eng in (capi.PG_REML_STREAM, capi.PG_REML_WARP):
+            b = outs[eng]
+            for c in COLS:
+                assert rel(a[c], b[c]).max() < 1e-9, (n, eng, c, float(rel(a[c], b[c]).max()))
+            assert np.array_equal(a["n_eval2"], b["n_eval2"]) and np.array_equal(a["n_eval3"], b["n_eval3"])
 
-    outs = []
-    for v1 in (False, True):
-        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
-            env = dict(os.environ)
-            env.pop("PG_REML_V1", None)
-            if v1:
-                env["PG_REML_V1"] = "1"
-            subprocess.check_call([sys.executable, "-c", code, f.name], env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
-            outs.append(np.load(f.name))
-    assert rel(outs[0], outs[1]).max() < 1e-9
+
+def test_unsorted_and_degenerate_spectra():
+    """Eigenvalues supplied in arbitrary order, with a large null space, exact ties and isolated outliers: the handle
+    sorts internally (compression needs ascending d); results must equal the oracle's on the caller's order."""
+    from oracle import oracle
+
+    capi = _capi()
+    rng = np.random.default_rng(11)
+    n, m, c0 = 900, 96, 4
+    d = np.concatenate([np.zeros(300), np.full(200, 0.37), rng.chisquare(3, 395), [1e-12, 1e-30, 40.0, 900.0, 3e4]])
+    rng.shuffle(d)
+    W = np.c_[np.ones(n), rng.standard_normal((n, c0 - 1))]
+    X = rng.standard_normal((n, m))
+    y = rng.standard_normal(n) * np.sqrt(0.7 * d + 1.0) + 0.2 * X[:, 0]
+    ref = oracle.scan_rotated(d, y, W, np.ascontiguousarray(X.T))
+    with capi.Handle(n, c0) as h:
+        h.set_eigen(None, d)
+        h.set_design(W, y, already_rotated=True)
+        for eng in (capi.PG_REML_COMPRESSED, capi.PG_REML_STREAM):
+            h.set_reml_engine(eng)
+            o = h.scan(X)
+            _check(o, ref, tag=("unsorted", eng))
+            o2 = h.scan(np.ascontiguousarray(X.T), layout=capi.PG_X_SNP_MAJOR)
+            for c in COLS:
+                assert np.array_equal(o[c], o2[c], equal_nan=True), c
+        assert o["timing"]["n_nodes"] <= n

@@ -26,7 +26,7 @@ def main():
                 wall = time.time() - t
             tm = o["timing"]
             out["grid" if grid else "default"] = {
-                "reml_ms": tm["reml_ms"], "snps_per_s_reml": m / (tm["reml_ms"] * 1e-3), "total_ms": tm["total_ms"],
+                "reml_ms": tm["reml_ms"], "compress_ms": tm["compress_ms"], "n_nodes": tm["n_nodes"], "snps_per_s_reml": m / (tm["reml_ms"] * 1e-3), "total_ms": tm["total_ms"],
                 "wall_s": wall, "ev2": float(o["n_eval2"].mean()), "ev3": float(o["n_eval3"].mean()),
                 "status_bad": int((o["status"] != 0).sum())}
     # rotation timing with a random (non-orthogonal) U: timing only
@@ -39,7 +39,7 @@ def main():
         for rep in range(2):
             o = h.scan(X8)
         tm = o["timing"]
-        out["rotate_int8"] = {k: tm[k] for k in ("total_ms", "h2d_ms", "convert_ms", "rotate_ms", "reml_ms", "d2h_ms", "n_blocks")}
+        out["rotate_int8"] = {k: tm[k] for k in ("total_ms", "h2d_ms", "convert_ms", "rotate_ms", "reml_ms", "compress_ms", "d2h_ms", "n_blocks", "n_nodes")}
         out["rotate_int8"]["snps_per_s_total"] = m / (tm["total_ms"] * 1e-3)
         out["rotate_int8"]["dgemm_tflops"] = 2.0 * n * n * m / (tm["rotate_ms"] * 1e-3) / 1e12
     print(json.dumps(out))
