@@ -288,7 +288,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, tag="pg_timed"):
         for _ in range(warmup):
             fn()
         sampler = ClockSampler(local) if sample_clocks else None
@@ -299,8 +299,10 @@ def run_ours(args):
         t0 = time.perf_counter()
         e0.record(stream)
         tms = []
+        torch.cuda.nvtx.range_push(tag)  # lets `ncu --nvtx --nvtx-include "<tag>/"` list exactly the timed launches
         for _ in range(steps):
             tms.append(fn())
+        torch.cuda.nvtx.range_pop()
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -311,11 +313,11 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1]), tms, clocks
 
-    dev_ms, wall_ms, tms, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    dev_ms, wall_ms, tms, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True, tag="pg_timed_resident")
     res_tm = tms[-1]
     ms_per_step = dev_ms / args.steps
     value = world * m / (ms_per_step * 1e-3)
-    e2e_dev_ms, e2e_wall_ms, e2e_tms, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    e2e_dev_ms, e2e_wall_ms, e2e_tms, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1), tag="pg_timed_e2e")
     e2e_ms = e2e_wall_ms / args.steps  # host-visible time of the synchronous call (>= device time)
     e2e_value = world * m / (e2e_ms * 1e-3)
     counts = st_dev.cpu().numpy()
@@ -324,30 +326,46 @@ def run_ours(args):
 
     peaks = load_peaks()
     # ---- roofline of the dominant kernel (per launch = per SNP block; times are CUDA-event sums of the last step)
-    nb = res_tm["n_blocks"]
-    rot_ms, reml_ms = res_tm["rotate_ms"], res_tm["reml_ms"]
-    k0 = c0 + 2
-    reml_flops = m * (n * (ev2 * 2 * 2 * (c0 + 3) + ev3 * 2 * 3 * (c0 + 3)))  # 2 n K (c0+3) per pass
-    if rot_ms >= reml_ms:
-        rot_engine = res_tm.get("rot_engine", "fp64")
-        flops = 2.0 * n * n * m
-        ach = flops / (rot_ms * 1e-3) / 1e12
-        peak = peaks["fp64_dmma_tflops"]
-        roofline = {"kernel": "rotation U^T X (cuBLAS DGEMM, FP64 tensor pipe)", "bound": "tensor", "achieved": ach,
-                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": "FP64 DMMA rate " + peaks["source_fp64"],
-                    "algorithmic_flops_per_snp": 2.0 * n * n, "share_of_step": rot_ms / (rot_ms + reml_ms + res_tm["convert_ms"])}
-    else:
-        ach = reml_flops / (reml_ms * 1e-3) / 1e12
-        peak = peaks["fp64_fma_tflops"]
-        roofline = {"kernel": "reml_scan_kernel", "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": "FP64 FMA rate " + peaks["source_fp64"],
-                    "algorithmic_flops_per_snp": reml_flops / m,
-                    "share_of_step": reml_ms / (rot_ms + reml_ms + res_tm["convert_ms"])}
-    roofline["per_kernel_ms_last_step"] = {"convert": res_tm["convert_ms"], "rotate": rot_ms, "reml": reml_ms}
-    roofline["reml_tflops"] = reml_flops / (reml_ms * 1e-3) / 1e12
-    roofline["reml_hbm_gbs"] = 8.0 * n * m / (reml_ms * 1e-3) / 1e9
+    rot_ms, reml_ms, cmp_ms, conv_ms = res_tm["rotate_ms"], res_tm["reml_ms"], res_tm["compress_ms"], res_tm["convert_ms"]
+    solve_ms = reml_ms - cmp_ms
+    step_ms = rot_ms + reml_ms + conv_ms
+    nodes = res_tm["n_nodes"]
+    i8 = res_tm.get("rot_engine") == _capi.PG_ROT_I8SPLIT
+    n_planes = 7
+    rot_ops = (n_planes if i8 else 1) * 2.0 * n * n          # int8 (or fp64) multiply-add ops per SNP
+    cmp_flops = 2.0 * n * 10 * (c0 + 2)                       # compression: n x kCq x (c0+2) FP64 FMAs per SNP
+    stages = {
+        "rotation": {"ms": rot_ms, "achieved": rot_ops * m / (rot_ms * 1e-3) / 1e12,
+                     "peak": peaks["int8_gemm_tops"] if i8 else peaks["fp64_dmma_tflops"],
+                     "kernel": ("rotation U^T X, exact int8-split (7 base-256 digit planes): cuBLAS int8 GEMM on the int8 "
+                                "tensor pipe + stage_i8_kernel + combine_i8_kernel") if i8 else
+                               "rotation U^T X (cuBLAS DGEMM, FP64 tensor pipe)",
+                     "peak_source": ("int8 tensor rate (cuBLAS int8 GEMM 16384x8192x8192) " if i8 else "FP64 DMMA rate ")
+                                    + peaks["source_fp64"],
+                     "algorithmic_ops_per_snp": rot_ops},
+        "compress": {"ms": cmp_ms, "achieved": cmp_flops * m / (max(cmp_ms, 1e-9) * 1e-3) / 1e12,
+                     "peak": peaks["fp64_dmma_tflops"], "kernel": "compress_dmma_kernel (FP64 tensor pipe, mma.sync m8n8k4)",
+                     "peak_source": "FP64 DMMA rate " + peaks["source_fp64"], "algorithmic_ops_per_snp": cmp_flops},
+    }
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    if solve_ms > stages[dom]["ms"]:
+        # the optimiser on the compressed moments: FP64 FMA work = passes x nodes x (c0+2) x powers
+        sol_flops = 2.0 * nodes * (c0 + 2) * (2 * ev2 + 3 * ev3)
+        stages["solve"] = {"ms": solve_ms, "achieved": sol_flops * m / (solve_ms * 1e-3) / 1e12, "peak": peaks["fp64_fma_tflops"],
+                           "kernel": "reml_solve_kernel", "peak_source": "FP64 FMA rate " + peaks["source_fp64"],
+                           "algorithmic_ops_per_snp": sol_flops}
+        dom = "solve"
+    st = stages[dom]
+    roofline = {"kernel": st["kernel"], "bound": "tensor" if dom != "solve" else "fp64", "achieved": st["achieved"],
+                "peak": st["peak"], "unit": "TFLOP/s", "frac": st["achieved"] / st["peak"], "traffic": None,
+                "peak_source": st["peak_source"], "algorithmic_ops_per_snp": st["algorithmic_ops_per_snp"],
+                "ops": "int8 multiply-add ops counted 2 per MAC" if (dom == "rotation" and i8) else "fp64 flops",
+                "share_of_step": st["ms"] / step_ms}
+    roofline["per_kernel_ms_last_step"] = {"convert": conv_ms, "rotate": rot_ms, "compress": cmp_ms, "solve": solve_ms}
     roofline["rotate_tflops_fp64_equiv"] = 2.0 * n * n * m / (rot_ms * 1e-3) / 1e12
+    roofline["compress_frac_of_dmma_peak"] = stages["compress"]["achieved"] / stages["compress"]["peak"]
+    roofline["rotated_genotype_hbm_gbs"] = 2 * 8.0 * n * m / ((rot_ms + cmp_ms) * 1e-3) / 1e9  # written once, read once
+    roofline["nodes_per_snp"] = nodes
 
     line = {
         "metric": METRIC, "value": value, "unit": "SNPs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -356,7 +374,8 @@ def run_ours(args):
         "config": {"workload": f"synthetic UKB-shape n={n} samples x {m} SNPs per GPU, c0={c0} covariates, "
                                f"{'grid-search' if grid else 'Brent+Newton'} lambda, int8 dosages (BASELINE.json configs[2])",
                    "n": n, "snps_per_gpu": m, "c0": c0, "grid": grid, "parallelism": f"snp-shard x{world}",
-                   "l2": "inputs_larger_than_l2 (1 GB int8 genotypes + 80 KB/SNP rotated fp64 per step)"},
+                   "l2": "inputs_larger_than_l2 (1 GB int8 genotypes + 80 KB/SNP rotated fp64 per step)",
+                   "reml_engine": "compressed (eigenvalue-space moments)", "rotation_engine": "int8-split" if i8 else "fp64"},
         "e2e": {"value": e2e_value, "unit": "SNPs/s", "h2d_bytes_per_step": int(n) * int(m) * world,
                 "d2h_bytes_per_step": int(m) * (6 * 8 + 3 * 4) * world, "ms_per_step": e2e_ms,
                 "device_ms_per_step": e2e_dev_ms / args.steps,
@@ -406,7 +425,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--snps", type=int, default=100000, help="SNPs per GPU per step")

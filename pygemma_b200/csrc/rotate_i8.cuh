@@ -2,13 +2,14 @@
 //
 // U^T x for an integer genotype vector x is a sum of (double) * (small integer).  Each eigenvector
 // (row i of U^T) is rewritten in fixed point relative to its own largest entry,
-//     U[j,i] * 2^-e_i  =  sum_{t=0..7} q_t[i][j] * 128^-(t+1) ,   q_t in int8 (balanced base-128 digits),
-// which is exact to 2^-56 of the row maximum (finer than the 2^-53 relative rounding of the entries that
-// dominate the dot product).  The eight digit planes times the int8 genotypes are eight int8 x int8 ->
-// int32 tensor-core GEMMs whose results are exact integers; they are recombined in int64 and rounded to
-// fp64 once.  The result is at least as accurate as an FP64 GEMM and runs on the int8 tensor pipe
-// (B200: ~3.6 Pop/s measured vs ~36 TFLOP/s FP64), which is what lifts the rotation from ~180 k to
-// >1 M SNPs/s at n = 10 000.
+//     U[j,i] * 2^-e_i  =  sum_{t=1..7} q_t[i][j] * 256^-t ,   q_t in int8 (balanced base-256 digits),
+// with e_i chosen so that |U[j,i]| 2^-e_i < 1/4 (the leading digit then stays within [-65, 65]).  The
+// truncation is 2^-57 of 2^e_i, i.e. at most 2^-54 of the row maximum -- finer than the 2^-53 relative
+// rounding of the entries that dominate the dot product.  The seven digit planes times the int8 genotypes
+// are seven int8 x int8 -> int32 tensor-core GEMMs whose results are exact integers; they are recombined
+// in int64 and rounded to fp64 once.  The result is at least as accurate as an FP64 GEMM and runs on the
+// int8 tensor pipe (B200: ~3.6 Pop/s measured vs ~36 TFLOP/s FP64), which is what lifts the rotation from
+// ~180 k to >1.5 M SNPs/s at n = 10 000.
 #pragma once
 
 #include <cublas_v2.h>
@@ -18,12 +19,12 @@
 
 namespace pg {
 
-constexpr int kSlices = 8;
+constexpr int kSlices = 7;
 
-// one CTA per eigenvector i: find e_i, write the 8 digit planes
+// one CTA per eigenvector i: find e_i, write the digit planes
 // U is n x n; eigenvector i is at U + i*n when u_cols_contig (column-major U), else strided (U + i, stride n)
 __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__ U, int u_cols_contig, int n, int npad,
-                                                       int ldk, int8_t* __restrict__ planes /* [8][npad][ldk] */,
+                                                       int ldk, int8_t* __restrict__ planes /* [kSlices][npad][ldk] */,
                                                        int* __restrict__ exps)
 {
     const int i = blockIdx.x;
@@ -41,8 +42,8 @@ __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__
     if (threadIdx.x == 0) {
         double m = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
-        // |u| * 2^-e < 0.5 for every entry
-        e_sh = (m > 0.0 && isfinite(m)) ? ilogb(m) + 2 : 0;
+        // |u| * 2^-e < 0.25 for every entry
+        e_sh = (m > 0.0 && isfinite(m)) ? ilogb(m) + 3 : 0;
         if (i < n) exps[i] = e_sh;
     }
     __syncthreads();
@@ -50,13 +51,13 @@ __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__
     const size_t plane = (size_t)npad * ldk;
     for (int j = threadIdx.x; j < ldk; j += blockDim.x) {
         long long Q = 0;
-        if (i < n && j < n) Q = llrint(ldexp(u[(size_t)j * stride], 56 - e));
+        if (i < n && j < n) Q = llrint(ldexp(u[(size_t)j * stride], 8 * kSlices - e));
         int8_t dig[kSlices];
 #pragma unroll
         for (int t = kSlices - 1; t >= 1; --t) {
-            long long r = ((Q + 64) & 127) - 64;  // balanced digit in [-64, 63]
+            long long r = ((Q + 128) & 255) - 128;  // balanced digit in [-128, 127]
             dig[t] = (int8_t)r;
-            Q = (Q - r) >> 7;
+            Q = (Q - r) >> 8;
         }
         dig[0] = (int8_t)Q;  // |Q| <= 65 here
 #pragma unroll
@@ -93,7 +94,7 @@ __global__ void stage_i8_kernel(const int8_t* __restrict__ src, long long ld, in
     }
 }
 
-// P: [g][8*npad] int32 (column-major (8*npad) x mb as cuBLAS writes it).  xr[g*n + i] fp64.
+// P: [g][kSlices*npad] int32 (column-major (kSlices*npad) x mb as cuBLAS writes it).  xr[g*n + i] fp64.
 __global__ void __launch_bounds__(256) combine_i8_kernel(const int32_t* __restrict__ P, const int* __restrict__ exps,
                                                           int n, int npad, long long mb, double* __restrict__ xr, long long ldx)
 {
@@ -101,13 +102,14 @@ __global__ void __launch_bounds__(256) combine_i8_kernel(const int32_t* __restri
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || g >= mb) return;
     const int32_t* p = P + (size_t)g * kSlices * npad + i;
+    // sum_t P_t 256^(7-t): planes 0..2 (<= 2^46) and planes 3..6 (<= 2^54) separately, then one fp64 sum
     long long hi = 0, lo = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) hi = hi * 128 + (long long)p[(size_t)t * npad];
+    for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[(size_t)t * npad];
 #pragma unroll
-    for (int t = 4; t < 8; ++t) lo = lo * 128 + (long long)p[(size_t)t * npad];
-    const double v = (double)hi + ldexp((double)lo, -28);
-    xr[(size_t)g * ldx + i] = ldexp(v, exps[i] - 28);
+    for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[(size_t)t * npad];
+    const double v = (double)hi + ldexp((double)lo, -32);
+    xr[(size_t)g * ldx + i] = ldexp(v, exps[i] - 24);
 }
 
 }  // namespace pg
