@@ -4,6 +4,7 @@
 // (compress_plan.h), the moments
 //     Z[s][j][k] = sum_{l in segment(k)} L_k(log d_l) x_l w_jl     j = 0..c0   ([W0, y] columns)
 //     Z[s][c0+1][k] = sum_l L_k(log d_l) x_l^2
+// (Z rows are padded to k1p = (c0+2) rounded up to a multiple of 4; the padding rows stay zero)
 // which replace the reference's per-SNP, per-lambda dsyrk over n samples (pygemma_model.pyx:938-943,:1002).
 // For one segment this is a dense contraction  Z_seg (SNPs x (c0+1) kq)  =  X[:, l0:l1]  .  V[l0:l1, :]  with
 // V[l, j kq + k] = L_k(log d_l) w_jl  -- the FP64 tensor pipe (DMMA m8n8k4) -- and the x^2 moments reuse the
@@ -107,7 +108,7 @@ __global__ void build_v_kernel(int n, int c0, const double* __restrict__ Lw, con
 
 __global__ void __launch_bounds__(256, 1)
 compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb, const CompItem* __restrict__ items,
-                     const double* __restrict__ V, int vpitch, int c0, int Kcp, double* __restrict__ Z, int ntiles)
+                     const double* __restrict__ V, int vpitch, int c0, int k1p, int Kcp, double* __restrict__ Z, int ntiles)
 {
     extern __shared__ __align__(16) double csm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -187,13 +188,12 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
     }
     cpa_wait<0>();
 
-    const int k1 = c0 + 2;
     const int ncol_lin = it.nj * it.kq;
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
         const long long snp = snp0 + warp * 16 + b * 8 + (lane >> 2);
         if (snp >= mb) continue;
-        double* Zs = Z + (size_t)snp * k1 * Kcp;
+        double* Zs = Z + (size_t)snp * k1p * Kcp;
 #pragma unroll
         for (int t = 0; t < kLinTiles; ++t) {
             if (t < nt_lin) {
@@ -224,18 +224,17 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
 __global__ void __launch_bounds__(128)
 compress_copy_kernel(const double* __restrict__ xr, long long ldx, long long mb, const int* __restrict__ copy_l,
                      const int* __restrict__ copy_node, int ncopy, const double* __restrict__ wy, long long ldw, int c0,
-                     int Kcp, double* __restrict__ Z)
+                     int k1p, int Kcp, double* __restrict__ Z)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncopy) return;
     const int l = copy_l[i], node = copy_node[i];
-    const int k1 = c0 + 2;
     const long long s0 = (long long)blockIdx.y * 8;
     for (int r = 0; r < 8; ++r) {
         const long long snp = s0 + r;
         if (snp >= mb) break;
         const double x = xr[(size_t)snp * ldx + l];
-        double* Zs = Z + (size_t)snp * k1 * Kcp + node;
+        double* Zs = Z + (size_t)snp * k1p * Kcp + node;
         for (int j = 0; j <= c0; ++j) Zs[(size_t)j * Kcp] = x * wy[(size_t)j * ldw + l];
         Zs[(size_t)(c0 + 1) * Kcp] = x * x;
     }

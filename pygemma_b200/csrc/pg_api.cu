@@ -67,8 +67,12 @@ struct pg_handle {
     // eigenvalue-space compression (compress_plan.h / compress.cuh)
     CompressPlan hplan;
     DevPlan plan;
-    double* Z = nullptr;  // [blk][c0+2][Kcp]
+    double* Z = nullptr;  // [blk][k1p][Kcp]
     size_t z_elems = 0;
+    int k1p = 0;          // c0+2 rounded up to a multiple of 4
+    // table-2 rows (covariate levels eliminated per table lambda, pg_eval.cuh)
+    double *fix2 = nullptr, *itab2 = nullptr, *t2work = nullptr;
+    Tables2 tab2{};
 };
 
 static void free_plan(pg_handle* h)
@@ -139,7 +143,7 @@ static int free_all(pg_handle* h)
     }
     free_plan(h);
     void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr, h->counter,
-                    h->perm_dev};
+                    h->perm_dev, h->fix2, h->itab2, h->t2work};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->blas) cublasDestroy(h->blas);
@@ -217,6 +221,13 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
         for (int r = 0; r < kNumTableRows; ++r) lams[r] = table_lambda(r);
         CK(cudaMemcpy(h->basis, basis.data(), sizeof(double) * basis.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h->lambdas, lams.data(), sizeof(double) * lams.size(), cudaMemcpyHostToDevice));
+        const int NF2 = t2_nf(c0);
+        CK(cudaMalloc(&h->fix2, sizeof(double) * (size_t)kNumFixed * NF2));
+        CK(cudaMalloc(&h->itab2, sizeof(double) * (size_t)kNumIntervals * kNodes * NF2));
+        CK(cudaMalloc(&h->t2work, sizeof(double) * (size_t)kNumTableRows * 3 * T0));
+        h->tab2.c0 = c0; h->tab2.Tp = t2_pairs(c0); h->tab2.NF2 = NF2;
+        h->tab2.fix2 = h->fix2; h->tab2.itab2 = h->itab2; h->tab2.basis = h->basis;
+        h->k1p = (c0 + 2 + 3) / 4 * 4;
         h->tab.c0 = c0; h->tab.k0 = k0; h->tab.T0 = T0; h->tab.NF = NF;
         h->tab.fixtab = h->fixtab; h->tab.itab = h->itab; h->tab.basis = h->basis; h->tab.tri_ab = h->tri_ab;
         return PG_OK;
@@ -451,6 +462,9 @@ static int build_tables(pg_handle* h)
     build_tables_kernel<<<grid, 256, 0, h->compute>>>(h->n, h->c0, h->d, h->wy, h->ldw, h->lambdas, h->fixtab, h->itab,
                                                       h->tri_ab);
     CK(cudaGetLastError());
+    eliminate_tables_kernel<<<(kNumTableRows + 63) / 64, 64, 0, h->compute>>>(h->c0, h->tab.NF, h->tab2.NF2, h->fixtab, h->itab,
+                                                                              h->fix2, h->itab2, h->t2work);
+    CK(cudaGetLastError());
     return PG_OK;
 }
 
@@ -548,7 +562,7 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         // keep at least four blocks in flight on large inputs so uploads overlap compute
         if (m >= 4 * 8192) blk = std::min<long long>(blk, std::max<long long>(8192, ((m + 3) / 4 + 255) / 256 * 256));
         // compressed moments of a block: at most 2 GiB
-        const size_t zrow = sizeof(double) * (size_t)(h->c0 + 2) * std::max(h->plan.Kcp, 32);
+        const size_t zrow = sizeof(double) * (size_t)h->k1p * std::max(h->plan.Kcp, 32);
         blk = std::min<long long>(blk, std::max<long long>(256, (long long)((size_t(1) << 31) / zrow) / 256 * 256));
     }
     blk = std::min(blk, std::max<long long>(m, 1));
@@ -565,7 +579,7 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         h->xbuf_elems = need;
     }
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
-        const size_t zneed = (size_t)blk * (h->c0 + 2) * h->plan.Kcp;
+        const size_t zneed = (size_t)blk * h->k1p * h->plan.Kcp;
         if (zneed > h->z_elems) {
             if (h->Z) cudaFree(h->Z);
             h->Z = nullptr;
@@ -615,32 +629,35 @@ static int launch_reml(pg_handle* h, const double* xr, long long mb, long long r
         if (P.nitems) {
             CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
             compress_dmma_kernel<<<(unsigned)((long long)P.nitems * ntiles), 256, kCtSmemBytes, h->compute>>>(
-                xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, P.Kcp, h->Z, ntiles);
+                xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, h->k1p, P.Kcp, h->Z, ntiles);
             CK(cudaGetLastError());
         }
         if (P.ncopy) {
             dim3 grid((unsigned)((P.ncopy + 127) / 128), (unsigned)((mb + 7) / 8));
             compress_copy_kernel<<<grid, 128, 0, h->compute>>>(xr, h->ldx, mb, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw,
-                                                             h->c0, P.Kcp, h->Z);
+                                                             h->c0, h->k1p, P.Kcp, h->Z);
             CK(cudaGetLastError());
         }
         if (ev_mid) CK(cudaEventRecord(ev_mid[1], h->compute));
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
-        sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = h->Z; sa.tab = h->tab;
+        sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = h->Z; sa.k1p = h->k1p; sa.t2 = h->tab2;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = h->counter;
-        const int k = h->c0 + 2, TT = k * (k + 1) / 2;
-        const size_t per_warp = sizeof(double) * 3 * TT;
+        const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
         int warps = 8;
         while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
         const size_t smem = per_warp * warps;
-        if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(reml_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool two = (h->c0 + 2) > 32;
+        if (smem > 48 * 1024) {
+            if (two) CK(cudaFuncSetAttribute(reml_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CK(cudaFuncSetAttribute(reml_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / std::max<size_t>(smem, 1)));
         long long want = (mb + warps - 1) / warps;
         int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
-        reml_solve_kernel<<<grid, warps * 32, smem, h->compute>>>(sa);
+        if (two) reml_solve_kernel<2><<<grid, warps * 32, smem, h->compute>>>(sa);
+        else reml_solve_kernel<1><<<grid, warps * 32, smem, h->compute>>>(sa);
         CK(cudaGetLastError());
         return PG_OK;
     }
@@ -864,27 +881,32 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     CK(cudaMemcpyAsync(dx, xs.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
         const DevPlan& P = h->plan;
-        const int k1 = h->c0 + 2, TTc = k1 * (k1 + 1) / 2;
+        const int k1p = h->k1p;
         double* dz = nullptr;
-        CK(cudaMalloc(&dz, sizeof(double) * (size_t)k1 * P.Kcp));
-        CK(cudaMemsetAsync(dz, 0, sizeof(double) * (size_t)k1 * P.Kcp, h->compute));
+        CK(cudaMalloc(&dz, sizeof(double) * (size_t)k1p * P.Kcp));
+        CK(cudaMemsetAsync(dz, 0, sizeof(double) * (size_t)k1p * P.Kcp, h->compute));
         if (P.nitems) {
             CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
             compress_dmma_kernel<<<(unsigned)P.nitems, 256, kCtSmemBytes, h->compute>>>(dx, h->ldx, 1, P.items, P.V, P.vpitch,
-                                                                                     h->c0, P.Kcp, dz, 1);
+                                                                                     h->c0, k1p, P.Kcp, dz, 1);
             CK(cudaGetLastError());
         }
         if (P.ncopy) {
             compress_copy_kernel<<<dim3((unsigned)((P.ncopy + 127) / 128), 1), 128, 0, h->compute>>>(
-                dx, h->ldx, 1, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw, h->c0, P.Kcp, dz);
+                dx, h->ldx, 1, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw, h->c0, k1p, P.Kcp, dz);
             CK(cudaGetLastError());
         }
         SolveArgs sa{};
-        sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz; sa.tab = h->tab;
-        const size_t smemc = sizeof(double) * 3 * TTc;
-        if (smemc > 48 * 1024)
-            CK(cudaFuncSetAttribute(probe_precompute_compressed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
-        probe_precompute_compressed_kernel<<<1, 32, smemc, h->compute>>>(sa, lam, fixed_index, full, dout);
+        sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
+        sa.k1p = k1p; sa.t2 = h->tab2;
+        const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);
+        const bool two = (h->c0 + 2) > 32;
+        if (smemc > 48 * 1024) {
+            if (two) CK(cudaFuncSetAttribute(probe_precompute_compressed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
+            else CK(cudaFuncSetAttribute(probe_precompute_compressed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
+        }
+        if (two) probe_precompute_compressed_kernel<2><<<1, 32, smemc, h->compute>>>(sa, lam, fixed_index, full, dout);
+        else probe_precompute_compressed_kernel<1><<<1, 32, smemc, h->compute>>>(sa, lam, fixed_index, full, dout);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out9, dout, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->compute));
         CK(cudaStreamSynchronize(h->compute));

@@ -186,6 +186,158 @@ PG_HD_NOINLINE void pab_recursion(const Tables& t, double* A, double* B, double*
     PG_SYNCWARP();
 }
 
+// ------------------------------------------------------------------------------------------------
+// x-row form of the recursion.  Levels 1..c0 pivot on covariate columns; restricted to the [W0, y] block they
+// do not involve the SNP at all, so that part is run ONCE per table lambda (eliminate_w0y_row) and stored as
+//   per level p:  al2 = -1/a_pp, al4 = b_pp/a_pp^2, alc = c_pp/a_pp^2 - b_pp^2/a_pp^3     (pyx:1011-1031)
+//                 the pivot column of level p: A/B/C[s][p] for s = p+1..c0-1 and s = y
+//   finals:       A/B/C[y][y] after c0 levels, tr_Pi, tr_Pi_Pi, logdet_H, partial logdet_Wt_H_inv_W
+// ("table-2 row").  Per SNP only the x row (x.w_j, x.y, x.x at the three powers) is carried through the c0
+// levels -- O(c0^2) fused multiply-adds without a division -- followed by the one SNP-dependent pivot (x itself).
+// Arithmetic per entry is the expression of pab_recursion above, so both forms agree to rounding.
+// Table-2 rows at SNP-specific lambdas are Chebyshev-interpolated like the level-0 tables: Schur complements of
+// W^T H^-1 W are analytic for Re(lambda) > 0 (the Hermitian part stays positive definite), i.e. in the strip
+// |Im log(lambda)| < pi/2, which still gives rho ~ 22 per 1/8-decade interval and 22^-12 ~ 1e-16.
+// ------------------------------------------------------------------------------------------------
+struct Tables2 {
+    int c0, Tp, NF2;       // Tp = c0(c0+1)/2 pivot-column entries per power; NF2 = 3 c0 + 3 Tp + 7
+    const double* fix2;    // [kNumFixed][NF2]
+    const double* itab2;   // [kNumIntervals][kNodes][NF2]
+    const double* basis;   // as Tables::basis
+};
+
+PG_HD int t2_pairs(int c0) { return c0 * (c0 + 1) / 2; }
+PG_HD int t2_nf(int c0) { return 3 * c0 + 3 * t2_pairs(c0) + 7; }
+// column entry (s, p), p < s <= c0 (s == c0 is y), power 0: index; powers 1, 2 follow at +Tp, +2Tp
+PG_HD int t2_col(int c0, int p, int s) { return 3 * c0 + p * c0 - p * (p - 1) / 2 + (s - p - 1); }
+PG_HD int t2_fin(int c0) { return 3 * c0 + 3 * t2_pairs(c0); }
+
+// row0: level-0 table row (3 T0 + 3 doubles, [W0, y] packed with y at index c0); work: 3 T0 doubles; out: NF2
+PG_HD_NOINLINE void eliminate_w0y_row(int c0, const double* row0, double* work, double* out)
+{
+    const int k0 = c0 + 1, T0 = k0 * (k0 + 1) / 2, Tp = t2_pairs(c0);
+    double* A = work;
+    double* B = work + T0;
+    double* C = work + 2 * T0;
+    for (int q = 0; q < 3 * T0; ++q) work[q] = row0[q];
+    double trP = row0[3 * T0], trPP = row0[3 * T0 + 1], logdet = 0.0;
+    if (c0 >= 1) A[0] = cy_max(A[0], kMinVal);  // pyx:939 / :993
+    for (int i = 1; i <= c0; ++i) {
+        const int p = i - 1, pp = tri(p, p);
+        const double app = A[pp], bpp = B[pp], cpp = C[pp];
+        const double inv = 1.0 / app;
+        const double al2 = -inv, al4 = bpp / (app * app);
+        trPP = trPP + (bpp / app) * (bpp / app) - 2 * (cpp / app);
+        const double alc = (cpp / (app * app)) - ((bpp * bpp) / (app * app * app));
+        trP = trP - bpp / app;
+        logdet += log(app);
+        out[3 * p] = al2; out[3 * p + 1] = al4; out[3 * p + 2] = alc;
+        for (int s = i; s <= c0; ++s) {
+            const int q = t2_col(c0, p, s), sp = tri(s, p);
+            out[q] = A[sp]; out[Tp + q] = B[sp]; out[2 * Tp + q] = C[sp];
+        }
+        for (int r = i; r <= c0; ++r)
+            for (int s2 = i; s2 <= r; ++s2) {
+                const int rs = tri(r, s2), rp = tri(r, p), sp = tri(s2, p);
+                const double ar = A[rp], as = A[sp], br = B[rp], bs = B[sp], cr = C[rp], cs = C[sp];
+                const bool clamp = (r == i && s2 == i && i < c0);  // next pivot (i,i); at i == c0 that entry is (x,x)
+                double v = (C[rs] + alc * ar * as) + al2 * (ar * cs + cr * as) + al2 * (br * bs) + al4 * (ar * bs + br * as);
+                if (clamp) v = cy_max(v, kMinVal);
+                C[rs] = v;
+                v = (B[rs] + al4 * ar * as) + al2 * (ar * bs + br * as);
+                if (clamp) v = cy_max(v, kMinVal);
+                B[rs] = v;
+                v = A[rs] + al2 * ar * as;
+                if (clamp) v = cy_max(v, kMinVal);
+                A[rs] = v;
+            }
+    }
+    const int f = t2_fin(c0), yy = tri(c0, c0);
+    out[f] = A[yy]; out[f + 1] = B[yy]; out[f + 2] = C[yy];
+    out[f + 3] = trP; out[f + 4] = trPP; out[f + 5] = row0[3 * T0 + 2]; out[f + 6] = logdet;
+}
+
+// last level: pivot on x itself.  (app, bpp, cpp) = x diagonal after the covariate levels (clamped), (ar, br, cr) = the
+// (y, x) entries, fin = finals of the table-2 row.
+template <bool FULL>
+PG_HD void xrow_final_level(const double* fin, double app, double bpp, double cpp, double ar, double br, double cr,
+                            bool need_logdet, EvalOut* out)
+{
+    out->xPx = app;  // pyx:1529-1533
+    out->yPx = ar;
+    const double inv = 1.0 / app;
+    const double al2 = -inv, al4 = bpp / (app * app);
+    double trPP = fin[4], alc = 0.0;
+    if (FULL) {
+        trPP = trPP + (bpp / app) * (bpp / app) - 2 * (cpp / app);
+        alc = (cpp / (app * app)) - ((bpp * bpp) / (app * app * app));
+    }
+    const double trP = fin[3] - bpp / app;
+    double logdet = fin[6];
+    if (need_logdet) logdet += log(app);
+    double vc = NAN;
+    if (FULL) {
+        vc = (fin[2] + alc * ar * ar) + al2 * (ar * cr + cr * ar) + al2 * (br * br) + al4 * (ar * br + br * ar);
+        vc = cy_max(vc, kMinVal);
+    }
+    double vb = (fin[1] + al4 * ar * ar) + al2 * (ar * br + br * ar);
+    vb = cy_max(vb, kMinVal);
+    double va = fin[0] + al2 * ar * ar;
+    va = cy_max(va, kMinVal);
+    out->yPy = va; out->yPPy = vb; out->yPPPy = vc;
+    out->trP = trP; out->trPP = FULL ? trPP : NAN;
+    out->logdetH = fin[5]; out->logdetWHW = logdet;
+}
+
+// scalar form (host tests, probes): xa/xb/xc hold the level-0 x row, entries j < c0: x.w_j, c0: x.y, c0+1: x.x
+template <bool FULL>
+PG_HD_NOINLINE void xrow_recursion_scalar(int c0, const double* row2, double* xa, double* xb, double* xc,
+                                          bool need_logdet, EvalOut* out)
+{
+    const int Tp = t2_pairs(c0), dg = c0 + 1;
+    if (c0 == 0) xa[dg] = cy_max(xa[dg], kMinVal);
+    for (int p = 0; p < c0; ++p) {
+        const double al2 = row2[3 * p], al4 = row2[3 * p + 1], alc = row2[3 * p + 2];
+        const double ar = xa[p], br = xb[p], cr = xc[p];
+        for (int j = p + 1; j <= dg; ++j) {
+            double as = ar, bs = br, cs = cr;
+            if (j <= c0) {
+                const int q = t2_col(c0, p, j);
+                as = row2[q]; bs = row2[Tp + q]; cs = row2[2 * Tp + q];
+            }
+            const bool clamp = (p == c0 - 1 && j == dg);
+            if (FULL) {
+                double v = (xc[j] + alc * ar * as) + al2 * (ar * cs + cr * as) + al2 * (br * bs) + al4 * (ar * bs + br * as);
+                if (clamp) v = cy_max(v, kMinVal);
+                xc[j] = v;
+            }
+            double v = (xb[j] + al4 * ar * as) + al2 * (ar * bs + br * as);
+            if (clamp) v = cy_max(v, kMinVal);
+            xb[j] = v;
+            v = xa[j] + al2 * ar * as;
+            if (clamp) v = cy_max(v, kMinVal);
+            xa[j] = v;
+        }
+    }
+    xrow_final_level<FULL>(row2 + t2_fin(c0), xa[dg], xb[dg], FULL ? xc[dg] : 0.0, xa[c0], xb[c0], FULL ? xc[c0] : 0.0,
+                           need_logdet, out);
+}
+
+// Chebyshev weights L[k] of `lam` inside its table interval (shared by both table kinds)
+PG_HD void table_weights(const double* basis, double lam, int* interval, double* L /* kNodes */)
+{
+    double xloc;
+    interval_of(lam, interval, &xloc);
+    double T[kNodes];
+    T[0] = 1.0; T[1] = xloc;
+    for (int j = 2; j < kNodes; ++j) T[j] = 2.0 * xloc * T[j - 1] - T[j - 2];
+    for (int k = 0; k < kNodes; ++k) {
+        double s = 0.0;
+        for (int j = 0; j < kNodes; ++j) s += basis[k * kNodes + j] * T[j];
+        L[k] = s;
+    }
+}
+
 // Host-side helpers shared by the C-ABI implementation and the CPU shim -------------------------------
 
 inline void fill_tri_ab(TriAB* tab)

@@ -3,9 +3,11 @@
 // One warp owns one SNP.  Its moments Z[j][k] (compress.cuh) are all that is left of the genotype vector;
 // every optimiser iteration -- bracket scan, Brent, Newton, final likelihood, grid mode -- is
 //     x row   : sum_k Z[j][k] / (lambda d_k + 1)^p ,  p = 1,2(,3)     lanes over nodes, halving butterfly
-//     tables  : [W0,y] block from the exact / Chebyshev lambda tables   (pg_eval.cuh)
-//     Pab     : projection recursion over covariates, warp-parallel     (pg_eval.cuh)
-//     solver  : SnpSolver state machine                                 (pg_math.cuh)
+//     tables  : covariate levels of the Pab recursion, eliminated once per table lambda ("table-2" rows,
+//               exact at the 11 fixed lambdas, Chebyshev-interpolated elsewhere)    (pg_eval.cuh)
+//     Pab     : the x row carried through the c0 covariate levels in registers (lane j owns column j, pivots
+//               by shuffle, no division), then the SNP's own pivot                  (pg_eval.cuh)
+//     solver  : SnpSolver state machine                                             (pg_math.cuh)
 // and never touches HBM-resident genotype data again: Z (#nodes x (c0+2) doubles, ~10 KB at n = 10 000,
 // c0 = 10) stays in L1/L2 across the ~17 evaluations.
 //
@@ -24,8 +26,9 @@ struct SolveArgs {
     long long m, row0;
     const double* nodes;  // [Kcp] node eigenvalues (padding: 0)
     int Kcp;
-    const double* Z;      // [m][c0+2][Kcp]
-    Tables tab;
+    const double* Z;      // [m][k1p][Kcp]
+    int k1p;              // c0+2 rounded up to a multiple of 4 (padding rows are zero)
+    Tables2 t2;
     double* out[6];
     int* status;
     int* n_eval2;
@@ -74,10 +77,10 @@ __device__ __forceinline__ void warp_reduce_halving(double (&v)[V], int lane)
     }
 }
 
-// x row entries for moment rows [jb, jb+NC): row j < c0 -> x.w_j, j == c0 -> x.y, j == c0+1 -> x.x
+// level-0 x row for moment rows [jb, jb+NC) -> xs[p * k1p + j] (p = power index; row j < c0: x.w_j, c0: x.y, c0+1: x.x)
 template <int NC, bool FULL>
 __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double* __restrict__ Zs, double lam, int jb,
-                                                double* A, double* B, double* C)
+                                                double* xs)
 {
     constexpr int NP = FULL ? 3 : 2;
     constexpr int V = ((NP * NC + 7) / 8) * 8;
@@ -99,80 +102,143 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
     }
     warp_reduce_halving<V>(v, lane);
     if ((lane & 3) == 0) {
-        const int g = lane >> 2, c0 = a.c0;
+        const int g = lane >> 2;
         const int base = ((g >> 2) & 1) * (V / 2) + ((g >> 1) & 1) * (V / 4) + (g & 1) * (V / 8);
 #pragma unroll
         for (int i = 0; i < V / 8; ++i) {
             const int o = base + i;
             if (o < NP * NC) {
                 const int p = o / NC, j = jb + (o - p * NC);
-                const int dst = (j < c0) ? tri(c0, j) : ((j == c0) ? tri(c0 + 1, c0) : tri(c0, c0));
-                double* M = (p == 0) ? A : ((p == 1) ? B : C);
-                M[dst] = v[i];
+                xs[p * a.k1p + j] = v[i];
             }
         }
     }
 }
 
 template <bool FULL>
-__device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __restrict__ Zs, double lam, double* A,
-                                            double* B, double* C)
+__device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __restrict__ Zs, double lam, double* xs)
 {
-    const int k1 = a.c0 + 2;
     int jb = 0;
-    while (k1 - jb > kChunkCols) {
-        solve_xrow_pass<kChunkCols, FULL>(a, Zs, lam, jb, A, B, C);
-        jb += kChunkCols;
+    while (a.k1p - jb >= 12) {
+        solve_xrow_pass<12, FULL>(a, Zs, lam, jb, xs);
+        jb += 12;
     }
-#define PG_CASE(NCV)                                             \
-    case NCV:                                                    \
-        solve_xrow_pass<NCV, FULL>(a, Zs, lam, jb, A, B, C);     \
-        break;
-    switch (k1 - jb) {
-        PG_CASE(1) PG_CASE(2) PG_CASE(3) PG_CASE(4) PG_CASE(5) PG_CASE(6)
-        PG_CASE(7) PG_CASE(8) PG_CASE(9) PG_CASE(10) PG_CASE(11) PG_CASE(12)
-    default: break;
-    }
-#undef PG_CASE
+    if (a.k1p - jb == 8) solve_xrow_pass<8, FULL>(a, Zs, lam, jb, xs);
+    else if (a.k1p - jb == 4) solve_xrow_pass<4, FULL>(a, Zs, lam, jb, xs);
 }
 
-__device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const double* __restrict__ Zs, double lam,
-                                                    int fixed_t, int full, int need_ll, double* A, double* B, double* C,
-                                                    EvalOut* e)
+// The covariate levels applied to the x row held in registers: lane (j & 31), slot (j >> 5) owns entry j.
+// Pivot values travel by shuffle, pivot columns and level scalars come from the table-2 row (pg_eval.cuh).
+template <bool FULL, int NS>
+__device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __restrict__ row2, double (&xa)[NS],
+                                                    double (&xb)[NS], double (&xc)[NS], bool need_logdet, EvalOut* out)
 {
-    Level0 l0;
-    if (full) {
-        assemble_w0y<true>(a.tab, lam, fixed_t, A, B, C, &l0);
-        solve_xrow_all<true>(a, Zs, lam, A, B, C);
-        __syncwarp();
-        pab_recursion<true>(a.tab, A, B, C, l0, need_ll != 0, e);
-    } else {
-        assemble_w0y<false>(a.tab, lam, fixed_t, A, B, C, &l0);
-        solve_xrow_all<false>(a, Zs, lam, A, B, C);
-        __syncwarp();
-        pab_recursion<false>(a.tab, A, B, C, l0, need_ll != 0, e);
+    const int lane = threadIdx.x & 31, Tp = t2_pairs(c0), dg = c0 + 1;
+    if (c0 == 0 && lane == 1) xa[0] = cy_max(xa[0], kMinVal);  // pyx:939 / :993 hits (x,x) without covariates
+    auto pick = [&](const double (&x)[NS], int slot) -> double {
+        if (NS == 1) return x[0];
+        return slot ? x[NS - 1] : x[0];
+    };
+    for (int p = 0; p < c0; ++p) {
+        const int src = p & 31, sl = p >> 5;
+        const double ar = __shfl_sync(0xffffffffu, pick(xa, sl), src);
+        const double br = __shfl_sync(0xffffffffu, pick(xb, sl), src);
+        const double cr = FULL ? __shfl_sync(0xffffffffu, pick(xc, sl), src) : 0.0;
+        const double al2 = row2[3 * p], al4 = row2[3 * p + 1], alc = FULL ? row2[3 * p + 2] : 0.0;
+        const int cb = t2_col(c0, p, p + 1) - (p + 1);
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const int j = lane + 32 * q;
+            if (j > p && j <= dg) {
+                double as = ar, bs = br, cs = cr;
+                if (j <= c0) {
+                    as = row2[cb + j]; bs = row2[Tp + cb + j];
+                    if (FULL) cs = row2[2 * Tp + cb + j];
+                }
+                const bool clamp = (p == c0 - 1) && (j == dg);
+                if (FULL) {
+                    double v = (xc[q] + alc * ar * as) + al2 * (ar * cs + cr * as) + al2 * (br * bs) + al4 * (ar * bs + br * as);
+                    if (clamp) v = cy_max(v, kMinVal);
+                    xc[q] = v;
+                }
+                double v = (xb[q] + al4 * ar * as) + al2 * (ar * bs + br * as);
+                if (clamp) v = cy_max(v, kMinVal);
+                xb[q] = v;
+                v = xa[q] + al2 * ar * as;
+                if (clamp) v = cy_max(v, kMinVal);
+                xa[q] = v;
+            }
+        }
     }
+    const double app = __shfl_sync(0xffffffffu, pick(xa, dg >> 5), dg & 31);
+    const double bpp = __shfl_sync(0xffffffffu, pick(xb, dg >> 5), dg & 31);
+    const double cpp = FULL ? __shfl_sync(0xffffffffu, pick(xc, dg >> 5), dg & 31) : 0.0;
+    const double ar = __shfl_sync(0xffffffffu, pick(xa, c0 >> 5), c0 & 31);
+    const double br = __shfl_sync(0xffffffffu, pick(xb, c0 >> 5), c0 & 31);
+    const double cr = FULL ? __shfl_sync(0xffffffffu, pick(xc, c0 >> 5), c0 & 31) : 0.0;
+    xrow_final_level<FULL>(row2 + t2_fin(c0), app, bpp, cpp, ar, br, cr, need_logdet, out);
 }
 
+// One precompute_mat-equivalent evaluation from the compressed moments (warp-collective).
+// scratch (shared memory, per warp): 3 * k1p doubles for the level-0 x row, then NF2 for an interpolated table-2 row.
+template <int NS>
+__device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const double* __restrict__ Zs, double lam,
+                                                    int fixed_t, int full, int need_ll, double* scratch, EvalOut* e)
+{
+    const int lane = threadIdx.x & 31, c0 = a.c0, k1 = c0 + 2, k1p = a.k1p, NF2 = a.t2.NF2;
+    double* xs = scratch;
+    double* rowbuf = scratch + 3 * k1p;
+    if (full) solve_xrow_all<true>(a, Zs, lam, xs);
+    else solve_xrow_all<false>(a, Zs, lam, xs);
+    const double* row2;
+    if (fixed_t >= 0) {
+        row2 = a.t2.fix2 + (size_t)fixed_t * NF2;
+    } else {
+        int iv;
+        double L[kNodes];
+        table_weights(a.t2.basis, lam, &iv, L);
+        const double* __restrict__ base = a.t2.itab2 + (size_t)iv * kNodes * NF2;
+        for (int f = lane; f < NF2; f += 32) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < kNodes; ++k) v += L[k] * __ldg(base + (size_t)k * NF2 + f);
+            rowbuf[f] = v;
+        }
+        row2 = rowbuf;
+    }
+    __syncwarp();
+    double xa[NS], xb[NS], xc[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        const int j = lane + 32 * q;
+        const bool in = j < k1;
+        xa[q] = in ? xs[j] : 0.0;
+        xb[q] = in ? xs[k1p + j] : 0.0;
+        xc[q] = (in && full) ? xs[2 * k1p + j] : 0.0;
+    }
+    if (full) xrow_recursion_warp<true, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
+    else xrow_recursion_warp<false, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
+    __syncwarp();
+}
+
+template <int NS>
 __global__ void __launch_bounds__(256, 2) reml_solve_kernel(SolveArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = a.c0 + 2, TT = k * (k + 1) / 2;
-    double* A = smem + (size_t)warp * 3 * TT;
-    double* B = A + TT;
-    double* C = B + TT;
+    const int k1p = a.k1p;
+    double* scratch = smem + (size_t)warp * (3 * k1p + a.t2.NF2);
     for (;;) {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(a.counter, 1ULL);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= (unsigned long long)a.m) break;
-        const double* __restrict__ Zs = a.Z + (size_t)g * k * a.Kcp;
+        const double* __restrict__ Zs = a.Z + (size_t)g * k1p * a.Kcp;
         SnpSolver s;
         s.init(a.n, a.c0, a.grid);
         while (s.pending()) {
             EvalOut e;
-            eval_snp_compressed(a, Zs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), A, B, C, &e);
+            eval_snp_compressed<NS>(a, Zs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
             s.feed(e);
         }
         if (lane == 0) {
@@ -186,16 +252,26 @@ __global__ void __launch_bounds__(256, 2) reml_solve_kernel(SolveArgs a)
     }
 }
 
+// table-2 rows: one thread eliminates the covariate levels of one table lambda (pg_eval.cuh: eliminate_w0y_row)
+__global__ void eliminate_tables_kernel(int c0, int NF, int NF2, const double* __restrict__ fixtab,
+                                        const double* __restrict__ itab, double* __restrict__ fix2,
+                                        double* __restrict__ itab2, double* __restrict__ work)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= kNumTableRows) return;
+    const int k0 = c0 + 1, T0 = k0 * (k0 + 1) / 2;
+    const double* src = (row < kNumFixed) ? fixtab + (size_t)row * NF : itab + (size_t)(row - kNumFixed) * NF;
+    double* dst = (row < kNumFixed) ? fix2 + (size_t)row * NF2 : itab2 + (size_t)(row - kNumFixed) * NF2;
+    eliminate_w0y_row(c0, src, work + (size_t)row * 3 * T0, dst);
+}
+
 // single evaluation from compressed moments (one warp): unit probe
+template <int NS>
 __global__ void probe_precompute_compressed_kernel(SolveArgs a, double lam, int fixed_t, int full, double* out9)
 {
     extern __shared__ double smem[];
-    const int k = a.c0 + 2, TT = k * (k + 1) / 2;
-    double* A = smem;
-    double* B = A + TT;
-    double* C = B + TT;
     EvalOut e;
-    eval_snp_compressed(a, a.Z, lam, fixed_t, full, 1, A, B, C, &e);
+    eval_snp_compressed<NS>(a, a.Z, lam, fixed_t, full, 1, smem, &e);
     if ((threadIdx.x & 31) == 0) {
         out9[0] = e.yPy; out9[1] = e.yPPy; out9[2] = e.yPPPy; out9[3] = e.trP; out9[4] = e.trPP;
         out9[5] = e.logdetH; out9[6] = e.logdetWHW; out9[7] = e.xPx; out9[8] = e.yPx;

@@ -128,6 +128,58 @@ void eval_snp_compressed(const HostTables& H, const CompressPlan& P, const doubl
 }
 }  // namespace
 
+namespace {
+struct HostTables2 {
+    std::vector<double> fix2, itab2;
+    Tables2 t;
+};
+
+void build_tables2(const HostTables& H, HostTables2& H2)
+{
+    const int c0 = H.t.c0, NF = H.t.NF, NF2 = t2_nf(c0), T0 = H.t.T0;
+    H2.fix2.assign((size_t)kNumFixed * NF2, 0.0);
+    H2.itab2.assign((size_t)kNumIntervals * kNodes * NF2, 0.0);
+    std::vector<double> work(3 * T0);
+    for (int r = 0; r < kNumFixed; ++r) eliminate_w0y_row(c0, &H.fixtab[(size_t)r * NF], work.data(), &H2.fix2[(size_t)r * NF2]);
+    for (int r = 0; r < kNumIntervals * kNodes; ++r)
+        eliminate_w0y_row(c0, &H.itab[(size_t)r * NF], work.data(), &H2.itab2[(size_t)r * NF2]);
+    H2.t.c0 = c0; H2.t.Tp = t2_pairs(c0); H2.t.NF2 = NF2;
+    H2.t.fix2 = H2.fix2.data(); H2.t.itab2 = H2.itab2.data(); H2.t.basis = H.basis.data();
+}
+
+// evaluation through the x-row recursion + table-2 rows (what reml_solve_kernel does)
+void eval_snp_xrow(const HostTables2& H2, const CompressPlan& P, const double* z, double lam, int fixed_t, int full,
+                   int need_ll, EvalOut* out)
+{
+    const int c0 = H2.t.c0, k1 = c0 + 2, Kc = P.Kc, NF2 = H2.t.NF2;
+    std::vector<double> xa(k1), xb(k1), xc(k1), row(NF2);
+    for (int j = 0; j < k1; ++j) {
+        double a1 = 0, a2 = 0, a3 = 0;
+        for (int q = 0; q < Kc; ++q) {
+            const double h = 1.0 / (lam * P.nodes[q] + 1.0), zz = z[(size_t)j * Kc + q];
+            a1 += h * zz; a2 += h * h * zz; a3 += h * h * h * zz;
+        }
+        xa[j] = a1; xb[j] = a2; xc[j] = a3;
+    }
+    const double* row2;
+    if (fixed_t >= 0) {
+        row2 = &H2.fix2[(size_t)fixed_t * NF2];
+    } else {
+        int iv;
+        double L[kNodes];
+        table_weights(H2.t.basis, lam, &iv, L);
+        for (int f = 0; f < NF2; ++f) {
+            double v = 0.0;
+            for (int k = 0; k < kNodes; ++k) v += L[k] * H2.itab2[((size_t)iv * kNodes + k) * NF2 + f];
+            row[f] = v;
+        }
+        row2 = row.data();
+    }
+    if (full) xrow_recursion_scalar<true>(c0, row2, xa.data(), xb.data(), xc.data(), need_ll, out);
+    else xrow_recursion_scalar<false>(c0, row2, xa.data(), xb.data(), xc.data(), need_ll, out);
+}
+}  // namespace
+
 extern "C" {
 
 // number of nodes the compression plan gives for the (ascending) eigenvalues d
@@ -166,7 +218,7 @@ double pgh_compress_error(int n, const double* d_sorted, const double* a, int po
 
 // the scan on compressed moments: d / wy / xr in any eigenvalue order (sorted here)
 void pgh_scan_compressed(int n, int c0, long m, const double* d, const double* wy, const double* xr, int grid,
-                         double* out6, int32_t* status, int32_t* evals, int32_t* kc_out)
+                         int xrow_form, double* out6, int32_t* status, int32_t* evals, int32_t* kc_out)
 {
     std::vector<int> perm(n);
     for (int l = 0; l < n; ++l) perm[l] = l;
@@ -179,6 +231,8 @@ void pgh_scan_compressed(int n, int c0, long m, const double* d, const double* w
     }
     HostTables H;
     build_tables(H, n, c0, ds.data(), wys.data());
+    HostTables2 H2;
+    if (xrow_form) build_tables2(H, H2);
     CompressPlan P;
     build_compress_plan(ds.data(), n, &P);
     if (kc_out) *kc_out = P.Kc;
@@ -199,7 +253,8 @@ void pgh_scan_compressed(int n, int c0, long m, const double* d, const double* w
         s.init(n, c0, grid);
         while (s.pending()) {
             EvalOut e;
-            eval_snp_compressed(H, P, z.data(), s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), &e);
+            if (xrow_form) eval_snp_xrow(H2, P, z.data(), s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), &e);
+            else eval_snp_compressed(H, P, z.data(), s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), &e);
             s.feed(e);
         }
         double* o = out6 + g * 6;

@@ -40,8 +40,8 @@ def lib():
     L.pgh_compress_error.restype = ctypes.c_double
     L.pgh_compress_error.argtypes = [ctypes.c_int, _dp, _dp, ctypes.c_int]
     L.pgh_scan_compressed.restype = None
-    L.pgh_scan_compressed.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long, _dp, _dp, _dp, ctypes.c_int, _dp, _ip,
-                                      _ip, _ip]
+    L.pgh_scan_compressed.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long, _dp, _dp, _dp, ctypes.c_int,
+                                      ctypes.c_int, _dp, _ip, _ip, _ip]
     _lib = L
     return L
 
@@ -69,8 +69,9 @@ def scan(d, y, w0, xr_snp_major, grid=False, exact_w0y=False):
     return r
 
 
-def scan_compressed(d, y, w0, xr_snp_major, grid=False):
-    """The scan evaluated from the eigenvalue-space compressed moments (compress_plan.h)."""
+def scan_compressed(d, y, w0, xr_snp_major, grid=False, xrow_form=True):
+    """The scan evaluated from the eigenvalue-space compressed moments (compress_plan.h); xrow_form: covariate levels
+    of the Pab recursion taken from the table-2 rows (pg_eval.cuh), as reml_solve_kernel does."""
     d = np.ascontiguousarray(d, dtype=np.float64)
     w0 = np.asarray(w0, dtype=np.float64)
     wy = np.asfortranarray(np.concatenate([w0, np.asarray(y, dtype=np.float64).reshape(-1, 1)], axis=1))
@@ -80,7 +81,7 @@ def scan_compressed(d, y, w0, xr_snp_major, grid=False):
     st = np.zeros(m, dtype=np.int32)
     ev = np.zeros((m, 2), dtype=np.int32)
     kc = np.zeros(1, dtype=np.int32)
-    lib().pgh_scan_compressed(n, c0, m, _p(d), _p(wy), _p(xr), int(grid), _p(out), st.ctypes.data_as(_ip),
+    lib().pgh_scan_compressed(n, c0, m, _p(d), _p(wy), _p(xr), int(grid), int(xrow_form), _p(out), st.ctypes.data_as(_ip),
                               ev.ctypes.data_as(_ip), kc.ctypes.data_as(_ip))
     cols = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
     r = {c: out[:, i].copy() for i, c in enumerate(cols)}

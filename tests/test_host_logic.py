@@ -197,6 +197,20 @@ def test_compressed_scan_matches_ref64(path):
         assert rel(o[c][ok], g[f"r64_{c}"][ok]).max() < tol, (c, rel(o[c][ok], g[f"r64_{c}"][ok]).max())
 
 
+@pytest.mark.parametrize("path", SCANS, ids=[os.path.basename(p)[5:-4] for p in SCANS])
+def test_xrow_form_equals_full_recursion(path):
+    """Covariate levels from the table-2 rows + x-row recursion vs the full (c0+2)^2 recursion per evaluation:
+    same optimiser path, results equal far below the parity tolerance."""
+    g = np.load(path)
+    xt = np.ascontiguousarray(g["xr"].T)
+    a = hostshim.scan_compressed(g["d"], g["yr"], g["wr"], xt, grid=bool(g["grid"]), xrow_form=False)
+    b = hostshim.scan_compressed(g["d"], g["yr"], g["wr"], xt, grid=bool(g["grid"]), xrow_form=True)
+    ok = np.array([0, 2, 4, 5, 6, 7]) if "degenerate" in path else np.arange(xt.shape[0])
+    for c in COLS:  # lambda itself is ill-conditioned where the likelihood is flat (boundary_lo: 7e-9)
+        assert rel(a[c][ok], b[c][ok]).max() < (1e-7 if c == "lambda" else 1e-9), (c, rel(a[c][ok], b[c][ok]).max())
+    assert np.array_equal(a["n_eval2"][ok], b["n_eval2"][ok]) and np.array_equal(a["n_eval3"][ok], b["n_eval3"][ok])
+
+
 def test_compressed_scan_equals_direct_scan():
     """Same optimiser path (evaluation counts) and results to 1e-9 with and without the compression."""
     g = np.load(os.path.join(GOLDEN, "scan_interior.npz"))
