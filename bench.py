@@ -379,7 +379,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "SNPs/s", "h2d_bytes_per_step": int(n) * int(m) * world,
                 "d2h_bytes_per_step": int(m) * (6 * 8 + 3 * 4) * world, "ms_per_step": e2e_ms,
                 "device_ms_per_step": e2e_dev_ms / args.steps,
-                "api": "pg_scan (C ABI, host buffers) as called by pygemma_b200.lmm.pygemma"},
+                "api": "pg_scan (C ABI, host buffers) as called by pygemma_b200.lmm.pygemma",
+                "timing_last_call": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_tms[-1]["timing"].items()}},
         "gpu_launches": int(sum(t["convert_launches"] + t["reml_launches"] + t["rotate_launches"] for t in tms)),
         "clocks": clocks, "roofline": roofline,
         "setup": {"syevd_ms": eig_ms, "eigen_setup_s": setup_s, "design_tables_ms": design_ms},

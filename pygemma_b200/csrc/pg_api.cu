@@ -33,6 +33,17 @@ struct pg_handle {
     int sm_count = 148;
     std::string err;
     cudaStream_t compute = nullptr, copy = nullptr;
+    // scan pipeline: rotation GEMMs on `compute`, int8 recombination on `cmb`, compression + optimiser on `aux`,
+    // so that block b's REML stage (FP64 pipes) runs under block b+1's rotation (int8 tensor pipe)
+    cudaStream_t aux = nullptr, cmb = nullptr;
+    cudaEvent_t ev_xr_ready[2] = {nullptr, nullptr}, ev_xr_free[2] = {nullptr, nullptr}, ev_aux_done = nullptr;
+    bool overlap = false;
+    // per-call scratch kept across calls (grow-only): device result arrays, pinned host staging, timing events
+    double* res_d = nullptr;   // [6][cap] doubles
+    int* res_i = nullptr;      // [3][cap] ints
+    char* res_host = nullptr;  // pinned: 6*8*cap + 3*4*cap bytes
+    size_t res_cap = 0;
+    std::vector<cudaEvent_t> ev_pool;
     cudaStream_t own_compute = nullptr;  // compute defaults to this; pg_set_stream can point it at a caller stream
     cublasHandle_t blas = nullptr;
     cusolverDnHandle_t solver = nullptr;
@@ -54,8 +65,9 @@ struct pg_handle {
     long long blk = 0;  // allocated block size (SNPs)
     void* stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
-    double *xf = nullptr, *xr = nullptr;
+    double *xf = nullptr, *xr[2] = {nullptr, nullptr};
     size_t xbuf_elems = 0;
+    const double* last_xr = nullptr;
     unsigned long long* counter = nullptr;
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     RotWorkspace rot;
@@ -67,7 +79,7 @@ struct pg_handle {
     // eigenvalue-space compression (compress_plan.h / compress.cuh)
     CompressPlan hplan;
     DevPlan plan;
-    double* Z = nullptr;  // [blk][k1p][Kcp]
+    double* Z[2] = {nullptr, nullptr};  // [blk][k1p][Kcp], double-buffered like xr
     size_t z_elems = 0;
     int k1p = 0;          // c0+2 rounded up to a multiple of 4
     // table-2 rows (covariate levels eliminated per table lambda, pg_eval.cuh)
@@ -78,11 +90,11 @@ struct pg_handle {
 static void free_plan(pg_handle* h)
 {
     DevPlan& P = h->plan;
-    void* bufs[] = {P.nodes, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z};
+    void* bufs[] = {P.nodes, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z[0], h->Z[1]};
     for (void* b : bufs)
         if (b) cudaFree(b);
     P = DevPlan{};
-    h->Z = nullptr;
+    h->Z[0] = h->Z[1] = nullptr;
     h->z_elems = 0;
 }
 
@@ -142,7 +154,19 @@ static int free_all(pg_handle* h)
         if (h->ev_free[s]) cudaEventDestroy(h->ev_free[s]);
     }
     free_plan(h);
-    void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr, h->counter,
+    for (int s = 0; s < 2; ++s) {
+        if (h->ev_xr_ready[s]) cudaEventDestroy(h->ev_xr_ready[s]);
+        if (h->ev_xr_free[s]) cudaEventDestroy(h->ev_xr_free[s]);
+    }
+    if (h->ev_aux_done) cudaEventDestroy(h->ev_aux_done);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    h->ev_pool.clear();
+    if (h->res_d) cudaFree(h->res_d);
+    if (h->res_i) cudaFree(h->res_i);
+    if (h->res_host) cudaFreeHost(h->res_host);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->cmb) cudaStreamDestroy(h->cmb);
+    void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr[0], h->xr[1], h->counter,
                     h->perm_dev, h->fix2, h->itab2, h->t2work};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -194,6 +218,18 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
         CK(cudaStreamCreateWithFlags(&h->own_compute, cudaStreamNonBlocking));
         h->compute = h->own_compute;
         CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+        {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
+            CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
+            CK(cudaStreamCreateWithPriority(&h->cmb, cudaStreamNonBlocking, hi));
+            for (int s = 0; s < 2; ++s) {
+                CK(cudaEventCreateWithFlags(&h->ev_xr_ready[s], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->ev_xr_free[s], cudaEventDisableTiming));
+            }
+            CK(cudaEventCreateWithFlags(&h->ev_aux_done, cudaEventDisableTiming));
+            h->overlap = getenv("PG_OVERLAP") != nullptr;  // measured: no gain next to the cuBLAS GEMM
+        }
         CKB(cublasCreate(&h->blas));
         CKB(cublasSetStream(h->blas, h->compute));
         CKS(cusolverDnCreate(&h->solver));
@@ -570,22 +606,32 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
     const size_t need = (size_t)blk * h->ldx;
     if (need > h->xbuf_elems) {
         if (h->xf) cudaFree(h->xf);
-        if (h->xr) cudaFree(h->xr);
-        h->xf = h->xr = nullptr;
+        h->xf = nullptr;
+        for (int s = 0; s < 2; ++s) {
+            if (h->xr[s]) cudaFree(h->xr[s]);
+            h->xr[s] = nullptr;
+        }
         h->xbuf_elems = 0;
+        h->last_xr = nullptr;
         CK(cudaMalloc(&h->xf, sizeof(double) * need));
-        CK(cudaMalloc(&h->xr, sizeof(double) * need));
-        CK(cudaMemset(h->xr, 0, sizeof(double) * need));
+        for (int s = 0; s < 2; ++s) {
+            CK(cudaMalloc(&h->xr[s], sizeof(double) * need));
+            CK(cudaMemset(h->xr[s], 0, sizeof(double) * need));
+        }
         h->xbuf_elems = need;
     }
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
         const size_t zneed = (size_t)blk * h->k1p * h->plan.Kcp;
         if (zneed > h->z_elems) {
-            if (h->Z) cudaFree(h->Z);
-            h->Z = nullptr;
+            for (int s = 0; s < 2; ++s) {
+                if (h->Z[s]) cudaFree(h->Z[s]);
+                h->Z[s] = nullptr;
+            }
             h->z_elems = 0;
-            CK(cudaMalloc(&h->Z, sizeof(double) * zneed));
-            CK(cudaMemset(h->Z, 0, sizeof(double) * zneed));  // padding nodes stay zero for ever
+            for (int s = 0; s < 2; ++s) {
+                CK(cudaMalloc(&h->Z[s], sizeof(double) * zneed));
+                CK(cudaMemset(h->Z[s], 0, sizeof(double) * zneed));  // padding nodes / rows stay zero for ever
+            }
             h->z_elems = zneed;
         }
     }
@@ -613,35 +659,39 @@ static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld,
     return PG_OK;
 }
 
-static int launch_reml(pg_handle* h, const double* xr, long long mb, long long row0, int grid_mode, double* const out[6],
-                       int* status, int* e2, int* e3, cudaEvent_t* ev_mid = nullptr)
+// REML stage of one block on stream `st`: reads xr, uses moment buffer Zbuf.  `ev_xr_done` (nullable) is recorded once
+// the rotated genotypes are no longer needed (after the compression, or after the kernel for the streaming engines).
+static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* Zbuf, long long mb, long long row0,
+                       int grid_mode, double* const out[6], int* status, int* e2, int* e3, cudaEvent_t* ev_mid = nullptr,
+                       cudaEvent_t ev_xr_done = nullptr)
 {
     ScanArgs a;
     a.n = h->n; a.c0 = h->c0; a.grid = grid_mode; a.m = mb; a.row0 = row0;
     a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = xr; a.ldx = h->ldx; a.tab = h->tab;
     for (int i = 0; i < 6; ++i) a.out[i] = out[i];
     a.status = status; a.n_eval2 = e2; a.n_eval3 = e3; a.counter = h->counter;
-    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), h->compute));
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
         const DevPlan& P = h->plan;
         const int ntiles = (int)((mb + kCtSnps - 1) / kCtSnps);
-        if (ev_mid) CK(cudaEventRecord(ev_mid[0], h->compute));
+        if (ev_mid) CK(cudaEventRecord(ev_mid[0], st));
         if (P.nitems) {
             CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
-            compress_dmma_kernel<<<(unsigned)((long long)P.nitems * ntiles), 256, kCtSmemBytes, h->compute>>>(
-                xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, h->k1p, P.Kcp, h->Z, ntiles);
+            compress_dmma_kernel<<<(unsigned)((long long)P.nitems * ntiles), 256, kCtSmemBytes, st>>>(
+                xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, h->k1p, P.Kcp, Zbuf, ntiles);
             CK(cudaGetLastError());
         }
         if (P.ncopy) {
             dim3 grid((unsigned)((P.ncopy + 127) / 128), (unsigned)((mb + 7) / 8));
-            compress_copy_kernel<<<grid, 128, 0, h->compute>>>(xr, h->ldx, mb, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw,
-                                                             h->c0, h->k1p, P.Kcp, h->Z);
+            compress_copy_kernel<<<grid, 128, 0, st>>>(xr, h->ldx, mb, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw,
+                                                             h->c0, h->k1p, P.Kcp, Zbuf);
             CK(cudaGetLastError());
         }
-        if (ev_mid) CK(cudaEventRecord(ev_mid[1], h->compute));
+        if (ev_mid) CK(cudaEventRecord(ev_mid[1], st));
+        if (ev_xr_done) CK(cudaEventRecord(ev_xr_done, st));
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
-        sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = h->Z; sa.k1p = h->k1p; sa.t2 = h->tab2;
+        sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = h->counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
@@ -649,15 +699,21 @@ static int launch_reml(pg_handle* h, const double* xr, long long mb, long long r
         while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
         const size_t smem = per_warp * warps;
         const bool two = (h->c0 + 2) > 32;
-        if (smem > 48 * 1024) {
-            if (two) CK(cudaFuncSetAttribute(reml_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else CK(cudaFuncSetAttribute(reml_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / std::max<size_t>(smem, 1)));
-        long long want = (mb + warps - 1) / warps;
-        int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
-        if (two) reml_solve_kernel<2><<<grid, warps * 32, smem, h->compute>>>(sa);
-        else reml_solve_kernel<1><<<grid, warps * 32, smem, h->compute>>>(sa);
+        static int minb = getenv("PG_SOLVE_MINB") ? atoi(getenv("PG_SOLVE_MINB")) : 2;
+        auto launch = [&](auto kern, int ctas) -> int {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(ctas, (200 * 1024) / std::max<size_t>(smem, 1)));
+            long long want = (mb + warps - 1) / warps;
+            int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
+            kern<<<grid, warps * 32, smem, st>>>(sa);
+            return PG_OK;
+        };
+        int lr;
+        if (two) lr = launch(reml_solve_kernel<2, 2>, 2);
+        else if (minb == 3) lr = launch(reml_solve_kernel<1, 3>, 3);
+        else if (minb == 4) lr = launch(reml_solve_kernel<1, 4>, 4);
+        else lr = launch(reml_solve_kernel<1, 2>, 2);
+        if (lr) return lr;
         CK(cudaGetLastError());
         return PG_OK;
     }
@@ -668,8 +724,9 @@ static int launch_reml(pg_handle* h, const double* xr, long long mb, long long r
         const int ctas_per_sm = cfg.smem <= 110 * 1024 ? 2 : 1;
         long long want = (mb + cfg.nw - 1) / cfg.nw;
         int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
-        reml_stream_kernel<<<grid, cfg.nw * 32, cfg.smem, h->compute>>>(a, cfg.nw, ncmax);
+        reml_stream_kernel<<<grid, cfg.nw * 32, cfg.smem, st>>>(a, cfg.nw, ncmax);
         CK(cudaGetLastError());
+        if (ev_xr_done) CK(cudaEventRecord(ev_xr_done, st));
         return PG_OK;
     }
     const int k = h->c0 + 2, TT = k * (k + 1) / 2;
@@ -683,8 +740,9 @@ static int launch_reml(pg_handle* h, const double* xr, long long mb, long long r
     long long want = (mb + warps - 1) / warps;
     int grid = (int)std::min<long long>(want, (long long)h->sm_count * ctas_per_sm);
     grid = std::max(grid, 1);
-    reml_scan_kernel<<<grid, warps * 32, smem, h->compute>>>(a);
+    reml_scan_kernel<<<grid, warps * 32, smem, st>>>(a);
     CK(cudaGetLastError());
+    if (ev_xr_done) CK(cudaEventRecord(ev_xr_done, st));
     return PG_OK;
 }
 
@@ -725,23 +783,46 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         for (int i = 0; i < 6; ++i) dout[i] = out_user[i];
         dstatus = status; de2 = e2; de3 = e3;
     } else {
-        CK(cudaMalloc(&dtmp, sizeof(double) * 6 * (size_t)m));
-        CK(cudaMalloc(&itmp, sizeof(int) * 3 * (size_t)m));
+        if ((size_t)m > h->res_cap) {
+            if (h->res_d) cudaFree(h->res_d);
+            if (h->res_i) cudaFree(h->res_i);
+            if (h->res_host) cudaFreeHost(h->res_host);
+            h->res_d = nullptr; h->res_i = nullptr; h->res_host = nullptr; h->res_cap = 0;
+            const size_t cap = ((size_t)m + 1023) / 1024 * 1024;
+            CK(cudaMalloc(&h->res_d, sizeof(double) * 6 * cap));
+            CK(cudaMalloc(&h->res_i, sizeof(int) * 3 * cap));
+            CK(cudaMallocHost(&h->res_host, (sizeof(double) * 6 + sizeof(int) * 3) * cap));
+            h->res_cap = cap;
+        }
+        dtmp = h->res_d; itmp = h->res_i;
         for (int i = 0; i < 6; ++i) dout[i] = dtmp + (size_t)i * m;
         dstatus = itmp; de2 = itmp + m; de3 = itmp + 2 * (size_t)m;
     }
 
+    // timing events come from a pool owned by the handle (creating / destroying ~40 events per call costs host time)
+    size_t ev_next = 0;
+    auto take = [&]() -> cudaEvent_t {
+        if (ev_next == h->ev_pool.size()) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            h->ev_pool.push_back(e);
+        }
+        return h->ev_pool[ev_next++];
+    };
     std::vector<EvPair> ev_conv(nblocks), ev_rot(nblocks), ev_reml(nblocks), ev_h2d(nblocks), ev_cmp(nblocks);
-    auto mk = [&](EvPair& p) { cudaEventCreate(&p.a); cudaEventCreate(&p.b); };
+    auto mk = [&](EvPair& p) { p.a = take(); p.b = take(); };
     for (long long b = 0; b < nblocks; ++b) { mk(ev_conv[b]); mk(ev_rot[b]); mk(ev_reml[b]); mk(ev_cmp[b]); if (!on_device) mk(ev_h2d[b]); }
     const bool compressed = (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED);
-    cudaEvent_t t0, t1, t2;
-    cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+    cudaEvent_t t0 = take(), t1 = take(), t2 = take();
     int n_rot_launch = 0, last_engine = 0;
 
     rc = [&]() -> int {
         CK(cudaEventRecord(t0, h->compute));
         CK(cudaStreamWaitEvent(h->copy, t0, 0));
+        if (h->overlap) {
+            CK(cudaStreamWaitEvent(h->aux, t0, 0));
+            CK(cudaStreamWaitEvent(h->cmb, t0, 0));
+        }
         for (long long b = 0; b < nblocks; ++b) {
             const long long g0 = b * blk, mb = std::min(blk, m - g0);
             const int s = (int)(b & 1);
@@ -769,45 +850,66 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                 CK(cudaStreamWaitEvent(h->compute, h->ev_ready[s], 0));
                 src_dev = h->stage[s];
             }
-            const double* xr_block = nullptr;
+            // ---- rotation of block b into xr[s] (main stream + recombination stream)
+            cudaStream_t st_reml = h->overlap ? h->aux : h->compute;
+            cudaStream_t st_cmb = h->overlap ? h->cmb : h->compute;
+            double* xr_block = h->xr[s];
+            if (b >= 2) {  // the REML stage of block b-2 has finished reading xr[s]
+                CK(cudaStreamWaitEvent(h->compute, h->ev_xr_free[s], 0));
+                CK(cudaStreamWaitEvent(st_cmb, h->ev_xr_free[s], 0));
+            }
             CK(cudaEventRecord(ev_conv[b].a, h->compute));
             int used_i8 = 0;
             if (rotate) {
-                // try the fused-conversion rotation engines first (they read the raw block directly)
-                int r2 = rot_run(&h->rot, h->blas, h->compute, h->rotation, h->U, h->u_op_t, n, src_dev, xdtype, ld_dev,
-                                 layout, mb, blk, h->xf, h->xr, h->ldx, &used_i8, &n_rot_launch, ev_conv[b].b, ev_rot[b].a,
-                                 ev_rot[b].b);
+                int r2 = rot_run(&h->rot, h->blas, h->compute, st_cmb, h->rotation, h->U, h->u_op_t, n, src_dev, xdtype,
+                                 ld_dev, layout, mb, blk, h->xf, xr_block, h->ldx, &used_i8, &n_rot_launch, ev_conv[b].b,
+                                 ev_rot[b].a, ev_rot[b].b);
                 if (r2 != 0) return fail(h, r2, "rotation failed: %s", rot_error(&h->rot));
-                xr_block = h->xr;
                 last_engine = used_i8 ? PG_ROT_I8SPLIT : PG_ROT_FP64;
+                CK(cudaEventRecord(h->ev_xr_ready[s], used_i8 ? st_cmb : h->compute));
             } else {
-                int r2 = launch_stage(h, src_dev, xdtype, ld_dev, layout, mb, h->xr);
+                int r2 = launch_stage(h, src_dev, xdtype, ld_dev, layout, mb, xr_block);
                 if (r2) return r2;
                 CK(cudaEventRecord(ev_conv[b].b, h->compute));
                 CK(cudaEventRecord(ev_rot[b].a, h->compute));
                 CK(cudaEventRecord(ev_rot[b].b, h->compute));
-                xr_block = h->xr;
+                CK(cudaEventRecord(h->ev_xr_ready[s], h->compute));
             }
             if (!on_device) CK(cudaEventRecord(h->ev_free[s], h->compute));
-            CK(cudaEventRecord(ev_reml[b].a, h->compute));
+            // ---- REML stage of block b (aux stream): runs under the rotation of block b+1
+            CK(cudaStreamWaitEvent(st_reml, h->ev_xr_ready[s], 0));
+            CK(cudaEventRecord(ev_reml[b].a, st_reml));
             cudaEvent_t mid[2] = {ev_cmp[b].a, ev_cmp[b].b};
-            int r3 = launch_reml(h, xr_block, mb, g0, grid_mode, dout, dstatus, de2, de3, mid);
+            int r3 = launch_reml(h, st_reml, xr_block, h->Z[s], mb, g0, grid_mode, dout, dstatus, de2, de3, mid,
+                                 h->ev_xr_free[s]);
             if (r3) return r3;
-            CK(cudaEventRecord(ev_reml[b].b, h->compute));
+            CK(cudaEventRecord(ev_reml[b].b, st_reml));
             h->last_block_count = mb;
             h->last_block_row0 = g0;
+            h->last_xr = xr_block;
+        }
+        if (h->overlap) {
+            CK(cudaEventRecord(h->ev_aux_done, h->aux));
+            CK(cudaStreamWaitEvent(h->compute, h->ev_aux_done, 0));
         }
         CK(cudaEventRecord(t1, h->compute));
         if (!on_device) {
-            for (int i = 0; i < 6; ++i)
-                CK(cudaMemcpyAsync(out_user[i], dout[i], sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
-            if (status) CK(cudaMemcpyAsync(status, dstatus, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
-            if (e2) CK(cudaMemcpyAsync(e2, de2, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
-            if (e3) CK(cudaMemcpyAsync(e3, de3, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
+            // two D2H copies into pinned staging, then host memcpy into the caller's (pageable) arrays
+            CK(cudaMemcpyAsync(h->res_host, dtmp, sizeof(double) * 6 * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
+            CK(cudaMemcpyAsync(h->res_host + sizeof(double) * 6 * (size_t)m, itmp, sizeof(int) * 3 * (size_t)m,
+                               cudaMemcpyDeviceToHost, h->compute));
         }
         CK(cudaEventRecord(t2, h->compute));
         CK(cudaStreamSynchronize(h->compute));
         CK(cudaStreamSynchronize(h->copy));
+        if (!on_device) {
+            const double* hd = reinterpret_cast<const double*>(h->res_host);
+            const int* hi = reinterpret_cast<const int*>(h->res_host + sizeof(double) * 6 * (size_t)m);
+            for (int i = 0; i < 6; ++i) memcpy(out_user[i], hd + (size_t)i * m, sizeof(double) * (size_t)m);
+            if (status) memcpy(status, hi, sizeof(int) * (size_t)m);
+            if (e2) memcpy(e2, hi + m, sizeof(int) * (size_t)m);
+            if (e3) memcpy(e3, hi + 2 * (size_t)m, sizeof(int) * (size_t)m);
+        }
         return PG_OK;
     }();
 
@@ -832,19 +934,11 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->n_nodes = compressed ? h->plan.Kc : h->n;
         if (compressed) timing->reml_launches = (int32_t)(nblocks * (1 + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)));
     }
-    for (long long b = 0; b < nblocks; ++b) {
-        cudaEventDestroy(ev_conv[b].a); cudaEventDestroy(ev_conv[b].b);
-        cudaEventDestroy(ev_rot[b].a); cudaEventDestroy(ev_rot[b].b);
-        cudaEventDestroy(ev_reml[b].a); cudaEventDestroy(ev_reml[b].b);
-        cudaEventDestroy(ev_cmp[b].a); cudaEventDestroy(ev_cmp[b].b);
-        if (!on_device) { cudaEventDestroy(ev_h2d[b].a); cudaEventDestroy(ev_h2d[b].b); }
-    }
-    cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
-    if (dtmp) cudaFree(dtmp);
-    if (itmp) cudaFree(itmp);
     if (rc != PG_OK) {
         cudaStreamSynchronize(h->compute);
         cudaStreamSynchronize(h->copy);
+        cudaStreamSynchronize(h->aux);
+        cudaStreamSynchronize(h->cmb);
     }
     return rc;
 }
@@ -949,10 +1043,10 @@ extern "C" int pg_probe_f_sf(pg_handle* h, const double* F_host, double nu, int6
 extern "C" int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, int64_t* row0)
 {
     if (!h || !xr_host || count < 0) return fail(h, PG_ERR_ARG, "pg_probe_rotated: bad argument");
-    if (!h->xr || h->last_block_count == 0) return fail(h, PG_ERR_ARG, "pg_probe_rotated: no scan has run");
+    if (!h->last_xr || h->last_block_count == 0) return fail(h, PG_ERR_ARG, "pg_probe_rotated: no scan has run");
     CK(cudaSetDevice(h->device));
     const long long c = std::min<long long>(count, h->last_block_count);
-    CK(cudaMemcpy2D(xr_host, sizeof(double) * h->n, h->xr, sizeof(double) * h->ldx, sizeof(double) * h->n, (size_t)c,
+    CK(cudaMemcpy2D(xr_host, sizeof(double) * h->n, h->last_xr, sizeof(double) * h->ldx, sizeof(double) * h->n, (size_t)c,
                     cudaMemcpyDeviceToHost));
     if (!h->perm_identity) {  // report in the caller's eigen order
         std::vector<double> row(h->n);

@@ -194,9 +194,25 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
     if (fixed_t >= 0) {
         row2 = a.t2.fix2 + (size_t)fixed_t * NF2;
     } else {
+        // Chebyshev weights: lane k < kNodes computes L_k, everybody collects the twelve by shuffle
         int iv;
+        double xloc;
+        interval_of(lam, &iv, &xloc);
+        double Lk = 0.0;
+        {
+            const double* __restrict__ bk = a.t2.basis + (size_t)(lane < kNodes ? lane : 0) * kNodes;
+            double t0 = 1.0, t1 = xloc;
+            Lk = __ldg(bk) + __ldg(bk + 1) * xloc;
+#pragma unroll
+            for (int j = 2; j < kNodes; ++j) {
+                const double t2 = 2.0 * xloc * t1 - t0;
+                Lk = fma(__ldg(bk + j), t2, Lk);
+                t0 = t1; t1 = t2;
+            }
+        }
         double L[kNodes];
-        table_weights(a.t2.basis, lam, &iv, L);
+#pragma unroll
+        for (int k = 0; k < kNodes; ++k) L[k] = __shfl_sync(0xffffffffu, Lk, k);
         const double* __restrict__ base = a.t2.itab2 + (size_t)iv * kNodes * NF2;
         for (int f = lane; f < NF2; f += 32) {
             double v = 0.0;
@@ -221,8 +237,8 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
     __syncwarp();
 }
 
-template <int NS>
-__global__ void __launch_bounds__(256, 2) reml_solve_kernel(SolveArgs a)
+template <int NS, int MINB>
+__global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -30,7 +30,9 @@ struct RotWorkspace {
     int* exps = nullptr;       // [n]
     int8_t* x8 = nullptr;      // [cap_snps][ldk]
     long long cap_snps = 0;
-    int32_t* P = nullptr;      // [(8*npad) x sub] column-major
+    int32_t* P[2] = {nullptr, nullptr};  // [(kSlices*npad) x sub] column-major, double-buffered
+    cudaEvent_t ev_gemm[2] = {nullptr, nullptr}, ev_pfree[2] = {nullptr, nullptr};
+    unsigned pcount = 0;
     long long sub = 0;
     float slice_ms = 0.f;
 };
@@ -40,8 +42,16 @@ inline void rot_free(RotWorkspace* w)
     if (w->planes) cudaFree(w->planes);
     if (w->exps) cudaFree(w->exps);
     if (w->x8) cudaFree(w->x8);
-    if (w->P) cudaFree(w->P);
-    w->planes = nullptr; w->exps = nullptr; w->x8 = nullptr; w->P = nullptr;
+    for (int t = 0; t < 2; ++t) {
+        if (w->P[t]) cudaFree(w->P[t]);
+        w->P[t] = nullptr;
+    }
+    for (int t = 0; t < 2; ++t) {
+        if (w->ev_gemm[t]) cudaEventDestroy(w->ev_gemm[t]);
+        if (w->ev_pfree[t]) cudaEventDestroy(w->ev_pfree[t]);
+        w->ev_gemm[t] = w->ev_pfree[t] = nullptr;
+    }
+    w->planes = nullptr; w->exps = nullptr; w->x8 = nullptr;
     w->planes_valid = false; w->cap_snps = 0; w->sub = 0;
 }
 inline void rot_invalidate(RotWorkspace* w) { w->planes_valid = false; }
@@ -91,14 +101,21 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         PG_ROT_CK(cudaMemsetAsync(w->x8, 0, (size_t)cap * ldk, stream));
         w->cap_snps = cap;
     }
-    // int32 partial products: 8*npad x sub; keep the buffer near 1 GiB
+    // int32 partial products: kSlices*npad x sub, two buffers of about 1 GiB: the recombination of one sub-block
+    // (HBM-bound, combine stream) overlaps the tensor-core GEMM of the next
     long long sub = (long long)((size_t(1) << 30) / ((size_t)kSlices * npad * 4));
-    sub = std::max<long long>(64, std::min<long long>((sub / 64) * 64, cap));
+    sub = std::max<long long>(256, std::min<long long>((sub / 256) * 256, (cap + 255) / 256 * 256));
     if (sub > w->sub) {
-        if (w->P) cudaFree(w->P);
-        w->P = nullptr;
-        PG_ROT_CK(cudaMalloc(&w->P, (size_t)kSlices * npad * sub * sizeof(int32_t)));
+        for (int t = 0; t < 2; ++t) {
+            if (w->P[t]) cudaFree(w->P[t]);
+            w->P[t] = nullptr;
+            PG_ROT_CK(cudaMalloc(&w->P[t], (size_t)kSlices * npad * sub * sizeof(int32_t)));
+        }
         w->sub = sub;
+    }
+    for (int t = 0; t < 2; ++t) {
+        if (!w->ev_gemm[t]) PG_ROT_CK(cudaEventCreateWithFlags(&w->ev_gemm[t], cudaEventDisableTiming));
+        if (!w->ev_pfree[t]) PG_ROT_CK(cudaEventCreateWithFlags(&w->ev_pfree[t], cudaEventDisableTiming));
     }
     if (!w->planes_valid) {
         cudaEvent_t e0, e1;
@@ -116,10 +133,12 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
 }
 
 // Rotates one block.  xf: staging buffer (mb x n fp64), xr: output (mb x n fp64, SNP-major).
-inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, int rotation, const double* U, int u_op_t,
-                   int n, const void* src, int xdtype, long long ld, int layout, long long mb, long long blk, double* xf,
-                   double* xr, long long ldx, int* used_i8, int* n_launch, cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin,
-                   cudaEvent_t ev_rot_end)
+// `stream` carries staging and the GEMMs, `cmb` the int8 recombination kernels; the block's rotated vectors are
+// complete when `ev_rot_end` (recorded on the stream that wrote them last) has fired.
+inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cudaStream_t cmb, int rotation,
+                   const double* U, int u_op_t, int n, const void* src, int xdtype, long long ld, int layout, long long mb,
+                   long long blk, double* xf, double* xr, long long ldx, int* used_i8, int* n_launch,
+                   cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin, cudaEvent_t ev_rot_end)
 {
     const bool i8 = (xdtype == PG_X_I8) && (rotation == PG_ROT_AUTO || rotation == PG_ROT_I8SPLIT);
     if (rotation == PG_ROT_I8SPLIT && xdtype != PG_X_I8) {
@@ -156,16 +175,21 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, in
     for (long long g0 = 0; g0 < mb; g0 += w->sub) {
         const long long cnt = std::min(w->sub, mb - g0);
         const long long cnt_pad = (cnt + 15) / 16 * 16;  // x8 rows beyond mb are zero / stale: ignored downstream
+        const int t = (int)(w->pcount++ & 1);
+        PG_ROT_CK(cudaStreamWaitEvent(stream, w->ev_pfree[t], 0));  // the recombination that last read P[t] is done
         cublasStatus_t s = cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_N, M, (int)cnt_pad, w->ldk, &ione, w->planes,
-                                        CUDA_R_8I, w->ldk, w->x8 + (size_t)g0 * w->ldk, CUDA_R_8I, w->ldk, &izero, w->P,
+                                        CUDA_R_8I, w->ldk, w->x8 + (size_t)g0 * w->ldk, CUDA_R_8I, w->ldk, &izero, w->P[t],
                                         CUDA_R_32I, M, CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
         if (s != CUBLAS_STATUS_SUCCESS) { w->err = "cublasGemmEx(int8) failed, status " + std::to_string((int)s); return PG_ERR_CUBLAS; }
+        PG_ROT_CK(cudaEventRecord(w->ev_gemm[t], stream));
+        PG_ROT_CK(cudaStreamWaitEvent(cmb, w->ev_gemm[t], 0));
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)cnt);
-        combine_i8_kernel<<<grid, 256, 0, stream>>>(w->P, w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx);
+        combine_i8_kernel<<<grid, 256, 0, cmb>>>(w->P[t], w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx);
         PG_ROT_CK(cudaGetLastError());
+        PG_ROT_CK(cudaEventRecord(w->ev_pfree[t], cmb));
         (*n_launch)++;
     }
-    cudaEventRecord(ev_rot_end, stream);
+    cudaEventRecord(ev_rot_end, cmb);
     return 0;
 }
 
