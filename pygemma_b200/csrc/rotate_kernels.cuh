@@ -13,6 +13,7 @@
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/pygemma_b200.h"
@@ -103,7 +104,8 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
     }
     // int32 partial products: kSlices*npad x sub, two buffers of about 1 GiB: the recombination of one sub-block
     // (HBM-bound, combine stream) overlaps the tensor-core GEMM of the next
-    long long sub = (long long)((size_t(1) << 30) / ((size_t)kSlices * npad * 4));
+    static const double p_gib = getenv("PG_P_GIB") ? atof(getenv("PG_P_GIB")) : 1.0;
+    long long sub = (long long)((size_t)(p_gib * (double)(size_t(1) << 30)) / ((size_t)kSlices * npad * 4));
     sub = std::max<long long>(256, std::min<long long>((sub / 256) * 256, (cap + 255) / 256 * 256));
     if (sub > w->sub) {
         for (int t = 0; t < 2; ++t) {
@@ -162,7 +164,13 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     }
     int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
     if (rc) return rc;
-    {
+    // A sample-major int8 block is handed to the GEMM as a transposed (MN-major) operand: no staging kernel, no x8 copy,
+    // and the cuBLAS kernel picked for this layout is ~17 % faster here (10.7 vs 12.8 ms per 25 088 SNPs at n = 10 000).
+    // PG_GEMM_TT=0 forces the staged K-major path (also used for SNP-major input, ragged tails and n % 16 != 0).
+    static const bool gemm_tt = !(getenv("PG_GEMM_TT") && atoi(getenv("PG_GEMM_TT")) == 0);
+    const bool direct = gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
+                        (w->ldk == n) && (mb % 16 == 0);
+    if (!direct) {
         dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
         stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
         PG_ROT_CK(cudaGetLastError());
@@ -177,9 +185,16 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         const long long cnt_pad = (cnt + 15) / 16 * 16;  // x8 rows beyond mb are zero / stale: ignored downstream
         const int t = (int)(w->pcount++ & 1);
         PG_ROT_CK(cudaStreamWaitEvent(stream, w->ev_pfree[t], 0));  // the recombination that last read P[t] is done
-        cublasStatus_t s = cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_N, M, (int)cnt_pad, w->ldk, &ione, w->planes,
-                                        CUDA_R_8I, w->ldk, w->x8 + (size_t)g0 * w->ldk, CUDA_R_8I, w->ldk, &izero, w->P[t],
-                                        CUDA_R_32I, M, CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
+        cublasStatus_t s;
+        if (direct)
+            // B = X block as an (cnt x n) column-major matrix with leading dimension ld (sample-major storage), transposed
+            s = cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_T, M, (int)cnt, w->ldk, &ione, w->planes, CUDA_R_8I, w->ldk,
+                             (const int8_t*)src + g0, CUDA_R_8I, (int)ld, &izero, w->P[t], CUDA_R_32I, M, CUBLAS_COMPUTE_32I,
+                             CUBLAS_GEMM_DEFAULT);
+        else
+            s = cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_N, M, (int)cnt_pad, w->ldk, &ione, w->planes,
+                             CUDA_R_8I, w->ldk, w->x8 + (size_t)g0 * w->ldk, CUDA_R_8I, w->ldk, &izero, w->P[t],
+                             CUDA_R_32I, M, CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
         if (s != CUBLAS_STATUS_SUCCESS) { w->err = "cublasGemmEx(int8) failed, status " + std::to_string((int)s); return PG_ERR_CUBLAS; }
         PG_ROT_CK(cudaEventRecord(w->ev_gemm[t], stream));
         PG_ROT_CK(cudaStreamWaitEvent(cmb, w->ev_gemm[t], 0));
