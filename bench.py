@@ -197,7 +197,22 @@ def load_peaks():
     else:
         peaks.update({"fp64_fma_tflops": 34.0, "fp64_dmma_tflops": 37.0, "dgemm_tflops": 36.0, "int8_gemm_tops": 3600.0})
         peaks["source_fp64"] = "fallback"
+    # the rotation hands B over transposed: use the better of the two measured cuBLAS int8 rates as the denominator
+    peaks["int8_gemm_tops"] = max(peaks.get("int8_gemm_tops", 0.0), peaks.get("int8_gemm_tt_tops", 0.0))
     return peaks
+
+
+def ncu_traffic(kernel_substr: str):
+    """DRAM bytes per SNP of a kernel from the committed `ncu --set full` capture (profiles/ncu_r01_hot_kernels_8192snps.json:
+    tools/prof_rot.py 10000 8192 10; the first launch of each kernel covers 3584 SNPs, compress / solve 8192)."""
+    p = os.path.join(ROOT, "profiles", "ncu_r01_hot_kernels_8192snps.json")
+    if not os.path.exists(p):
+        return None
+    snps = {"cutlass": 3584, "combine_i8": 3584, "compress_dmma": 8192, "reml_solve": 8192}
+    for e in json.load(open(p)):
+        if kernel_substr in e["kernel"] and "dram_traffic_bytes" in e:
+            return e["dram_traffic_bytes"] / snps[kernel_substr]
+    return None
 
 
 def make_gpu_problem(torch, dev, n, m, c0, seed, rank):
@@ -337,8 +352,8 @@ def run_ours(args):
     stages = {
         "rotation": {"ms": rot_ms, "achieved": rot_ops * m / (rot_ms * 1e-3) / 1e12,
                      "peak": peaks["int8_gemm_tops"] if i8 else peaks["fp64_dmma_tflops"],
-                     "kernel": ("rotation U^T X, exact int8-split (7 base-256 digit planes): cuBLAS int8 GEMM on the int8 "
-                                "tensor pipe + stage_i8_kernel + combine_i8_kernel") if i8 else
+                     "kernel": ("rotation U^T X, exact int8-split (7 base-256 digit planes): cuBLAS int8 GEMM (cutlass3x sm100 "
+                                "tcgen05 2-SM kernel) + combine_i8_kernel") if i8 else
                                "rotation U^T X (cuBLAS DGEMM, FP64 tensor pipe)",
                      "peak_source": ("int8 tensor rate (cuBLAS int8 GEMM 16384x8192x8192) " if i8 else "FP64 DMMA rate ")
                                     + peaks["source_fp64"],
@@ -361,6 +376,19 @@ def run_ours(args):
                 "peak_source": st["peak_source"], "algorithmic_ops_per_snp": st["algorithmic_ops_per_snp"],
                 "ops": "int8 multiply-add ops counted 2 per MAC" if (dom == "rotation" and i8) else "fp64 flops",
                 "share_of_step": st["ms"] / step_ms}
+    # DRAM traffic of the dominant stage per launch (= per SNP block), from the committed ncu capture
+    per_snp = None
+    if dom == "rotation" and i8:
+        a_, b_ = ncu_traffic("cutlass"), ncu_traffic("combine_i8")
+        per_snp = (a_ + b_) if (a_ and b_) else None
+    elif dom == "compress":
+        per_snp = ncu_traffic("compress_dmma")
+    elif dom == "solve":
+        per_snp = ncu_traffic("reml_solve")
+    roofline["traffic"] = per_snp * res_tm["block_snps"] if per_snp else None
+    roofline["traffic_note"] = ("dram__bytes_read+write of the stage's kernels per SNP block (ncu --set full, n=10000, "
+                                "profiles/ncu_r01_hot_kernels_8192snps.json); algorithmic HBM bytes per SNP for the rotation "
+                                "stage: 10 KB int8 in + 280 KB int32 partial products out and back + 80 KB fp64 out")
     roofline["per_kernel_ms_last_step"] = {"convert": conv_ms, "rotate": rot_ms, "compress": cmp_ms, "solve": solve_ms}
     roofline["rotate_tflops_fp64_equiv"] = 2.0 * n * n * m / (rot_ms * 1e-3) / 1e12
     roofline["compress_frac_of_dmma_peak"] = stages["compress"]["achieved"] / stages["compress"]["peak"]

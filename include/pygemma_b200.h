@@ -59,7 +59,8 @@ typedef enum {
 typedef enum {
     PG_ROT_AUTO = 0,  /* integer dosages -> exact int8-split tensor-core path when available, else FP64 */
     PG_ROT_FP64 = 1,  /* FP64 GEMM */
-    PG_ROT_I8SPLIT = 2
+    PG_ROT_I8SPLIT = 2, /* exact int8 split: cuBLAS int8 GEMM + recombination kernel */
+    PG_ROT_I8TC = 3     /* exact int8 split as one hand-written TMA + tcgen05 kernel with the recombination fused in */
 } pg_rotation;
 
 /* REML stage engine (stage 2 of pg_scan) */

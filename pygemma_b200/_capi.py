@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libpygemma_b200.so")
 
 PG_X_I8, PG_X_F32, PG_X_F64 = 0, 1, 2
 PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1
-PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT = 0, 1, 2
+PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT, PG_ROT_I8TC = 0, 1, 2, 3
 PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
 
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)

@@ -570,7 +570,7 @@ extern "C" int pg_set_stream(pg_handle* h, void* stream)
 extern "C" int pg_set_options(pg_handle* h, int rotation, int64_t block_snps)
 {
     if (!h) return PG_ERR_ARG;
-    if (rotation < PG_ROT_AUTO || rotation > PG_ROT_I8SPLIT) return fail(h, PG_ERR_ARG, "pg_set_options: rotation %d", rotation);
+    if (rotation < PG_ROT_AUTO || rotation > PG_ROT_I8TC) return fail(h, PG_ERR_ARG, "pg_set_options: rotation %d", rotation);
     if (block_snps < 0) return fail(h, PG_ERR_ARG, "pg_set_options: block_snps %lld", (long long)block_snps);
     h->rotation = rotation;
     h->block_snps_opt = block_snps;
@@ -865,8 +865,8 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                                  ld_dev, layout, mb, blk, h->xf, xr_block, h->ldx, &used_i8, &n_rot_launch, ev_conv[b].b,
                                  ev_rot[b].a, ev_rot[b].b);
                 if (r2 != 0) return fail(h, r2, "rotation failed: %s", rot_error(&h->rot));
-                last_engine = used_i8 ? PG_ROT_I8SPLIT : PG_ROT_FP64;
-                CK(cudaEventRecord(h->ev_xr_ready[s], used_i8 ? st_cmb : h->compute));
+                last_engine = used_i8 ? (h->rotation == PG_ROT_I8TC ? PG_ROT_I8TC : PG_ROT_I8SPLIT) : PG_ROT_FP64;
+                CK(cudaEventRecord(h->ev_xr_ready[s], (used_i8 && h->rotation != PG_ROT_I8TC) ? st_cmb : h->compute));
             } else {
                 int r2 = launch_stage(h, src_dev, xdtype, ld_dev, layout, mb, xr_block);
                 if (r2) return r2;

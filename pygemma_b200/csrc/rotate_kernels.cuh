@@ -19,6 +19,7 @@
 #include "../../include/pygemma_b200.h"
 #include "reml_kernels.cuh"
 #include "rotate_i8.cuh"
+#include "rotate_i8_tc.cuh"
 
 namespace pg {
 
@@ -34,6 +35,7 @@ struct RotWorkspace {
     int32_t* P[2] = {nullptr, nullptr};  // [(kSlices*npad) x sub] column-major, double-buffered
     cudaEvent_t ev_gemm[2] = {nullptr, nullptr}, ev_pfree[2] = {nullptr, nullptr};
     unsigned pcount = 0;
+    double* scale = nullptr;   // [n] 2^(e_i - 24) for the fused tcgen05 engine
     long long sub = 0;
     float slice_ms = 0.f;
 };
@@ -42,6 +44,8 @@ inline void rot_free(RotWorkspace* w)
 {
     if (w->planes) cudaFree(w->planes);
     if (w->exps) cudaFree(w->exps);
+    if (w->scale) cudaFree(w->scale);
+    w->scale = nullptr;
     if (w->x8) cudaFree(w->x8);
     for (int t = 0; t < 2; ++t) {
         if (w->P[t]) cudaFree(w->P[t]);
@@ -93,6 +97,7 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         w->n = n; w->npad = npad; w->ldk = ldk;
         PG_ROT_CK(cudaMalloc(&w->planes, (size_t)kSlices * npad * ldk));
         PG_ROT_CK(cudaMalloc(&w->exps, sizeof(int) * n));
+        PG_ROT_CK(cudaMalloc(&w->scale, sizeof(double) * n));
     }
     const long long cap = (blk + 63) / 64 * 64;
     if (cap > w->cap_snps) {
@@ -125,6 +130,8 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         cudaEventRecord(e0, stream);
         slice_u_kernel<<<npad, 256, 0, stream>>>(U, u_op_t ? 1 : 0, n, npad, ldk, w->planes, w->exps);
         PG_ROT_CK(cudaGetLastError());
+        tc::plane_scale_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w->exps, n, w->scale);
+        PG_ROT_CK(cudaGetLastError());
         cudaEventRecord(e1, stream);
         PG_ROT_CK(cudaStreamSynchronize(stream));
         cudaEventElapsedTime(&w->slice_ms, e0, e1);
@@ -142,9 +149,9 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
                    long long blk, double* xf, double* xr, long long ldx, int* used_i8, int* n_launch,
                    cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin, cudaEvent_t ev_rot_end)
 {
-    const bool i8 = (xdtype == PG_X_I8) && (rotation == PG_ROT_AUTO || rotation == PG_ROT_I8SPLIT);
-    if (rotation == PG_ROT_I8SPLIT && xdtype != PG_X_I8) {
-        w->err = "PG_ROT_I8SPLIT needs int8 genotypes";
+    const bool i8 = (xdtype == PG_X_I8) && (rotation == PG_ROT_AUTO || rotation == PG_ROT_I8SPLIT || rotation == PG_ROT_I8TC);
+    if ((rotation == PG_ROT_I8SPLIT || rotation == PG_ROT_I8TC) && xdtype != PG_X_I8) {
+        w->err = "PG_ROT_I8SPLIT / PG_ROT_I8TC need int8 genotypes";
         return PG_ERR_ARG;
     }
     *used_i8 = i8 ? 1 : 0;
@@ -168,7 +175,8 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     // and the cuBLAS kernel picked for this layout is ~17 % faster here (10.7 vs 12.8 ms per 25 088 SNPs at n = 10 000).
     // PG_GEMM_TT=0 forces the staged K-major path (also used for SNP-major input, ragged tails and n % 16 != 0).
     static const bool gemm_tt = !(getenv("PG_GEMM_TT") && atoi(getenv("PG_GEMM_TT")) == 0);
-    const bool direct = gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
+    const bool fused_tc = (rotation == PG_ROT_I8TC);
+    const bool direct = !fused_tc && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
                         (w->ldk == n) && (mb % 16 == 0);
     if (!direct) {
         dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
@@ -178,6 +186,17 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     }
     cudaEventRecord(ev_conv_end, stream);
     cudaEventRecord(ev_rot_begin, stream);
+    if (fused_tc) {
+        // one kernel: TMA -> tcgen05.mma kind::i8 (7 planes in TMEM) -> exact recombination in the epilogue
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int r = tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx);
+        if (r) { w->err = "fused tcgen05 rotation launch failed, code " + std::to_string(r); return PG_ERR_CUDA; }
+        (*n_launch)++;
+        cudaEventRecord(ev_rot_end, stream);
+        return 0;
+    }
     const int32_t ione = 1, izero = 0;
     const int M = kSlices * w->npad;
     for (long long g0 = 0; g0 < mb; g0 += w->sub) {

@@ -317,3 +317,49 @@ def test_unsorted_and_degenerate_spectra():
             for c in COLS:
                 assert np.array_equal(o[c], o2[c], equal_nan=True), c
         assert o["timing"]["n_nodes"] <= n
+
+
+def test_transposed_gemm_operand_is_bit_identical_to_staged():
+    """The int8 rotation feeds the sample-major block to the GEMM as a transposed operand (default) or stages it
+    SNP-major first (PG_GEMM_TT=0): integer partial products, hence every output bit, must be identical."""
+    import subprocess
+    import sys
+    import tempfile
+
+    code = ("import numpy as np, sys; sys.path.insert(0, '.');"
+            "from pygemma_b200 import _capi; from pygemma_b200.synth import make_problem;"
+            "p = make_problem(640, 352, 3, seed=12, m_k=1500);"
+            "h = _capi.Handle(640, 3); h.set_kinship(p['K']); h.set_design(p['W'], p['Y']); h.set_options(block_snps=128);"
+            "o = h.scan(p['X']); np.save(sys.argv[1], np.stack([o[c] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]))")
+    outs = []
+    for tt in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            env = dict(os.environ, PG_GEMM_TT=tt)
+            subprocess.check_call([sys.executable, "-c", code, f.name], env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+            outs.append(np.load(f.name))
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+
+
+def test_fused_tcgen05_rotation_is_bit_identical_to_cublas_split():
+    """PG_ROT_I8TC (TMA + tcgen05.mma kind::i8, seven planes in TMEM, recombination in the epilogue) against
+    PG_ROT_I8SPLIT (cuBLAS int8 GEMM + combine kernel): exact integer partial products and the same single rounding,
+    so rotated vectors and every scan output must agree bit for bit -- ragged SNP / eigenvector / sample counts included."""
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    for (n, m, blk) in ((777, 300, 0), (1024, 640, 256), (333, 129, 0)):
+        p = make_problem(n, m, 3, seed=n, m_k=2 * n)
+        res = {}
+        with capi.Handle(n, 3) as h:
+            h.set_kinship(p["K"])
+            h.set_design(p["W"], p["Y"])
+            for eng in (capi.PG_ROT_I8SPLIT, capi.PG_ROT_I8TC):
+                h.set_options(rotation=eng, block_snps=blk)
+                o = h.scan(p["X"])
+                assert o["timing"]["rot_engine"] == eng
+                xr, _ = h.probe_rotated(min(m, 128))
+                res[eng] = (o, xr)
+        (oa, xa), (ob, xb) = res[capi.PG_ROT_I8SPLIT], res[capi.PG_ROT_I8TC]
+        assert np.array_equal(xa, xb), (n, m)
+        for c in COLS:
+            assert np.array_equal(oa[c], ob[c], equal_nan=True), (n, m, c)
