@@ -695,7 +695,8 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = h->counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
-        int warps = 8;
+        static const int warps_opt = getenv("PG_SOLVE_WARPS") ? atoi(getenv("PG_SOLVE_WARPS")) : 8;
+        int warps = std::max(1, std::min(8, warps_opt));
         while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
         const size_t smem = per_warp * warps;
         const bool two = (h->c0 + 2) > 32;
@@ -714,6 +715,9 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         else if (minb == 4) lr = launch(reml_solve_kernel<1, 4>, 4);
         else lr = launch(reml_solve_kernel<1, 2>, 2);
         if (lr) return lr;
+        CK(cudaGetLastError());
+        // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
+        pvalue_kernel<<<(unsigned)((mb + 255) / 256), 256, 0, st>>>(out[4], out[5], row0, mb, (double)(h->n - h->c0 - 1));
         CK(cudaGetLastError());
         return PG_OK;
     }
@@ -932,7 +936,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->rot_engine = last_engine;
         timing->reml_engine = compressed ? PG_REML_COMPRESSED : h->engine;
         timing->n_nodes = compressed ? h->plan.Kc : h->n;
-        if (compressed) timing->reml_launches = (int32_t)(nblocks * (1 + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)));
+        if (compressed) timing->reml_launches = (int32_t)(nblocks * (2 + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)));
     }
     if (rc != PG_OK) {
         cudaStreamSynchronize(h->compute);

@@ -304,8 +304,11 @@ struct SnpSolver {
     }
     PG_HD void request(double lam, int full, int ll) { rq_fixed = -1; rq_lambda = lam; rq_full = full; rq_ll = ll; }
 
-    PG_HD void init(int n_, int c0_, int grid_)
+    // defer_p != 0: finish() leaves p = NaN; the caller evaluates f_sf_1(F, n - c0 - 1) itself (the GPU scan does it one
+    // thread per SNP in a follow-up kernel instead of 32 lanes in lock step)
+    PG_HD void init(int n_, int c0_, int grid_, int defer_p_ = 0)
     {
+        defer_p = defer_p_;
         n = n_; c0 = c0_; cf = c0_ + 1; grid = grid_;
         idx = 0; status = 0; n_eval2 = 0; n_eval3 = 0;
         best_lambda = 0; best_ll = 0; best_xPx = best_yPx = best_yPy = 0;
@@ -334,7 +337,7 @@ struct SnpSolver {
         tau = (double)df / best_yPy;
         const double z = beta / se;
         F = z * z;
-        p = f_sf_1(F, (double)df);
+        p = defer_p ? NAN : f_sf_1(F, (double)df);
         if (status != 0) { lambda = beta = se = tau = F = p = NAN; }
     }
 
@@ -453,6 +456,7 @@ struct SnpSolver {
         }
     }
 
+    int defer_p;
     // grid-mode bookkeeping (lower boundary and running interior argmax)
     double grid_ll0, grid_in_ll, grid_in_lam;
     double grid_w0[3], grid_in_w[3];

@@ -102,6 +102,7 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = 0.0;
     const double* __restrict__ z = Zs + (size_t)jb * Kcp;
+#pragma unroll 2
     for (int k = lane; k < Kcp; k += 32) {
         const double h = rcp_ge1(fma(lam, __ldg(a.nodes + k), 1.0));
         const double h2 = h * h, h3 = h2 * h;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         if (g >= (unsigned long long)a.m) break;
         const double* __restrict__ Zs = a.Z + (size_t)g * k1p * a.Kcp;
         SnpSolver s;
-        s.init(a.n, a.c0, a.grid);
+        s.init(a.n, a.c0, a.grid, /*defer_p=*/1);
         while (s.pending()) {
             EvalOut e;
             eval_snp_compressed<NS>(a, Zs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
@@ -279,6 +280,14 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
             if (a.n_eval3) a.n_eval3[row] = s.n_eval3;
         }
     }
+}
+
+// p_wald = F(1, n - c0 - 1) survival function of F_wald (scipy.stats.f.sf, reference lmm/lmm.py:482), one thread per SNP:
+// reml_solve_kernel leaves p = NaN (SnpSolver defer_p) so that the continued fraction is not run 32 lanes wide
+__global__ void pvalue_kernel(const double* __restrict__ F, double* __restrict__ p, long long row0, long long m, double nu)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) p[row0 + i] = f_sf_1(F[row0 + i], nu);
 }
 
 // table-2 rows: one thread eliminates the covariate levels of one table lambda (pg_eval.cuh: eliminate_w0y_row)

@@ -32,8 +32,11 @@ namespace tc {
 constexpr int kTileSnps = 256;                 // two M = 128 accumulators
 constexpr int kTileEig = 32;                   // eigenvectors per tile
 constexpr int kTileN = kSlices * kTileEig;     // 224 accumulator columns
-constexpr int kStageK = 128;                   // samples (bytes) per shared-memory stage = one swizzle atom
-constexpr int kStages = 3;
+#ifndef PG_TC_STAGE_K
+#define PG_TC_STAGE_K 128
+#endif
+constexpr int kStageK = PG_TC_STAGE_K;         // samples (bytes) per shared-memory stage = one swizzle atom (64 or 128)
+constexpr int kStages = (kStageK == 128) ? 3 : 7;   // 180 / 210 KB of operands in flight
 constexpr int kABytes = 128 * kStageK;         // one 128-row A tile
 constexpr int kBBytes = kTileN * kStageK;
 constexpr int kStageBytes = 2 * kABytes + kBBytes;   // 61 440
@@ -91,15 +94,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-// K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), version 1 (Blackwell), layout type 2 (SWIZZLE_128B)
+// K-major, swizzle atom = one stage row (128 or 64 B): 8-row groups 8*kStageK B apart (SBO), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major), 16 B units
-    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
+    d |= (uint64_t)((8 * kStageK) >> 4) << 32;   // stride byte offset: 8 rows of one swizzle atom
     d |= (uint64_t)1 << 46;                  // descriptor version
-    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    d |= (uint64_t)(kStageK == 128 ? 2 : 4) << 61;   // SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 
@@ -314,7 +317,7 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
         cuuint32_t box[2] = {(cuuint32_t)kStageK, 128};
         cuuint32_t es[2] = {1, 1};
         if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)x8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                (kStageK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return -2;
     }
     {
@@ -323,7 +326,7 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
         cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)kTileEig, (cuuint32_t)kSlices};
         cuuint32_t es[3] = {1, 1, 1};
         if (enc(&mp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                (kStageK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return -3;
     }
     Args a;
