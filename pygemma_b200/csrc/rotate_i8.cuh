@@ -112,4 +112,121 @@ __global__ void __launch_bounds__(256) combine_i8_kernel(const int32_t* __restri
     xr[(size_t)g * ldx + i] = ldexp(v, exps[i] - 24);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Level coding of float genotypes.  Callers of the reference usually hand over dosages as floats, raw
+// (0.0 / 1.0 / 2.0) or standardised per SNP ((g - mean) / std, experiments/wtccc/run_pygemma.py:432): every column
+// then takes at most three distinct, equally spaced values  x = v0 + s * g,  g in {0, 1, 2}.  The rotation is linear,
+//     U^T x = v0 * (U^T 1) + s * (U^T g),
+// so such columns go through the exact int8-split tensor-core path on the codes g and an affine fix-up in the
+// recombination, instead of the 8x slower FP64 GEMM.  "Equally spaced" is tested to double rounding
+// (|v2 - 2 v1 + v0| <= 2^-50 max|v|): standardising in float64 produces exactly this much deviation; columns
+// standardised in float32 deviate by ~1e-7 and are not treated as affine.  Any column with NaN/Inf, more than
+// three levels or unequal spacing sends the whole block down the FP64 path.
+// ------------------------------------------------------------------------------------------------
+struct LevelInfo {
+    double v0, s;   // x = v0 + s * code
+    int nlev;       // 1..3: codeable; 0: not codeable
+    int pad;
+};
+
+// one thread per SNP column; element (j, g) at src[j*ld + g] (layout 0, sample-major) or src[g*ld + j] (layout 1)
+template <typename T>
+__global__ void find_levels_kernel(const T* __restrict__ src, long long ld, int layout, int n, long long mb, double tol,
+                                   LevelInfo* __restrict__ info, int* __restrict__ n_bad)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= mb) return;
+    double v[3] = {0.0, 0.0, 0.0};
+    int k = 0;
+    bool ok = true;
+    const size_t step = layout == 0 ? (size_t)ld : 1, base = layout == 0 ? (size_t)g : (size_t)g * ld;
+    for (int j = 0; j < n && ok; ++j) {
+        const double x = (double)src[base + (size_t)j * step];
+        if (!isfinite(x)) { ok = false; break; }
+        if ((k > 0 && x == v[0]) || (k > 1 && x == v[1]) || (k > 2 && x == v[2])) continue;
+        if (k == 3) { ok = false; break; }
+        v[k++] = x;
+    }
+    LevelInfo li;
+    li.v0 = 0.0; li.s = 0.0; li.nlev = 0; li.pad = 0;
+    if (ok) {
+        // sort the (at most three) levels ascending
+        if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
+        if (k > 2 && v[2] < v[1]) { const double t = v[1]; v[1] = v[2]; v[2] = t; }
+        if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
+        li.v0 = v[0];
+        li.nlev = k;
+        if (k >= 2) li.s = v[1] - v[0];
+        if (k == 3) {
+            const double mx = fmax(fabs(v[0]), fabs(v[2]));
+            if (fabs((v[2] - v[1]) - (v[1] - v[0])) > tol * mx) {
+                // two levels plus an outlier (e.g. a column without heterozygotes coded 0 / 2): still affine in a code
+                // if the middle value sits on the half grid -- not attempted; fall back
+                li.nlev = 0;
+            }
+        }
+    }
+    if (li.nlev == 0) atomicAdd(n_bad, 1);
+    info[g] = li;
+}
+
+// codes in the layout of the input: sample-major (n x mb, ld = mb) or SNP-major (mb x n, ld = n)
+template <typename T>
+__global__ void encode_levels_kernel(const T* __restrict__ src, long long ld, int layout, int n, long long mb,
+                                     const LevelInfo* __restrict__ info, int8_t* __restrict__ codes)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j0 = blockIdx.y * 64;
+    if (g >= mb) return;
+    const LevelInfo li = info[g];
+    const double inv = li.s != 0.0 ? 1.0 / li.s : 0.0;
+    for (int j = j0; j < min(n, j0 + 64); ++j) {
+        const size_t si = layout == 0 ? (size_t)j * ld + g : (size_t)g * ld + j;
+        const size_t di = layout == 0 ? (size_t)j * mb + g : (size_t)g * n + j;
+        codes[di] = (int8_t)__double2int_rn(((double)src[si] - li.v0) * inv);
+    }
+}
+
+// recombination with the affine fix-up: xr[g][i] = v0_g * u1_i + s_g * (U^T code_g)_i
+__global__ void __launch_bounds__(256) combine_i8_affine_kernel(const int32_t* __restrict__ P, const int* __restrict__ exps,
+                                                                 int n, int npad, long long mb, double* __restrict__ xr,
+                                                                 long long ldx, const LevelInfo* __restrict__ info,
+                                                                 const double* __restrict__ u1)
+{
+    const long long g = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || g >= mb) return;
+    const int32_t* p = P + (size_t)g * kSlices * npad + i;
+    long long hi = 0, lo = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[(size_t)t * npad];
+#pragma unroll
+    for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[(size_t)t * npad];
+    const double r = ldexp((double)hi + ldexp((double)lo, -32), exps[i] - 24);
+    const LevelInfo li = info[g];
+    xr[(size_t)g * ldx + i] = fma(li.s, r, li.v0 * u1[i]);
+}
+
+// u1 = U^T 1: column sums of U (eigenvector i at U + i*n when cols_contig, else strided)
+__global__ void __launch_bounds__(256) column_sums_kernel(const double* __restrict__ U, int cols_contig, int n,
+                                                           double* __restrict__ u1)
+{
+    const int i = blockIdx.x;
+    __shared__ double red[8];
+    const size_t stride = cols_contig ? 1 : (size_t)n;
+    const double* u = cols_contig ? U + (size_t)i * n : U + i;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) s += u[(size_t)j * stride];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        u1[i] = t;
+    }
+}
+
 }  // namespace pg

@@ -36,6 +36,13 @@ struct RotWorkspace {
     cudaEvent_t ev_gemm[2] = {nullptr, nullptr}, ev_pfree[2] = {nullptr, nullptr};
     unsigned pcount = 0;
     double* scale = nullptr;   // [n] 2^(e_i - 24) for the fused tcgen05 engine
+    // level coding of float genotypes (rotate_i8.cuh)
+    double* u1 = nullptr;      // [n] U^T 1
+    LevelInfo* info = nullptr; // [cap_snps]
+    int8_t* codes = nullptr;   // [cap_snps * n] codes in the layout of the input block
+    int* n_bad = nullptr;      // device counter
+    long long code_cap = 0;
+    long long blocks_coded = 0, blocks_dense = 0;
     long long sub = 0;
     float slice_ms = 0.f;
 };
@@ -46,6 +53,11 @@ inline void rot_free(RotWorkspace* w)
     if (w->exps) cudaFree(w->exps);
     if (w->scale) cudaFree(w->scale);
     w->scale = nullptr;
+    if (w->u1) cudaFree(w->u1);
+    if (w->info) cudaFree(w->info);
+    if (w->codes) cudaFree(w->codes);
+    if (w->n_bad) cudaFree(w->n_bad);
+    w->u1 = nullptr; w->info = nullptr; w->codes = nullptr; w->n_bad = nullptr; w->code_cap = 0;
     if (w->x8) cudaFree(w->x8);
     for (int t = 0; t < 2; ++t) {
         if (w->P[t]) cudaFree(w->P[t]);
@@ -98,6 +110,8 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         PG_ROT_CK(cudaMalloc(&w->planes, (size_t)kSlices * npad * ldk));
         PG_ROT_CK(cudaMalloc(&w->exps, sizeof(int) * n));
         PG_ROT_CK(cudaMalloc(&w->scale, sizeof(double) * n));
+        PG_ROT_CK(cudaMalloc(&w->u1, sizeof(double) * n));
+        PG_ROT_CK(cudaMalloc(&w->n_bad, sizeof(int)));
     }
     const long long cap = (blk + 63) / 64 * 64;
     if (cap > w->cap_snps) {
@@ -132,6 +146,8 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         PG_ROT_CK(cudaGetLastError());
         tc::plane_scale_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w->exps, n, w->scale);
         PG_ROT_CK(cudaGetLastError());
+        column_sums_kernel<<<n, 256, 0, stream>>>(U, u_op_t ? 1 : 0, n, w->u1);
+        PG_ROT_CK(cudaGetLastError());
         cudaEventRecord(e1, stream);
         PG_ROT_CK(cudaStreamSynchronize(stream));
         cudaEventElapsedTime(&w->slice_ms, e0, e1);
@@ -155,7 +171,54 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         return PG_ERR_ARG;
     }
     *used_i8 = i8 ? 1 : 0;
-    if (!i8) {
+    // float genotypes whose columns are (affine images of) dosage codes go through the int8 path on the codes
+    static const bool level_coding = !(getenv("PG_LEVEL_CODING") && atoi(getenv("PG_LEVEL_CODING")) == 0);
+    const LevelInfo* affine = nullptr;
+    if (!i8 && rotation == PG_ROT_AUTO && level_coding && xdtype != PG_X_I8) {
+        int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
+        if (rc) return rc;
+        const long long cap = (blk + 63) / 64 * 64;
+        if (cap > w->code_cap) {
+            if (w->info) cudaFree(w->info);
+            if (w->codes) cudaFree(w->codes);
+            w->info = nullptr; w->codes = nullptr; w->code_cap = 0;
+            PG_ROT_CK(cudaMalloc(&w->info, sizeof(LevelInfo) * cap));
+            PG_ROT_CK(cudaMalloc(&w->codes, (size_t)cap * n));
+            w->code_cap = cap;
+        }
+        PG_ROT_CK(cudaMemsetAsync(w->n_bad, 0, sizeof(int), stream));
+        const unsigned gb = (unsigned)((mb + 127) / 128);
+        // equal spacing to double rounding: float32-standardised columns deviate by ~1e-7 of |x| and stay on the FP64 path
+        // (their non-affinity moved beta by 1.4e-6 in the parity test; raw float32 dosages 0/1/2 are exactly affine)
+        const double tol = ldexp(1.0, -50);
+        if (xdtype == PG_X_F32)
+            find_levels_kernel<float><<<gb, 128, 0, stream>>>((const float*)src, ld, layout, n, mb, tol, w->info, w->n_bad);
+        else
+            find_levels_kernel<double><<<gb, 128, 0, stream>>>((const double*)src, ld, layout, n, mb, tol, w->info, w->n_bad);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch)++;
+        int bad = 1;
+        PG_ROT_CK(cudaMemcpyAsync(&bad, w->n_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PG_ROT_CK(cudaStreamSynchronize(stream));  // one small sync per block: the path choice is made on the host
+        if (bad == 0) {
+            dim3 ge(gb, (unsigned)((n + 63) / 64));
+            if (xdtype == PG_X_F32)
+                encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)src, ld, layout, n, mb, w->info, w->codes);
+            else
+                encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)src, ld, layout, n, mb, w->info, w->codes);
+            PG_ROT_CK(cudaGetLastError());
+            (*n_launch)++;
+            affine = w->info;
+            src = w->codes;
+            ld = (layout == PG_X_SAMPLE_MAJOR) ? mb : n;
+            xdtype = PG_X_I8;
+            *used_i8 = 1;
+            w->blocks_coded++;
+        } else {
+            w->blocks_dense++;
+        }
+    }
+    if (!i8 && !affine) {
         int rc = stage_to_snp_major(stream, n, src, xdtype, ld, layout, mb, xf, n);
         if (rc) { w->err = "staging kernel launch failed"; return rc; }
         (*n_launch)++;
@@ -175,7 +238,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     // and the cuBLAS kernel picked for this layout is ~17 % faster here (10.7 vs 12.8 ms per 25 088 SNPs at n = 10 000).
     // PG_GEMM_TT=0 forces the staged K-major path (also used for SNP-major input, ragged tails and n % 16 != 0).
     static const bool gemm_tt = !(getenv("PG_GEMM_TT") && atoi(getenv("PG_GEMM_TT")) == 0);
-    const bool fused_tc = (rotation == PG_ROT_I8TC);
+    const bool fused_tc = (rotation == PG_ROT_I8TC) && !affine;
     const bool direct = !fused_tc && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
                         (w->ldk == n) && (mb % 16 == 0);
     if (!direct) {
@@ -218,7 +281,11 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         PG_ROT_CK(cudaEventRecord(w->ev_gemm[t], stream));
         PG_ROT_CK(cudaStreamWaitEvent(cmb, w->ev_gemm[t], 0));
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)cnt);
-        combine_i8_kernel<<<grid, 256, 0, cmb>>>(w->P[t], w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx);
+        if (affine)
+            combine_i8_affine_kernel<<<grid, 256, 0, cmb>>>(w->P[t], w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx,
+                                                            affine + g0, w->u1);
+        else
+            combine_i8_kernel<<<grid, 256, 0, cmb>>>(w->P[t], w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx);
         PG_ROT_CK(cudaGetLastError());
         PG_ROT_CK(cudaEventRecord(w->ev_pfree[t], cmb));
         (*n_launch)++;

@@ -363,3 +363,57 @@ def test_fused_tcgen05_rotation_is_bit_identical_to_cublas_split():
         assert np.array_equal(xa, xb), (n, m)
         for c in COLS:
             assert np.array_equal(oa[c], ob[c], equal_nan=True), (n, m, c)
+
+
+def test_float_dosages_take_the_level_coded_int8_path():
+    """Float genotypes as the reference's callers pass them -- raw 0.0/1.0/2.0 or standardised per SNP
+    (experiments/wtccc/run_pygemma.py:432) -- are affine images of dosage codes: they must take the exact int8
+    tensor-core rotation (rot_engine == I8SPLIT) and still match the oracle run on the very same float values.
+    A block holding one imputed (non-codeable) column falls back to the FP64 GEMM."""
+    from oracle import oracle
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    n, m, c0 = 600, 200, 4
+    p = make_problem(n, m, c0, seed=21, m_k=1500)
+    g = p["X"].astype(np.float64)
+    g[:, 7] = 1.0            # constant column (one level)
+    g[:, 9] = (g[:, 9] > 0)  # two levels
+    sd = g.std(axis=0)
+    sd[sd == 0] = 1.0
+    variants = {
+        "raw_f64": g,
+        "raw_f32": g.astype(np.float32),
+        "std_f64": (g - g.mean(axis=0)) / sd,
+        "std_f32": ((g - g.mean(axis=0)) / sd).astype(np.float32),
+    }
+    with capi.Handle(n, c0) as h:
+        h.set_kinship(p["K"])
+        h.set_design(p["W"], p["Y"])
+        for name, X in variants.items():
+            ref = oracle.pygemma(p["Y"], X.astype(np.float64), p["W"], p["K"])
+            for layout_snp in (False, True):
+                Xin = np.ascontiguousarray(X.T) if layout_snp else np.ascontiguousarray(X)
+                o = h.scan(Xin, layout=capi.PG_X_SNP_MAJOR if layout_snp else capi.PG_X_SAMPLE_MAJOR)
+                # float32-standardised columns are not affine to double rounding: they stay on the exact FP64 path
+                want = capi.PG_ROT_FP64 if name == "std_f32" else capi.PG_ROT_I8SPLIT
+                assert o["timing"]["rot_engine"] == want, name
+                ok = np.ones(m, dtype=bool)
+                ok[7] = False  # constant column: degenerate (x is collinear with the intercept), finite garbage in both
+                _check(o, ref, idx=np.where(ok)[0], tag=(name, layout_snp))
+        # forcing the FP64 GEMM gives the same numbers to rounding
+        h.set_options(rotation=capi.PG_ROT_FP64)
+        o64 = h.scan(np.ascontiguousarray(variants["std_f64"]))
+        assert o64["timing"]["rot_engine"] == capi.PG_ROT_FP64
+        h.set_options(rotation=capi.PG_ROT_AUTO)
+        o8 = h.scan(np.ascontiguousarray(variants["std_f64"]))
+        ok = np.arange(m) != 7
+        for c in COLS:
+            assert rel(o8[c][ok], o64[c][ok]).max() < 1e-8, c
+        # an imputed column (4th level) makes the block dense
+        Xi = variants["std_f64"].copy()
+        Xi[3, 11] = 0.123456
+        oi = h.scan(Xi)
+        assert oi["timing"]["rot_engine"] == capi.PG_ROT_FP64
+        refi = oracle.pygemma(p["Y"], Xi, p["W"], p["K"])
+        _check(oi, refi, idx=np.where(ok)[0], tag="imputed")
