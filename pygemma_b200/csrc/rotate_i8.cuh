@@ -130,28 +130,65 @@ struct LevelInfo {
     int pad;
 };
 
-// one thread per SNP column; element (j, g) at src[j*ld + g] (layout 0, sample-major) or src[g*ld + j] (layout 1)
+struct LevelPartial {
+    double v[3];
+    int k;      // number of distinct values seen in this sample chunk; -1: more than three or a non-finite value
+    int pad;
+};
+
+__device__ __forceinline__ void level_insert(double x, double (&v)[3], int& k)
+{
+    if (k < 0) return;
+    if (!isfinite(x)) { k = -1; return; }
+    if ((k > 0 && x == v[0]) || (k > 1 && x == v[1]) || (k > 2 && x == v[2])) return;
+    if (k == 3) { k = -1; return; }
+    v[k++] = x;
+}
+
+// pass 1: thread (g, chunk) collects the distinct values of SNP column g over one chunk of kLevelChunk samples.
+// Element (j, g) at src[j*ld + g] (layout 0, sample-major: coalesced over g) or src[g*ld + j] (layout 1).
+constexpr int kLevelChunk = 256;
 template <typename T>
-__global__ void find_levels_kernel(const T* __restrict__ src, long long ld, int layout, int n, long long mb, double tol,
-                                   LevelInfo* __restrict__ info, int* __restrict__ n_bad)
+__global__ void __launch_bounds__(128) find_levels_kernel(const T* __restrict__ src, long long ld, int layout, int n,
+                                                           long long mb, LevelPartial* __restrict__ part)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= mb) return;
+    const int j0 = blockIdx.y * kLevelChunk, j1 = min(n, j0 + kLevelChunk);
+    const size_t step = layout == 0 ? (size_t)ld : 1, base = layout == 0 ? (size_t)g : (size_t)g * ld;
+    double v[3] = {0.0, 0.0, 0.0};
+    int k = 0;
+    int j = j0;
+    for (; j + 8 <= j1; j += 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (double)src[base + (size_t)(j + u) * step];  // eight loads in flight
+#pragma unroll
+        for (int u = 0; u < 8; ++u) level_insert(x[u], v, k);
+    }
+    for (; j < j1; ++j) level_insert((double)src[base + (size_t)j * step], v, k);
+    LevelPartial lp;
+    lp.v[0] = v[0]; lp.v[1] = v[1]; lp.v[2] = v[2]; lp.k = k; lp.pad = 0;
+    part[(size_t)blockIdx.y * mb + g] = lp;
+}
+
+// pass 2: merge the chunk results of one SNP, sort the levels, test the spacing
+__global__ void merge_levels_kernel(const LevelPartial* __restrict__ part, int nchunks, long long mb, double tol,
+                                    LevelInfo* __restrict__ info, int* __restrict__ n_bad)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= mb) return;
     double v[3] = {0.0, 0.0, 0.0};
     int k = 0;
-    bool ok = true;
-    const size_t step = layout == 0 ? (size_t)ld : 1, base = layout == 0 ? (size_t)g : (size_t)g * ld;
-    for (int j = 0; j < n && ok; ++j) {
-        const double x = (double)src[base + (size_t)j * step];
-        if (!isfinite(x)) { ok = false; break; }
-        if ((k > 0 && x == v[0]) || (k > 1 && x == v[1]) || (k > 2 && x == v[2])) continue;
-        if (k == 3) { ok = false; break; }
-        v[k++] = x;
+    for (int c = 0; c < nchunks; ++c) {
+        const LevelPartial lp = part[(size_t)c * mb + g];
+        if (lp.k < 0) { k = -1; break; }
+        for (int u = 0; u < lp.k; ++u) level_insert(lp.v[u], v, k);
+        if (k < 0) break;
     }
     LevelInfo li;
     li.v0 = 0.0; li.s = 0.0; li.nlev = 0; li.pad = 0;
-    if (ok) {
-        // sort the (at most three) levels ascending
+    if (k > 0) {
         if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
         if (k > 2 && v[2] < v[1]) { const double t = v[1]; v[1] = v[2]; v[2] = t; }
         if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
@@ -160,11 +197,7 @@ __global__ void find_levels_kernel(const T* __restrict__ src, long long ld, int 
         if (k >= 2) li.s = v[1] - v[0];
         if (k == 3) {
             const double mx = fmax(fabs(v[0]), fabs(v[2]));
-            if (fabs((v[2] - v[1]) - (v[1] - v[0])) > tol * mx) {
-                // two levels plus an outlier (e.g. a column without heterozygotes coded 0 / 2): still affine in a code
-                // if the middle value sits on the half grid -- not attempted; fall back
-                li.nlev = 0;
-            }
+            if (fabs((v[2] - v[1]) - (v[1] - v[0])) > tol * mx) li.nlev = 0;  // unequal spacing: not an affine image of a dosage
         }
     }
     if (li.nlev == 0) atomicAdd(n_bad, 1);
@@ -181,7 +214,17 @@ __global__ void encode_levels_kernel(const T* __restrict__ src, long long ld, in
     if (g >= mb) return;
     const LevelInfo li = info[g];
     const double inv = li.s != 0.0 ? 1.0 / li.s : 0.0;
-    for (int j = j0; j < min(n, j0 + 64); ++j) {
+    const int j1 = min(n, j0 + 64);
+    int j = j0;
+    for (; j + 8 <= j1; j += 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (double)src[layout == 0 ? (size_t)(j + u) * ld + g : (size_t)g * ld + j + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            codes[layout == 0 ? (size_t)(j + u) * mb + g : (size_t)g * n + j + u] = (int8_t)__double2int_rn((x[u] - li.v0) * inv);
+    }
+    for (; j < j1; ++j) {
         const size_t si = layout == 0 ? (size_t)j * ld + g : (size_t)g * ld + j;
         const size_t di = layout == 0 ? (size_t)j * mb + g : (size_t)g * n + j;
         codes[di] = (int8_t)__double2int_rn(((double)src[si] - li.v0) * inv);

@@ -39,6 +39,7 @@ struct RotWorkspace {
     // level coding of float genotypes (rotate_i8.cuh)
     double* u1 = nullptr;      // [n] U^T 1
     LevelInfo* info = nullptr; // [cap_snps]
+    LevelPartial* part = nullptr;  // [chunks][cap_snps]
     int8_t* codes = nullptr;   // [cap_snps * n] codes in the layout of the input block
     int* n_bad = nullptr;      // device counter
     long long code_cap = 0;
@@ -55,9 +56,10 @@ inline void rot_free(RotWorkspace* w)
     w->scale = nullptr;
     if (w->u1) cudaFree(w->u1);
     if (w->info) cudaFree(w->info);
+    if (w->part) cudaFree(w->part);
     if (w->codes) cudaFree(w->codes);
     if (w->n_bad) cudaFree(w->n_bad);
-    w->u1 = nullptr; w->info = nullptr; w->codes = nullptr; w->n_bad = nullptr; w->code_cap = 0;
+    w->u1 = nullptr; w->info = nullptr; w->part = nullptr; w->codes = nullptr; w->n_bad = nullptr; w->code_cap = 0;
     if (w->x8) cudaFree(w->x8);
     for (int t = 0; t < 2; ++t) {
         if (w->P[t]) cudaFree(w->P[t]);
@@ -180,23 +182,28 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         const long long cap = (blk + 63) / 64 * 64;
         if (cap > w->code_cap) {
             if (w->info) cudaFree(w->info);
+            if (w->part) cudaFree(w->part);
             if (w->codes) cudaFree(w->codes);
-            w->info = nullptr; w->codes = nullptr; w->code_cap = 0;
+            w->info = nullptr; w->part = nullptr; w->codes = nullptr; w->code_cap = 0;
             PG_ROT_CK(cudaMalloc(&w->info, sizeof(LevelInfo) * cap));
+            PG_ROT_CK(cudaMalloc(&w->part, sizeof(LevelPartial) * cap * ((n + kLevelChunk - 1) / kLevelChunk)));
             PG_ROT_CK(cudaMalloc(&w->codes, (size_t)cap * n));
             w->code_cap = cap;
         }
         PG_ROT_CK(cudaMemsetAsync(w->n_bad, 0, sizeof(int), stream));
         const unsigned gb = (unsigned)((mb + 127) / 128);
+        const int nchunks = (n + kLevelChunk - 1) / kLevelChunk;
         // equal spacing to double rounding: float32-standardised columns deviate by ~1e-7 of |x| and stay on the FP64 path
         // (their non-affinity moved beta by 1.4e-6 in the parity test; raw float32 dosages 0/1/2 are exactly affine)
         const double tol = ldexp(1.0, -50);
         if (xdtype == PG_X_F32)
-            find_levels_kernel<float><<<gb, 128, 0, stream>>>((const float*)src, ld, layout, n, mb, tol, w->info, w->n_bad);
+            find_levels_kernel<float><<<dim3(gb, nchunks), 128, 0, stream>>>((const float*)src, ld, layout, n, mb, w->part);
         else
-            find_levels_kernel<double><<<gb, 128, 0, stream>>>((const double*)src, ld, layout, n, mb, tol, w->info, w->n_bad);
+            find_levels_kernel<double><<<dim3(gb, nchunks), 128, 0, stream>>>((const double*)src, ld, layout, n, mb, w->part);
         PG_ROT_CK(cudaGetLastError());
-        (*n_launch)++;
+        merge_levels_kernel<<<gb, 128, 0, stream>>>(w->part, nchunks, mb, tol, w->info, w->n_bad);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch) += 2;
         int bad = 1;
         PG_ROT_CK(cudaMemcpyAsync(&bad, w->n_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
         PG_ROT_CK(cudaStreamSynchronize(stream));  // one small sync per block: the path choice is made on the host
