@@ -120,12 +120,17 @@ __global__ void __launch_bounds__(256) combine_i8_kernel(const int32_t* __restri
 //     U^T x = v0 * (U^T 1) + s * (U^T g),
 // so such columns go through the exact int8-split tensor-core path on the codes g and an affine fix-up in the
 // recombination, instead of the 8x slower FP64 GEMM.  "Equally spaced" is tested to double rounding
-// (|v2 - 2 v1 + v0| <= 2^-50 max|v|): standardising in float64 produces exactly this much deviation; columns
-// standardised in float32 deviate by ~1e-7 and are not treated as affine.  Any column with NaN/Inf, more than
-// three levels or unequal spacing sends the whole block down the FP64 path.
+// (|v2 - 2 v1 + v0| <= 2^-50 max|v|): standardising in float64 produces exactly this much deviation.  Columns whose
+// three levels are NOT equally spaced (standardised in float32: ~1e-7 off; or any three-valued coding) are
+//     x = v0 + s g + eps [g = 2] ,   U^T x = v0 (U^T 1) + s (U^T g) + eps (U^T [g = 2]) :
+// a second exact int8 rotation of the indicator [g = 2] is accumulated with weight eps (2x the tensor work, still
+// ~4x faster than the FP64 GEMM).  Any column with NaN/Inf or more than three levels sends the whole block down
+// the FP64 path.
 // ------------------------------------------------------------------------------------------------
 struct LevelInfo {
-    double v0, s;   // x = v0 + s * code
+    double v0, s;   // x = v0 + s * code (+ eps where code == 2)
+    double eps;     // v2 - v0 - 2 s when the three levels are not equally spaced to double rounding, else 0
+    double t01, t12; // code = (x > t01) + (x > t12): midpoints between the sorted levels (+inf when absent)
     int nlev;       // 1..3: codeable; 0: not codeable
     int pad;
 };
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(128) find_levels_kernel(const T* __restrict__ 
 
 // pass 2: merge the chunk results of one SNP, sort the levels, test the spacing
 __global__ void merge_levels_kernel(const LevelPartial* __restrict__ part, int nchunks, long long mb, double tol,
-                                    LevelInfo* __restrict__ info, int* __restrict__ n_bad)
+                                    LevelInfo* __restrict__ info, int* __restrict__ n_bad /* [0]: not codeable, [1]: need eps */)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= mb) return;
@@ -187,17 +192,21 @@ __global__ void merge_levels_kernel(const LevelPartial* __restrict__ part, int n
         if (k < 0) break;
     }
     LevelInfo li;
-    li.v0 = 0.0; li.s = 0.0; li.nlev = 0; li.pad = 0;
+    li.v0 = 0.0; li.s = 0.0; li.eps = 0.0; li.t01 = INFINITY; li.t12 = INFINITY; li.nlev = 0; li.pad = 0;
     if (k > 0) {
         if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
         if (k > 2 && v[2] < v[1]) { const double t = v[1]; v[1] = v[2]; v[2] = t; }
         if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
         li.v0 = v[0];
         li.nlev = k;
-        if (k >= 2) li.s = v[1] - v[0];
+        if (k >= 2) { li.s = v[1] - v[0]; li.t01 = 0.5 * v[0] + 0.5 * v[1]; }
         if (k == 3) {
+            li.t12 = 0.5 * v[1] + 0.5 * v[2];
             const double mx = fmax(fabs(v[0]), fabs(v[2]));
-            if (fabs((v[2] - v[1]) - (v[1] - v[0])) > tol * mx) li.nlev = 0;  // unequal spacing: not an affine image of a dosage
+            if (fabs((v[2] - v[1]) - (v[1] - v[0])) > tol * mx) {
+                li.eps = (v[2] - v[0]) - 2.0 * li.s;  // unequal spacing: needs the second (indicator) rotation
+                atomicAdd(n_bad + 1, 1);
+            }
         }
     }
     if (li.nlev == 0) atomicAdd(n_bad, 1);
@@ -205,15 +214,15 @@ __global__ void merge_levels_kernel(const LevelPartial* __restrict__ part, int n
 }
 
 // codes in the layout of the input: sample-major (n x mb, ld = mb) or SNP-major (mb x n, ld = n)
+// indicator != 0: write [code == 2] instead of the code (operand of the eps rotation)
 template <typename T>
 __global__ void encode_levels_kernel(const T* __restrict__ src, long long ld, int layout, int n, long long mb,
-                                     const LevelInfo* __restrict__ info, int8_t* __restrict__ codes)
+                                     const LevelInfo* __restrict__ info, int8_t* __restrict__ codes, int indicator)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int j0 = blockIdx.y * 64;
     if (g >= mb) return;
     const LevelInfo li = info[g];
-    const double inv = li.s != 0.0 ? 1.0 / li.s : 0.0;
     const int j1 = min(n, j0 + 64);
     int j = j0;
     for (; j + 8 <= j1; j += 8) {
@@ -222,20 +231,26 @@ __global__ void encode_levels_kernel(const T* __restrict__ src, long long ld, in
         for (int u = 0; u < 8; ++u) x[u] = (double)src[layout == 0 ? (size_t)(j + u) * ld + g : (size_t)g * ld + j + u];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            codes[layout == 0 ? (size_t)(j + u) * mb + g : (size_t)g * n + j + u] = (int8_t)__double2int_rn((x[u] - li.v0) * inv);
+        {
+            const int c = (x[u] > li.t01) + (x[u] > li.t12);
+            codes[layout == 0 ? (size_t)(j + u) * mb + g : (size_t)g * n + j + u] = (int8_t)(indicator ? (c == 2) : c);
+        }
     }
     for (; j < j1; ++j) {
         const size_t si = layout == 0 ? (size_t)j * ld + g : (size_t)g * ld + j;
         const size_t di = layout == 0 ? (size_t)j * mb + g : (size_t)g * n + j;
-        codes[di] = (int8_t)__double2int_rn(((double)src[si] - li.v0) * inv);
+        const double xv = (double)src[si];
+        const int c = (xv > li.t01) + (xv > li.t12);
+        codes[di] = (int8_t)(indicator ? (c == 2) : c);
     }
 }
 
 // recombination with the affine fix-up: xr[g][i] = v0_g * u1_i + s_g * (U^T code_g)_i
+// accumulate != 0 (second pass, indicator rotation): xr[g][i] += eps_g * (U^T [code_g == 2])_i
 __global__ void __launch_bounds__(256) combine_i8_affine_kernel(const int32_t* __restrict__ P, const int* __restrict__ exps,
                                                                  int n, int npad, long long mb, double* __restrict__ xr,
                                                                  long long ldx, const LevelInfo* __restrict__ info,
-                                                                 const double* __restrict__ u1)
+                                                                 const double* __restrict__ u1, int accumulate)
 {
     const long long g = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,7 +263,12 @@ __global__ void __launch_bounds__(256) combine_i8_affine_kernel(const int32_t* _
     for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[(size_t)t * npad];
     const double r = ldexp((double)hi + ldexp((double)lo, -32), exps[i] - 24);
     const LevelInfo li = info[g];
-    xr[(size_t)g * ldx + i] = fma(li.s, r, li.v0 * u1[i]);
+    double* dst = xr + (size_t)g * ldx + i;
+    if (accumulate) {
+        if (li.eps != 0.0) *dst = fma(li.eps, r, *dst);
+    } else {
+        *dst = fma(li.s, r, li.v0 * u1[i]);
+    }
 }
 
 // u1 = U^T 1: column sums of U (eigenvector i at U + i*n when cols_contig, else strided)

@@ -113,7 +113,7 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         PG_ROT_CK(cudaMalloc(&w->exps, sizeof(int) * n));
         PG_ROT_CK(cudaMalloc(&w->scale, sizeof(double) * n));
         PG_ROT_CK(cudaMalloc(&w->u1, sizeof(double) * n));
-        PG_ROT_CK(cudaMalloc(&w->n_bad, sizeof(int)));
+        PG_ROT_CK(cudaMalloc(&w->n_bad, 2 * sizeof(int)));
     }
     const long long cap = (blk + 63) / 64 * 64;
     if (cap > w->cap_snps) {
@@ -176,6 +176,10 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     // float genotypes whose columns are (affine images of) dosage codes go through the int8 path on the codes
     static const bool level_coding = !(getenv("PG_LEVEL_CODING") && atoi(getenv("PG_LEVEL_CODING")) == 0);
     const LevelInfo* affine = nullptr;
+    bool need_eps = false;
+    const void* fsrc = nullptr;   // the float block (for the indicator pass)
+    long long fld = 0;
+    int fdtype = 0;
     if (!i8 && rotation == PG_ROT_AUTO && level_coding && xdtype != PG_X_I8) {
         int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
         if (rc) return rc;
@@ -190,7 +194,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             PG_ROT_CK(cudaMalloc(&w->codes, (size_t)cap * n));
             w->code_cap = cap;
         }
-        PG_ROT_CK(cudaMemsetAsync(w->n_bad, 0, sizeof(int), stream));
+        PG_ROT_CK(cudaMemsetAsync(w->n_bad, 0, 2 * sizeof(int), stream));
         const unsigned gb = (unsigned)((mb + 127) / 128);
         const int nchunks = (n + kLevelChunk - 1) / kLevelChunk;
         // equal spacing to double rounding: float32-standardised columns deviate by ~1e-7 of |x| and stay on the FP64 path
@@ -204,18 +208,20 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         merge_levels_kernel<<<gb, 128, 0, stream>>>(w->part, nchunks, mb, tol, w->info, w->n_bad);
         PG_ROT_CK(cudaGetLastError());
         (*n_launch) += 2;
-        int bad = 1;
-        PG_ROT_CK(cudaMemcpyAsync(&bad, w->n_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        int bad[2] = {1, 0};
+        PG_ROT_CK(cudaMemcpyAsync(bad, w->n_bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         PG_ROT_CK(cudaStreamSynchronize(stream));  // one small sync per block: the path choice is made on the host
-        if (bad == 0) {
+        if (bad[0] == 0) {
+            affine = w->info;
+            need_eps = bad[1] > 0;
+            fsrc = src; fld = ld; fdtype = xdtype;
             dim3 ge(gb, (unsigned)((n + 63) / 64));
             if (xdtype == PG_X_F32)
-                encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)src, ld, layout, n, mb, w->info, w->codes);
+                encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)src, ld, layout, n, mb, w->info, w->codes, 0);
             else
-                encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)src, ld, layout, n, mb, w->info, w->codes);
+                encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)src, ld, layout, n, mb, w->info, w->codes, 0);
             PG_ROT_CK(cudaGetLastError());
             (*n_launch)++;
-            affine = w->info;
             src = w->codes;
             ld = (layout == PG_X_SAMPLE_MAJOR) ? mb : n;
             xdtype = PG_X_I8;
@@ -269,6 +275,25 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     }
     const int32_t ione = 1, izero = 0;
     const int M = kSlices * w->npad;
+    const int npass = (affine && need_eps) ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+    if (pass == 1) {
+        // second component: indicator [code == 2] with weight eps (columns whose levels are not equally spaced)
+        PG_ROT_CK(cudaStreamWaitEvent(stream, w->ev_pfree[0], 0));
+        PG_ROT_CK(cudaStreamWaitEvent(stream, w->ev_pfree[1], 0));  // the codes of pass 0 are no longer read
+        dim3 ge((unsigned)((mb + 127) / 128), (unsigned)((n + 63) / 64));
+        if (fdtype == PG_X_F32)
+            encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
+        else
+            encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch)++;
+        if (!direct) {
+            dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
+            stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
+            PG_ROT_CK(cudaGetLastError());
+        }
+    }
     for (long long g0 = 0; g0 < mb; g0 += w->sub) {
         const long long cnt = std::min(w->sub, mb - g0);
         const long long cnt_pad = (cnt + 15) / 16 * 16;  // x8 rows beyond mb are zero / stale: ignored downstream
@@ -290,12 +315,13 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)cnt);
         if (affine)
             combine_i8_affine_kernel<<<grid, 256, 0, cmb>>>(w->P[t], w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx,
-                                                            affine + g0, w->u1);
+                                                            affine + g0, w->u1, pass);
         else
             combine_i8_kernel<<<grid, 256, 0, cmb>>>(w->P[t], w->exps, n, w->npad, cnt, xr + (size_t)g0 * ldx, ldx);
         PG_ROT_CK(cudaGetLastError());
         PG_ROT_CK(cudaEventRecord(w->ev_pfree[t], cmb));
         (*n_launch)++;
+    }
     }
     cudaEventRecord(ev_rot_end, cmb);
     return 0;

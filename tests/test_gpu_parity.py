@@ -367,9 +367,10 @@ def test_fused_tcgen05_rotation_is_bit_identical_to_cublas_split():
 
 def test_float_dosages_take_the_level_coded_int8_path():
     """Float genotypes as the reference's callers pass them -- raw 0.0/1.0/2.0 or standardised per SNP
-    (experiments/wtccc/run_pygemma.py:432) -- are affine images of dosage codes: they must take the exact int8
-    tensor-core rotation (rot_engine == I8SPLIT) and still match the oracle run on the very same float values.
-    A block holding one imputed (non-codeable) column falls back to the FP64 GEMM."""
+    (experiments/wtccc/run_pygemma.py:432) -- take at most three values per column: they must go through the exact int8
+    tensor-core rotation on their level codes (rot_engine == I8SPLIT; one pass when the levels are equally spaced to
+    double rounding, code + indicator passes otherwise) and match the oracle run on the very same float values.
+    A block holding one imputed (four-valued) column falls back to the FP64 GEMM."""
     from oracle import oracle
     from pygemma_b200.synth import make_problem
 
@@ -381,7 +382,11 @@ def test_float_dosages_take_the_level_coded_int8_path():
     g[:, 9] = (g[:, 9] > 0)  # two levels
     sd = g.std(axis=0)
     sd[sd == 0] = 1.0
+    odd = g.copy()
+    odd[:, 20] = np.where(g[:, 20] == 2, 10.0, g[:, 20])       # levels {0, 1, 10}: unequal spacing
+    odd[:, 21] = np.where(g[:, 21] == 0, -3.5, g[:, 21] * 0.25)  # levels {-3.5, 0.25, 0.5}
     variants = {
+        "odd_levels_f64": odd,
         "raw_f64": g,
         "raw_f32": g.astype(np.float32),
         "std_f64": (g - g.mean(axis=0)) / sd,
@@ -395,9 +400,9 @@ def test_float_dosages_take_the_level_coded_int8_path():
             for layout_snp in (False, True):
                 Xin = np.ascontiguousarray(X.T) if layout_snp else np.ascontiguousarray(X)
                 o = h.scan(Xin, layout=capi.PG_X_SNP_MAJOR if layout_snp else capi.PG_X_SAMPLE_MAJOR)
-                # float32-standardised columns are not affine to double rounding: they stay on the exact FP64 path
-                want = capi.PG_ROT_FP64 if name == "std_f32" else capi.PG_ROT_I8SPLIT
-                assert o["timing"]["rot_engine"] == want, name
+                # float32-standardised columns are not equally spaced to double rounding: they take the two-component
+                # (code + indicator) form of the same int8 path
+                assert o["timing"]["rot_engine"] == capi.PG_ROT_I8SPLIT, name
                 ok = np.ones(m, dtype=bool)
                 ok[7] = False  # constant column: degenerate (x is collinear with the intercept), finite garbage in both
                 _check(o, ref, idx=np.where(ok)[0], tag=(name, layout_snp))
