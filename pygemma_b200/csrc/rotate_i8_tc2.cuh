@@ -1,0 +1,303 @@
+// rotate_i8_tc2.cuh -- the fused int8-split rotation on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Same mathematics and the same bits as rotate_i8_tc.cuh; the difference is the operand economy.  A pair of CTAs on
+// one TPC executes M = 256 MMAs: each CTA supplies its own 128 SNP rows of A and only HALF of B (112 of the 224
+// plane-eigen rows), the tensor cores exchange the B halves.  Per CTA and k-step the shared-memory reads drop from
+// 2 x (4 + 7) KB to 2 x (4 + 3.5) KB and the TMA fill from 60 KB to 46 KB per 128 samples, which is what the
+// single-CTA kernel was bound by.  Cluster tile: 512 SNPs (2 CTAs x 2 accumulators x 128) x 32 eigenvectors x 7 planes.
+//
+// Accumulator columns are eigen-major here (column e*7 + p) so that one CTA's half of B is a contiguous range of
+// eigenvectors: the B tensor map walks (sample, plane, eigenvector) with box (128, 7, 16).
+//
+//   warp 0    TMA producer (both CTAs): own A0, A1, B-half into own shared memory, transaction bytes onto the LEADER's
+//             `full[s]` (peer bit of the mbarrier address cleared, as cute::SM100_TMA_2SM_LOAD does)
+//   warp 1    TMEM allocation (both CTAs, cta_group::2); MMA issue by the leader CTA only; tcgen05.commit multicast
+//             to `empty[s]` / `tmem_full` of both CTAs
+//   warps 2-5 epilogue on the CTA's own TMEM; arrival on the leader's `tmem_empty` (remote for the peer CTA)
+#pragma once
+
+#include "rotate_i8_tc.cuh"
+
+namespace pg {
+namespace tc2 {
+
+using tc::kABytes;
+using tc::kAcc1Col;
+using tc::kStageK;
+using tc::kTileEig;
+using tc::kTileN;
+using tc::kTmemCols;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_u32;
+using tc::tmem_ld8;
+using tc::umma_desc_sw128;
+
+constexpr int kClusterSnps = 512;
+constexpr int kCtaSnps = 256;
+constexpr int kBHalfRows = kTileN / 2;              // 112
+constexpr int kBHalfBytes = kBHalfRows * kStageK;   // 14 336
+constexpr int kStageBytes = 2 * kABytes + kBHalfBytes;   // 47 104 per CTA
+constexpr int kStages = 4;
+constexpr int kEigGroup = 24;
+constexpr int kThreads = 192;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // cute::Sm100MmaPeerBitMask: address of the even CTA of the pair
+
+// S32 accumulate, S8 x S8, K-major, N = 224, M = 256 (pair)
+constexpr uint32_t kInstrDesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads whose completion bytes land on the leader CTA's barrier
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc2), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_local(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint64_t* bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+
+struct Args {
+    long long mb;
+    int n;
+    int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors
+    const double* scale;
+    double* xr;
+    long long ldx;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_p, Args a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* tmem_full = bars + 2 * kStages;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const long long total_tiles = (long long)a.snp_tiles * a.eig_tiles;
+    const int ksteps = (a.n + kStageK - 1) / kStageK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 256);   // 128 epilogue threads of each CTA of the pair (only the leader's barrier is used)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / TMA signal
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    auto decode = [&](long long t, int& st, int& et) {
+        const long long per_group = (long long)kEigGroup * a.snp_tiles;
+        const int g = (int)(t / per_group);
+        const long long r = t - (long long)g * per_group;
+        const int e0 = g * kEigGroup;
+        const int ecount = min(kEigGroup, a.eig_tiles - e0);
+        st = (int)(r / ecount);
+        et = e0 + (int)(r % ecount);
+    };
+
+    if (warp == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = cluster_id; t < total_tiles; t += num_clusters) {
+            int st, et;
+            decode(t, st, et);
+            const int snp0 = st * kClusterSnps + (int)rank * kCtaSnps;
+            for (int k = 0; k < ksteps; ++k) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sA = smem + (size_t)stage * kStageBytes;
+                    if (leader) mbar_expect_tx_local(&full[stage], 2 * kStageBytes);   // both CTAs' bytes land here
+                    tma2_load_2d(sA, &map_x, &full[stage], k * kStageK, snp0);
+                    tma2_load_2d(sA + kABytes, &map_x, &full[stage], k * kStageK, snp0 + 128);
+                    tma2_load_3d(sA + 2 * kABytes, &map_p, &full[stage], k * kStageK, 0, et * kTileEig + (int)rank * (kTileEig / 2));
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long long t = cluster_id; t < total_tiles; t += num_clusters) {
+                mbar_wait(tmem_empty, acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int k = 0; k < ksteps; ++k) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t sA = smem_u32(smem + (size_t)stage * kStageBytes);
+                        const uint64_t da0 = umma_desc_sw128(sA), da1 = umma_desc_sw128(sA + kABytes);
+                        const uint64_t db = umma_desc_sw128(sA + 2 * kABytes);
+#pragma unroll
+                        for (int kk = 0; kk < kStageK / 32; ++kk) {
+                            const uint32_t accum = (k | kk) ? 1u : 0u;
+                            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                            umma2_i8(tmem_base, da0 + adv, db + adv, accum);
+                            umma2_i8(tmem_base + kAcc1Col, da1 + adv, db + adv, accum);
+                        }
+                        umma2_commit(&empty[stage]);
+                        if (k == ksteps - 1) umma2_commit(tmem_full);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        uint32_t acc_phase = 0;
+        for (long long t = cluster_id; t < total_tiles; t += num_clusters) {
+            int st, et;
+            decode(t, st, et);
+            mbar_wait(tmem_full, acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int eig0 = et * kTileEig;
+#pragma unroll 1
+            for (int acc = 0; acc < 2; ++acc) {
+                const long long snp = (long long)st * kClusterSnps + (long long)rank * kCtaSnps + acc * 128 + quarter * 32 + lane;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAcc1Col);
+#pragma unroll 1
+                for (int c = 0; c < kTileEig / 8; ++c) {
+                    // eight eigenvectors x seven planes = 56 consecutive columns (eigen-major)
+                    uint32_t r[kSlices][8];
+#pragma unroll
+                    for (int q = 0; q < kSlices; ++q) tmem_ld8(tbase + (uint32_t)(c * 8 * kSlices + q * 8), r[q]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (snp < a.mb) {
+                        double* dst = a.xr + (size_t)snp * a.ldx + eig0 + c * 8;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int e = eig0 + c * 8 + j;
+                            if (e < a.n) {
+#define PG_PL(P) ((double)(int)r[(j * kSlices + (P)) >> 3][(j * kSlices + (P)) & 7])
+                                const double hi = fma(PG_PL(0), 65536.0, fma(PG_PL(1), 256.0, PG_PL(2)));
+                                const double lo = fma(PG_PL(3), 16777216.0, fma(PG_PL(4), 65536.0, fma(PG_PL(5), 256.0, PG_PL(6))));
+#undef PG_PL
+                                const double v = fma(lo, 2.3283064365386963e-10 /* 2^-32 */, hi);
+                                dst[j] = v * __ldg(a.scale + e);
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_on_cta(tmem_empty, 0);   // the leader's barrier gates the next tile's first MMA
+            acc_phase ^= 1;
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();   // the peer may still be reading this CTA's shared memory / finishing its epilogue
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long x8_rows, const int8_t* planes, int npad,
+                  int ldk, int n, long long mb, const double* scale, double* xr, long long ldx)
+{
+    tc::EncodeTiledFn enc = tc::encode_tiled_fn();
+    if (!enc) return -1;
+    CUtensorMap mx, mp;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ldk, (cuuint64_t)x8_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)ldk};
+        cuuint32_t box[2] = {(cuuint32_t)kStageK, 128};
+        cuuint32_t es[2] = {1, 1};
+        if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)x8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -2;
+    }
+    {
+        // (sample, plane, eigenvector): a box of 16 eigenvectors x 7 planes lands eigen-major, 112 rows of 128 B
+        cuuint64_t dims[3] = {(cuuint64_t)ldk, (cuuint64_t)kSlices, (cuuint64_t)npad};
+        cuuint64_t strides[2] = {(cuuint64_t)ldk * (cuuint64_t)npad, (cuuint64_t)ldk};
+        cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)kSlices, (cuuint32_t)(kTileEig / 2)};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (enc(&mp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -3;
+    }
+    Args a;
+    a.mb = mb; a.n = n;
+    a.snp_tiles = (int)((mb + kClusterSnps - 1) / kClusterSnps);
+    a.eig_tiles = (n + kTileEig - 1) / kTileEig;
+    a.scale = scale; a.xr = xr; a.ldx = ldx;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(rotate_i8_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+            return -4;
+        attr_set = true;
+    }
+    const long long tiles = (long long)a.snp_tiles * a.eig_tiles;
+    const int clusters = (int)std::min<long long>(tiles, sm_count / 2);
+    rotate_i8_tc2_kernel<<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+}  // namespace tc2
+}  // namespace pg

@@ -20,6 +20,7 @@
 #include "reml_kernels.cuh"
 #include "rotate_i8.cuh"
 #include "rotate_i8_tc.cuh"
+#include "rotate_i8_tc2.cuh"
 
 namespace pg {
 
@@ -267,7 +268,10 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int r = tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx);
+        // CTA-pair kernel (cta_group::2) unless PG_TC_SINGLE is set
+        static const bool single = getenv("PG_TC_SINGLE") != nullptr;
+        const int r = single ? tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx)
+                             : tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx);
         if (r) { w->err = "fused tcgen05 rotation launch failed, code " + std::to_string(r); return PG_ERR_CUDA; }
         (*n_launch)++;
         cudaEventRecord(ev_rot_end, stream);
