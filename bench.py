@@ -272,6 +272,9 @@ def run_ours(args):
     h = _capi.Handle(n, c0, local)
     stream = torch.cuda.current_stream(dev)
     h.set_stream(stream.cuda_stream)
+    rot_opt = {"auto": _capi.PG_ROT_AUTO, "fp64": _capi.PG_ROT_FP64, "i8split": _capi.PG_ROT_I8SPLIT,
+               "i8tc": _capi.PG_ROT_I8TC}[args.rotation]
+    h.set_options(rotation=rot_opt)
 
     # ---- setup (excluded from the metric): eigendecomposition on rank 0, NCCL broadcast of U and d
     t0 = time.perf_counter()
@@ -345,14 +348,17 @@ def run_ours(args):
     solve_ms = reml_ms - cmp_ms
     step_ms = rot_ms + reml_ms + conv_ms
     nodes = res_tm["n_nodes"]
-    i8 = res_tm.get("rot_engine") == _capi.PG_ROT_I8SPLIT
+    i8 = res_tm.get("rot_engine") in (_capi.PG_ROT_I8SPLIT, _capi.PG_ROT_I8TC)
+    fused = res_tm.get("rot_engine") == _capi.PG_ROT_I8TC
     n_planes = 7
     rot_ops = (n_planes if i8 else 1) * 2.0 * n * n          # int8 (or fp64) multiply-add ops per SNP
     cmp_flops = 2.0 * n * 10 * (c0 + 2)                       # compression: n x kCq x (c0+2) FP64 FMAs per SNP
     stages = {
         "rotation": {"ms": rot_ms, "achieved": rot_ops * m / (rot_ms * 1e-3) / 1e12,
                      "peak": peaks["int8_gemm_tops"] if i8 else peaks["fp64_dmma_tflops"],
-                     "kernel": ("rotation U^T X, exact int8-split (7 base-256 digit planes): cuBLAS int8 GEMM (cutlass3x sm100 "
+                     "kernel": ("rotation U^T X, exact int8-split (7 base-256 digit planes): rotate_i8_tc2_kernel (hand-written TMA + "
+                                "tcgen05 cta_group::2 kind::i8, recombination fused)") if (i8 and fused) else
+                               ("rotation U^T X, exact int8-split (7 base-256 digit planes): cuBLAS int8 GEMM (cutlass3x sm100 "
                                 "tcgen05 2-SM kernel) + combine_i8_kernel") if i8 else
                                "rotation U^T X (cuBLAS DGEMM, FP64 tensor pipe)",
                      "peak_source": ("int8 tensor rate (cuBLAS int8 GEMM 16384x8192x8192) " if i8 else "FP64 DMMA rate ")
@@ -403,7 +409,8 @@ def run_ours(args):
                                f"{'grid-search' if grid else 'Brent+Newton'} lambda, int8 dosages (BASELINE.json configs[2])",
                    "n": n, "snps_per_gpu": m, "c0": c0, "grid": grid, "parallelism": f"snp-shard x{world}",
                    "l2": "inputs_larger_than_l2 (1 GB int8 genotypes + 80 KB/SNP rotated fp64 per step)",
-                   "reml_engine": "compressed (eigenvalue-space moments)", "rotation_engine": "int8-split" if i8 else "fp64"},
+                   "reml_engine": "compressed (eigenvalue-space moments)",
+                   "rotation_engine": ("int8-split fused tcgen05" if fused else "int8-split cuBLAS") if i8 else "fp64"},
         "e2e": {"value": e2e_value, "unit": "SNPs/s", "h2d_bytes_per_step": int(n) * int(m) * world,
                 "d2h_bytes_per_step": int(m) * (6 * 8 + 3 * 4) * world, "ms_per_step": e2e_ms,
                 "device_ms_per_step": e2e_dev_ms / args.steps,
@@ -461,6 +468,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_SAMPLES)
     ap.add_argument("--c0", type=int, default=C0)
     ap.add_argument("--grid", action="store_true")
+    ap.add_argument("--rotation", default="auto", choices=["auto", "fp64", "i8split", "i8tc"],
+                    help="rotation engine (auto = library default; i8tc = hand-written fused tcgen05 kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--_cpu_worker", default=None)
     args = ap.parse_args()

@@ -39,7 +39,10 @@ constexpr int kBHalfRows = kTileN / 2;              // 112
 constexpr int kBHalfBytes = kBHalfRows * kStageK;   // 14 336
 constexpr int kStageBytes = 2 * kABytes + kBHalfBytes;   // 47 104 per CTA
 constexpr int kStages = 4;
-constexpr int kEigGroup = 24;
+#ifndef PG_TC2_EIG_GROUP
+#define PG_TC2_EIG_GROUP 24
+#endif
+constexpr int kEigGroup = PG_TC2_EIG_GROUP;
 constexpr int kThreads = 192;
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // cute::Sm100MmaPeerBitMask: address of the even CTA of the pair
@@ -73,13 +76,13 @@ __device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, 
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate, uint32_t idesc)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc2), "r"(accumulate), "r"(0u)
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void umma2_commit(uint64_t* bar)
@@ -102,18 +105,37 @@ __device__ __forceinline__ void mbar_arrive_on_cta(uint64_t* bar, uint32_t cta)
         : "memory");
 }
 
+// MN-major A tile straight from the caller's sample-major block: 128 sample rows of 128 SNP bytes, 128 B swizzle.
+// Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute make_umma_desc<Major::MN>): SBO = 8 rows of
+// 128 B; LBO (next 128-element chunk along M) is not exercised by an M = 128 tile.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(kABytes >> 4) << 16;     // leading byte offset: one whole tile
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 sample rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+
 struct Args {
     long long mb;
     int n;
     int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors
+    int eig_group;              // eigen tiles swept together (L2 residency of the B panels)
     const double* scale;
     double* xr;
     long long ldx;
 };
 
+// A_MN: the A tensor map walks the caller's sample-major block (SNP, sample) and A is an MN-major operand;
+// otherwise it walks the staged SNP-major copy (sample, SNP) and A is K-major.
+template <bool A_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_p, Args a)
 {
+    constexpr uint32_t idesc = kInstrDesc2 | (A_MN ? (1u << 15) : 0u);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
@@ -147,11 +169,11 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t tmem_base = *tmem_base_slot;
 
     auto decode = [&](long long t, int& st, int& et) {
-        const long long per_group = (long long)kEigGroup * a.snp_tiles;
+        const long long per_group = (long long)a.eig_group * a.snp_tiles;
         const int g = (int)(t / per_group);
         const long long r = t - (long long)g * per_group;
-        const int e0 = g * kEigGroup;
-        const int ecount = min(kEigGroup, a.eig_tiles - e0);
+        const int e0 = g * a.eig_group;
+        const int ecount = min(a.eig_group, a.eig_tiles - e0);
         st = (int)(r / ecount);
         et = e0 + (int)(r % ecount);
     };
@@ -168,8 +190,13 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 if (lane == 0) {
                     uint8_t* sA = smem + (size_t)stage * kStageBytes;
                     if (leader) mbar_expect_tx_local(&full[stage], 2 * kStageBytes);   // both CTAs' bytes land here
-                    tma2_load_2d(sA, &map_x, &full[stage], k * kStageK, snp0);
-                    tma2_load_2d(sA + kABytes, &map_x, &full[stage], k * kStageK, snp0 + 128);
+                    if (A_MN) {
+                        tma2_load_2d(sA, &map_x, &full[stage], snp0, k * kStageK);
+                        tma2_load_2d(sA + kABytes, &map_x, &full[stage], snp0 + 128, k * kStageK);
+                    } else {
+                        tma2_load_2d(sA, &map_x, &full[stage], k * kStageK, snp0);
+                        tma2_load_2d(sA + kABytes, &map_x, &full[stage], k * kStageK, snp0 + 128);
+                    }
                     tma2_load_3d(sA + 2 * kABytes, &map_p, &full[stage], k * kStageK, 0, et * kTileEig + (int)rank * (kTileEig / 2));
                 }
                 __syncwarp();
@@ -188,14 +215,16 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (lane == 0) {
                         const uint32_t sA = smem_u32(smem + (size_t)stage * kStageBytes);
-                        const uint64_t da0 = umma_desc_sw128(sA), da1 = umma_desc_sw128(sA + kABytes);
+                        const uint64_t da0 = A_MN ? umma_desc_mn_sw128(sA) : umma_desc_sw128(sA);
+                        const uint64_t da1 = A_MN ? umma_desc_mn_sw128(sA + kABytes) : umma_desc_sw128(sA + kABytes);
                         const uint64_t db = umma_desc_sw128(sA + 2 * kABytes);
 #pragma unroll
                         for (int kk = 0; kk < kStageK / 32; ++kk) {
                             const uint32_t accum = (k | kk) ? 1u : 0u;
-                            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                            umma2_i8(tmem_base, da0 + adv, db + adv, accum);
-                            umma2_i8(tmem_base + kAcc1Col, da1 + adv, db + adv, accum);
+                            const uint64_t adv = (uint64_t)((kk * 32) >> 4);                      // K-major: 32 bytes along the row
+                            const uint64_t adv_a = A_MN ? (uint64_t)((kk * 32 * 128) >> 4) : adv;   // MN-major: 32 sample rows
+                            umma2_i8(tmem_base, da0 + adv_a, db + adv, accum, idesc);
+                            umma2_i8(tmem_base + kAcc1Col, da1 + adv_a, db + adv, accum, idesc);
                         }
                         umma2_commit(&empty[stage]);
                         if (k == ksteps - 1) umma2_commit(tmem_full);
@@ -257,13 +286,24 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
 }
 
+// xsm != nullptr: the caller's sample-major int8 block (element (sample j, SNP g) at xsm[j*ld_sm + g]) is used directly
+// as an MN-major operand; otherwise x8 (SNP-major, staged) is the K-major operand.
 inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long x8_rows, const int8_t* planes, int npad,
-                  int ldk, int n, long long mb, const double* scale, double* xr, long long ldx)
+                  int ldk, int n, long long mb, const double* scale, double* xr, long long ldx,
+                  const int8_t* xsm = nullptr, long long ld_sm = 0)
 {
     tc::EncodeTiledFn enc = tc::encode_tiled_fn();
     if (!enc) return -1;
     CUtensorMap mx, mp;
-    {
+    if (xsm) {
+        cuuint64_t dims[2] = {(cuuint64_t)mb, (cuuint64_t)n};
+        cuuint64_t strides[1] = {(cuuint64_t)ld_sm};
+        cuuint32_t box[2] = {128, (cuuint32_t)kStageK};
+        cuuint32_t es[2] = {1, 1};
+        if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)xsm, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -2;
+    } else {
         cuuint64_t dims[2] = {(cuuint64_t)ldk, (cuuint64_t)x8_rows};
         cuuint64_t strides[1] = {(cuuint64_t)ldk};
         cuuint32_t box[2] = {(cuuint32_t)kStageK, 128};
@@ -287,15 +327,19 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     a.snp_tiles = (int)((mb + kClusterSnps - 1) / kClusterSnps);
     a.eig_tiles = (n + kTileEig - 1) / kTileEig;
     a.scale = scale; a.xr = xr; a.ldx = ldx;
+    static const int eg_env = getenv("PG_TC2_EG") ? atoi(getenv("PG_TC2_EG")) : 0;
+    a.eig_group = eg_env > 0 ? eg_env : kEigGroup;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(rotate_i8_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(rotate_i8_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
             return -4;
         attr_set = true;
     }
     const long long tiles = (long long)a.snp_tiles * a.eig_tiles;
     const int clusters = (int)std::min<long long>(tiles, sm_count / 2);
-    rotate_i8_tc2_kernel<<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, a);
+    if (xsm) rotate_i8_tc2_kernel<true><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, a);
+    else rotate_i8_tc2_kernel<false><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 

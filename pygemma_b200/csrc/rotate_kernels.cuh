@@ -106,7 +106,8 @@ inline int stage_to_snp_major(cudaStream_t stream, int n, const void* src, int x
 
 inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U, int u_op_t, int n, long long blk)
 {
-    const int npad = (n + 15) / 16 * 16, ldk = npad;
+    // rows of the K-contiguous operands start on 128-byte lines (TMA boxes and GEMM tiles then touch whole sectors)
+    const int npad = (n + 15) / 16 * 16, ldk = (n + 127) / 128 * 128;
     if (w->n != n || !w->planes) {
         rot_free(w);
         w->n = n; w->npad = npad; w->ldk = ldk;
@@ -253,8 +254,9 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     // PG_GEMM_TT=0 forces the staged K-major path (also used for SNP-major input, ragged tails and n % 16 != 0).
     static const bool gemm_tt = !(getenv("PG_GEMM_TT") && atoi(getenv("PG_GEMM_TT")) == 0);
     const bool fused_tc = (rotation == PG_ROT_I8TC) && !affine;
-    const bool direct = !fused_tc && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
-                        (w->ldk == n) && (mb % 16 == 0);
+    static const bool tc_single = getenv("PG_TC_SINGLE") != nullptr;
+    const bool direct = (!fused_tc || !tc_single) && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
+                        (n % 16 == 0) && (mb % 16 == 0);
     if (!direct) {
         dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
         stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
@@ -269,9 +271,9 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         // CTA-pair kernel (cta_group::2) unless PG_TC_SINGLE is set
-        static const bool single = getenv("PG_TC_SINGLE") != nullptr;
-        const int r = single ? tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx)
-                             : tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx);
+        const int r = tc_single ? tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx)
+                                : tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                                              direct ? (const int8_t*)src : nullptr, ld);
         if (r) { w->err = "fused tcgen05 rotation launch failed, code " + std::to_string(r); return PG_ERR_CUDA; }
         (*n_launch)++;
         cudaEventRecord(ev_rot_end, stream);
@@ -306,7 +308,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         cublasStatus_t s;
         if (direct)
             // B = X block as an (cnt x n) column-major matrix with leading dimension ld (sample-major storage), transposed
-            s = cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_T, M, (int)cnt, w->ldk, &ione, w->planes, CUDA_R_8I, w->ldk,
+            s = cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_T, M, (int)cnt, n, &ione, w->planes, CUDA_R_8I, w->ldk,
                              (const int8_t*)src + g0, CUDA_R_8I, (int)ld, &izero, w->P[t], CUDA_R_32I, M, CUBLAS_COMPUTE_32I,
                              CUBLAS_GEMM_DEFAULT);
         else
