@@ -869,8 +869,9 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                                  ld_dev, layout, mb, blk, h->xf, xr_block, h->ldx, &used_i8, &n_rot_launch, ev_conv[b].b,
                                  ev_rot[b].a, ev_rot[b].b);
                 if (r2 != 0) return fail(h, r2, "rotation failed: %s", rot_error(&h->rot));
-                last_engine = used_i8 ? (h->rotation == PG_ROT_I8TC ? PG_ROT_I8TC : PG_ROT_I8SPLIT) : PG_ROT_FP64;
-                CK(cudaEventRecord(h->ev_xr_ready[s], (used_i8 && h->rotation != PG_ROT_I8TC) ? st_cmb : h->compute));
+                last_engine = used_i8;  // rot_run reports PG_ROT_I8SPLIT / PG_ROT_I8TC, 0 for the FP64 GEMM
+                if (!last_engine) last_engine = PG_ROT_FP64;
+                CK(cudaEventRecord(h->ev_xr_ready[s], (used_i8 == PG_ROT_I8SPLIT) ? st_cmb : h->compute));
             } else {
                 int r2 = launch_stage(h, src_dev, xdtype, ld_dev, layout, mb, xr_block);
                 if (r2) return r2;

@@ -61,19 +61,35 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// L2 eviction policies: the digit planes of an eigen-tile group are re-read by every SNP tile (keep), genotype tiles
+// are streamed once per group (evict first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // TMA loads whose completion bytes land on the leader CTA's barrier
-__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(pol)
         : "memory");
 }
-__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t pol)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
         : "memory");
 }
 __device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate, uint32_t idesc)
@@ -124,6 +140,7 @@ struct Args {
     int n;
     int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors
     int eig_group;              // eigen tiles swept together (L2 residency of the B panels)
+    int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes (default 0)
     const double* scale;
     double* xr;
     long long ldx;
@@ -181,6 +198,13 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (warp == 0) {
         int stage = 0;
         uint32_t phase = 0;
+        uint64_t pol_a, pol_b;
+        {
+            uint64_t pol_n;
+            asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_n));
+            pol_a = (a.hints & 1) ? l2_policy_evict_first() : pol_n;
+            pol_b = (a.hints & 2) ? l2_policy_evict_last() : pol_n;
+        }
         for (long long t = cluster_id; t < total_tiles; t += num_clusters) {
             int st, et;
             decode(t, st, et);
@@ -191,13 +215,13 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     uint8_t* sA = smem + (size_t)stage * kStageBytes;
                     if (leader) mbar_expect_tx_local(&full[stage], 2 * kStageBytes);   // both CTAs' bytes land here
                     if (A_MN) {
-                        tma2_load_2d(sA, &map_x, &full[stage], snp0, k * kStageK);
-                        tma2_load_2d(sA + kABytes, &map_x, &full[stage], snp0 + 128, k * kStageK);
+                        tma2_load_2d(sA, &map_x, &full[stage], snp0, k * kStageK, pol_a);
+                        tma2_load_2d(sA + kABytes, &map_x, &full[stage], snp0 + 128, k * kStageK, pol_a);
                     } else {
-                        tma2_load_2d(sA, &map_x, &full[stage], k * kStageK, snp0);
-                        tma2_load_2d(sA + kABytes, &map_x, &full[stage], k * kStageK, snp0 + 128);
+                        tma2_load_2d(sA, &map_x, &full[stage], k * kStageK, snp0, pol_a);
+                        tma2_load_2d(sA + kABytes, &map_x, &full[stage], k * kStageK, snp0 + 128, pol_a);
                     }
-                    tma2_load_3d(sA + 2 * kABytes, &map_p, &full[stage], k * kStageK, 0, et * kTileEig + (int)rank * (kTileEig / 2));
+                    tma2_load_3d(sA + 2 * kABytes, &map_p, &full[stage], k * kStageK, 0, et * kTileEig + (int)rank * (kTileEig / 2), pol_b);
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -257,17 +281,24 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (snp < a.mb) {
                         double* dst = a.xr + (size_t)snp * a.ldx + eig0 + c * 8;
+                        double out[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int e = eig0 + c * 8 + j;
-                            if (e < a.n) {
+                            const int e = min(eig0 + c * 8 + j, a.n - 1);
 #define PG_PL(P) ((double)(int)r[(j * kSlices + (P)) >> 3][(j * kSlices + (P)) & 7])
-                                const double hi = fma(PG_PL(0), 65536.0, fma(PG_PL(1), 256.0, PG_PL(2)));
-                                const double lo = fma(PG_PL(3), 16777216.0, fma(PG_PL(4), 65536.0, fma(PG_PL(5), 256.0, PG_PL(6))));
+                            const double hi = fma(PG_PL(0), 65536.0, fma(PG_PL(1), 256.0, PG_PL(2)));
+                            const double lo = fma(PG_PL(3), 16777216.0, fma(PG_PL(4), 65536.0, fma(PG_PL(5), 256.0, PG_PL(6))));
 #undef PG_PL
-                                const double v = fma(lo, 2.3283064365386963e-10 /* 2^-32 */, hi);
-                                dst[j] = v * __ldg(a.scale + e);
-                            }
+                            const double v = fma(lo, 2.3283064365386963e-10 /* 2^-32 */, hi);
+                            out[j] = v * __ldg(a.scale + e);
+                        }
+                        if (eig0 + c * 8 + 8 <= a.n) {   // rows are 128-byte aligned (ldx % 16 == 0): four 16-byte stores
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (eig0 + c * 8 + j < a.n) dst[j] = out[j];
                         }
                     }
                 }
@@ -329,6 +360,9 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     a.scale = scale; a.xr = xr; a.ldx = ldx;
     static const int eg_env = getenv("PG_TC2_EG") ? atoi(getenv("PG_TC2_EG")) : 0;
     a.eig_group = eg_env > 0 ? eg_env : kEigGroup;
+    // measured at n = 10 000 per 25 088 SNPs: no hint 10.17 ms, evict_last(B) 10.13, evict_first(A) 10.86, both 10.81
+    static const int hints_env = getenv("PG_TC2_HINTS") ? atoi(getenv("PG_TC2_HINTS")) : 2;
+    a.hints = hints_env;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||

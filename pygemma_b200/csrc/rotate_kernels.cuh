@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "../../include/pygemma_b200.h"
@@ -45,7 +46,7 @@ struct RotWorkspace {
     int* n_bad = nullptr;      // device counter
     long long code_cap = 0;
     long long blocks_coded = 0, blocks_dense = 0;
-    long long sub = 0;
+    long long sub = 0, want_cap = 0;
     float slice_ms = 0.f;
 };
 
@@ -75,6 +76,27 @@ inline void rot_free(RotWorkspace* w)
     w->planes_valid = false; w->cap_snps = 0; w->sub = 0;
 }
 inline void rot_invalidate(RotWorkspace* w) { w->planes_valid = false; }
+
+// int32 partial products of the cuBLAS split path: kSlices*npad x sub, two buffers of about 1 GiB (allocated on first
+// use: the fused tcgen05 engine never materialises them)
+inline int rot_ensure_P(RotWorkspace* w)
+{
+    static const double p_gib = getenv("PG_P_GIB") ? atof(getenv("PG_P_GIB")) : 1.0;
+    long long sub = (long long)((size_t)(p_gib * (double)(size_t(1) << 30)) / ((size_t)kSlices * w->npad * 4));
+    sub = std::max<long long>(256, std::min<long long>((sub / 256) * 256, (w->want_cap + 255) / 256 * 256));
+    if (sub > w->sub) {
+        for (int t = 0; t < 2; ++t) {
+            if (w->P[t]) cudaFree(w->P[t]);
+            w->P[t] = nullptr;
+            if (cudaMalloc(&w->P[t], (size_t)kSlices * w->npad * sub * sizeof(int32_t)) != cudaSuccess) {
+                w->err = "cudaMalloc of the int32 partial-product buffer failed";
+                return PG_ERR_CUDA;
+            }
+        }
+        w->sub = sub;
+    }
+    return 0;
+}
 inline const char* rot_error(RotWorkspace* w) { return w->err.c_str(); }
 
 inline int stage_to_snp_major(cudaStream_t stream, int n, const void* src, int xdtype, long long ld, int layout,
@@ -125,19 +147,7 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         PG_ROT_CK(cudaMemsetAsync(w->x8, 0, (size_t)cap * ldk, stream));
         w->cap_snps = cap;
     }
-    // int32 partial products: kSlices*npad x sub, two buffers of about 1 GiB: the recombination of one sub-block
-    // (HBM-bound, combine stream) overlaps the tensor-core GEMM of the next
-    static const double p_gib = getenv("PG_P_GIB") ? atof(getenv("PG_P_GIB")) : 1.0;
-    long long sub = (long long)((size_t)(p_gib * (double)(size_t(1) << 30)) / ((size_t)kSlices * npad * 4));
-    sub = std::max<long long>(256, std::min<long long>((sub / 256) * 256, (cap + 255) / 256 * 256));
-    if (sub > w->sub) {
-        for (int t = 0; t < 2; ++t) {
-            if (w->P[t]) cudaFree(w->P[t]);
-            w->P[t] = nullptr;
-            PG_ROT_CK(cudaMalloc(&w->P[t], (size_t)kSlices * npad * sub * sizeof(int32_t)));
-        }
-        w->sub = sub;
-    }
+    w->want_cap = cap;
     for (int t = 0; t < 2; ++t) {
         if (!w->ev_gemm[t]) PG_ROT_CK(cudaEventCreateWithFlags(&w->ev_gemm[t], cudaEventDisableTiming));
         if (!w->ev_pfree[t]) PG_ROT_CK(cudaEventCreateWithFlags(&w->ev_pfree[t], cudaEventDisableTiming));
@@ -174,7 +184,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         w->err = "PG_ROT_I8SPLIT / PG_ROT_I8TC need int8 genotypes";
         return PG_ERR_ARG;
     }
-    *used_i8 = i8 ? 1 : 0;
+    *used_i8 = i8 ? PG_ROT_I8SPLIT : 0;   // engine actually used (refined below)
     // float genotypes whose columns are (affine images of) dosage codes go through the int8 path on the codes
     static const bool level_coding = !(getenv("PG_LEVEL_CODING") && atoi(getenv("PG_LEVEL_CODING")) == 0);
     const LevelInfo* affine = nullptr;
@@ -227,7 +237,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             src = w->codes;
             ld = (layout == PG_X_SAMPLE_MAJOR) ? mb : n;
             xdtype = PG_X_I8;
-            *used_i8 = 1;
+            *used_i8 = PG_ROT_I8SPLIT;
             w->blocks_coded++;
         } else {
             w->blocks_dense++;
@@ -253,7 +263,10 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     // and the cuBLAS kernel picked for this layout is ~17 % faster here (10.7 vs 12.8 ms per 25 088 SNPs at n = 10 000).
     // PG_GEMM_TT=0 forces the staged K-major path (also used for SNP-major input, ragged tails and n % 16 != 0).
     static const bool gemm_tt = !(getenv("PG_GEMM_TT") && atoi(getenv("PG_GEMM_TT")) == 0);
-    const bool fused_tc = (rotation == PG_ROT_I8TC) && !affine;
+    // PG_ROT_AUTO on int8 dosages: the hand-written fused tcgen05 kernel (PG_ROT_DEFAULT=cublas selects the library GEMM
+    // + recombination pair, which level-coded float blocks always use: their affine fix-up lives in the recombination)
+    static const bool default_tc = !(getenv("PG_ROT_DEFAULT") && !strcmp(getenv("PG_ROT_DEFAULT"), "cublas"));
+    const bool fused_tc = (rotation == PG_ROT_I8TC || (rotation == PG_ROT_AUTO && default_tc)) && !affine;
     static const bool tc_single = getenv("PG_TC_SINGLE") != nullptr;
     const bool direct = (!fused_tc || !tc_single) && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
                         (n % 16 == 0) && (mb % 16 == 0);
@@ -266,6 +279,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     cudaEventRecord(ev_conv_end, stream);
     cudaEventRecord(ev_rot_begin, stream);
     if (fused_tc) {
+        *used_i8 = PG_ROT_I8TC;
         // one kernel: TMA -> tcgen05.mma kind::i8 (7 planes in TMEM) -> exact recombination in the epilogue
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -279,6 +293,8 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         cudaEventRecord(ev_rot_end, stream);
         return 0;
     }
+    rc = rot_ensure_P(w);
+    if (rc) return rc;
     const int32_t ione = 1, izero = 0;
     const int M = kSlices * w->npad;
     const int npass = (affine && need_eps) ? 2 : 1;

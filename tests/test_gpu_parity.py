@@ -329,7 +329,8 @@ def test_transposed_gemm_operand_is_bit_identical_to_staged():
     code = ("import numpy as np, sys; sys.path.insert(0, '.');"
             "from pygemma_b200 import _capi; from pygemma_b200.synth import make_problem;"
             "p = make_problem(640, 352, 3, seed=12, m_k=1500);"
-            "h = _capi.Handle(640, 3); h.set_kinship(p['K']); h.set_design(p['W'], p['Y']); h.set_options(block_snps=128);"
+            "h = _capi.Handle(640, 3); h.set_kinship(p['K']); h.set_design(p['W'], p['Y']);"
+            "h.set_options(rotation=_capi.PG_ROT_I8SPLIT, block_snps=128);"
             "o = h.scan(p['X']); np.save(sys.argv[1], np.stack([o[c] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]))")
     outs = []
     for tt in ("1", "0"):
