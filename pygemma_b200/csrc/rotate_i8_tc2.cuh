@@ -144,6 +144,10 @@ struct Args {
     const double* scale;
     double* xr;
     long long ldx;
+    // level-coded float genotypes (rotate_i8.cuh): xr = v0 * u1 + s * (U^T code); second pass: xr += eps * (U^T [code == 2])
+    const LevelInfo* info;   // nullable
+    const double* u1;
+    int accumulate;
 };
 
 // A_MN: the A tensor map walks the caller's sample-major block (SNP, sample) and A is an MN-major operand;
@@ -271,6 +275,8 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll 1
             for (int acc = 0; acc < 2; ++acc) {
                 const long long snp = (long long)st * kClusterSnps + (long long)rank * kCtaSnps + acc * 128 + quarter * 32 + lane;
+                double lv0 = 0.0, ls = 1.0, leps = 0.0;
+                if (a.info && snp < a.mb) { const LevelInfo li = a.info[snp]; lv0 = li.v0; ls = li.s; leps = li.eps; }
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAcc1Col);
 #pragma unroll 1
                 for (int c = 0; c < kTileEig / 8; ++c) {
@@ -291,6 +297,10 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #undef PG_PL
                             const double v = fma(lo, 2.3283064365386963e-10 /* 2^-32 */, hi);
                             out[j] = v * __ldg(a.scale + e);
+                            if (a.info) {
+                                if (a.accumulate) out[j] = (leps != 0.0) ? fma(leps, out[j], dst[j]) : dst[j];
+                                else out[j] = fma(ls, out[j], lv0 * __ldg(a.u1 + e));
+                            }
                         }
                         if (eig0 + c * 8 + 8 <= a.n) {   // rows are 128-byte aligned (ldx % 16 == 0): four 16-byte stores
 #pragma unroll
@@ -321,7 +331,8 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 // as an MN-major operand; otherwise x8 (SNP-major, staged) is the K-major operand.
 inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long x8_rows, const int8_t* planes, int npad,
                   int ldk, int n, long long mb, const double* scale, double* xr, long long ldx,
-                  const int8_t* xsm = nullptr, long long ld_sm = 0)
+                  const int8_t* xsm = nullptr, long long ld_sm = 0, const LevelInfo* info = nullptr,
+                  const double* u1 = nullptr, int accumulate = 0)
 {
     tc::EncodeTiledFn enc = tc::encode_tiled_fn();
     if (!enc) return -1;
@@ -358,6 +369,7 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     a.snp_tiles = (int)((mb + kClusterSnps - 1) / kClusterSnps);
     a.eig_tiles = (n + kTileEig - 1) / kTileEig;
     a.scale = scale; a.xr = xr; a.ldx = ldx;
+    a.info = info; a.u1 = u1; a.accumulate = accumulate;
     static const int eg_env = getenv("PG_TC2_EG") ? atoi(getenv("PG_TC2_EG")) : 0;
     a.eig_group = eg_env > 0 ? eg_env : kEigGroup;
     // measured at n = 10 000 per 25 088 SNPs: no hint 10.17 ms, evict_last(B) 10.13, evict_first(A) 10.86, both 10.81

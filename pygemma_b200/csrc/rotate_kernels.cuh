@@ -180,10 +180,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
                    cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin, cudaEvent_t ev_rot_end)
 {
     const bool i8 = (xdtype == PG_X_I8) && (rotation == PG_ROT_AUTO || rotation == PG_ROT_I8SPLIT || rotation == PG_ROT_I8TC);
-    if ((rotation == PG_ROT_I8SPLIT || rotation == PG_ROT_I8TC) && xdtype != PG_X_I8) {
-        w->err = "PG_ROT_I8SPLIT / PG_ROT_I8TC need int8 genotypes";
-        return PG_ERR_ARG;
-    }
+    const bool forced_i8 = (rotation == PG_ROT_I8SPLIT || rotation == PG_ROT_I8TC);
     *used_i8 = i8 ? PG_ROT_I8SPLIT : 0;   // engine actually used (refined below)
     // float genotypes whose columns are (affine images of) dosage codes go through the int8 path on the codes
     static const bool level_coding = !(getenv("PG_LEVEL_CODING") && atoi(getenv("PG_LEVEL_CODING")) == 0);
@@ -192,7 +189,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     const void* fsrc = nullptr;   // the float block (for the indicator pass)
     long long fld = 0;
     int fdtype = 0;
-    if (!i8 && rotation == PG_ROT_AUTO && level_coding && xdtype != PG_X_I8) {
+    if (!i8 && rotation != PG_ROT_FP64 && level_coding && xdtype != PG_X_I8) {
         int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
         if (rc) return rc;
         const long long cap = (blk + 63) / 64 * 64;
@@ -243,6 +240,10 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             w->blocks_dense++;
         }
     }
+    if (!i8 && !affine && forced_i8) {
+        w->err = "PG_ROT_I8SPLIT / PG_ROT_I8TC need int8 genotypes or float genotypes with at most three levels per SNP";
+        return PG_ERR_ARG;
+    }
     if (!i8 && !affine) {
         int rc = stage_to_snp_major(stream, n, src, xdtype, ld, layout, mb, xf, n);
         if (rc) { w->err = "staging kernel launch failed"; return rc; }
@@ -266,8 +267,9 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     // PG_ROT_AUTO on int8 dosages: the hand-written fused tcgen05 kernel (PG_ROT_DEFAULT=cublas selects the library GEMM
     // + recombination pair, which level-coded float blocks always use: their affine fix-up lives in the recombination)
     static const bool default_tc = !(getenv("PG_ROT_DEFAULT") && !strcmp(getenv("PG_ROT_DEFAULT"), "cublas"));
-    const bool fused_tc = (rotation == PG_ROT_I8TC || (rotation == PG_ROT_AUTO && default_tc)) && !affine;
     static const bool tc_single = getenv("PG_TC_SINGLE") != nullptr;
+    const bool fused_tc = (rotation == PG_ROT_I8TC || (rotation == PG_ROT_AUTO && default_tc)) && !(affine && tc_single);
+    (void)forced_i8;
     const bool direct = (!fused_tc || !tc_single) && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
                         (n % 16 == 0) && (mb % 16 == 0);
     if (!direct) {
@@ -285,9 +287,31 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         // CTA-pair kernel (cta_group::2) unless PG_TC_SINGLE is set
-        const int r = tc_single ? tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx)
-                                : tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
-                                              direct ? (const int8_t*)src : nullptr, ld);
+        int r;
+        if (tc_single) {
+            r = tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx);
+        } else {
+            r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                            direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 0);
+            if (r == 0 && affine && need_eps) {
+                // second component of unequally spaced levels: indicator [code == 2], accumulated with weight eps
+                dim3 ge((unsigned)((mb + 127) / 128), (unsigned)((n + 63) / 64));
+                if (fdtype == PG_X_F32)
+                    encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
+                else
+                    encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
+                PG_ROT_CK(cudaGetLastError());
+                (*n_launch)++;
+                if (!direct) {
+                    dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
+                    stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
+                    PG_ROT_CK(cudaGetLastError());
+                }
+                r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                                direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 1);
+                (*n_launch)++;
+            }
+        }
         if (r) { w->err = "fused tcgen05 rotation launch failed, code " + std::to_string(r); return PG_ERR_CUDA; }
         (*n_launch)++;
         cudaEventRecord(ev_rot_end, stream);

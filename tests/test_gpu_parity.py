@@ -258,8 +258,8 @@ def test_i8split_rotation_equals_fp64_rotation():
             assert row0 == 128
             res[eng] = (o, xr)
         h.set_options(rotation=capi.PG_ROT_I8SPLIT)
-        with pytest.raises(capi.PgError):
-            h.scan(p["X"].astype(np.float32))
+        with pytest.raises(capi.PgError):  # float genotypes that are not level-codeable cannot take an int8 engine
+            h.scan(p["X"].astype(np.float32) + np.random.default_rng(0).random(p["X"].shape, dtype=np.float32))
     (o64, x64), (o8, x8) = res[capi.PG_ROT_FP64], res[capi.PG_ROT_I8SPLIT]
     scale = np.sqrt((p["X"].astype(np.float64) ** 2).sum(0))[128:192, None]
     assert (np.abs(x64 - x8) / scale).max() < 1e-13
@@ -403,7 +403,7 @@ def test_float_dosages_take_the_level_coded_int8_path():
                 o = h.scan(Xin, layout=capi.PG_X_SNP_MAJOR if layout_snp else capi.PG_X_SAMPLE_MAJOR)
                 # float32-standardised columns are not equally spaced to double rounding: they take the two-component
                 # (code + indicator) form of the same int8 path
-                assert o["timing"]["rot_engine"] == capi.PG_ROT_I8SPLIT, name
+                assert o["timing"]["rot_engine"] in (capi.PG_ROT_I8SPLIT, capi.PG_ROT_I8TC), name
                 ok = np.ones(m, dtype=bool)
                 ok[7] = False  # constant column: degenerate (x is collinear with the intercept), finite garbage in both
                 _check(o, ref, idx=np.where(ok)[0], tag=(name, layout_snp))
@@ -413,6 +413,17 @@ def test_float_dosages_take_the_level_coded_int8_path():
         assert o64["timing"]["rot_engine"] == capi.PG_ROT_FP64
         h.set_options(rotation=capi.PG_ROT_AUTO)
         o8 = h.scan(np.ascontiguousarray(variants["std_f64"]))
+        # the library-GEMM form of the level-coded path gives the same bits as the fused kernel
+        h.set_options(rotation=capi.PG_ROT_I8SPLIT)
+        for name in ("std_f64", "std_f32", "odd_levels_f64"):
+            ol = h.scan(np.ascontiguousarray(variants[name]))
+            h.set_options(rotation=capi.PG_ROT_AUTO)
+            oa = h.scan(np.ascontiguousarray(variants[name]))
+            h.set_options(rotation=capi.PG_ROT_I8SPLIT)
+            assert ol["timing"]["rot_engine"] == capi.PG_ROT_I8SPLIT and oa["timing"]["rot_engine"] == capi.PG_ROT_I8TC
+            for c in COLS:
+                assert np.array_equal(ol[c], oa[c], equal_nan=True), (name, c)
+        h.set_options(rotation=capi.PG_ROT_AUTO)
         ok = np.arange(m) != 7
         for c in COLS:
             assert rel(o8[c][ok], o64[c][ok]).max() < 1e-8, c
