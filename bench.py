@@ -208,7 +208,11 @@ def ncu_traffic(kernel_substr: str):
     p = os.path.join(ROOT, "profiles", "ncu_r01_hot_kernels_8192snps.json")
     if not os.path.exists(p):
         return None
-    snps = {"cutlass": 3584, "combine_i8": 3584, "compress_dmma": 8192, "reml_solve": 8192}
+    snps = {"cutlass": 3584, "combine_i8": 3584, "compress_dmma": 8192, "reml_solve": 8192, "rotate_i8_tc2": 16384}
+    if kernel_substr == "rotate_i8_tc2":  # captured separately: tools/prof_tc.py 10000 16384
+        p = os.path.join(ROOT, "profiles", "ncu_r01_tc2_16384snps.json")
+        if not os.path.exists(p):
+            return None
     for e in json.load(open(p)):
         if kernel_substr in e["kernel"] and "dram_traffic_bytes" in e:
             return e["dram_traffic_bytes"] / snps[kernel_substr]
@@ -384,7 +388,9 @@ def run_ours(args):
                 "share_of_step": st["ms"] / step_ms}
     # DRAM traffic of the dominant stage per launch (= per SNP block), from the committed ncu capture
     per_snp = None
-    if dom == "rotation" and i8:
+    if dom == "rotation" and i8 and fused:
+        per_snp = ncu_traffic("rotate_i8_tc2")
+    elif dom == "rotation" and i8:
         a_, b_ = ncu_traffic("cutlass"), ncu_traffic("combine_i8")
         per_snp = (a_ + b_) if (a_ and b_) else None
     elif dom == "compress":
@@ -393,8 +399,9 @@ def run_ours(args):
         per_snp = ncu_traffic("reml_solve")
     roofline["traffic"] = per_snp * res_tm["block_snps"] if per_snp else None
     roofline["traffic_note"] = ("dram__bytes_read+write of the stage's kernels per SNP block (ncu --set full, n=10000, "
-                                "profiles/ncu_r01_hot_kernels_8192snps.json); algorithmic HBM bytes per SNP for the rotation "
-                                "stage: 10 KB int8 in + 280 KB int32 partial products out and back + 80 KB fp64 out")
+                                "profiles/ncu_r01_tc2_16384snps.json / ncu_r01_hot_kernels_8192snps.json); algorithmic HBM bytes "
+                                "per SNP for the fused rotation: 10 KB int8 in + 80 KB fp64 out (+ the 70 MB digit planes "
+                                "once per eigen-tile group); the cuBLAS form adds 2 x 280 KB of int32 partial products")
     roofline["per_kernel_ms_last_step"] = {"convert": conv_ms, "rotate": rot_ms, "compress": cmp_ms, "solve": solve_ms}
     roofline["rotate_tflops_fp64_equiv"] = 2.0 * n * n * m / (rot_ms * 1e-3) / 1e12
     roofline["compress_frac_of_dmma_peak"] = stages["compress"]["achieved"] / stages["compress"]["peak"]

@@ -717,7 +717,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         if (lr) return lr;
         CK(cudaGetLastError());
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
-        pvalue_kernel<<<(unsigned)((mb + 255) / 256), 256, 0, st>>>(out[4], out[5], row0, mb, (double)(h->n - h->c0 - 1));
+        pvalue_kernel<<<(unsigned)((mb + 63) / 64), 64, 0, st>>>(out[4], out[5], row0, mb, (double)(h->n - h->c0 - 1));
         CK(cudaGetLastError());
         return PG_OK;
     }
