@@ -107,6 +107,18 @@ int pg_destroy(pg_handle* h);
 int pg_set_kinship(pg_handle* h, const double* K_host, double* d_out_host, float* eig_ms);
 
 /*
+ * Genetic relatedness matrix on the device (the step right before the scan in the reference's callers):
+ *   sd = std(X, axis=0); sd[sd == 0] = 1; Z = (X - mean(X, axis=0)) / sd; K = Z Z^T / p
+ * (calculate_genetic_relatedness_matrix, experiments/animal_gwas/run_gwas.py:45-55; K = X_s X_s^T / p after
+ * StandardScaler in experiments/wtccc/run_pygemma.py:432,:447).  X holds p marker columns for the handle's n samples
+ * (host pointer; dtype / layout / ld as in pg_scan).  K_host_out (nullable) receives the n*n matrix; with
+ * set_kinship != 0 the matrix stays on the device and is eigendecomposed in place as by pg_set_kinship
+ * (d_out_host / eig_ms as there).  grm_ms (nullable): device time of the standardisation + FP64 SYRK.
+ */
+int pg_grm(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout, int64_t p, double* K_host_out,
+           int set_kinship, double* d_out_host, float* grm_ms, float* eig_ms);
+
+/*
  * Supply an eigendecomposition computed elsewhere.  u_row_major = 1: U[j*n + i] is component j of
  * eigenvector i (NumPy C-order result of eigh); 0: column-major (LAPACK / cuSOLVER order).
  * U may be NULL when the inputs of pg_set_design / pg_scan are already rotated (eigen=False,

@@ -22,7 +22,7 @@ PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
 SYMBOLS = [
     "pg_abi_version", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_stream", "pg_set_options",
-    "pg_set_reml_engine",
+    "pg_set_reml_engine", "pg_grm",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
 
@@ -73,6 +73,8 @@ def load():
     L.pg_set_options.argtypes = [vp, i32, i64]
     L.pg_set_stream.argtypes = [vp, vp]
     L.pg_set_reml_engine.argtypes = [vp, i32]
+    L.pg_grm.argtypes = [vp, vp, i32, i64, i32, i64, vp, i32, vp, ctypes.POINTER(ctypes.c_float),
+                         ctypes.POINTER(ctypes.c_float)]
     scan_args = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 9 + [ctypes.POINTER(PgTiming)]
     L.pg_scan.argtypes = scan_args
     L.pg_scan_device.argtypes = scan_args
@@ -142,6 +144,24 @@ class Handle:
         ms = ctypes.c_float(0)
         self._ck(self.L.pg_set_kinship(self.h, _ptr(K), _ptr(d), ctypes.byref(ms)))
         return d, float(ms.value)
+
+    def grm(self, X, layout=PG_X_SAMPLE_MAJOR, return_K=True, set_kinship=False):
+        """Genetic relatedness matrix K = Z Z^T / p of the marker matrix X on the device (pg_grm); optionally
+        eigendecomposed in place for the scan.  Returns dict(K, d, grm_ms, eig_ms)."""
+        if X.ndim != 2:
+            raise ValueError("X must be 2-D")
+        n, p = X.shape if layout == PG_X_SAMPLE_MAJOR else X.shape[::-1]
+        if n != self.n:
+            raise ValueError(f"X has {n} samples, handle was created for {self.n}")
+        if X.strides[1] != X.itemsize or (X.shape[0] > 1 and X.strides[0] % X.itemsize) or X.strides[0] < 0:
+            X = np.ascontiguousarray(X)
+        ld = max(X.strides[0] // X.itemsize if X.shape[0] > 1 else X.shape[1], X.shape[1])
+        K = np.empty((self.n, self.n)) if return_K else None
+        d = np.empty(self.n) if set_kinship else None
+        gms, ems = ctypes.c_float(0), ctypes.c_float(0)
+        self._ck(self.L.pg_grm(self.h, _ptr(X), xdtype_of(X), ld, layout, p, _ptr(K), int(bool(set_kinship)), _ptr(d),
+                               ctypes.byref(gms), ctypes.byref(ems)))
+        return {"K": K, "d": d, "grm_ms": float(gms.value), "eig_ms": float(ems.value)}
 
     def set_eigen(self, U, d):
         d = np.ascontiguousarray(d, dtype=np.float64).reshape(-1)

@@ -393,14 +393,27 @@ static int canonicalise_eigen(pg_handle* h)
     return upload_plan(h, ds);
 }
 
+static int set_kinship_common(pg_handle* h, const double* K, cudaMemcpyKind kind, double* d_out_host, float* eig_ms);
+
 extern "C" int pg_set_kinship(pg_handle* h, const double* K_host, double* d_out_host, float* eig_ms)
+{
+    return set_kinship_common(h, K_host, cudaMemcpyHostToDevice, d_out_host, eig_ms);
+}
+
+// K already on the device (pg_grm)
+static int set_kinship_device(pg_handle* h, const double* K_dev, double* d_out_host, float* eig_ms)
+{
+    return set_kinship_common(h, K_dev, cudaMemcpyDeviceToDevice, d_out_host, eig_ms);
+}
+
+static int set_kinship_common(pg_handle* h, const double* K_host, cudaMemcpyKind kind, double* d_out_host, float* eig_ms)
 {
     if (!h || !K_host) return fail(h, PG_ERR_ARG, "pg_set_kinship: NULL argument");
     CK(cudaSetDevice(h->device));
     const int n = h->n;
     int rc = ensure_U(h);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->U, K_host, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, h->compute));
+    CK(cudaMemcpyAsync(h->U, K_host, sizeof(double) * (size_t)n * n, kind, h->compute));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -962,6 +975,159 @@ extern "C" int pg_scan_device(pg_handle* h, const void* X_dev, int xdtype, int64
 {
     double* out[6] = {beta, se_beta, tau, lambda, F_wald, p_wald};
     return scan_impl(h, X_dev, xdtype, ld, layout, m, grid, out, status, n_eval2, n_eval3, timing, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Genetic relatedness matrix on the device ("next" row of the scope table: the step right before the path).
+// Reference: calculate_genetic_relatedness_matrix, experiments/animal_gwas/run_gwas.py:45-55 --
+//   sd = np.std(X, axis=0); sd[sd == 0] = 1; Z = (X - X.mean(axis=0)) / sd; K = Z @ Z.T / X.shape[1]
+// (the same K = X_s X_s^T / p the other callers build after StandardScaler, experiments/wtccc/run_pygemma.py:432,:447).
+// SNP blocks are standardised on the device (two-pass mean / variance like NumPy) and accumulated with FP64 SYRK.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGrmChunk = 512;
+
+// partial sums of one SNP column over a chunk of samples: pass 0 -> sum(x), pass 1 -> sum((x - mean)^2)
+template <typename T>
+__global__ void __launch_bounds__(128) grm_partial_kernel(const T* __restrict__ src, long long ld, int layout, int n,
+                                                           long long pb, const double* __restrict__ mean, int pass,
+                                                           double* __restrict__ part)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pb) return;
+    const int j0 = blockIdx.y * kGrmChunk, j1 = min(n, j0 + kGrmChunk);
+    const size_t step = layout == 0 ? (size_t)ld : 1, base = layout == 0 ? (size_t)g : (size_t)g * ld;
+    const double mu = pass ? mean[g] : 0.0;
+    double acc = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const double x = (double)src[base + (size_t)j * step];
+        const double d = x - mu;
+        acc += pass ? d * d : x;
+    }
+    part[(size_t)blockIdx.y * pb + g] = acc;
+}
+
+// pass 0: mean[g] = sum / n; pass 1: isd[g] = 1 / sqrt(sum / n), 1 when the column is constant (sd[sd == 0] = 1)
+__global__ void grm_reduce_kernel(const double* __restrict__ part, int nchunks, long long pb, int n, int pass,
+                                  double* __restrict__ out)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pb) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[(size_t)c * pb + g];
+    if (pass == 0) {
+        out[g] = s / (double)n;
+    } else {
+        const double sd = sqrt(s / (double)n);
+        out[g] = sd == 0.0 ? 1.0 : 1.0 / sd;
+    }
+}
+
+// Z^T block, column-major (pb x n, ld = pb): element (g, j) = (x_jg - mean_g) * isd_g
+template <typename T>
+__global__ void __launch_bounds__(128) grm_standardise_kernel(const T* __restrict__ src, long long ld, int layout, int n,
+                                                               long long pb, const double* __restrict__ mean,
+                                                               const double* __restrict__ isd, double* __restrict__ zt)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pb) return;
+    const int j0 = blockIdx.y * 64, j1 = min(n, j0 + 64);
+    const double mu = mean[g], is = isd[g];
+    for (int j = j0; j < j1; ++j) {
+        const size_t si = layout == 0 ? (size_t)j * ld + g : (size_t)g * ld + j;
+        zt[(size_t)j * pb + g] = ((double)src[si] - mu) * is;
+    }
+}
+
+__global__ void grm_symmetrise_kernel(double* __restrict__ K, int n)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int c = (int)(idx / n), r = (int)(idx % n);   // column-major element (r, c)
+    if (r < c) K[idx] = K[(size_t)r * n + c];           // upper <- lower
+}
+
+template <typename T>
+static int grm_block(pg_handle* h, const T* dsrc, long long ld_dev, int layout, long long pb, double* part, double* mean,
+                     double* isd, double* zt)
+{
+    const int n = h->n;
+    const int nchunks = (n + kGrmChunk - 1) / kGrmChunk;
+    const unsigned gb = (unsigned)((pb + 127) / 128);
+    for (int pass = 0; pass < 2; ++pass) {
+        grm_partial_kernel<T><<<dim3(gb, nchunks), 128, 0, h->compute>>>(dsrc, ld_dev, layout, n, pb, mean, pass, part);
+        CK(cudaGetLastError());
+        grm_reduce_kernel<<<gb, 128, 0, h->compute>>>(part, nchunks, pb, n, pass, pass ? isd : mean);
+        CK(cudaGetLastError());
+    }
+    grm_standardise_kernel<T><<<dim3(gb, (unsigned)((n + 63) / 64)), 128, 0, h->compute>>>(dsrc, ld_dev, layout, n, pb, mean, isd, zt);
+    CK(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_grm(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout, int64_t p, double* K_host_out,
+                      int set_kinship, double* d_out_host, float* grm_ms, float* eig_ms)
+{
+    if (!h || !X || p <= 0) return fail(h, PG_ERR_ARG, "pg_grm: NULL X or p <= 0");
+    if (xdtype < PG_X_I8 || xdtype > PG_X_F64) return fail(h, PG_ERR_ARG, "pg_grm: xdtype %d", xdtype);
+    if (layout != PG_X_SAMPLE_MAJOR && layout != PG_X_SNP_MAJOR) return fail(h, PG_ERR_ARG, "pg_grm: layout %d", layout);
+    const int n = h->n;
+    if ((layout == PG_X_SAMPLE_MAJOR && ld < p) || (layout == PG_X_SNP_MAJOR && ld < n)) return fail(h, PG_ERR_ARG, "pg_grm: ld too small");
+    CK(cudaSetDevice(h->device));
+    const size_t esz = xdtype_size(xdtype);
+    long long pb = (long long)((size_t(1) << 30) / (sizeof(double) * (size_t)n));
+    pb = std::max<long long>(256, std::min<long long>(pb, p));
+    const int nchunks = (n + kGrmChunk - 1) / kGrmChunk;
+    double *Kd = nullptr, *zt = nullptr, *part = nullptr, *mean = nullptr, *isd = nullptr;
+    void* raw = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = [&]() -> int {
+        CK(cudaMalloc(&Kd, sizeof(double) * (size_t)n * n));
+        CK(cudaMalloc(&zt, sizeof(double) * (size_t)n * pb));
+        CK(cudaMalloc(&part, sizeof(double) * (size_t)nchunks * pb));
+        CK(cudaMalloc(&mean, sizeof(double) * pb));
+        CK(cudaMalloc(&isd, sizeof(double) * pb));
+        CK(cudaMalloc(&raw, esz * (size_t)n * pb));
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, h->compute));
+        const double alpha = 1.0 / (double)p;
+        for (long long g0 = 0; g0 < p; g0 += pb) {
+            const long long cnt = std::min(pb, p - g0);
+            long long ld_dev;
+            if (layout == PG_X_SAMPLE_MAJOR) {
+                CK(cudaMemcpy2DAsync(raw, (size_t)cnt * esz, (const char*)X + (size_t)g0 * esz, (size_t)ld * esz,
+                                     (size_t)cnt * esz, (size_t)n, cudaMemcpyHostToDevice, h->compute));
+                ld_dev = cnt;
+            } else {
+                CK(cudaMemcpy2DAsync(raw, (size_t)n * esz, (const char*)X + (size_t)g0 * ld * esz, (size_t)ld * esz,
+                                     (size_t)n * esz, (size_t)cnt, cudaMemcpyHostToDevice, h->compute));
+                ld_dev = n;
+            }
+            int r2;
+            if (xdtype == PG_X_I8) r2 = grm_block<int8_t>(h, (const int8_t*)raw, ld_dev, layout, cnt, part, mean, isd, zt);
+            else if (xdtype == PG_X_F32) r2 = grm_block<float>(h, (const float*)raw, ld_dev, layout, cnt, part, mean, isd, zt);
+            else r2 = grm_block<double>(h, (const double*)raw, ld_dev, layout, cnt, part, mean, isd, zt);
+            if (r2) return r2;
+            // zt is Z^T (cnt x n, column-major): K(lower) += (1/p) Z Z^T = (1/p) (Z^T)^T (Z^T)
+            const double beta = g0 == 0 ? 0.0 : 1.0;
+            CKB(cublasDsyrk(h->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, n, (int)cnt, &alpha, zt, (int)cnt, &beta, Kd, n));
+        }
+        const size_t total = (size_t)n * n;
+        grm_symmetrise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->compute>>>(Kd, n);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, h->compute));
+        if (K_host_out) CK(cudaMemcpyAsync(K_host_out, Kd, sizeof(double) * total, cudaMemcpyDeviceToHost, h->compute));
+        CK(cudaStreamSynchronize(h->compute));
+        if (grm_ms) cudaEventElapsedTime(grm_ms, e0, e1);
+        return PG_OK;
+    }();
+    if (rc == PG_OK && set_kinship) rc = set_kinship_device(h, Kd, d_out_host, eig_ms);
+    void* bufs[] = {Kd, zt, part, mean, isd, raw};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
 }
 
 extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, double lam, int fixed_index, int full,

@@ -434,3 +434,44 @@ def test_float_dosages_take_the_level_coded_int8_path():
         assert oi["timing"]["rot_engine"] == capi.PG_ROT_FP64
         refi = oracle.pygemma(p["Y"], Xi, p["W"], p["K"])
         _check(oi, refi, idx=np.where(ok)[0], tag="imputed")
+
+
+def test_grm_on_device_matches_reference_definition():
+    """pg_grm against the reference's calculate_genetic_relatedness_matrix (experiments/animal_gwas/run_gwas.py:45-55)
+    restated in NumPy, for int8 / float32 / float64 markers, both layouts, a constant column, several blocks; and the
+    fused GRM -> syevd -> scan pipeline against the same steps with K passed through the host."""
+    from pygemma_b200 import grm
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    rng = np.random.default_rng(4)
+    n, p = 500, 3000
+    G = rng.binomial(2, rng.uniform(0.05, 0.5, p), size=(n, p)).astype(np.int8)
+    G[:, 17] = 1  # constant column: sd -> 1
+    def ref(X):
+        X = X.astype(np.float64)
+        sd = X.std(axis=0)
+        sd[sd == 0] = 1
+        Z = (X - X.mean(axis=0)) / sd
+        return Z @ Z.T / X.shape[1]
+    Kref = ref(G)
+    for X in (G, G.astype(np.float32), G.astype(np.float64)):
+        K = grm.calculate_genetic_relatedness_matrix(X)
+        assert K.shape == (n, n) and np.allclose(K, K.T, rtol=0, atol=0)
+        assert np.abs(K - Kref).max() < 1e-12 * np.abs(Kref).max(), str(X.dtype)
+    with capi.Handle(n, 1) as h:
+        Ks = h.grm(np.ascontiguousarray(G.T), layout=capi.PG_X_SNP_MAJOR)["K"]
+    assert np.abs(Ks - Kref).max() < 1e-12 * np.abs(Kref).max()
+    # GRM kept on the device and eigendecomposed in place == K through the host
+    pr = make_problem(n, 64, 3, seed=2, m_k=400)
+    with capi.Handle(n, 3) as h:
+        r = h.grm(G, return_K=False, set_kinship=True)
+        assert (np.diff(r["d"]) >= 0).all() and r["d"].min() >= 0
+        h.set_design(pr["W"], pr["Y"])
+        o1 = h.scan(pr["X"])
+    with capi.Handle(n, 3) as h:
+        h.set_kinship(Kref)
+        h.set_design(pr["W"], pr["Y"])
+        o2 = h.scan(pr["X"])
+    for c in COLS:
+        assert rel(o1[c], o2[c]).max() < 1e-7, (c, float(rel(o1[c], o2[c]).max()))
