@@ -787,7 +787,21 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     int rc = ensure_workspace(h, m, xdtype);
     if (rc) return rc;
     const long long blk = h->blk;
-    const long long nblocks = (m + blk - 1) / blk;
+    // Block boundaries.  Host input with automatic blocking: the first two blocks are short (1/16 and 1/4 of a block) so
+    // that compute starts after ~0.4 ms of upload instead of a whole block's worth; every later upload hides behind
+    // the previous block's compute.
+    std::vector<long long> bstart;
+    {
+        long long g = 0;
+        if (!on_device && h->block_snps_opt <= 0 && m >= 2 * blk) {
+            for (long long first : {std::max<long long>(1024, blk / 16 / 256 * 256), std::max<long long>(4096, blk / 4 / 256 * 256)}) {
+                if (first < blk && g + first < m) { bstart.push_back(g); g += first; }
+            }
+        }
+        for (; g < m; g += blk) bstart.push_back(g);
+        bstart.push_back(m);
+    }
+    const long long nblocks = (long long)bstart.size() - 1;
     const size_t esz = xdtype_size(xdtype);
     const bool rotate = !h->rotated_inputs;
 
@@ -841,7 +855,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             CK(cudaStreamWaitEvent(h->cmb, t0, 0));
         }
         for (long long b = 0; b < nblocks; ++b) {
-            const long long g0 = b * blk, mb = std::min(blk, m - g0);
+            const long long g0 = bstart[b], mb = bstart[b + 1] - g0;
             const int s = (int)(b & 1);
             const void* src_dev;
             long long ld_dev;

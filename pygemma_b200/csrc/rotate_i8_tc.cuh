@@ -334,12 +334,9 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     a.snp_tiles = (int)((mb + kTileSnps - 1) / kTileSnps);
     a.eig_tiles = (n + kTileEig - 1) / kTileEig;
     a.scale = scale; a.xr = xr; a.ldx = ldx;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(rotate_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-            return -4;
-        attr_set = true;
-    }
+    // per call: the attribute is per device, and a process may hold handles on several devices
+    if (cudaFuncSetAttribute(rotate_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+        return -4;
     const long long tiles = (long long)a.snp_tiles * a.eig_tiles;
     const int grid = (int)std::min<long long>(tiles, sm_count);
     rotate_i8_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mx, mp, a);

@@ -375,13 +375,10 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     // measured at n = 10 000 per 25 088 SNPs: no hint 10.17 ms, evict_last(B) 10.13, evict_first(A) 10.86, both 10.81
     static const int hints_env = getenv("PG_TC2_HINTS") ? atoi(getenv("PG_TC2_HINTS")) : 2;
     a.hints = hints_env;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(rotate_i8_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-            return -4;
-        attr_set = true;
-    }
+    // per call: the attribute is per device, and a process may hold handles on several devices
+    if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rotate_i8_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+        return -4;
     const long long tiles = (long long)a.snp_tiles * a.eig_tiles;
     const int clusters = (int)std::min<long long>(tiles, sm_count / 2);
     if (xsm) rotate_i8_tc2_kernel<true><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, a);
