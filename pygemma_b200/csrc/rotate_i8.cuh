@@ -124,29 +124,36 @@ __global__ void __launch_bounds__(256) combine_i8_kernel(const int32_t* __restri
 // three levels are NOT equally spaced (standardised in float32: ~1e-7 off; or any three-valued coding) are
 //     x = v0 + s g + eps [g = 2] ,   U^T x = v0 (U^T 1) + s (U^T g) + eps (U^T [g = 2]) :
 // a second exact int8 rotation of the indicator [g = 2] is accumulated with weight eps (2x the tensor work, still
-// ~4x faster than the FP64 GEMM).  Any column with NaN/Inf or more than three levels sends the whole block down
-// the FP64 path.
+// ~4x faster than the FP64 GEMM).  The same two-component form covers FOUR-valued columns made of three equally
+// spaced levels plus one outlier -- mean-imputed dosages {0, 1, 2, mean} as the reference's callers produce them
+// (SimpleImputer(strategy='mean'), experiments/animal_gwas/run_gwas.py:93-94), also after standardisation: the
+// outlier gets code 0 and the indicator carries eps = outlier - v0.  Any column with NaN/Inf, more than four levels,
+// or four levels without such a triple sends the whole block down the FP64 path.
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxLevels = 4;
+
 struct LevelInfo {
-    double v0, s;   // x = v0 + s * code (+ eps where code == 2)
-    double eps;     // v2 - v0 - 2 s when the three levels are not equally spaced to double rounding, else 0
-    double t01, t12; // code = (x > t01) + (x > t12): midpoints between the sorted levels (+inf when absent)
-    int nlev;       // 1..3: codeable; 0: not codeable
+    double v0, s;   // x = v0 + s * code + eps * indicator
+    double eps;     // weight of the indicator component, 0 when the column is an exact affine image of its code
+    double t[3];    // level index = (x > t[0]) + (x > t[1]) + (x > t[2]): midpoints of the sorted levels (+inf when absent)
+    unsigned char code_of[kMaxLevels];  // code (0, 1, 2) of each sorted level
+    unsigned char ind_of[kMaxLevels];   // indicator (0 / 1) of each sorted level
+    int nlev;       // 1..4: codeable; 0: not codeable
     int pad;
 };
 
 struct LevelPartial {
-    double v[3];
-    int k;      // number of distinct values seen in this sample chunk; -1: more than three or a non-finite value
+    double v[kMaxLevels];
+    int k;      // number of distinct values seen in this sample chunk; -1: more than four or a non-finite value
     int pad;
 };
 
-__device__ __forceinline__ void level_insert(double x, double (&v)[3], int& k)
+__device__ __forceinline__ void level_insert(double x, double (&v)[kMaxLevels], int& k)
 {
     if (k < 0) return;
     if (!isfinite(x)) { k = -1; return; }
-    if ((k > 0 && x == v[0]) || (k > 1 && x == v[1]) || (k > 2 && x == v[2])) return;
-    if (k == 3) { k = -1; return; }
+    if ((k > 0 && x == v[0]) || (k > 1 && x == v[1]) || (k > 2 && x == v[2]) || (k > 3 && x == v[3])) return;
+    if (k == kMaxLevels) { k = -1; return; }
     v[k++] = x;
 }
 
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(128) find_levels_kernel(const T* __restrict__ 
     if (g >= mb) return;
     const int j0 = blockIdx.y * kLevelChunk, j1 = min(n, j0 + kLevelChunk);
     const size_t step = layout == 0 ? (size_t)ld : 1, base = layout == 0 ? (size_t)g : (size_t)g * ld;
-    double v[3] = {0.0, 0.0, 0.0};
+    double v[kMaxLevels] = {0.0, 0.0, 0.0, 0.0};
     int k = 0;
     int j = j0;
     for (; j + 8 <= j1; j += 8) {
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(128) find_levels_kernel(const T* __restrict__ 
     }
     for (; j < j1; ++j) level_insert((double)src[base + (size_t)j * step], v, k);
     LevelPartial lp;
-    lp.v[0] = v[0]; lp.v[1] = v[1]; lp.v[2] = v[2]; lp.k = k; lp.pad = 0;
+    lp.v[0] = v[0]; lp.v[1] = v[1]; lp.v[2] = v[2]; lp.v[3] = v[3]; lp.k = k; lp.pad = 0;
     part[(size_t)blockIdx.y * mb + g] = lp;
 }
 
@@ -183,7 +190,7 @@ __global__ void merge_levels_kernel(const LevelPartial* __restrict__ part, int n
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= mb) return;
-    double v[3] = {0.0, 0.0, 0.0};
+    double v[kMaxLevels] = {0.0, 0.0, 0.0, 0.0};
     int k = 0;
     for (int c = 0; c < nchunks; ++c) {
         const LevelPartial lp = part[(size_t)c * mb + g];
@@ -192,29 +199,59 @@ __global__ void merge_levels_kernel(const LevelPartial* __restrict__ part, int n
         if (k < 0) break;
     }
     LevelInfo li;
-    li.v0 = 0.0; li.s = 0.0; li.eps = 0.0; li.t01 = INFINITY; li.t12 = INFINITY; li.nlev = 0; li.pad = 0;
+    li.v0 = 0.0; li.s = 0.0; li.eps = 0.0; li.nlev = 0; li.pad = 0;
+    for (int u = 0; u < 3; ++u) li.t[u] = INFINITY;
+    for (int u = 0; u < kMaxLevels; ++u) { li.code_of[u] = 0; li.ind_of[u] = 0; }
     if (k > 0) {
-        if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
-        if (k > 2 && v[2] < v[1]) { const double t = v[1]; v[1] = v[2]; v[2] = t; }
-        if (k > 1 && v[1] < v[0]) { const double t = v[0]; v[0] = v[1]; v[1] = t; }
-        li.v0 = v[0];
+        for (int a = 1; a < k; ++a)   // insertion sort, ascending
+            for (int b = a; b > 0 && v[b] < v[b - 1]; --b) { const double t = v[b]; v[b] = v[b - 1]; v[b - 1] = t; }
+        for (int u = 0; u + 1 < k; ++u) li.t[u] = 0.5 * v[u] + 0.5 * v[u + 1];
+        const double mx = fmax(fabs(v[0]), fabs(v[k - 1]));
         li.nlev = k;
-        if (k >= 2) { li.s = v[1] - v[0]; li.t01 = 0.5 * v[0] + 0.5 * v[1]; }
+        li.v0 = v[0];
+        if (k == 2) { li.s = v[1] - v[0]; li.code_of[1] = 1; }
         if (k == 3) {
-            li.t12 = 0.5 * v[1] + 0.5 * v[2];
-            const double mx = fmax(fabs(v[0]), fabs(v[2]));
-            if (fabs((v[2] - v[1]) - (v[1] - v[0])) > tol * mx) {
-                li.eps = (v[2] - v[0]) - 2.0 * li.s;  // unequal spacing: needs the second (indicator) rotation
-                atomicAdd(n_bad + 1, 1);
+            li.s = v[1] - v[0];
+            li.code_of[1] = 1; li.code_of[2] = 2;
+            if (fabs((v[2] - v[1]) - (v[1] - v[0])) > tol * mx) {   // unequal spacing: the top level carries the indicator
+                li.ind_of[2] = 1;
+                li.eps = (v[2] - v[0]) - 2.0 * li.s;
             }
         }
+        if (k == 4) {
+            // three equally spaced levels plus one outlier (mean-imputed dosages): outlier -> code 0 + indicator
+            int out = -1;
+            for (int o = 0; o < 4 && out < 0; ++o) {
+                double w[3];
+                int q = 0;
+                for (int u = 0; u < 4; ++u)
+                    if (u != o) w[q++] = v[u];
+                if (fabs((w[2] - w[1]) - (w[1] - w[0])) <= tol * mx) out = o;
+            }
+            if (out < 0) {
+                li.nlev = 0;
+            } else {
+                int q = 0;
+                double w0 = 0.0, w1 = 0.0;
+                for (int u = 0; u < 4; ++u) {
+                    if (u == out) continue;
+                    if (q == 0) w0 = v[u];
+                    if (q == 1) w1 = v[u];
+                    li.code_of[u] = (unsigned char)q++;
+                }
+                li.v0 = w0; li.s = w1 - w0;
+                li.code_of[out] = 0; li.ind_of[out] = 1;
+                li.eps = v[out] - w0;
+            }
+        }
+        if (li.nlev > 0 && li.eps != 0.0) atomicAdd(n_bad + 1, 1);
     }
     if (li.nlev == 0) atomicAdd(n_bad, 1);
     info[g] = li;
 }
 
 // codes in the layout of the input: sample-major (n x mb, ld = mb) or SNP-major (mb x n, ld = n)
-// indicator != 0: write [code == 2] instead of the code (operand of the eps rotation)
+// indicator != 0: write the indicator of the level instead of its code (operand of the eps rotation)
 template <typename T>
 __global__ void encode_levels_kernel(const T* __restrict__ src, long long ld, int layout, int n, long long mb,
                                      const LevelInfo* __restrict__ info, int8_t* __restrict__ codes, int indicator)
@@ -232,21 +269,22 @@ __global__ void encode_levels_kernel(const T* __restrict__ src, long long ld, in
 #pragma unroll
         for (int u = 0; u < 8; ++u)
         {
-            const int c = (x[u] > li.t01) + (x[u] > li.t12);
-            codes[layout == 0 ? (size_t)(j + u) * mb + g : (size_t)g * n + j + u] = (int8_t)(indicator ? (c == 2) : c);
+            const int idx = (x[u] > li.t[0]) + (x[u] > li.t[1]) + (x[u] > li.t[2]);
+            codes[layout == 0 ? (size_t)(j + u) * mb + g : (size_t)g * n + j + u] =
+                (int8_t)(indicator ? li.ind_of[idx] : li.code_of[idx]);
         }
     }
     for (; j < j1; ++j) {
         const size_t si = layout == 0 ? (size_t)j * ld + g : (size_t)g * ld + j;
         const size_t di = layout == 0 ? (size_t)j * mb + g : (size_t)g * n + j;
         const double xv = (double)src[si];
-        const int c = (xv > li.t01) + (xv > li.t12);
-        codes[di] = (int8_t)(indicator ? (c == 2) : c);
+        const int idx = (xv > li.t[0]) + (xv > li.t[1]) + (xv > li.t[2]);
+        codes[di] = (int8_t)(indicator ? li.ind_of[idx] : li.code_of[idx]);
     }
 }
 
 // recombination with the affine fix-up: xr[g][i] = v0_g * u1_i + s_g * (U^T code_g)_i
-// accumulate != 0 (second pass, indicator rotation): xr[g][i] += eps_g * (U^T [code_g == 2])_i
+// accumulate != 0 (second pass, indicator rotation): xr[g][i] += eps_g * (U^T indicator_g)_i
 __global__ void __launch_bounds__(256) combine_i8_affine_kernel(const int32_t* __restrict__ P, const int* __restrict__ exps,
                                                                  int n, int npad, long long mb, double* __restrict__ xr,
                                                                  long long ldx, const LevelInfo* __restrict__ info,

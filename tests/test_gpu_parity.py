@@ -371,7 +371,8 @@ def test_float_dosages_take_the_level_coded_int8_path():
     (experiments/wtccc/run_pygemma.py:432) -- take at most three values per column: they must go through the exact int8
     tensor-core rotation on their level codes (rot_engine == I8SPLIT; one pass when the levels are equally spaced to
     double rounding, code + indicator passes otherwise) and match the oracle run on the very same float values.
-    A block holding one imputed (four-valued) column falls back to the FP64 GEMM."""
+    Mean-imputed dosages (a fourth level) stay on that path; a block holding a five-valued column falls back to the
+    FP64 GEMM."""
     from oracle import oracle
     from pygemma_b200.synth import make_problem
 
@@ -427,13 +428,27 @@ def test_float_dosages_take_the_level_coded_int8_path():
         ok = np.arange(m) != 7
         for c in COLS:
             assert rel(o8[c][ok], o64[c][ok]).max() < 1e-8, c
-        # an imputed column (4th level) makes the block dense
-        Xi = variants["std_f64"].copy()
-        Xi[3, 11] = 0.123456
-        oi = h.scan(Xi)
-        assert oi["timing"]["rot_engine"] == capi.PG_ROT_FP64
-        refi = oracle.pygemma(p["Y"], Xi, p["W"], p["K"])
-        _check(oi, refi, idx=np.where(ok)[0], tag="imputed")
+        # mean-imputed dosages (SimpleImputer(strategy='mean'), experiments/animal_gwas/run_gwas.py:93-94): three equally
+        # spaced levels + the column mean -> still the int8 path (code + indicator), raw and standardised
+        gm = g.copy()
+        miss = np.random.default_rng(3).random(gm.shape) < 0.03
+        gm[miss] = np.nan
+        gm = np.where(np.isnan(gm), np.nanmean(gm, axis=0), gm)
+        sdm = gm.std(axis=0)
+        sdm[sdm == 0] = 1.0
+        for name, Xi in (("imputed_raw", gm), ("imputed_std", (gm - gm.mean(axis=0)) / sdm)):
+            oi = h.scan(np.ascontiguousarray(Xi))
+            assert oi["timing"]["rot_engine"] == capi.PG_ROT_I8TC, name
+            refi = oracle.pygemma(p["Y"], Xi, p["W"], p["K"])
+            _check(oi, refi, idx=np.where(ok)[0], tag=name)
+        # a column with five distinct values makes the block dense (FP64 GEMM)
+        Xd = variants["std_f64"].copy()
+        Xd[3, 11] = 0.123456
+        Xd[4, 11] = -0.654321
+        od = h.scan(Xd)
+        assert od["timing"]["rot_engine"] == capi.PG_ROT_FP64
+        refd = oracle.pygemma(p["Y"], Xd, p["W"], p["K"])
+        _check(od, refd, idx=np.where(ok)[0], tag="dense")
 
 
 def test_grm_on_device_matches_reference_definition():
