@@ -708,12 +708,10 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = h->counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
-        static const int warps_opt = getenv("PG_SOLVE_WARPS") ? atoi(getenv("PG_SOLVE_WARPS")) : 8;
-        int warps = std::max(1, std::min(8, warps_opt));
+        int warps = 8;
         while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
         const size_t smem = per_warp * warps;
         const bool two = (h->c0 + 2) > 32;
-        static int minb = getenv("PG_SOLVE_MINB") ? atoi(getenv("PG_SOLVE_MINB")) : 2;
         auto launch = [&](auto kern, int ctas) -> int {
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(ctas, (200 * 1024) / std::max<size_t>(smem, 1)));
@@ -722,11 +720,8 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
             kern<<<grid, warps * 32, smem, st>>>(sa);
             return PG_OK;
         };
-        int lr;
-        if (two) lr = launch(reml_solve_kernel<2, 2>, 2);
-        else if (minb == 3) lr = launch(reml_solve_kernel<1, 3>, 3);
-        else if (minb == 4) lr = launch(reml_solve_kernel<1, 4>, 4);
-        else lr = launch(reml_solve_kernel<1, 2>, 2);
+        // 2 CTAs of 8 warps per SM (128 registers): 3 and 4 CTAs/SM and 4-6 warps per CTA were measured slower
+        const int lr = two ? launch(reml_solve_kernel<2, 2>, 2) : launch(reml_solve_kernel<1, 2>, 2);
         if (lr) return lr;
         CK(cudaGetLastError());
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
