@@ -22,9 +22,12 @@
 namespace pg {
 
 constexpr int kCtSnps = 128;    // SNPs per CTA (8 warps x 16)
-constexpr int kCtL = 16;        // eigen-indices per pipeline stage
-constexpr int kCtStages = 4;
-constexpr int kXsPitch = 20;    // doubles; 20 mod 16 == 4 -> conflict-free A-fragment reads
+#ifndef PG_CT_L
+#define PG_CT_L 16
+#endif
+constexpr int kCtL = PG_CT_L;   // eigen-indices per pipeline stage (16 or 32; rows of xr / V are padded to 32)
+constexpr int kCtStages = (kCtL == 16) ? 4 : 3;
+constexpr int kXsPitch = kCtL + 4;   // doubles; pitch mod 16 == 4 -> conflict-free A-fragment reads
 constexpr int kVsPitch = 132;   // doubles; 132 mod 16 == 4 -> conflict-free B-fragment reads
 constexpr int kLinTiles = 14;   // 8-column tiles of the linear moments (112 >= 11 * kCq)
 constexpr int kSqTiles = 2;     // 8-column tiles of the x^2 moments (16 >= kCq)
@@ -47,7 +50,7 @@ struct DevPlan {
     double* Lw = nullptr;       // [n][kCq]
     int* seg_kq = nullptr;      // [n] kq of the COMPRESS segment of l, 0 for COPY rows
     double* V = nullptr;        // [npad16][vpitch]
-    int vpitch = 0, ngroups = 0, npad16 = 0;
+    int vpitch = 0, ngroups = 0, npad16 = 0;   // npad16: rows of V, n rounded up to 32
     CompItem* items = nullptr;
     int nitems = 0;
     int* copy_l = nullptr;      // COPY rows: eigen index and node
@@ -126,7 +129,7 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
         const int lbase = c_begin + chunk * kCtL;
 #pragma unroll
         for (int c = tid; c < kCtSnps * (kCtL / 2); c += 256) {
-            const int r = c >> 3, o = (c & 7) * 2;
+            const int r = c / (kCtL / 2), o = (c % (kCtL / 2)) * 2;
             const long long snp = snp0 + r;
             const bool valid = snp < mb;
             cpa16_zfill(Xs + r * kXsPitch + o, xr + (size_t)(valid ? snp : 0) * ldx + lbase + o, valid ? 16 : 0);

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pygemma_b200.h"
@@ -44,6 +45,11 @@ struct pg_handle {
     char* res_host = nullptr;  // pinned: 6*8*cap + 3*4*cap bytes
     size_t res_cap = 0;
     std::vector<cudaEvent_t> ev_pool;
+    // pageable host genotypes: blocks are packed into pinned bounce buffers by a few host threads while the GPU
+    // works on the previous block (a pageable cudaMemcpy2D runs at ~10 GB/s, the bounce path at host-memcpy speed)
+    char* bounce[2] = {nullptr, nullptr};
+    size_t bounce_bytes = 0;
+    cudaEvent_t ev_bounce_done[2] = {nullptr, nullptr};
     cudaStream_t own_compute = nullptr;  // compute defaults to this; pg_set_stream can point it at a caller stream
     cublasHandle_t blas = nullptr;
     cusolverDnHandle_t solver = nullptr;
@@ -164,6 +170,10 @@ static int free_all(pg_handle* h)
     if (h->res_d) cudaFree(h->res_d);
     if (h->res_i) cudaFree(h->res_i);
     if (h->res_host) cudaFreeHost(h->res_host);
+    for (int s = 0; s < 2; ++s) {
+        if (h->bounce[s]) cudaFreeHost(h->bounce[s]);
+        if (h->ev_bounce_done[s]) cudaEventDestroy(h->ev_bounce_done[s]);
+    }
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->cmb) cudaStreamDestroy(h->cmb);
     void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr[0], h->xr[1], h->counter,
@@ -201,7 +211,7 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
     pg_handle* h = new pg_handle;
     h->n = n; h->c0 = c0; h->device = device;
     h->ldw = ((long long)n + kTile - 1) / kTile * kTile;
-    h->ldx = ((long long)n + 15) / 16 * 16;
+    h->ldx = ((long long)n + 31) / 32 * 32;
     if (const char* e = getenv("PG_REML_ENGINE")) {
         if (!strcmp(e, "stream")) h->engine = PG_REML_STREAM;
         else if (!strcmp(e, "warp")) h->engine = PG_REML_WARP;
@@ -316,7 +326,7 @@ static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
     std::vector<CompItem> items;
     P.ngroups = (k0 + kJGroup - 1) / kJGroup;
     P.vpitch = P.ngroups * kGroupCols;
-    P.npad16 = (n + 15) / 16 * 16;
+    P.npad16 = (n + 31) / 32 * 32;
     std::vector<int> order;
     for (int si = 0; si < (int)H.segs.size(); ++si) {
         const Segment& sg = H.segs[si];
@@ -758,6 +768,29 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
     return PG_OK;
 }
 
+// Packs the strided host block (rows of `width` bytes, `rows` of them, source pitch `pitch`) into dst, contiguously.
+static void pack_block_threads(char* dst, const char* src, size_t pitch, size_t width, size_t rows)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(hw ? hw : 4), rows}));
+    auto work = [=](size_t t) {
+        const size_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
+        for (size_t r = r0; r < r1; ++r) memcpy(dst + r * width, src + r * pitch, width);
+    };
+    if (nt == 1 || width * rows < (size_t(1) << 22)) { for (size_t t = 0; t < nt; ++t) work(t); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+static bool host_pointer_is_pinned(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
 struct EvPair {
     cudaEvent_t a, b;
 };
@@ -782,6 +815,24 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     int rc = ensure_workspace(h, m, xdtype);
     if (rc) return rc;
     const long long blk = h->blk;
+    // worth it for large pageable inputs only; very wide element types would need multi-GB pinned buffers
+    const size_t total_bytes = (size_t)m * n * xdtype_size(xdtype), block_bytes = (size_t)blk * n * xdtype_size(xdtype);
+    const bool use_bounce = !on_device && total_bytes >= (size_t(64) << 20) && block_bytes <= (size_t(1) << 30) &&
+                            !getenv("PG_NO_BOUNCE") && !host_pointer_is_pinned(X);
+    if (use_bounce) {
+        const size_t need_b = (size_t)blk * n * xdtype_size(xdtype);
+        if (need_b > h->bounce_bytes) {
+            for (int s = 0; s < 2; ++s) {
+                if (h->bounce[s]) cudaFreeHost(h->bounce[s]);
+                h->bounce[s] = nullptr;
+            }
+            h->bounce_bytes = 0;
+            for (int s = 0; s < 2; ++s) CK(cudaMallocHost(&h->bounce[s], need_b));
+            h->bounce_bytes = need_b;
+        }
+        for (int s = 0; s < 2; ++s)
+            if (!h->ev_bounce_done[s]) CK(cudaEventCreateWithFlags(&h->ev_bounce_done[s], cudaEventDisableTiming));
+    }
     // Block boundaries.  Host input with automatic blocking: the first two blocks are short (1/16 and 1/4 of a block) so
     // that compute starts after ~0.4 ms of upload instead of a whole block's worth; every later upload hides behind
     // the previous block's compute.
@@ -860,6 +911,19 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                 ld_dev = ld;
             } else {
                 if (b >= 2) CK(cudaStreamWaitEvent(h->copy, h->ev_free[s], 0));
+                if (use_bounce) {
+                    // host threads pack the block while the GPU is busy with the previous one
+                    if (b >= 2) CK(cudaEventSynchronize(h->ev_bounce_done[s]));  // the upload that last read bounce[s]
+                    const size_t width = (layout == PG_X_SAMPLE_MAJOR ? (size_t)mb : (size_t)n) * esz;
+                    const size_t rows = layout == PG_X_SAMPLE_MAJOR ? (size_t)n : (size_t)mb;
+                    const char* src0 = layout == PG_X_SAMPLE_MAJOR ? (const char*)X + (size_t)g0 * esz
+                                                                    : (const char*)X + (size_t)g0 * ld * esz;
+                    pack_block_threads(h->bounce[s], src0, (size_t)ld * esz, width, rows);
+                    CK(cudaEventRecord(ev_h2d[b].a, h->copy));
+                    CK(cudaMemcpyAsync(h->stage[s], h->bounce[s], width * rows, cudaMemcpyHostToDevice, h->copy));
+                    CK(cudaEventRecord(h->ev_bounce_done[s], h->copy));
+                    ld_dev = layout == PG_X_SAMPLE_MAJOR ? mb : n;
+                } else {
                 CK(cudaEventRecord(ev_h2d[b].a, h->copy));
                 if (layout == PG_X_SAMPLE_MAJOR) {
                     // n rows of mb elements, host pitch ld
@@ -870,6 +934,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                     CK(cudaMemcpy2DAsync(h->stage[s], (size_t)n * esz, (const char*)X + (size_t)g0 * ld * esz,
                                          (size_t)ld * esz, (size_t)n * esz, (size_t)mb, cudaMemcpyHostToDevice, h->copy));
                     ld_dev = n;
+                }
                 }
                 CK(cudaEventRecord(ev_h2d[b].b, h->copy));
                 CK(cudaEventRecord(h->ev_ready[s], h->copy));

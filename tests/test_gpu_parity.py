@@ -490,3 +490,32 @@ def test_grm_on_device_matches_reference_definition():
         o2 = h.scan(pr["X"])
     for c in COLS:
         assert rel(o1[c], o2[c]).max() < 1e-7, (c, float(rel(o1[c], o2[c]).max()))
+
+
+def test_pageable_host_input_bounce_path_is_identical():
+    """Large pageable genotype arrays are packed into pinned bounce buffers by host threads (pg_scan) instead of a
+    pageable 2-D copy: same bits as the direct copy (PG_NO_BOUNCE=1) and as a strided view of a wider array."""
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    n, m = 2048, 36000  # 74 MB of int8: above the 64 MB threshold of the bounce path
+    p = make_problem(n, 64, 3, seed=8, m_k=3000)
+    rng = np.random.default_rng(1)
+    X = rng.integers(0, 3, size=(n, m), dtype=np.int8)
+    wide = rng.integers(0, 3, size=(n, m + 500), dtype=np.int8)
+    wide[:, 100:100 + m] = X
+    outs = []
+    with capi.Handle(n, 3) as h:
+        h.set_kinship(p["K"])
+        h.set_design(p["W"], p["Y"])
+        h.set_options(block_snps=8192)
+        for env, arr in (("", X), ("1", X), ("", wide[:, 100:100 + m])):
+            if env:
+                os.environ["PG_NO_BOUNCE"] = env
+            else:
+                os.environ.pop("PG_NO_BOUNCE", None)
+            outs.append(h.scan(arr))
+        os.environ.pop("PG_NO_BOUNCE", None)
+    for o in outs[1:]:
+        for c in COLS:
+            assert np.array_equal(outs[0][c], o[c], equal_nan=True), c
