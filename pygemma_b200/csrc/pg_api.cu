@@ -1020,7 +1020,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->block_snps = (int32_t)blk;
         timing->reml_launches = (int32_t)nblocks;
         timing->rotate_launches = n_rot_launch;
-        timing->convert_launches = (int32_t)nblocks;
+        timing->convert_launches = rotate ? 0 : (int32_t)nblocks;  // staging kernels of the rotation are in rotate_launches
         timing->rot_engine = last_engine;
         timing->reml_engine = compressed ? PG_REML_COMPRESSED : h->engine;
         timing->n_nodes = compressed ? h->plan.Kc : h->n;
