@@ -189,6 +189,25 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     const void* fsrc = nullptr;   // the float block (for the indicator pass)
     long long fld = 0;
     int fdtype = 0;
+    // level codes (indicator = 0) or indicators (1) of the float block -> w->codes, in the layout of the input
+    auto encode_block = [&](int indicator) -> int {
+        dim3 ge((unsigned)((mb + 127) / 128), (unsigned)((n + 63) / 64));
+        if (fdtype == PG_X_F32)
+            encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)fsrc, fld, layout, n, mb, w->info, w->codes, indicator);
+        else
+            encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)fsrc, fld, layout, n, mb, w->info, w->codes, indicator);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch)++;
+        return 0;
+    };
+    // int8 block (src, ld, layout) -> SNP-major K-contiguous copy x8
+    auto stage_block = [&]() -> int {
+        dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
+        stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch)++;
+        return 0;
+    };
     if (!i8 && rotation != PG_ROT_FP64 && level_coding && xdtype != PG_X_I8) {
         int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
         if (rc) return rc;
@@ -206,8 +225,8 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         PG_ROT_CK(cudaMemsetAsync(w->n_bad, 0, 2 * sizeof(int), stream));
         const unsigned gb = (unsigned)((mb + 127) / 128);
         const int nchunks = (n + kLevelChunk - 1) / kLevelChunk;
-        // equal spacing to double rounding: float32-standardised columns deviate by ~1e-7 of |x| and stay on the FP64 path
-        // (their non-affinity moved beta by 1.4e-6 in the parity test; raw float32 dosages 0/1/2 are exactly affine)
+        // "equally spaced" means to double rounding; anything looser goes to the indicator component (treating
+        // float32-standardised columns as affine moved beta by 1.4e-6 in the parity test)
         const double tol = ldexp(1.0, -50);
         if (xdtype == PG_X_F32)
             find_levels_kernel<float><<<dim3(gb, nchunks), 128, 0, stream>>>((const float*)src, ld, layout, n, mb, w->part);
@@ -224,13 +243,8 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             affine = w->info;
             need_eps = bad[1] > 0;
             fsrc = src; fld = ld; fdtype = xdtype;
-            dim3 ge(gb, (unsigned)((n + 63) / 64));
-            if (xdtype == PG_X_F32)
-                encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)src, ld, layout, n, mb, w->info, w->codes, 0);
-            else
-                encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)src, ld, layout, n, mb, w->info, w->codes, 0);
-            PG_ROT_CK(cudaGetLastError());
-            (*n_launch)++;
+            int er = encode_block(0);
+            if (er) return er;
             src = w->codes;
             ld = (layout == PG_X_SAMPLE_MAJOR) ? mb : n;
             xdtype = PG_X_I8;
@@ -273,10 +287,8 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     const bool direct = (!fused_tc || !tc_single) && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
                         (n % 16 == 0) && (mb % 16 == 0);
     if (!direct) {
-        dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
-        stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
-        PG_ROT_CK(cudaGetLastError());
-        (*n_launch)++;
+        rc = stage_block();
+        if (rc) return rc;
     }
     cudaEventRecord(ev_conv_end, stream);
     cudaEventRecord(ev_rot_begin, stream);
@@ -294,19 +306,10 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
                             direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 0);
             if (r == 0 && affine && need_eps) {
-                // second component of unequally spaced levels: indicator [code == 2], accumulated with weight eps
-                dim3 ge((unsigned)((mb + 127) / 128), (unsigned)((n + 63) / 64));
-                if (fdtype == PG_X_F32)
-                    encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
-                else
-                    encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
-                PG_ROT_CK(cudaGetLastError());
-                (*n_launch)++;
-                if (!direct) {
-                    dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
-                    stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
-                    PG_ROT_CK(cudaGetLastError());
-                }
+                // second component (unequally spaced levels / an outlier level): the indicator, accumulated with weight eps
+                rc = encode_block(1);
+                if (rc == 0 && !direct) rc = stage_block();
+                if (rc) return rc;
                 r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
                                 direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 1);
                 (*n_launch)++;
@@ -323,23 +326,13 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     const int M = kSlices * w->npad;
     const int npass = (affine && need_eps) ? 2 : 1;
     for (int pass = 0; pass < npass; ++pass) {
-    if (pass == 1) {
-        // second component: indicator [code == 2] with weight eps (columns whose levels are not equally spaced)
-        PG_ROT_CK(cudaStreamWaitEvent(stream, w->ev_pfree[0], 0));
-        PG_ROT_CK(cudaStreamWaitEvent(stream, w->ev_pfree[1], 0));  // the codes of pass 0 are no longer read
-        dim3 ge((unsigned)((mb + 127) / 128), (unsigned)((n + 63) / 64));
-        if (fdtype == PG_X_F32)
-            encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
-        else
-            encode_levels_kernel<double><<<ge, 128, 0, stream>>>((const double*)fsrc, fld, layout, n, mb, w->info, w->codes, 1);
-        PG_ROT_CK(cudaGetLastError());
-        (*n_launch)++;
-        if (!direct) {
-            dim3 block(64, 4), grid((unsigned)((mb + 63) / 64), (unsigned)((w->ldk + 63) / 64));
-            stage_i8_kernel<<<grid, block, 0, stream>>>((const int8_t*)src, ld, layout, n, mb, w->ldk, w->x8);
-            PG_ROT_CK(cudaGetLastError());
+        if (pass == 1) {
+            // second component (unequally spaced levels / an outlier level): the indicator, weight eps; the GEMMs of
+            // pass 0 that read the codes precede this on the same stream
+            rc = encode_block(1);
+            if (rc == 0 && !direct) rc = stage_block();
+            if (rc) return rc;
         }
-    }
     for (long long g0 = 0; g0 < mb; g0 += w->sub) {
         const long long cnt = std::min(w->sub, mb - g0);
         const long long cnt_pad = (cnt + 15) / 16 * 16;  // x8 rows beyond mb are zero / stale: ignored downstream
