@@ -47,7 +47,13 @@ typedef enum {
 } pg_status;
 
 /* element type of the genotype matrix handed to pg_scan */
-typedef enum { PG_X_I8 = 0, PG_X_F32 = 1, PG_X_F64 = 2 } pg_xdtype;
+typedef enum {
+    PG_X_I8 = 0,
+    PG_X_F32 = 1,
+    PG_X_F64 = 2,
+    PG_X_BED = 3 /* packed PLINK .bed body (2 bits per genotype): SNP-major only, ld = bytes per SNP >= ceil(n/4);
+                    missing genotypes are mean-imputed on the device, see pg_set_bed_options */
+} pg_xdtype;
 
 /* memory layout of the genotype matrix */
 typedef enum {
@@ -144,6 +150,14 @@ int pg_set_stream(pg_handle* h, void* stream);
 
 /* rotation engine selection and block size (0 = automatic) */
 int pg_set_options(pg_handle* h, int rotation, int64_t block_snps);
+/*
+ * Decoding of PG_X_BED input.  count_a1 != 0: dosage = number of A1 alleles (00 -> 2, 10 -> 1, 11 -> 0), else number of
+ * A2 alleles (pysnptools Bed(count_A1=...)); the code 01 is missing and is replaced by the column mean of the observed
+ * dosages (SimpleImputer(strategy='mean'), experiments/benchmarks/benchmarks.py:22).  standardize != 0: the imputed
+ * column is centred and divided by its population standard deviation (1 when it is constant), as StandardScaler does
+ * (experiments/wtccc/run_pygemma.py:432).  Default: count_a1 = 0, standardize = 0.
+ */
+int pg_set_bed_options(pg_handle* h, int count_a1, int standardize);
 /* REML stage engine selection (default PG_REML_AUTO); all engines give the same results to rounding */
 int pg_set_reml_engine(pg_handle* h, int engine);
 

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpygemma_b200.so")
 
-PG_X_I8, PG_X_F32, PG_X_F64 = 0, 1, 2
+PG_X_I8, PG_X_F32, PG_X_F64, PG_X_BED = 0, 1, 2, 3
 PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1
 PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT, PG_ROT_I8TC = 0, 1, 2, 3
 PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
@@ -22,7 +22,7 @@ PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
 SYMBOLS = [
     "pg_abi_version", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_stream", "pg_set_options",
-    "pg_set_reml_engine", "pg_grm",
+    "pg_set_reml_engine", "pg_grm", "pg_set_bed_options",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
 
@@ -73,6 +73,7 @@ def load():
     L.pg_set_options.argtypes = [vp, i32, i64]
     L.pg_set_stream.argtypes = [vp, vp]
     L.pg_set_reml_engine.argtypes = [vp, i32]
+    L.pg_set_bed_options.argtypes = [vp, i32, i32]
     L.pg_grm.argtypes = [vp, vp, i32, i64, i32, i64, vp, i32, vp, ctypes.POINTER(ctypes.c_float),
                          ctypes.POINTER(ctypes.c_float)]
     scan_args = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 9 + [ctypes.POINTER(PgTiming)]
@@ -223,6 +224,29 @@ class Handle:
         e3 = np.zeros(m, dtype=np.int32) if with_counts else None
         tm = PgTiming()
         self._ck(self.L.pg_scan(self.h, _ptr(X), xdtype_of(X), ld, layout, m, int(bool(grid)),
+                                _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
+                                _ptr(out["F_wald"]), _ptr(out["p_wald"]), _ptr(st), _ptr(e2), _ptr(e3),
+                                ctypes.byref(tm)))
+        out["status"] = st
+        if with_counts:
+            out["n_eval2"], out["n_eval3"] = e2, e3
+        out["timing"] = tm.as_dict()
+        return out
+
+    def scan_bed(self, packed, grid=False, count_A1=False, standardize=False, with_counts=True):
+        """Scan a packed PLINK .bed body: `packed` is a C-contiguous (m, bytes_per_snp) uint8 array, bytes_per_snp >=
+        ceil(n/4).  Missing genotypes are mean-imputed (and the columns optionally standardised) on the device."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        if packed.ndim != 2 or packed.shape[1] < (self.n + 3) // 4:
+            raise ValueError(f"packed .bed block must have shape (m, >= {(self.n + 3) // 4})")
+        m = packed.shape[0]
+        self._ck(self.L.pg_set_bed_options(self.h, int(bool(count_A1)), int(bool(standardize))))
+        out = {k: np.empty(m) for k in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald")}
+        st = np.zeros(m, dtype=np.int32)
+        e2 = np.zeros(m, dtype=np.int32) if with_counts else None
+        e3 = np.zeros(m, dtype=np.int32) if with_counts else None
+        tm = PgTiming()
+        self._ck(self.L.pg_scan(self.h, _ptr(packed), PG_X_BED, packed.shape[1], PG_X_SNP_MAJOR, m, int(bool(grid)),
                                 _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
                                 _ptr(out["F_wald"]), _ptr(out["p_wald"]), _ptr(st), _ptr(e2), _ptr(e3),
                                 ctypes.byref(tm)))

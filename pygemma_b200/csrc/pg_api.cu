@@ -600,6 +600,14 @@ extern "C" int pg_set_options(pg_handle* h, int rotation, int64_t block_snps)
     return PG_OK;
 }
 
+extern "C" int pg_set_bed_options(pg_handle* h, int count_a1, int standardize)
+{
+    if (!h) return PG_ERR_ARG;
+    h->rot.bed_count_a1 = count_a1 != 0;
+    h->rot.bed_standardize = standardize != 0;
+    return PG_OK;
+}
+
 extern "C" int pg_set_reml_engine(pg_handle* h, int engine)
 {
     if (!h) return PG_ERR_ARG;
@@ -608,7 +616,7 @@ extern "C" int pg_set_reml_engine(pg_handle* h, int engine)
     return PG_OK;
 }
 
-static size_t xdtype_size(int t) { return t == PG_X_I8 ? 1 : (t == PG_X_F32 ? 4 : 8); }
+static size_t xdtype_size(int t) { return (t == PG_X_I8 || t == PG_X_BED) ? 1 : (t == PG_X_F32 ? 4 : 8); }
 
 static int ensure_workspace(pg_handle* h, long long m, int xdtype)
 {
@@ -803,11 +811,14 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     if (!X || m < 0) return fail(h, PG_ERR_ARG, "pg_scan: NULL X or negative m");
     for (int i = 0; i < 6; ++i)
         if (!out_user[i] && m > 0) return fail(h, PG_ERR_ARG, "pg_scan: NULL output %d", i);
-    if (xdtype < PG_X_I8 || xdtype > PG_X_F64) return fail(h, PG_ERR_ARG, "pg_scan: xdtype %d", xdtype);
+    if (xdtype < PG_X_I8 || xdtype > PG_X_BED) return fail(h, PG_ERR_ARG, "pg_scan: xdtype %d", xdtype);
     if (layout != PG_X_SAMPLE_MAJOR && layout != PG_X_SNP_MAJOR) return fail(h, PG_ERR_ARG, "pg_scan: layout %d", layout);
     if (!h->have_design) return fail(h, PG_ERR_ARG, "pg_scan: call pg_set_design first");
     const int n = h->n;
-    if ((layout == PG_X_SAMPLE_MAJOR && ld < m) || (layout == PG_X_SNP_MAJOR && ld < n))
+    const bool bed = xdtype == PG_X_BED;
+    if (bed && layout != PG_X_SNP_MAJOR) return fail(h, PG_ERR_ARG, "pg_scan: PLINK .bed data is SNP-major");
+    if (bed && h->rotated_inputs) return fail(h, PG_ERR_ARG, "pg_scan: PLINK .bed genotypes cannot be pre-rotated");
+    if ((layout == PG_X_SAMPLE_MAJOR && ld < m) || (layout == PG_X_SNP_MAJOR && ld < (bed ? (n + 3) / 4 : n)))
         return fail(h, PG_ERR_ARG, "pg_scan: ld %lld too small", ld);
     if (timing) memset(timing, 0, sizeof *timing);
     if (m == 0) return PG_OK;
@@ -849,6 +860,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     }
     const long long nblocks = (long long)bstart.size() - 1;
     const size_t esz = xdtype_size(xdtype);
+    const size_t snp_row_bytes = bed ? (size_t)((n + 3) / 4) : (size_t)n * esz;   // one SNP of an SNP-major block
     const bool rotate = !h->rotated_inputs;
 
     // outputs: device arrays (user's when on_device, temporaries otherwise)
@@ -914,7 +926,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                 if (use_bounce) {
                     // host threads pack the block while the GPU is busy with the previous one
                     if (b >= 2) CK(cudaEventSynchronize(h->ev_bounce_done[s]));  // the upload that last read bounce[s]
-                    const size_t width = (layout == PG_X_SAMPLE_MAJOR ? (size_t)mb : (size_t)n) * esz;
+                    const size_t width = layout == PG_X_SAMPLE_MAJOR ? (size_t)mb * esz : snp_row_bytes;
                     const size_t rows = layout == PG_X_SAMPLE_MAJOR ? (size_t)n : (size_t)mb;
                     const char* src0 = layout == PG_X_SAMPLE_MAJOR ? (const char*)X + (size_t)g0 * esz
                                                                     : (const char*)X + (size_t)g0 * ld * esz;
@@ -922,7 +934,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                     CK(cudaEventRecord(ev_h2d[b].a, h->copy));
                     CK(cudaMemcpyAsync(h->stage[s], h->bounce[s], width * rows, cudaMemcpyHostToDevice, h->copy));
                     CK(cudaEventRecord(h->ev_bounce_done[s], h->copy));
-                    ld_dev = layout == PG_X_SAMPLE_MAJOR ? mb : n;
+                    ld_dev = layout == PG_X_SAMPLE_MAJOR ? mb : (long long)(snp_row_bytes / esz);
                 } else {
                 CK(cudaEventRecord(ev_h2d[b].a, h->copy));
                 if (layout == PG_X_SAMPLE_MAJOR) {
@@ -931,9 +943,9 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                                          (size_t)ld * esz, (size_t)mb * esz, (size_t)n, cudaMemcpyHostToDevice, h->copy));
                     ld_dev = mb;
                 } else {
-                    CK(cudaMemcpy2DAsync(h->stage[s], (size_t)n * esz, (const char*)X + (size_t)g0 * ld * esz,
-                                         (size_t)ld * esz, (size_t)n * esz, (size_t)mb, cudaMemcpyHostToDevice, h->copy));
-                    ld_dev = n;
+                    CK(cudaMemcpy2DAsync(h->stage[s], snp_row_bytes, (const char*)X + (size_t)g0 * ld * esz,
+                                         (size_t)ld * esz, snp_row_bytes, (size_t)mb, cudaMemcpyHostToDevice, h->copy));
+                    ld_dev = (long long)(snp_row_bytes / esz);
                 }
                 }
                 CK(cudaEventRecord(ev_h2d[b].b, h->copy));

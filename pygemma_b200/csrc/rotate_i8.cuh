@@ -309,6 +309,80 @@ __global__ void __launch_bounds__(256) combine_i8_affine_kernel(const int32_t* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PLINK .bed ingest.  A .bed body is SNP-major: ceil(n/4) bytes per SNP, four samples per byte, sample
+// 4b+i in bits 2i..2i+1; 00 = homozygous A1, 01 = missing, 10 = heterozygous, 11 = homozygous A2.  The reference's
+// callers read it with pysnptools (NaN for missing), impute the column mean (SimpleImputer(strategy='mean'),
+// experiments/benchmarks/benchmarks.py:22, experiments/animal_gwas/run_gwas.py:93-94) and optionally standardise.
+// Here the packed block is uploaded as it is (2 bits per genotype over PCIe) and one CTA per SNP
+//   mode 0: counts the genotype classes, writes the dosage codes (missing -> 0) straight into the K-contiguous int8
+//           operand of the rotation, and the affine description of the imputed (standardised) column
+//               x = v0 + s * code + eps * [missing]      (v0 = 0, s = 1, eps = mean;  standardised: (x - mean) / sd)
+//   mode 1: writes the missing indicator (operand of the eps rotation)
+// so that imputed .bed genotypes run on the exact int8 tensor path without ever existing as floats.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bed_decode_kernel(const uint8_t* __restrict__ bed, long long ld_bytes, int n,
+                                                          long long mb, int ldk, int count_a1, int standardize, int mode,
+                                                          int8_t* __restrict__ x8, LevelInfo* __restrict__ info,
+                                                          int* __restrict__ n_bad)
+{
+    const long long g = blockIdx.x;
+    if (g >= mb) return;
+    const uint8_t* row = bed + (size_t)g * ld_bytes;
+    const int nbytes = (n + 3) >> 2;
+    __shared__ int red[3][4];
+    int c1 = 0, c2 = 0, cm = 0;
+    uint32_t* out = reinterpret_cast<uint32_t*>(x8 + (size_t)g * ldk);   // ldk is a multiple of 128: 4-byte aligned rows
+    for (int b = threadIdx.x; b < ldk / 4; b += blockDim.x) {
+        uint32_t word = 0;
+        if (b < nbytes) {
+            const unsigned v = row[b];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (4 * b + i >= n) break;
+                const unsigned two = (v >> (2 * i)) & 3u;
+                int code = 0, miss = 0;
+                if (two == 1u) miss = 1;
+                else if (two == 2u) code = 1;
+                else code = ((two == 0u) == (count_a1 != 0)) ? 2 : 0;
+                c1 += (code == 1); c2 += (code == 2); cm += miss;
+                word |= (uint32_t)(mode ? miss : code) << (8 * i);
+            }
+        }
+        out[b] = word;
+    }
+    if (mode != 0) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        cm += __shfl_xor_sync(0xffffffffu, cm, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = c1; red[1][threadIdx.x >> 5] = c2; red[2][threadIdx.x >> 5] = cm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t1 = 0, t2 = 0, tm = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t1 += red[0][w]; t2 += red[1][w]; tm += red[2][w]; }
+        const int nobs = n - tm, t0 = nobs - t1 - t2;
+        const double mu = nobs > 0 ? (double)(t1 + 2 * t2) / (double)nobs : 0.0;   // np.nanmean; all-missing column -> 0
+        LevelInfo li;
+        li.pad = 0; li.nlev = 4;
+        for (int u = 0; u < 3; ++u) li.t[u] = INFINITY;
+        for (int u = 0; u < kMaxLevels; ++u) { li.code_of[u] = 0; li.ind_of[u] = 0; }
+        if (!standardize) {
+            li.v0 = 0.0; li.s = 1.0; li.eps = mu;
+        } else {
+            // population variance of the imputed column (imputed entries sit on the mean); sd == 0 -> 1 (StandardScaler)
+            const double var = ((double)t0 * mu * mu + (double)t1 * (1.0 - mu) * (1.0 - mu) + (double)t2 * (2.0 - mu) * (2.0 - mu)) / (double)n;
+            const double sd = var > 0.0 ? sqrt(var) : 1.0;
+            li.s = 1.0 / sd; li.v0 = -mu / sd; li.eps = mu / sd;
+        }
+        if (tm == 0) li.eps = 0.0;
+        else atomicAdd(n_bad + 1, 1);
+        info[g] = li;
+    }
+}
+
 // u1 = U^T 1: column sums of U (eigenvector i at U + i*n when cols_contig, else strided)
 __global__ void __launch_bounds__(256) column_sums_kernel(const double* __restrict__ U, int cols_contig, int n,
                                                            double* __restrict__ u1)

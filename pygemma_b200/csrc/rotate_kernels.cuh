@@ -46,6 +46,7 @@ struct RotWorkspace {
     int* n_bad = nullptr;      // device counter
     long long code_cap = 0;
     long long blocks_coded = 0, blocks_dense = 0;
+    int bed_count_a1 = 0, bed_standardize = 0;   // PG_X_BED decoding options (pg_set_bed_options)
     long long sub = 0, want_cap = 0;
     float slice_ms = 0.f;
 };
@@ -191,6 +192,13 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     int fdtype = 0;
     // level codes (indicator = 0) or indicators (1) of the float block -> w->codes, in the layout of the input
     auto encode_block = [&](int indicator) -> int {
+        if (fdtype == PG_X_BED) {   // the indicator of a .bed block goes straight into x8
+            bed_decode_kernel<<<(unsigned)mb, 128, 0, stream>>>((const uint8_t*)fsrc, fld, n, mb, w->ldk, w->bed_count_a1,
+                                                                w->bed_standardize, indicator, w->x8, w->info, w->n_bad);
+            PG_ROT_CK(cudaGetLastError());
+            (*n_launch)++;
+            return 0;
+        }
         dim3 ge((unsigned)((mb + 127) / 128), (unsigned)((n + 63) / 64));
         if (fdtype == PG_X_F32)
             encode_levels_kernel<float><<<ge, 128, 0, stream>>>((const float*)fsrc, fld, layout, n, mb, w->info, w->codes, indicator);
@@ -208,7 +216,39 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         (*n_launch)++;
         return 0;
     };
-    if (!i8 && rotation != PG_ROT_FP64 && level_coding && xdtype != PG_X_I8) {
+    bool pre_staged = false;   // x8 already holds the K-contiguous int8 operand
+    const bool bed = (xdtype == PG_X_BED);
+    if (bed) {
+        // packed PLINK block -> dosage codes in x8 + the affine description of every (imputed, standardised) column
+        if (rotation == PG_ROT_FP64) { w->err = "PLINK .bed input runs on the int8 engines only"; return PG_ERR_ARG; }
+        int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
+        if (rc) return rc;
+        const long long cap = (blk + 63) / 64 * 64;
+        if (cap > w->code_cap) {   // only `info` is needed; keep the three buffers in step
+            if (w->info) cudaFree(w->info);
+            if (w->part) cudaFree(w->part);
+            if (w->codes) cudaFree(w->codes);
+            w->info = nullptr; w->part = nullptr; w->codes = nullptr; w->code_cap = 0;
+            PG_ROT_CK(cudaMalloc(&w->info, sizeof(LevelInfo) * cap));
+            PG_ROT_CK(cudaMalloc(&w->part, sizeof(LevelPartial) * cap * ((n + kLevelChunk - 1) / kLevelChunk)));
+            PG_ROT_CK(cudaMalloc(&w->codes, (size_t)cap * n));
+            w->code_cap = cap;
+        }
+        PG_ROT_CK(cudaMemsetAsync(w->n_bad, 0, 2 * sizeof(int), stream));
+        bed_decode_kernel<<<(unsigned)mb, 128, 0, stream>>>((const uint8_t*)src, ld, n, mb, w->ldk, w->bed_count_a1,
+                                                            w->bed_standardize, 0, w->x8, w->info, w->n_bad);
+        PG_ROT_CK(cudaGetLastError());
+        (*n_launch)++;
+        int bad[2] = {0, 0};
+        PG_ROT_CK(cudaMemcpyAsync(bad, w->n_bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PG_ROT_CK(cudaStreamSynchronize(stream));
+        affine = w->info;
+        need_eps = bad[1] > 0;
+        fsrc = src; fld = ld; fdtype = PG_X_BED;
+        pre_staged = true;
+        *used_i8 = PG_ROT_I8SPLIT;
+    }
+    if (!bed && !i8 && rotation != PG_ROT_FP64 && level_coding && xdtype != PG_X_I8) {
         int rc = rot_prepare_i8(w, stream, U, u_op_t, n, blk);
         if (rc) return rc;
         const long long cap = (blk + 63) / 64 * 64;
@@ -284,9 +324,9 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     static const bool tc_single = getenv("PG_TC_SINGLE") != nullptr;
     const bool fused_tc = (rotation == PG_ROT_I8TC || (rotation == PG_ROT_AUTO && default_tc)) && !(affine && tc_single);
     (void)forced_i8;
-    const bool direct = (!fused_tc || !tc_single) && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
+    const bool direct = !pre_staged && (!fused_tc || !tc_single) && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
                         (n % 16 == 0) && (mb % 16 == 0);
-    if (!direct) {
+    if (!direct && !pre_staged) {
         rc = stage_block();
         if (rc) return rc;
     }
@@ -308,7 +348,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             if (r == 0 && affine && need_eps) {
                 // second component (unequally spaced levels / an outlier level): the indicator, accumulated with weight eps
                 rc = encode_block(1);
-                if (rc == 0 && !direct) rc = stage_block();
+                if (rc == 0 && !direct && !pre_staged) rc = stage_block();
                 if (rc) return rc;
                 r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
                                 direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 1);
@@ -330,7 +370,7 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             // second component (unequally spaced levels / an outlier level): the indicator, weight eps; the GEMMs of
             // pass 0 that read the codes precede this on the same stream
             rc = encode_block(1);
-            if (rc == 0 && !direct) rc = stage_block();
+            if (rc == 0 && !direct && !pre_staged) rc = stage_block();
             if (rc) return rc;
         }
     for (long long g0 = 0; g0 < mb; g0 += w->sub) {

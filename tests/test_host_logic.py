@@ -221,3 +221,32 @@ def test_compressed_scan_equals_direct_scan():
     for c in COLS:
         assert rel(a[c], b[c]).max() < 1e-9, (c, rel(a[c], b[c]).max())
     assert np.array_equal(a["n_eval2"], b["n_eval2"]) and np.array_equal(a["n_eval3"], b["n_eval3"])
+
+
+def test_bed_pack_unpack_and_files(tmp_path):
+    """pygemma_b200.bed: NumPy decode / encode of packed PLINK genotypes and the file reader (header, .bim / .fam counts)."""
+    from pygemma_b200 import bed
+
+    rng = np.random.default_rng(0)
+    for n in (5, 8, 13, 64):
+        G = rng.integers(0, 3, size=(n, 7)).astype(np.float64)
+        G[rng.random(G.shape) < 0.2] = np.nan
+        for a1 in (False, True):
+            packed = bed.encode_packed(G, count_A1=a1)
+            assert packed.shape == (7, (n + 3) // 4) and packed.dtype == np.uint8
+            back = bed.decode_packed(packed, n, count_A1=a1)
+            assert np.array_equal(back, G, equal_nan=True)
+    # PLINK's own convention on a hand-made byte: samples 0..3 = 00 (hom A1), 01 (missing), 10 (het), 11 (hom A2)
+    byte = np.array([[0b11100100]], dtype=np.uint8)
+    assert np.array_equal(bed.decode_packed(byte, 4, count_A1=False)[:, 0], [0.0, np.nan, 1.0, 2.0], equal_nan=True)
+    assert np.array_equal(bed.decode_packed(byte, 4, count_A1=True)[:, 0], [2.0, np.nan, 1.0, 0.0], equal_nan=True)
+    prefix = str(tmp_path / "toy")
+    G = rng.integers(0, 3, size=(11, 5)).astype(np.float64)
+    G[3, 2] = np.nan
+    bed.write_bed(prefix, G)
+    packed, n, ids = bed.read_packed(prefix)
+    assert n == 11 and packed.shape == (5, 3) and list(ids) == [f"rs{i}" for i in range(5)]
+    assert np.array_equal(bed.read_bed(prefix), G, equal_nan=True)
+    open(prefix + ".bed", "r+b").write(b"\x00")
+    with pytest.raises(ValueError):
+        bed.read_packed(prefix)
