@@ -38,6 +38,7 @@ struct pg_handle {
     // so that block b's REML stage (FP64 pipes) runs under block b+1's rotation (int8 tensor pipe)
     cudaStream_t aux = nullptr, cmb = nullptr;
     cudaEvent_t ev_xr_ready[2] = {nullptr, nullptr}, ev_xr_free[2] = {nullptr, nullptr}, ev_aux_done = nullptr;
+    cudaEvent_t ev_z_ready[2] = {nullptr, nullptr}, ev_z_free[2] = {nullptr, nullptr};
     bool overlap = false;
     // per-call scratch kept across calls (grow-only): device result arrays, pinned host staging, timing events
     double* res_d = nullptr;   // [6][cap] doubles
@@ -163,6 +164,8 @@ static int free_all(pg_handle* h)
     for (int s = 0; s < 2; ++s) {
         if (h->ev_xr_ready[s]) cudaEventDestroy(h->ev_xr_ready[s]);
         if (h->ev_xr_free[s]) cudaEventDestroy(h->ev_xr_free[s]);
+        if (h->ev_z_ready[s]) cudaEventDestroy(h->ev_z_ready[s]);
+        if (h->ev_z_free[s]) cudaEventDestroy(h->ev_z_free[s]);
     }
     if (h->ev_aux_done) cudaEventDestroy(h->ev_aux_done);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -231,14 +234,21 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
         {
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
-            CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
+            // LOW priority: when block b's compression ends, the rotation clusters of block b+1 must be placed first
+            // (they need 190 KB of shared memory per SM); the optimiser CTAs of block b then fill the room left beside them
+            CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, lo));
             CK(cudaStreamCreateWithPriority(&h->cmb, cudaStreamNonBlocking, hi));
             for (int s = 0; s < 2; ++s) {
                 CK(cudaEventCreateWithFlags(&h->ev_xr_ready[s], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&h->ev_xr_free[s], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->ev_z_ready[s], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->ev_z_free[s], cudaEventDisableTiming));
             }
             CK(cudaEventCreateWithFlags(&h->ev_aux_done, cudaEventDisableTiming));
-            h->overlap = getenv("PG_OVERLAP") != nullptr;  // measured: no gain next to the cuBLAS GEMM
+            // PG_OVERLAP=1: the optimiser kernel of block b runs on the auxiliary stream under the fused rotation of
+            // block b+1.  Measured in the sustained bench: 67.1 vs 65.7 ms per step -- the step is power-capped (~900 W,
+            // 1.7 GHz), so overlapping pipes does not buy time; off by default, stage timings stay disjoint.
+            h->overlap = getenv("PG_OVERLAP") && atoi(getenv("PG_OVERLAP")) != 0;
         }
         CKB(cublasCreate(&h->blas));
         CKB(cublasSetStream(h->blas, h->compute));
@@ -258,7 +268,7 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
         CK(cudaMalloc(&h->basis, sizeof(double) * kNodes * kNodes));
         CK(cudaMalloc(&h->lambdas, sizeof(double) * kNumTableRows));
         CK(cudaMalloc(&h->tri_ab, sizeof(TriAB) * kMaxTri));
-        CK(cudaMalloc(&h->counter, sizeof(unsigned long long)));
+        CK(cudaMalloc(&h->counter, 2 * sizeof(unsigned long long)));  // one work-queue counter per block parity
         std::vector<TriAB> tab(kMaxTri);
         fill_tri_ab(tab.data());
         CK(cudaMemcpy(h->tri_ab, tab.data(), sizeof(TriAB) * kMaxTri, cudaMemcpyHostToDevice));
@@ -692,16 +702,23 @@ static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld,
 
 // REML stage of one block on stream `st`: reads xr, uses moment buffer Zbuf.  `ev_xr_done` (nullable) is recorded once
 // the rotated genotypes are no longer needed (after the compression, or after the kernel for the streaming engines).
+// `st` carries the compression, `st_solve` the optimiser + p-value kernels (the same stream, or the auxiliary stream
+// when the optimiser of this block is to run under the next block's rotation: then `ev_z[0]` is recorded after the
+// compression, `ev_z[1]` after the optimiser, and the optimiser is limited to one CTA per SM so that a rotation CTA
+// still fits beside it).
 static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* Zbuf, long long mb, long long row0,
                        int grid_mode, double* const out[6], int* status, int* e2, int* e3, cudaEvent_t* ev_mid = nullptr,
-                       cudaEvent_t ev_xr_done = nullptr)
+                       cudaEvent_t ev_xr_done = nullptr, cudaStream_t st_solve = nullptr, cudaEvent_t* ev_z = nullptr,
+                       int parity = 0)
 {
+    if (!st_solve) st_solve = st;
+    const bool split = st_solve != st;
+    unsigned long long* counter = h->counter + (parity & 1);
     ScanArgs a;
     a.n = h->n; a.c0 = h->c0; a.grid = grid_mode; a.m = mb; a.row0 = row0;
     a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = xr; a.ldx = h->ldx; a.tab = h->tab;
     for (int i = 0; i < 6; ++i) a.out[i] = out[i];
-    a.status = status; a.n_eval2 = e2; a.n_eval3 = e3; a.counter = h->counter;
-    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+    a.status = status; a.n_eval2 = e2; a.n_eval3 = e3; a.counter = counter;
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
         const DevPlan& P = h->plan;
         const int ntiles = (int)((mb + kCtSnps - 1) / kCtSnps);
@@ -720,11 +737,16 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         }
         if (ev_mid) CK(cudaEventRecord(ev_mid[1], st));
         if (ev_xr_done) CK(cudaEventRecord(ev_xr_done, st));
+        if (split) {
+            CK(cudaEventRecord(ev_z[0], st));
+            CK(cudaStreamWaitEvent(st_solve, ev_z[0], 0));
+        }
+        CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st_solve));
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
         sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
-        sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = h->counter;
+        sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
         int warps = 8;
         while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
@@ -735,18 +757,22 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
             const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(ctas, (200 * 1024) / std::max<size_t>(smem, 1)));
             long long want = (mb + warps - 1) / warps;
             int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
-            kern<<<grid, warps * 32, smem, st>>>(sa);
+            kern<<<grid, warps * 32, smem, st_solve>>>(sa);
             return PG_OK;
         };
-        // 2 CTAs of 8 warps per SM (128 registers): 3 and 4 CTAs/SM and 4-6 warps per CTA were measured slower
-        const int lr = two ? launch(reml_solve_kernel<2, 2>, 2) : launch(reml_solve_kernel<1, 2>, 2);
+        // 2 CTAs of 8 warps per SM (128 registers): 3 and 4 CTAs/SM and 4-6 warps per CTA were measured slower.
+        // Under the next block's rotation: 1 CTA per SM (32 K registers + 15 KB shared memory fit beside a rotation CTA).
+        const int per_sm = split ? 1 : 2;
+        const int lr = two ? launch(reml_solve_kernel<2, 2>, per_sm) : launch(reml_solve_kernel<1, 2>, per_sm);
         if (lr) return lr;
         CK(cudaGetLastError());
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
-        pvalue_kernel<<<(unsigned)((mb + 63) / 64), 64, 0, st>>>(out[4], out[5], row0, mb, (double)(h->n - h->c0 - 1));
+        pvalue_kernel<<<(unsigned)((mb + 63) / 64), 64, 0, st_solve>>>(out[4], out[5], row0, mb, (double)(h->n - h->c0 - 1));
         CK(cudaGetLastError());
+        if (split) CK(cudaEventRecord(ev_z[1], st_solve));
         return PG_OK;
     }
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     if (h->engine == PG_REML_STREAM) {
         const StreamCfg cfg = stream_config(h->c0);
         const int ncmax = std::min(h->c0 + 1, (int)kChunkCols);
@@ -954,8 +980,13 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                 src_dev = h->stage[s];
             }
             // ---- rotation of block b into xr[s] (main stream + recombination stream)
-            cudaStream_t st_reml = h->overlap ? h->aux : h->compute;
-            cudaStream_t st_cmb = h->overlap ? h->cmb : h->compute;
+            // compression on the main stream; with `overlap` the optimiser goes to the auxiliary stream and runs under
+            // the rotation of block b+1 (it needs the fused rotation kernel as neighbour: the cuBLAS GEMM fills the SM)
+            const bool compressed_engine = (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED);
+            cudaStream_t st_reml = h->compute;
+            cudaStream_t st_solve = (h->overlap && compressed_engine) ? h->aux : h->compute;
+            cudaStream_t st_cmb = h->compute;
+            if (st_solve != st_reml && b >= 2) CK(cudaStreamWaitEvent(st_reml, h->ev_z_free[s], 0));  // Z[s] is free again
             double* xr_block = h->xr[s];
             if (b >= 2) {  // the REML stage of block b-2 has finished reading xr[s]
                 CK(cudaStreamWaitEvent(h->compute, h->ev_xr_free[s], 0));
@@ -984,10 +1015,11 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             CK(cudaStreamWaitEvent(st_reml, h->ev_xr_ready[s], 0));
             CK(cudaEventRecord(ev_reml[b].a, st_reml));
             cudaEvent_t mid[2] = {ev_cmp[b].a, ev_cmp[b].b};
+            cudaEvent_t evz[2] = {h->ev_z_ready[s], h->ev_z_free[s]};
             int r3 = launch_reml(h, st_reml, xr_block, h->Z[s], mb, g0, grid_mode, dout, dstatus, de2, de3, mid,
-                                 h->ev_xr_free[s]);
+                                 h->ev_xr_free[s], st_solve, evz, s);
             if (r3) return r3;
-            CK(cudaEventRecord(ev_reml[b].b, st_reml));
+            CK(cudaEventRecord(ev_reml[b].b, st_solve));
             h->last_block_count = mb;
             h->last_block_row0 = g0;
             h->last_xr = xr_block;
