@@ -142,6 +142,17 @@ int pg_get_eigen_device(pg_handle* h, double* U_dev_out, double* d_dev_out);
 int pg_set_design(pg_handle* h, const double* W_host, const double* y_host, int already_rotated, float* ms);
 
 /*
+ * Several phenotypes on one eigen-system and one covariate matrix: Y_host is (n, q) C-order (the reference's 2-D Y,
+ * lmm/lmm.py:108-110 takes one column; a caller loops lmm.pygemma over traits, e.g.
+ * experiments/benchmarks/benchmarks.py).  Every later pg_scan / pg_scan_device rotates each genotype block ONCE and
+ * runs the REML stage per phenotype: all output arrays then hold q * m values, phenotype-major
+ * (out[ph * m + g]); each phenotype's rows are bit-identical to a pg_set_design + pg_scan of that column alone.
+ * pg_set_design resets the handle to one phenotype.
+ */
+int pg_set_design_multi(pg_handle* h, const double* W_host, const double* Y_host, int q, int already_rotated,
+                        float* ms);
+
+/*
  * Run all device work of this handle on a caller-owned CUDA stream (a cudaStream_t passed as void*),
  * e.g. torch's current stream, so the caller can bracket calls with its own CUDA events.  NULL restores
  * the handle's private stream.  Genotype uploads still use a private copy stream, ordered by events.

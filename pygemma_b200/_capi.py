@@ -21,7 +21,7 @@ PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)
 SYMBOLS = [
     "pg_abi_version", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
-    "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_stream", "pg_set_options",
+    "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
     "pg_set_reml_engine", "pg_grm", "pg_set_bed_options",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
@@ -70,6 +70,7 @@ def load():
     L.pg_set_eigen_device.argtypes = [vp, vp, i32, vp]
     L.pg_get_eigen_device.argtypes = [vp, vp, vp]
     L.pg_set_design.argtypes = [vp, vp, vp, i32, ctypes.POINTER(ctypes.c_float)]
+    L.pg_set_design_multi.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float)]
     L.pg_set_options.argtypes = [vp, i32, i64]
     L.pg_set_stream.argtypes = [vp, vp]
     L.pg_set_reml_engine.argtypes = [vp, i32]
@@ -110,6 +111,7 @@ class Handle:
     def __init__(self, n: int, c0: int, device: int = 0):
         self.L = load()
         self.n, self.c0, self.device = int(n), int(c0), int(device)
+        self.q = 1   # phenotypes of the current design (set_design with an (n, q) matrix)
         h = ctypes.c_void_p()
         rc = self.L.pg_create(self.n, self.c0, self.device, ctypes.byref(h))
         if rc != 0:
@@ -185,12 +187,21 @@ class Handle:
         self._ck(self.L.pg_get_eigen_device(self.h, ctypes.c_void_p(U_ptr), ctypes.c_void_p(d_ptr)))
 
     def set_design(self, W, y, already_rotated=False):
+        """y: n values, or an (n, q) matrix of q phenotypes scanned together (outputs become (q, m) arrays)."""
         W = np.ascontiguousarray(W, dtype=np.float64).reshape(self.n, self.c0)
-        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
-        assert y.shape[0] == self.n
+        y = np.ascontiguousarray(y, dtype=np.float64)
         ms = ctypes.c_float(0)
+        if y.ndim == 2 and y.shape[1] > 1:
+            assert y.shape[0] == self.n
+            self._ck(self.L.pg_set_design_multi(self.h, _ptr(W) if self.c0 else None, _ptr(y), int(y.shape[1]),
+                                                int(already_rotated), ctypes.byref(ms)))
+            self.q = int(y.shape[1])
+            return float(ms.value)
+        y = y.reshape(-1)
+        assert y.shape[0] == self.n
         self._ck(self.L.pg_set_design(self.h, _ptr(W) if self.c0 else None, _ptr(y), int(already_rotated),
                                       ctypes.byref(ms)))
+        self.q = 1
         return float(ms.value)
 
     def set_stream(self, stream_ptr: int):
@@ -218,10 +229,11 @@ class Handle:
             X = np.ascontiguousarray(X)
         ld = X.strides[0] // X.itemsize if X.shape[0] > 1 else X.shape[1]
         ld = max(ld, X.shape[1])
-        out = {k: np.empty(m) for k in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald")}
-        st = np.zeros(m, dtype=np.int32)
-        e2 = np.zeros(m, dtype=np.int32) if with_counts else None
-        e3 = np.zeros(m, dtype=np.int32) if with_counts else None
+        shape = m if self.q == 1 else (self.q, m)
+        out = {k: np.empty(shape) for k in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald")}
+        st = np.zeros(shape, dtype=np.int32)
+        e2 = np.zeros(shape, dtype=np.int32) if with_counts else None
+        e3 = np.zeros(shape, dtype=np.int32) if with_counts else None
         tm = PgTiming()
         self._ck(self.L.pg_scan(self.h, _ptr(X), xdtype_of(X), ld, layout, m, int(bool(grid)),
                                 _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
@@ -241,10 +253,11 @@ class Handle:
             raise ValueError(f"packed .bed block must have shape (m, >= {(self.n + 3) // 4})")
         m = packed.shape[0]
         self._ck(self.L.pg_set_bed_options(self.h, int(bool(count_A1)), int(bool(standardize))))
-        out = {k: np.empty(m) for k in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald")}
-        st = np.zeros(m, dtype=np.int32)
-        e2 = np.zeros(m, dtype=np.int32) if with_counts else None
-        e3 = np.zeros(m, dtype=np.int32) if with_counts else None
+        shape = m if self.q == 1 else (self.q, m)
+        out = {k: np.empty(shape) for k in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald")}
+        st = np.zeros(shape, dtype=np.int32)
+        e2 = np.zeros(shape, dtype=np.int32) if with_counts else None
+        e3 = np.zeros(shape, dtype=np.int32) if with_counts else None
         tm = PgTiming()
         self._ck(self.L.pg_scan(self.h, _ptr(packed), PG_X_BED, packed.shape[1], PG_X_SNP_MAJOR, m, int(bool(grid)),
                                 _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),

@@ -2,9 +2,12 @@
 //
 // For SNP s with rotated genotypes x (n doubles) the REML kernel needs, per node k of the plan
 // (compress_plan.h), the moments
-//     Z[s][j][k] = sum_{l in segment(k)} L_k(log d_l) x_l w_jl     j = 0..c0   ([W0, y] columns)
-//     Z[s][c0+1][k] = sum_l L_k(log d_l) x_l^2
-// (Z rows are padded to k1p = (c0+2) rounded up to a multiple of 4; the padding rows stay zero)
+//     Z[s][row(j)][k] = sum_{l in segment(k)} L_k(log d_l) x_l w_jl     j = 0..klin-1   ([W0, y..] columns)
+//     Z[s][c0][k]     = sum_l L_k(log d_l) x_l^2
+// Row layout of one SNP's slab (z_row / z_xx_row below; k1p = (c0+2) rounded up to a multiple of 4):
+//     rows 0..c0-1: x.w_j    row c0: x.x    rows c0+1..k1p-2: padding (stay zero)    row k1p-1+t: x.y_t, t = 0..q-1
+// so that the k1p rows the solver reads for one phenotype are contiguous except for its own y row, and q phenotypes
+// on the same covariates (pg_set_design_multi) share one compression: the linear columns are [W0, y_0 .. y_{q-1}].
 // which replace the reference's per-SNP, per-lambda dsyrk over n samples (pygemma_model.pyx:938-943,:1002).
 // For one segment this is a dense contraction  Z_seg (SNPs x (c0+1) kq)  =  X[:, l0:l1]  .  V[l0:l1, :]  with
 // V[l, j kq + k] = L_k(log d_l) w_jl  -- the FP64 tensor pipe (DMMA m8n8k4) -- and the x^2 moments reuse the
@@ -44,6 +47,9 @@ struct CompItem {
     int pad;
 };
 
+// slab row of linear column j of [W0, y_0, y_1, ...]
+__host__ __device__ __forceinline__ int z_row(int j, int c0, int k1p) { return j < c0 ? j : k1p - 1 + (j - c0); }
+
 struct DevPlan {
     int Kc = 0, Kcp = 0;        // nodes, padded to a multiple of 32 (padding nodes: d = 0, moments 0)
     double* nodes = nullptr;    // [Kcp]
@@ -51,6 +57,7 @@ struct DevPlan {
     int* seg_kq = nullptr;      // [n] kq of the COMPRESS segment of l, 0 for COPY rows
     double* V = nullptr;        // [npad16][vpitch]
     int vpitch = 0, ngroups = 0, npad16 = 0;   // npad16: rows of V, n rounded up to 32
+    int klin = 0;               // linear columns the items / V were built for: c0 + q
     CompItem* items = nullptr;
     int nitems = 0;
     int* copy_l = nullptr;      // COPY rows: eigen index and node
@@ -83,14 +90,14 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 }
 
 // V[l][g*128 + j*kq + k] = Lw[l][k] * wy[j0_g + j][l]  (k < kq, j < nj_g);  V[l][g*128 + 112 + k] = Lw[l][k] (g == 0)
-__global__ void build_v_kernel(int n, int c0, const double* __restrict__ Lw, const int* __restrict__ seg_kq,
+__global__ void build_v_kernel(int n, int klin, const double* __restrict__ Lw, const int* __restrict__ seg_kq,
                                const double* __restrict__ wy, long long ldw, double* __restrict__ V, int vpitch,
                                int ngroups)
 {
     const int l = blockIdx.x;
     if (l >= n) return;
     const int kq = seg_kq[l];
-    const int k0 = c0 + 1;
+    const int k0 = klin;
     for (int col = threadIdx.x; col < vpitch; col += blockDim.x) {
         const int g = col / kGroupCols, c = col - g * kGroupCols;
         double v = 0.0;
@@ -111,7 +118,8 @@ __global__ void build_v_kernel(int n, int c0, const double* __restrict__ Lw, con
 
 __global__ void __launch_bounds__(256, 1)
 compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb, const CompItem* __restrict__ items,
-                     const double* __restrict__ V, int vpitch, int c0, int k1p, int Kcp, double* __restrict__ Z, int ntiles)
+                     const double* __restrict__ V, int vpitch, int c0, int k1p, int zrows, int Kcp, double* __restrict__ Z,
+                     int ntiles)
 {
     extern __shared__ __align__(16) double csm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -196,7 +204,7 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
     for (int b = 0; b < 2; ++b) {
         const long long snp = snp0 + warp * 16 + b * 8 + (lane >> 2);
         if (snp >= mb) continue;
-        double* Zs = Z + (size_t)snp * k1p * Kcp;
+        double* Zs = Z + (size_t)snp * zrows * Kcp;
 #pragma unroll
         for (int t = 0; t < kLinTiles; ++t) {
             if (t < nt_lin) {
@@ -205,7 +213,7 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
                     const int col = 8 * t + 2 * (lane & 3) + e;
                     if (col < ncol_lin) {
                         const int jl = col / it.kq, k = col - jl * it.kq;
-                        Zs[(size_t)(it.j0 + jl) * Kcp + it.kb + k] = acc[b][t][e];
+                        Zs[(size_t)z_row(it.j0 + jl, c0, k1p) * Kcp + it.kb + k] = acc[b][t][e];
                     }
                 }
             }
@@ -216,18 +224,18 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int col = 8 * t + 2 * (lane & 3) + e;
-                    if (col < it.kq) Zs[(size_t)(c0 + 1) * Kcp + it.kb + col] = acc[b][kLinTiles + t][e];
+                    if (col < it.kq) Zs[(size_t)c0 * Kcp + it.kb + col] = acc[b][kLinTiles + t][e];
                 }
             }
         }
     }
 }
 
-// COPY rows: node(l) holds the single eigenvalue d_l:  Z[s][j][node] = x_l w_jl,  Z[s][c0+1][node] = x_l^2
+// COPY rows: node(l) holds the single eigenvalue d_l:  Z[s][row(j)][node] = x_l w_jl,  Z[s][c0][node] = x_l^2
 __global__ void __launch_bounds__(128)
 compress_copy_kernel(const double* __restrict__ xr, long long ldx, long long mb, const int* __restrict__ copy_l,
                      const int* __restrict__ copy_node, int ncopy, const double* __restrict__ wy, long long ldw, int c0,
-                     int k1p, int Kcp, double* __restrict__ Z)
+                     int klin, int k1p, int zrows, int Kcp, double* __restrict__ Z)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncopy) return;
@@ -237,9 +245,9 @@ compress_copy_kernel(const double* __restrict__ xr, long long ldx, long long mb,
         const long long snp = s0 + r;
         if (snp >= mb) break;
         const double x = xr[(size_t)snp * ldx + l];
-        double* Zs = Z + (size_t)snp * k1p * Kcp + node;
-        for (int j = 0; j <= c0; ++j) Zs[(size_t)j * Kcp] = x * wy[(size_t)j * ldw + l];
-        Zs[(size_t)(c0 + 1) * Kcp] = x * x;
+        double* Zs = Z + (size_t)snp * zrows * Kcp + node;
+        for (int j = 0; j < klin; ++j) Zs[(size_t)z_row(j, c0, k1p) * Kcp] = x * wy[(size_t)j * ldw + l];
+        Zs[(size_t)c0 * Kcp] = x * x;
     }
 }
 

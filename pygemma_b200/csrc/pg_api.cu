@@ -89,10 +89,21 @@ struct pg_handle {
     double* Z[2] = {nullptr, nullptr};  // [blk][k1p][Kcp], double-buffered like xr
     size_t z_elems = 0;
     int k1p = 0;          // c0+2 rounded up to a multiple of 4
+    // several phenotypes on one eigen-system (pg_set_design_multi): each has its own rotated [W0, y] and lambda tables;
+    // slot 0 owns the buffers allocated with the handle, `activate` points the handle's working fields at a slot
+    // before its kernels are launched (launches copy the pointers, so slots can alternate per block)
+    struct DesignSlot { double *wy, *fixtab, *itab, *fix2, *itab2; };
+    std::vector<DesignSlot> slots;
+    int q = 1;
+    double* wy_all = nullptr;   // q > 1: rotated [W0, y_0 .. y_{q-1}], the linear columns of the shared compression
+    int wy_all_cols = 0;
+    int z_rows = 0;             // slab rows per SNP the Z buffers were last laid out for (k1p - 1 + q)
     // table-2 rows (covariate levels eliminated per table lambda, pg_eval.cuh)
     double *fix2 = nullptr, *itab2 = nullptr, *t2work = nullptr;
     Tables2 tab2{};
 };
+
+static void activate(pg_handle* h, int ph);
 
 static void free_plan(pg_handle* h)
 {
@@ -103,6 +114,7 @@ static void free_plan(pg_handle* h)
     P = DevPlan{};
     h->Z[0] = h->Z[1] = nullptr;
     h->z_elems = 0;
+    h->z_rows = 0;
 }
 
 static int fail(pg_handle* h, int code, const char* fmt, ...)
@@ -154,6 +166,16 @@ extern "C" const char* pg_last_error(const pg_handle* h) { return h ? h->err.c_s
 static int free_all(pg_handle* h)
 {
     cudaSetDevice(h->device);
+    if (!h->slots.empty()) {
+        activate(h, 0);   // the handle's own fields point at slot 0 again before they are freed below
+        for (size_t ph = 1; ph < h->slots.size(); ++ph) {
+            void* bufs[] = {h->slots[ph].wy, h->slots[ph].fixtab, h->slots[ph].itab, h->slots[ph].fix2, h->slots[ph].itab2};
+            for (void* b : bufs)
+                if (b) cudaFree(b);
+        }
+    }
+    if (h->wy_all) cudaFree(h->wy_all);
+    h->wy_all = nullptr;
     rot_free(&h->rot);
     for (int s = 0; s < 2; ++s) {
         if (h->stage[s]) cudaFree(h->stage[s]);
@@ -316,6 +338,45 @@ __global__ void permute_u_kernel(const double* __restrict__ src, double* __restr
     dst[idx] = cols_contig ? src[(size_t)perm[a] * n + b] : src[(size_t)a * n + perm[b]];
 }
 
+// Work items and the V operand of the compression for `klin` linear columns [W0, y_0 .. y_{q-1}] (klin = c0 + q):
+// one item per COMPRESS segment and group of kJGroup columns.  The V contents are written by build_v_kernel.
+static int build_groups(pg_handle* h, int klin)
+{
+    const CompressPlan& H = h->hplan;
+    DevPlan& P = h->plan;
+    if (P.items) cudaFree(P.items);
+    if (P.V) cudaFree(P.V);
+    P.items = nullptr; P.V = nullptr; P.nitems = 0;
+    P.klin = klin;
+    P.ngroups = (klin + kJGroup - 1) / kJGroup;
+    P.vpitch = P.ngroups * kGroupCols;
+    std::vector<int> order;
+    for (int si = 0; si < (int)H.segs.size(); ++si)
+        if (H.segs[si].type == kSegCompress) order.push_back(si);
+    // longest segments first: the tail of the grid is made of short work items
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (H.segs[a].l1 - H.segs[a].l0) > (H.segs[b].l1 - H.segs[b].l0);
+    });
+    std::vector<CompItem> items;
+    for (int si : order) {
+        const Segment& sg = H.segs[si];
+        for (int g = 0; g < P.ngroups; ++g) {
+            CompItem it;
+            it.l0 = sg.l0; it.l1 = sg.l1; it.kb = sg.kb; it.kq = sg.kq;
+            it.j0 = g * kJGroup; it.nj = std::min<int>(kJGroup, klin - it.j0); it.vcol0 = g * kGroupCols; it.pad = 0;
+            items.push_back(it);
+        }
+    }
+    P.nitems = (int)items.size();
+    if (P.nitems) {
+        CK(cudaMalloc(&P.items, sizeof(CompItem) * items.size()));
+        CK(cudaMemcpy(P.items, items.data(), sizeof(CompItem) * items.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&P.V, sizeof(double) * (size_t)P.npad16 * P.vpitch));
+        CK(cudaMemset(P.V, 0, sizeof(double) * (size_t)P.npad16 * P.vpitch));
+    }
+    return PG_OK;
+}
+
 // Builds the compression plan for the handle's (ascending, clipped) eigenvalues and uploads it.
 static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
 {
@@ -333,42 +394,19 @@ static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
     CK(cudaMalloc(&P.Lw, sizeof(double) * (size_t)n * kCq));
     CK(cudaMemcpy(P.Lw, H.Lw.data(), sizeof(double) * (size_t)n * kCq, cudaMemcpyHostToDevice));
     std::vector<int> seg_kq(n, 0), copy_l, copy_node;
-    std::vector<CompItem> items;
-    P.ngroups = (k0 + kJGroup - 1) / kJGroup;
-    P.vpitch = P.ngroups * kGroupCols;
     P.npad16 = (n + 31) / 32 * 32;
-    std::vector<int> order;
     for (int si = 0; si < (int)H.segs.size(); ++si) {
         const Segment& sg = H.segs[si];
         if (sg.type == kSegCompress) {
             for (int l = sg.l0; l < sg.l1; ++l) seg_kq[l] = sg.kq;
-            order.push_back(si);
         } else {
             for (int l = sg.l0; l < sg.l1; ++l) { copy_l.push_back(l); copy_node.push_back(sg.kb + (l - sg.l0)); }
         }
     }
-    // longest segments first: the tail of the grid is made of short work items
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return (H.segs[a].l1 - H.segs[a].l0) > (H.segs[b].l1 - H.segs[b].l0);
-    });
-    for (int si : order) {
-        const Segment& sg = H.segs[si];
-        for (int g = 0; g < P.ngroups; ++g) {
-            CompItem it;
-            it.l0 = sg.l0; it.l1 = sg.l1; it.kb = sg.kb; it.kq = sg.kq;
-            it.j0 = g * kJGroup; it.nj = std::min<int>(kJGroup, k0 - it.j0); it.vcol0 = g * kGroupCols; it.pad = 0;
-            items.push_back(it);
-        }
-    }
     CK(cudaMalloc(&P.seg_kq, sizeof(int) * n));
     CK(cudaMemcpy(P.seg_kq, seg_kq.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-    P.nitems = (int)items.size();
-    if (P.nitems) {
-        CK(cudaMalloc(&P.items, sizeof(CompItem) * items.size()));
-        CK(cudaMemcpy(P.items, items.data(), sizeof(CompItem) * items.size(), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&P.V, sizeof(double) * (size_t)P.npad16 * P.vpitch));
-        CK(cudaMemset(P.V, 0, sizeof(double) * (size_t)P.npad16 * P.vpitch));
-    }
+    int rcg = build_groups(h, k0);
+    if (rcg) return rcg;
     P.ncopy = (int)copy_l.size();
     if (P.ncopy) {
         CK(cudaMalloc(&P.copy_l, sizeof(int) * P.ncopy));
@@ -523,6 +561,31 @@ extern "C" int pg_get_eigen_device(pg_handle* h, double* U_dev_out, double* d_de
     return PG_OK;
 }
 
+static void activate(pg_handle* h, int ph)
+{
+    const pg_handle::DesignSlot& S = h->slots[ph];
+    h->wy = S.wy; h->fixtab = S.fixtab; h->itab = S.itab; h->fix2 = S.fix2; h->itab2 = S.itab2;
+    h->tab.fixtab = S.fixtab; h->tab.itab = S.itab; h->tab2.fix2 = S.fix2; h->tab2.itab2 = S.itab2;
+}
+
+// makes sure slots 0..q-1 exist (slot 0 = the handle's own buffers)
+static int ensure_slots(pg_handle* h, int q)
+{
+    const int c0 = h->c0, k0 = c0 + 1, T0 = k0 * (k0 + 1) / 2, NF = 3 * T0 + 3, NF2 = t2_nf(c0);
+    if (h->slots.empty()) h->slots.push_back(pg_handle::DesignSlot{h->wy, h->fixtab, h->itab, h->fix2, h->itab2});
+    while ((int)h->slots.size() < q) {
+        pg_handle::DesignSlot S{nullptr, nullptr, nullptr, nullptr, nullptr};
+        CK(cudaMalloc(&S.wy, sizeof(double) * (size_t)h->ldw * k0));
+        CK(cudaMemset(S.wy, 0, sizeof(double) * (size_t)h->ldw * k0));
+        CK(cudaMalloc(&S.fixtab, sizeof(double) * (size_t)kNumFixed * NF));
+        CK(cudaMalloc(&S.itab, sizeof(double) * (size_t)kNumIntervals * kNodes * NF));
+        CK(cudaMalloc(&S.fix2, sizeof(double) * (size_t)kNumFixed * NF2));
+        CK(cudaMalloc(&S.itab2, sizeof(double) * (size_t)kNumIntervals * kNodes * NF2));
+        h->slots.push_back(S);
+    }
+    return PG_OK;
+}
+
 static int build_tables(pg_handle* h)
 {
     const int T0 = h->tab.T0;
@@ -537,7 +600,83 @@ static int build_tables(pg_handle* h)
     return PG_OK;
 }
 
+static int set_design_active(pg_handle* h, const double* W_host, const double* y_host, int already_rotated, float* ms);
+
+// (Re)builds the compression operand V for the handle's current phenotypes: linear columns [W0, y_0 .. y_{q-1}].
+static int build_v(pg_handle* h, int q)
+{
+    const int n = h->n, c0 = h->c0, klin = c0 + q;
+    if (h->plan.klin != klin) {
+        int rc = build_groups(h, klin);
+        if (rc) return rc;
+    }
+    const double* cols = h->slots[0].wy;   // q == 1: the slot's own [W0, y]
+    if (q > 1) {
+        if (h->wy_all_cols < klin) {
+            if (h->wy_all) cudaFree(h->wy_all);
+            h->wy_all = nullptr; h->wy_all_cols = 0;
+            CK(cudaMalloc(&h->wy_all, sizeof(double) * (size_t)h->ldw * klin));
+            h->wy_all_cols = klin;
+        }
+        CK(cudaMemcpyAsync(h->wy_all, h->slots[0].wy, sizeof(double) * (size_t)h->ldw * c0, cudaMemcpyDeviceToDevice,
+                           h->compute));
+        for (int ph = 0; ph < q; ++ph)
+            CK(cudaMemcpyAsync(h->wy_all + (size_t)h->ldw * (c0 + ph), h->slots[ph].wy + (size_t)h->ldw * c0,
+                               sizeof(double) * (size_t)h->ldw, cudaMemcpyDeviceToDevice, h->compute));
+        cols = h->wy_all;
+    }
+    if (h->plan.nitems) {
+        build_v_kernel<<<n, 128, 0, h->compute>>>(n, klin, h->plan.Lw, h->plan.seg_kq, cols, h->ldw, h->plan.V,
+                                                  h->plan.vpitch, h->plan.ngroups);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->compute));
+    return PG_OK;
+}
+
 extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y_host, int already_rotated, float* ms)
+{
+    if (!h) return PG_ERR_ARG;
+    int rc = ensure_slots(h, 1);
+    if (rc) return rc;
+    activate(h, 0);
+    h->have_design = false;
+    rc = set_design_active(h, W_host, y_host, already_rotated, ms);
+    if (rc) return rc;
+    rc = build_v(h, 1);
+    if (rc) return rc;
+    h->q = 1;
+    h->have_design = true;
+    return PG_OK;
+}
+
+extern "C" int pg_set_design_multi(pg_handle* h, const double* W_host, const double* Y_host, int q, int already_rotated,
+                                   float* ms)
+{
+    if (!h || !Y_host || q < 1) return fail(h, PG_ERR_ARG, "pg_set_design_multi: bad argument");
+    int rc = ensure_slots(h, q);
+    if (rc) return rc;
+    h->have_design = false;
+    std::vector<double> y(h->n);
+    float total = 0.f;
+    for (int ph = 0; ph < q; ++ph) {
+        for (int l = 0; l < h->n; ++l) y[l] = Y_host[(size_t)l * q + ph];   // (n, q) C-order
+        activate(h, ph);
+        float t = 0.f;
+        rc = set_design_active(h, W_host, y.data(), already_rotated, &t);
+        if (rc) { activate(h, 0); return rc; }
+        total += t;
+    }
+    activate(h, 0);
+    rc = build_v(h, q);
+    if (rc) return rc;
+    h->q = q;
+    h->have_design = true;
+    if (ms) *ms = total;
+    return PG_OK;
+}
+
+static int set_design_active(pg_handle* h, const double* W_host, const double* y_host, int already_rotated, float* ms)
 {
     if (!h || !y_host || (!W_host && h->c0 > 0)) return fail(h, PG_ERR_ARG, "pg_set_design: NULL argument");
     if (!h->have_d) return fail(h, PG_ERR_ARG, "pg_set_design: call pg_set_kinship / pg_set_eigen first");
@@ -573,11 +712,6 @@ extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y
     h->rotated_inputs = already_rotated != 0;
     int rc = build_tables(h);
     if (rc) return rc;
-    if (h->plan.nitems) {
-        build_v_kernel<<<n, 128, 0, h->compute>>>(n, c0, h->plan.Lw, h->plan.seg_kq, h->wy, h->ldw, h->plan.V,
-                                                  h->plan.vpitch, h->plan.ngroups);
-        CK(cudaGetLastError());
-    }
     CK(cudaEventRecord(e1, h->compute));
     CK(cudaStreamSynchronize(h->compute));
     float t = 0;
@@ -585,7 +719,6 @@ extern "C" int pg_set_design(pg_handle* h, const double* W_host, const double* y
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms) *ms = t;
-    h->have_design = true;
     return PG_OK;
 }
 
@@ -639,7 +772,7 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         // keep at least four blocks in flight on large inputs so uploads overlap compute
         if (m >= 4 * 8192) blk = std::min<long long>(blk, std::max<long long>(8192, ((m + 3) / 4 + 255) / 256 * 256));
         // compressed moments of a block: at most 2 GiB
-        const size_t zrow = sizeof(double) * (size_t)h->k1p * std::max(h->plan.Kcp, 32);
+        const size_t zrow = sizeof(double) * (size_t)(h->k1p - 1 + h->q) * std::max(h->plan.Kcp, 32);
         blk = std::min<long long>(blk, std::max<long long>(256, (long long)((size_t(1) << 31) / zrow) / 256 * 256));
     }
     blk = std::min(blk, std::max<long long>(m, 1));
@@ -662,7 +795,13 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         h->xbuf_elems = need;
     }
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
-        const size_t zneed = (size_t)blk * h->k1p * h->plan.Kcp;
+        const int zrows = h->k1p - 1 + h->q;
+        const size_t zneed = (size_t)blk * zrows * h->plan.Kcp;
+        if (zneed <= h->z_elems && zrows != h->z_rows) {
+            // another slab layout than the one the buffers last held: padding rows / nodes must read as zero again
+            for (int s = 0; s < 2; ++s) CK(cudaMemsetAsync(h->Z[s], 0, sizeof(double) * h->z_elems, h->compute));
+        }
+        h->z_rows = zrows;
         if (zneed > h->z_elems) {
             for (int s = 0; s < 2; ++s) {
                 if (h->Z[s]) cudaFree(h->Z[s]);
@@ -709,8 +848,11 @@ static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld,
 static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* Zbuf, long long mb, long long row0,
                        int grid_mode, double* const out[6], int* status, int* e2, int* e3, cudaEvent_t* ev_mid = nullptr,
                        cudaEvent_t ev_xr_done = nullptr, cudaStream_t st_solve = nullptr, cudaEvent_t* ev_z = nullptr,
-                       int parity = 0)
+                       int parity = 0, int ph = 0)
 {
+    // ph: phenotype slot of this launch (the caller has activated it).  The compressed engine compresses the block for
+    // all h->q phenotypes at ph == 0; the direct engines read xr for every phenotype.
+    const int q = h->q;
     if (!st_solve) st_solve = st;
     const bool split = st_solve != st;
     unsigned long long* counter = h->counter + (parity & 1);
@@ -722,29 +864,34 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
         const DevPlan& P = h->plan;
         const int ntiles = (int)((mb + kCtSnps - 1) / kCtSnps);
-        if (ev_mid) CK(cudaEventRecord(ev_mid[0], st));
-        if (P.nitems) {
-            CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
-            compress_dmma_kernel<<<(unsigned)((long long)P.nitems * ntiles), 256, kCtSmemBytes, st>>>(
-                xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, h->k1p, P.Kcp, Zbuf, ntiles);
-            CK(cudaGetLastError());
-        }
-        if (P.ncopy) {
-            dim3 grid((unsigned)((P.ncopy + 127) / 128), (unsigned)((mb + 7) / 8));
-            compress_copy_kernel<<<grid, 128, 0, st>>>(xr, h->ldx, mb, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw,
-                                                             h->c0, h->k1p, P.Kcp, Zbuf);
-            CK(cudaGetLastError());
-        }
-        if (ev_mid) CK(cudaEventRecord(ev_mid[1], st));
-        if (ev_xr_done) CK(cudaEventRecord(ev_xr_done, st));
-        if (split) {
-            CK(cudaEventRecord(ev_z[0], st));
-            CK(cudaStreamWaitEvent(st_solve, ev_z[0], 0));
+        const int zrows = h->k1p - 1 + q;
+        if (ph == 0) {
+            if (ev_mid) CK(cudaEventRecord(ev_mid[0], st));
+            if (P.nitems) {
+                CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
+                compress_dmma_kernel<<<(unsigned)((long long)P.nitems * ntiles), 256, kCtSmemBytes, st>>>(
+                    xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, h->k1p, zrows, P.Kcp, Zbuf, ntiles);
+                CK(cudaGetLastError());
+            }
+            if (P.ncopy) {
+                dim3 grid((unsigned)((P.ncopy + 127) / 128), (unsigned)((mb + 7) / 8));
+                compress_copy_kernel<<<grid, 128, 0, st>>>(xr, h->ldx, mb, P.copy_l, P.copy_node, P.ncopy,
+                                                           q > 1 ? h->wy_all : h->wy, h->ldw, h->c0, P.klin, h->k1p, zrows,
+                                                           P.Kcp, Zbuf);
+                CK(cudaGetLastError());
+            }
+            if (ev_mid) CK(cudaEventRecord(ev_mid[1], st));
+            if (ev_xr_done) CK(cudaEventRecord(ev_xr_done, st));
+            if (split) {
+                CK(cudaEventRecord(ev_z[0], st));
+                CK(cudaStreamWaitEvent(st_solve, ev_z[0], 0));
+            }
         }
         CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st_solve));
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
         sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
+        sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
@@ -769,9 +916,10 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
         pvalue_kernel<<<(unsigned)((mb + 63) / 64), 64, 0, st_solve>>>(out[4], out[5], row0, mb, (double)(h->n - h->c0 - 1));
         CK(cudaGetLastError());
-        if (split) CK(cudaEventRecord(ev_z[1], st_solve));
+        if (split && ph == q - 1) CK(cudaEventRecord(ev_z[1], st_solve));
         return PG_OK;
     }
+    if (ph != q - 1) ev_xr_done = nullptr;   // the direct engines read xr for every phenotype
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     if (h->engine == PG_REML_STREAM) {
         const StreamCfg cfg = stream_config(h->c0);
@@ -894,24 +1042,26 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     int *dstatus = nullptr, *de2 = nullptr, *de3 = nullptr;
     double* dtmp = nullptr;
     int* itmp = nullptr;
+    const int q = h->q;                       // phenotypes of the current design (pg_set_design_multi)
+    const size_t mq = (size_t)m * (size_t)q;  // every output array holds q * m values, phenotype-major
     if (on_device) {
         for (int i = 0; i < 6; ++i) dout[i] = out_user[i];
         dstatus = status; de2 = e2; de3 = e3;
     } else {
-        if ((size_t)m > h->res_cap) {
+        if (mq > h->res_cap) {
             if (h->res_d) cudaFree(h->res_d);
             if (h->res_i) cudaFree(h->res_i);
             if (h->res_host) cudaFreeHost(h->res_host);
             h->res_d = nullptr; h->res_i = nullptr; h->res_host = nullptr; h->res_cap = 0;
-            const size_t cap = ((size_t)m + 1023) / 1024 * 1024;
+            const size_t cap = (mq + 1023) / 1024 * 1024;
             CK(cudaMalloc(&h->res_d, sizeof(double) * 6 * cap));
             CK(cudaMalloc(&h->res_i, sizeof(int) * 3 * cap));
             CK(cudaMallocHost(&h->res_host, (sizeof(double) * 6 + sizeof(int) * 3) * cap));
             h->res_cap = cap;
         }
         dtmp = h->res_d; itmp = h->res_i;
-        for (int i = 0; i < 6; ++i) dout[i] = dtmp + (size_t)i * m;
-        dstatus = itmp; de2 = itmp + m; de3 = itmp + 2 * (size_t)m;
+        for (int i = 0; i < 6; ++i) dout[i] = dtmp + (size_t)i * mq;
+        dstatus = itmp; de2 = itmp + mq; de3 = itmp + 2 * mq;
     }
 
     // timing events come from a pool owned by the handle (creating / destroying ~40 events per call costs host time)
@@ -1016,9 +1166,17 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             CK(cudaEventRecord(ev_reml[b].a, st_reml));
             cudaEvent_t mid[2] = {ev_cmp[b].a, ev_cmp[b].b};
             cudaEvent_t evz[2] = {h->ev_z_ready[s], h->ev_z_free[s]};
-            int r3 = launch_reml(h, st_reml, xr_block, h->Z[s], mb, g0, grid_mode, dout, dstatus, de2, de3, mid,
-                                 h->ev_xr_free[s], st_solve, evz, s);
-            if (r3) return r3;
+            for (int ph = 0; ph < q; ++ph) {
+                // one solve per phenotype on the block's rotated genotypes; rotation and compression are shared
+                activate(h, ph);
+                double* outp[6];
+                for (int i = 0; i < 6; ++i) outp[i] = dout[i] + (size_t)ph * m;
+                int r3 = launch_reml(h, st_reml, xr_block, h->Z[s], mb, g0, grid_mode, outp,
+                                     dstatus ? dstatus + (size_t)ph * m : nullptr, de2 ? de2 + (size_t)ph * m : nullptr,
+                                     de3 ? de3 + (size_t)ph * m : nullptr, mid, h->ev_xr_free[s], st_solve, evz, s, ph);
+                if (r3) { activate(h, 0); return r3; }
+            }
+            activate(h, 0);
             CK(cudaEventRecord(ev_reml[b].b, st_solve));
             h->last_block_count = mb;
             h->last_block_row0 = g0;
@@ -1031,8 +1189,8 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         CK(cudaEventRecord(t1, h->compute));
         if (!on_device) {
             // two D2H copies into pinned staging, then host memcpy into the caller's (pageable) arrays
-            CK(cudaMemcpyAsync(h->res_host, dtmp, sizeof(double) * 6 * (size_t)m, cudaMemcpyDeviceToHost, h->compute));
-            CK(cudaMemcpyAsync(h->res_host + sizeof(double) * 6 * (size_t)m, itmp, sizeof(int) * 3 * (size_t)m,
+            CK(cudaMemcpyAsync(h->res_host, dtmp, sizeof(double) * 6 * mq, cudaMemcpyDeviceToHost, h->compute));
+            CK(cudaMemcpyAsync(h->res_host + sizeof(double) * 6 * mq, itmp, sizeof(int) * 3 * mq,
                                cudaMemcpyDeviceToHost, h->compute));
         }
         CK(cudaEventRecord(t2, h->compute));
@@ -1040,11 +1198,11 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         CK(cudaStreamSynchronize(h->copy));
         if (!on_device) {
             const double* hd = reinterpret_cast<const double*>(h->res_host);
-            const int* hi = reinterpret_cast<const int*>(h->res_host + sizeof(double) * 6 * (size_t)m);
-            for (int i = 0; i < 6; ++i) memcpy(out_user[i], hd + (size_t)i * m, sizeof(double) * (size_t)m);
-            if (status) memcpy(status, hi, sizeof(int) * (size_t)m);
-            if (e2) memcpy(e2, hi + m, sizeof(int) * (size_t)m);
-            if (e3) memcpy(e3, hi + 2 * (size_t)m, sizeof(int) * (size_t)m);
+            const int* hi = reinterpret_cast<const int*>(h->res_host + sizeof(double) * 6 * mq);
+            for (int i = 0; i < 6; ++i) memcpy(out_user[i], hd + (size_t)i * mq, sizeof(double) * mq);
+            if (status) memcpy(status, hi, sizeof(int) * mq);
+            if (e2) memcpy(e2, hi + mq, sizeof(int) * mq);
+            if (e3) memcpy(e3, hi + 2 * mq, sizeof(int) * mq);
         }
         return PG_OK;
     }();
@@ -1264,24 +1422,25 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     CK(cudaMemcpyAsync(dx, xs.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
         const DevPlan& P = h->plan;
-        const int k1p = h->k1p;
+        const int k1p = h->k1p, zrows = k1p - 1 + h->q;   // probes phenotype 0
         double* dz = nullptr;
-        CK(cudaMalloc(&dz, sizeof(double) * (size_t)k1p * P.Kcp));
-        CK(cudaMemsetAsync(dz, 0, sizeof(double) * (size_t)k1p * P.Kcp, h->compute));
+        CK(cudaMalloc(&dz, sizeof(double) * (size_t)zrows * P.Kcp));
+        CK(cudaMemsetAsync(dz, 0, sizeof(double) * (size_t)zrows * P.Kcp, h->compute));
         if (P.nitems) {
             CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
             compress_dmma_kernel<<<(unsigned)P.nitems, 256, kCtSmemBytes, h->compute>>>(dx, h->ldx, 1, P.items, P.V, P.vpitch,
-                                                                                     h->c0, k1p, P.Kcp, dz, 1);
+                                                                                     h->c0, k1p, zrows, P.Kcp, dz, 1);
             CK(cudaGetLastError());
         }
         if (P.ncopy) {
             compress_copy_kernel<<<dim3((unsigned)((P.ncopy + 127) / 128), 1), 128, 0, h->compute>>>(
-                dx, h->ldx, 1, P.copy_l, P.copy_node, P.ncopy, h->wy, h->ldw, h->c0, k1p, P.Kcp, dz);
+                dx, h->ldx, 1, P.copy_l, P.copy_node, P.ncopy, h->q > 1 ? h->wy_all : h->wy, h->ldw, h->c0, P.klin, k1p, zrows,
+                P.Kcp, dz);
             CK(cudaGetLastError());
         }
         SolveArgs sa{};
         sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
-        sa.k1p = k1p; sa.t2 = h->tab2;
+        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1;
         const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);
         const bool two = (h->c0 + 2) > 32;
         if (smemc > 48 * 1024) {

@@ -26,8 +26,10 @@ struct SolveArgs {
     long long m, row0;
     const double* nodes;  // [Kcp] node eigenvalues (padding: 0)
     int Kcp;
-    const double* Z;      // [m][k1p][Kcp]
+    const double* Z;      // [m][zrows][Kcp], slab rows as laid out in compress.cuh
     int k1p;              // c0+2 rounded up to a multiple of 4 (padding rows are zero)
+    int zrows;            // rows per SNP slab: k1p - 1 + number of phenotypes
+    int yrow;             // slab row of this launch's phenotype (k1p - 1 + phenotype index)
     Tables2 t2;
     double* out[6];
     int* status;
@@ -90,7 +92,8 @@ __device__ __forceinline__ void warp_reduce_halving(double (&v)[V], int lane)
     }
 }
 
-// level-0 x row for moment rows [jb, jb+NC) -> xs[p * k1p + j] (p = power index; row j < c0: x.w_j, c0: x.y, c0+1: x.x)
+// level-0 x row for slab rows [jb, jb+NC) -> xs[p * k1p + j] (p = power index; row j < c0: x.w_j, c0: x.x, k1p-1: x.y,
+// the last one read from the launch's own phenotype row a.yrow)
 template <int NC, bool FULL>
 __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double* __restrict__ Zs, double lam, int jb,
                                                 double* xs)
@@ -102,13 +105,14 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = 0.0;
     const double* __restrict__ z = Zs + (size_t)jb * Kcp;
+    const double* __restrict__ zl = Zs + (size_t)(jb + NC == a.k1p ? a.yrow : jb + NC - 1) * Kcp;
 #pragma unroll 2
     for (int k = lane; k < Kcp; k += 32) {
         const double h = rcp_ge1(fma(lam, __ldg(a.nodes + k), 1.0));
         const double h2 = h * h, h3 = h2 * h;
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-            const double zz = __ldg(z + (size_t)j * Kcp + k);
+            const double zz = (j == NC - 1) ? __ldg(zl + k) : __ldg(z + (size_t)j * Kcp + k);
             v[j] = fma(h, zz, v[j]);
             v[NC + j] = fma(h2, zz, v[NC + j]);
             if (FULL) v[2 * NC + j] = fma(h3, zz, v[2 * NC + j]);
@@ -242,9 +246,10 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
     for (int q = 0; q < NS; ++q) {
         const int j = lane + 32 * q;
         const bool in = j < k1;
-        xa[q] = in ? xs[j] : 0.0;
-        xb[q] = in ? xs[k1p + j] : 0.0;
-        xc[q] = (in && full) ? xs[2 * k1p + j] : 0.0;
+        const int r = j < c0 ? j : (j == c0 ? k1p - 1 : c0);   // Pab column order [W0, y, x] -> slab rows
+        xa[q] = in ? xs[r] : 0.0;
+        xb[q] = in ? xs[k1p + r] : 0.0;
+        xc[q] = (in && full) ? xs[2 * k1p + r] : 0.0;
     }
     if (full) xrow_recursion_warp<true, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
     else xrow_recursion_warp<false, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         if (lane == 0) g = atomicAdd(a.counter, 1ULL);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= (unsigned long long)a.m) break;
-        const double* __restrict__ Zs = a.Z + (size_t)g * k1p * a.Kcp;
+        const double* __restrict__ Zs = a.Z + (size_t)g * a.zrows * a.Kcp;
         SnpSolver s;
         s.init(a.n, a.c0, a.grid, /*defer_p=*/1);
         while (s.pending()) {

@@ -71,6 +71,27 @@ def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=Fa
     Brent + Newton.  `device` (extension) selects the CUDA device; default 0 or the
     torch.distributed local rank.
     """
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)  # lmm/lmm.py:115-116
+    return _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device)[0]
+
+
+def pygemma_multi(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, grid=False, eigen=True, device=None):
+    """Several phenotypes in one pass (extension; the reference is called once per trait, e.g.
+    experiments/benchmarks/benchmarks.py loops lmm.pygemma over simulated phenotypes).
+
+    Y is (n, q); every other argument is as in `pygemma`.  Returns a list of q DataFrames, the i-th identical (bit for
+    bit) to `pygemma(Y[:, i], X, W, K, ...)`: eigh(K) and the rotation U^T X, which dominate a single-trait scan, are
+    done once, and only the REML stage runs per trait.
+    """
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y.reshape(-1, 1)
+    if Y.ndim != 2:
+        raise ValueError("Y must be (n, q)")
+    return _run(Y, X, W, K, Z, snps, verbose, disable_checks, False, grid, eigen, device)
+
+
+def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
     global last_timing
     t_start = time.time()
     if de:
@@ -80,7 +101,7 @@ def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=Fa
     from . import multi  # torch.distributed plumbing, only active when a process group exists
 
     X = _as_genotypes(X)
-    Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)  # lmm/lmm.py:115-116
+    q = Y.shape[1]
     W = np.asarray(W, dtype=np.float64)
     if W.ndim == 1:
         W = W.reshape(-1, 1)
@@ -104,7 +125,7 @@ def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=Fa
             raise ValueError("NaNs present in data")
 
     ctx = multi.context(device)
-    timing = {"n": n, "m": m, "c0": c0, "world_size": ctx.world_size}
+    timing = {"n": n, "m": m, "c0": c0, "q": q, "world_size": ctx.world_size}
     h = _capi.Handle(n, c0, ctx.device)
     try:
         t0 = time.time()
@@ -115,33 +136,40 @@ def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=Fa
         else:
             h.set_eigen(None, K.reshape(-1))
         t0 = time.time()
-        timing["design_ms"] = h.set_design(W, Y.reshape(-1), already_rotated=not eigen)
+        timing["design_ms"] = h.set_design(W, Y if q > 1 else Y.reshape(-1), already_rotated=not eigen)
         _log(verbose, f"Rotated Y, W and built lambda tables - {round(time.time() - t0, 3)} s")
         _log(verbose, f"Running {m} SNPs with {n} individuals...")
         t0 = time.time()
         a, b = ctx.shard(m)  # contiguous SNP range of this rank (SampleIter, lmm/lmm.py:427-434)
         res = h.scan(X[:, a:b], grid=grid)
         timing["scan"] = res["timing"]
-        out = multi.gather_results(ctx, res, m)
+        if q == 1:
+            outs = [multi.gather_results(ctx, res, m)]
+        else:
+            outs = [multi.gather_results(ctx, {k: v[ph] for k, v in res.items() if k != "timing"}, m)
+                    for ph in range(q)]
         timing["scan_wall_s"] = time.time() - t0
         _log(verbose, f"Finished testing {m} SNPs in {round(time.time() - t0, 3)} s "
                       f"(device: rotate {res['timing']['rotate_ms']:.1f} ms, REML {res['timing']['reml_ms']:.1f} ms)")
     finally:
         h.close()
 
-    bad = out["status"] != 0
-    data = {}
-    for c in COLUMNS:
-        col = out[c]
-        if bad.any():
-            col = col.copy()
-            col[bad] = np.nan  # lmm/lmm.py:484-493
-        data[c] = col
-    results_df = pd.DataFrame(data, columns=COLUMNS)
-    if snps is not None:
-        results_df["SNPs"] = snps  # lmm/lmm.py:408-409 (same statement: pandas alignment semantics preserved)
+    frames = []
+    for out in outs:
+        bad = out["status"] != 0
+        data = {}
+        for c in COLUMNS:
+            col = out[c]
+            if bad.any():
+                col = col.copy()
+                col[bad] = np.nan  # lmm/lmm.py:484-493
+            data[c] = col
+        results_df = pd.DataFrame(data, columns=COLUMNS)
+        if snps is not None:
+            results_df["SNPs"] = snps  # lmm/lmm.py:408-409 (same statement: pandas alignment semantics preserved)
+        frames.append(results_df)
     timing["total_s"] = time.time() - t_start
-    timing["n_eval2_mean"] = float(out["n_eval2"].mean()) if m else 0.0
-    timing["n_eval3_mean"] = float(out["n_eval3"].mean()) if m else 0.0
+    timing["n_eval2_mean"] = float(np.mean([o["n_eval2"].mean() for o in outs])) if m else 0.0
+    timing["n_eval3_mean"] = float(np.mean([o["n_eval3"].mean() for o in outs])) if m else 0.0
     last_timing = timing
-    return results_df
+    return frames

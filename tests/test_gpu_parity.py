@@ -571,3 +571,40 @@ def test_packed_bed_scan_matches_oracle_on_imputed_genotypes(tmp_path):
     assert list(df.columns) == COLS + ["SNPs"] and list(df["SNPs"][:3]) == ["rs0", "rs1", "rs2"]
     for c in COLS:
         assert np.array_equal(df[c].values, o1[c], equal_nan=True), c
+
+
+def test_multi_phenotype_scan_equals_one_scan_per_trait():
+    """pg_set_design_multi: genotype blocks are rotated once and the REML stage runs per trait; every trait's rows
+    are bit-identical to a single-trait pg_set_design + pg_scan, for every REML engine, several blocks, grid mode,
+    and through lmm.pygemma_multi; pg_set_design afterwards returns the handle to one trait."""
+    from pygemma_b200 import lmm
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    n, m, c0, q = 900, 2500, 4, 3
+    p = make_problem(n, m, c0, seed=21, m_k=2000)
+    rng = np.random.default_rng(5)
+    Y = np.stack([p["Y"].reshape(-1), rng.standard_normal(n),
+                  p["Y"].reshape(-1) * 0.3 + p["X"][:, 7] * 0.2 + rng.standard_normal(n)], axis=1)
+    keys = COLS + ["status", "n_eval2", "n_eval3"]
+    with capi.Handle(n, c0) as h:
+        h.set_kinship(p["K"])
+        h.set_options(block_snps=1024)  # several blocks, ragged tail
+        for engine in (capi.PG_REML_AUTO, capi.PG_REML_STREAM, capi.PG_REML_WARP):
+            h.set_reml_engine(engine)
+            for grid in (False, True):
+                h.set_design(p["W"], Y)
+                om = h.scan(p["X"], grid=grid)
+                assert om["beta"].shape == (q, m)
+                for ph in range(q):
+                    h.set_design(p["W"], Y[:, ph])
+                    o1 = h.scan(p["X"], grid=grid)
+                    assert o1["beta"].shape == (m,)
+                    for c in keys:
+                        assert np.array_equal(om[c][ph], o1[c], equal_nan=True), (engine, grid, ph, c)
+    frames = lmm.pygemma_multi(Y, p["X"], p["W"], p["K"], snps=p["snps"] if "snps" in p else None)
+    assert len(frames) == q
+    for ph in range(q):
+        one = lmm.pygemma(Y[:, ph], p["X"], p["W"], p["K"])
+        for c in COLS:
+            assert np.array_equal(frames[ph][c].to_numpy(), one[c].to_numpy(), equal_nan=True), (ph, c)
