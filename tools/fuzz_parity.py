@@ -1,0 +1,98 @@
+"""Randomised parity sweep on the GPU: odd shapes, covariate counts around the kernel's template switches, both
+layouts, all genotype dtypes, grid / Brent+Newton, h2 from 0 (lambda at the lower boundary) to 0.95, against the CPU
+oracle (test infrastructure).  Development tool: the fixed cases that came out of it live in tests/test_gpu_parity.py.
+
+    python tools/fuzz_parity.py [n_cases] [seed] [time_limit_s]
+"""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from oracle import oracle
+from pygemma_b200 import _capi
+from pygemma_b200.synth import make_problem
+
+COLS = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
+
+
+def rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def one_case(rng, idx):
+    n = int(rng.choice([6, 9, 17, 31, 33, 64, 97, 130, 257, 511, 1023, 1500, 2049]))
+    c0 = int(rng.choice([0, 1, 2, 3, 5, 9, 10, 11, 12, 13, 21, 30, 31, 32, 33, 45]))
+    c0 = min(c0, max(0, n - 4))
+    m = int(rng.choice([1, 7, 31, 97, 200]))
+    grid = bool(rng.integers(0, 2))
+    h2 = float(rng.choice([0.0, 0.2, 0.5, 0.95]))
+    xkind = str(rng.choice(["int8", "f32", "f64", "f64std", "f64real"]))
+    layout = int(rng.integers(0, 2))
+    blk = int(rng.choice([0, 32, 96]))
+    engine = int(rng.choice([_capi.PG_REML_AUTO, _capi.PG_REML_AUTO, _capi.PG_REML_STREAM, _capi.PG_REML_WARP]))
+    p = make_problem(n, m, c0, seed=1000 + idx, h2=h2, m_k=max(50, n // 2))
+    X = p["X"]
+    if xkind == "f32":
+        X = X.astype(np.float32)
+    elif xkind == "f64":
+        X = X.astype(np.float64)
+    elif xkind == "f64std":
+        Xf = X.astype(np.float64)
+        sd = Xf.std(axis=0)
+        sd[sd == 0] = 1.0
+        X = (Xf - Xf.mean(axis=0)) / sd
+    elif xkind == "f64real":
+        X = X.astype(np.float64) + rng.uniform(-0.3, 0.3, size=X.shape)
+    cfg = dict(idx=idx, n=n, c0=c0, m=m, grid=grid, h2=h2, xkind=xkind, layout=layout, blk=blk, engine=engine)
+    with _capi.Handle(n, c0) as h:
+        h.set_options(block_snps=blk)
+        h.set_reml_engine(engine)
+        h.set_kinship(p["K"])
+        h.set_design(p["W"], p["Y"])
+        if layout == 0:
+            o = h.scan(np.ascontiguousarray(X), grid=grid)
+        else:
+            o = h.scan(np.ascontiguousarray(X.T), grid=grid, layout=_capi.PG_X_SNP_MAJOR)
+    ref = oracle.pygemma(p["Y"], np.asarray(X, dtype=np.float64), p["W"], p["K"], grid=grid)
+    worst = 0.0
+    for c in COLS:
+        a, b = np.asarray(o[c]), np.asarray(ref[c])
+        nan_mismatch = int((np.isnan(a) != np.isnan(b)).sum())
+        ok = ~np.isnan(b) & ~np.isnan(a)
+        e = float(rel(a[ok], b[ok]).max()) if ok.any() else 0.0
+        cfg[c] = e
+        cfg[c + "_nan_mismatch"] = nan_mismatch
+        worst = max(worst, e, 1.0 if nan_mismatch else 0.0)
+    cfg["bad_status"] = int((o["status"] != 0).sum())
+    cfg["worst"] = worst
+    return cfg
+
+
+def main():
+    ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    limit = float(sys.argv[3]) if len(sys.argv) > 3 else 400.0
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    fails = 0
+    done = 0
+    for i in range(ncases):
+        if time.time() - t0 > limit:
+            break
+        try:
+            r = one_case(rng, seed * 1000 + i)
+        except Exception as ex:  # noqa: BLE001 - report and go on
+            r = {"idx": i, "error": repr(ex), "worst": 1.0}
+        done += 1
+        flag = r["worst"] >= 1e-6
+        fails += flag
+        if flag or i % 10 == 0:
+            print(("FAIL " if flag else "ok   ") + json.dumps(r), flush=True)
+    print(json.dumps({"cases": done, "fails": fails, "seconds": time.time() - t0}))
+
+
+if __name__ == "__main__":
+    main()
