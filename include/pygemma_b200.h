@@ -147,8 +147,11 @@ int pg_set_design(pg_handle* h, const double* W_host, const double* y_host, int 
  * experiments/benchmarks/benchmarks.py).  Every later pg_scan / pg_scan_device rotates each genotype block ONCE and
  * runs the REML stage per phenotype: all output arrays then hold q * m values, phenotype-major
  * (out[ph * m + g]); each phenotype's rows are bit-identical to a pg_set_design + pg_scan of that column alone.
- * pg_set_design resets the handle to one phenotype.
+ * pg_set_design resets the handle to one phenotype.  1 <= q <= PG_MAX_TRAITS per pass (the moment slab of a SNP
+ * grows by one row per trait); callers with more traits scan the genotypes once per group of PG_MAX_TRAITS
+ * (pygemma_b200.lmm.pygemma_multi does), which keeps the rotation below 10 % of the pass.
  */
+#define PG_MAX_TRAITS 64
 int pg_set_design_multi(pg_handle* h, const double* W_host, const double* Y_host, int q, int already_rotated,
                         float* ms);
 

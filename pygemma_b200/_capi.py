@@ -17,6 +17,7 @@ PG_X_I8, PG_X_F32, PG_X_F64, PG_X_BED = 0, 1, 2, 3
 PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1
 PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT, PG_ROT_I8TC = 0, 1, 2, 3
 PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
+PG_MAX_TRAITS = 64  # traits per pass of pg_set_design_multi (include/pygemma_b200.h)
 
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)
 SYMBOLS = [

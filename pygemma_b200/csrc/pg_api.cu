@@ -95,6 +95,7 @@ struct pg_handle {
     struct DesignSlot { double *wy, *fixtab, *itab, *fix2, *itab2; };
     std::vector<DesignSlot> slots;
     int q = 1;
+    double* design_raw = nullptr;   // staging of the unrotated [W, y] columns (pg_set_design), n x (c0+1)
     double* wy_all = nullptr;   // q > 1: rotated [W0, y_0 .. y_{q-1}], the linear columns of the shared compression
     int wy_all_cols = 0;
     int z_rows = 0;             // slab rows per SNP the Z buffers were last laid out for (k1p - 1 + q)
@@ -176,6 +177,8 @@ static int free_all(pg_handle* h)
     }
     if (h->wy_all) cudaFree(h->wy_all);
     h->wy_all = nullptr;
+    if (h->design_raw) cudaFree(h->design_raw);
+    h->design_raw = nullptr;
     rot_free(&h->rot);
     for (int s = 0; s < 2; ++s) {
         if (h->stage[s]) cudaFree(h->stage[s]);
@@ -654,6 +657,8 @@ extern "C" int pg_set_design_multi(pg_handle* h, const double* W_host, const dou
                                    float* ms)
 {
     if (!h || !Y_host || q < 1) return fail(h, PG_ERR_ARG, "pg_set_design_multi: bad argument");
+    if (q > PG_MAX_TRAITS)
+        return fail(h, PG_ERR_ARG, "pg_set_design_multi: %d traits, at most %d per pass (scan in groups)", q, PG_MAX_TRAITS);
     int rc = ensure_slots(h, q);
     if (rc) return rc;
     h->have_design = false;
@@ -698,15 +703,14 @@ static int set_design_active(pg_handle* h, const double* W_host, const double* y
         CK(cudaMemcpy2DAsync(h->wy, sizeof(double) * h->ldw, col.data(), sizeof(double) * n, sizeof(double) * n, k0,
                              cudaMemcpyHostToDevice, h->compute));
     } else {
-        double* raw = nullptr;
-        CK(cudaMalloc(&raw, sizeof(double) * col.size()));
+        if (!h->design_raw) CK(cudaMalloc(&h->design_raw, sizeof(double) * col.size()));
+        double* raw = h->design_raw;
         CK(cudaMemcpyAsync(raw, col.data(), sizeof(double) * col.size(), cudaMemcpyHostToDevice, h->compute));
         const double one = 1.0, zero = 0.0;
         // wy = U^T [W, y]  (lmm/lmm.py:245-246)
         cublasStatus_t s = cublasDgemm(h->blas, h->u_op_t ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, n, k0, n, &one, h->U,
                                        n, raw, n, &zero, h->wy, (int)h->ldw);
-        cudaStreamSynchronize(h->compute);
-        cudaFree(raw);
+        cudaStreamSynchronize(h->compute);   // col is a local buffer: the copy must have left it
         if (s != CUBLAS_STATUS_SUCCESS) return fail(h, PG_ERR_CUBLAS, "pg_set_design: dgemm status %d", (int)s);
     }
     h->rotated_inputs = already_rotated != 0;

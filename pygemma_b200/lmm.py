@@ -135,21 +135,27 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
             _log(verbose, f"Eigendecomposition computed - {round(time.time() - t0, 3)} s")
         else:
             h.set_eigen(None, K.reshape(-1))
-        t0 = time.time()
-        timing["design_ms"] = h.set_design(W, Y if q > 1 else Y.reshape(-1), already_rotated=not eigen)
-        _log(verbose, f"Rotated Y, W and built lambda tables - {round(time.time() - t0, 3)} s")
-        _log(verbose, f"Running {m} SNPs with {n} individuals...")
-        t0 = time.time()
         a, b = ctx.shard(m)  # contiguous SNP range of this rank (SampleIter, lmm/lmm.py:427-434)
-        res = h.scan(X[:, a:b], grid=grid)
-        timing["scan"] = res["timing"]
-        if q == 1:
-            outs = [multi.gather_results(ctx, res, m)]
-        else:
-            outs = [multi.gather_results(ctx, {k: v[ph] for k, v in res.items() if k != "timing"}, m)
-                    for ph in range(q)]
-        timing["scan_wall_s"] = time.time() - t0
-        _log(verbose, f"Finished testing {m} SNPs in {round(time.time() - t0, 3)} s "
+        outs = []
+        timing["design_ms"], timing["scan_wall_s"] = 0.0, 0.0
+        # traits go through in groups of PG_MAX_TRAITS per pass over the genotypes (one group for lmm.pygemma)
+        for q0 in range(0, q, _capi.PG_MAX_TRAITS):
+            Yg = Y[:, q0:q0 + _capi.PG_MAX_TRAITS]
+            qg = Yg.shape[1]
+            t0 = time.time()
+            timing["design_ms"] += h.set_design(W, Yg if qg > 1 else Yg.reshape(-1), already_rotated=not eigen)
+            _log(verbose, f"Rotated Y, W and built lambda tables - {round(time.time() - t0, 3)} s")
+            _log(verbose, f"Running {m} SNPs with {n} individuals...")
+            t0 = time.time()
+            res = h.scan(X[:, a:b], grid=grid)
+            timing["scan"] = res["timing"]
+            if qg == 1:
+                outs.append(multi.gather_results(ctx, res, m))
+            else:
+                outs.extend(multi.gather_results(ctx, {k: v[ph] for k, v in res.items() if k != "timing"}, m)
+                            for ph in range(qg))
+            timing["scan_wall_s"] += time.time() - t0
+        _log(verbose, f"Finished testing {m} SNPs in {round(timing['scan_wall_s'], 3)} s "
                       f"(device: rotate {res['timing']['rotate_ms']:.1f} ms, REML {res['timing']['reml_ms']:.1f} ms)")
     finally:
         h.close()

@@ -608,3 +608,29 @@ def test_multi_phenotype_scan_equals_one_scan_per_trait():
         one = lmm.pygemma(Y[:, ph], p["X"], p["W"], p["K"])
         for c in COLS:
             assert np.array_equal(frames[ph][c].to_numpy(), one[c].to_numpy(), equal_nan=True), (ph, c)
+
+
+def test_more_traits_than_one_pass_holds():
+    """pg_set_design_multi takes at most PG_MAX_TRAITS traits (PG_ERR_ARG beyond); lmm.pygemma_multi scans in groups and
+    still returns one frame per trait, identical to single-trait calls."""
+    from pygemma_b200 import lmm
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    n, m, c0 = 300, 150, 3
+    q = capi.PG_MAX_TRAITS + 3
+    p = make_problem(n, m, c0, seed=33, m_k=600)
+    rng = np.random.default_rng(9)
+    Y = p["Y"].reshape(-1, 1) * rng.uniform(0.2, 1.0, size=(1, q)) + rng.standard_normal((n, q))
+    with capi.Handle(n, c0) as h:
+        h.set_kinship(p["K"])
+        with pytest.raises(capi.PgError):
+            h.set_design(p["W"], Y)
+        h.set_design(p["W"], Y[:, :capi.PG_MAX_TRAITS])
+        assert h.scan(p["X"])["beta"].shape == (capi.PG_MAX_TRAITS, m)
+    frames = lmm.pygemma_multi(Y, p["X"], p["W"], p["K"])
+    assert len(frames) == q
+    for ph in (0, capi.PG_MAX_TRAITS - 1, capi.PG_MAX_TRAITS, q - 1):
+        one = lmm.pygemma(Y[:, ph], p["X"], p["W"], p["K"])
+        for c in COLS:
+            assert np.array_equal(frames[ph][c].to_numpy(), one[c].to_numpy(), equal_nan=True), (ph, c)

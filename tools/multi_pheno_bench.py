@@ -25,13 +25,15 @@ def main():
         h.set_eigen(U, np.abs(p["d"]))
         for q in qs:
             Y = rng.standard_normal((n, q))
+            t = time.time()
             design_ms = h.set_design(p["W"], Y if q > 1 else Y[:, 0])
+            design_wall = time.time() - t
             for rep in range(2):
                 t = time.time()
                 o = h.scan(X8, with_counts=False)
                 wall = time.time() - t
             tm = o["timing"]
-            rows.append({"q": q, "design_ms": design_ms, "total_ms": tm["total_ms"], "rotate_ms": tm["rotate_ms"],
+            rows.append({"q": q, "design_ms": design_ms, "design_wall_s": design_wall, "total_ms": tm["total_ms"], "rotate_ms": tm["rotate_ms"],
                          "reml_ms": tm["reml_ms"], "wall_s": wall,
                          "snps_per_s": m / (tm["total_ms"] * 1e-3),
                          "tests_per_s": m * q / (tm["total_ms"] * 1e-3),
