@@ -53,6 +53,7 @@ __host__ __device__ __forceinline__ int z_row(int j, int c0, int k1p) { return j
 struct DevPlan {
     int Kc = 0, Kcp = 0;        // nodes, padded to a multiple of 32 (padding nodes: d = 0, moments 0)
     double* nodes = nullptr;    // [Kcp]
+    double* H = nullptr;        // [Kcp][kFxCols] powers of 1/(lambda_t d_k + 1) at the fixed lambdas (reml_solve.cuh)
     double* Lw = nullptr;       // [n][kCq]
     int* seg_kq = nullptr;      // [n] kq of the COMPRESS segment of l, 0 for COPY rows
     double* V = nullptr;        // [npad16][vpitch]

@@ -88,6 +88,8 @@ struct pg_handle {
     DevPlan plan;
     double* Z[2] = {nullptr, nullptr};  // [blk][k1p][Kcp], double-buffered like xr
     size_t z_elems = 0;
+    double* F[2] = {nullptr, nullptr};  // [blk][zrows][kFxCols] x rows of the fixed-lambda evaluations, per Z buffer
+    size_t f_elems = 0;
     int k1p = 0;          // c0+2 rounded up to a multiple of 4
     // several phenotypes on one eigen-system (pg_set_design_multi): each has its own rotated [W0, y] and lambda tables;
     // slot 0 owns the buffers allocated with the handle, `activate` points the handle's working fields at a slot
@@ -109,12 +111,14 @@ static void activate(pg_handle* h, int ph);
 static void free_plan(pg_handle* h)
 {
     DevPlan& P = h->plan;
-    void* bufs[] = {P.nodes, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z[0], h->Z[1]};
+    void* bufs[] = {P.nodes, P.H, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z[0], h->Z[1], h->F[0], h->F[1]};
     for (void* b : bufs)
         if (b) cudaFree(b);
     P = DevPlan{};
     h->Z[0] = h->Z[1] = nullptr;
+    h->F[0] = h->F[1] = nullptr;
     h->z_elems = 0;
+    h->f_elems = 0;
     h->z_rows = 0;
 }
 
@@ -394,6 +398,9 @@ static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
     std::copy(H.nodes.begin(), H.nodes.end(), nodes.begin());
     CK(cudaMalloc(&P.nodes, sizeof(double) * P.Kcp));
     CK(cudaMemcpy(P.nodes, nodes.data(), sizeof(double) * P.Kcp, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&P.H, sizeof(double) * (size_t)P.Kcp * kFxCols));
+    build_h_kernel<<<(P.Kcp * kFxCols + 127) / 128, 128, 0, h->compute>>>(P.nodes, P.Kcp, P.H);
+    CK(cudaGetLastError());
     CK(cudaMalloc(&P.Lw, sizeof(double) * (size_t)n * kCq));
     CK(cudaMemcpy(P.Lw, H.Lw.data(), sizeof(double) * (size_t)n * kCq, cudaMemcpyHostToDevice));
     std::vector<int> seg_kq(n, 0), copy_l, copy_node;
@@ -818,6 +825,16 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
             }
             h->z_elems = zneed;
         }
+        const size_t fneed = (size_t)blk * zrows * kFxCols;
+        if (fneed > h->f_elems) {
+            for (int s = 0; s < 2; ++s) {
+                if (h->F[s]) cudaFree(h->F[s]);
+                h->F[s] = nullptr;
+            }
+            h->f_elems = 0;
+            for (int s = 0; s < 2; ++s) CK(cudaMalloc(&h->F[s], sizeof(double) * fneed));
+            h->f_elems = fneed;
+        }
     }
     const size_t sbytes = need * xdtype_size(xdtype);
     if (sbytes > h->stage_bytes) {
@@ -860,6 +877,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
     if (!st_solve) st_solve = st;
     const bool split = st_solve != st;
     unsigned long long* counter = h->counter + (parity & 1);
+    double* Fbuf = Zbuf == h->Z[1] ? h->F[1] : h->F[0];
     ScanArgs a;
     a.n = h->n; a.c0 = h->c0; a.grid = grid_mode; a.m = mb; a.row0 = row0;
     a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = xr; a.ldx = h->ldx; a.tab = h->tab;
@@ -886,6 +904,15 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
             }
             if (ev_mid) CK(cudaEventRecord(ev_mid[1], st));
             if (ev_xr_done) CK(cudaEventRecord(ev_xr_done, st));
+            {
+                // x rows of the kNumFixed fixed-lambda evaluations of every slab row, all phenotypes at once
+                const long long rows = mb * zrows;
+                const size_t hs = sizeof(double) * (size_t)P.Kcp * kFxCols;
+                if (hs > 48 * 1024)
+                    CK(cudaFuncSetAttribute(fixed_xrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+                fixed_xrow_kernel<<<(unsigned)((rows + 255) / 256), 256, hs, st>>>(Zbuf, rows, P.Kcp, P.H, Fbuf);
+                CK(cudaGetLastError());
+            }
             if (split) {
                 CK(cudaEventRecord(ev_z[0], st));
                 CK(cudaStreamWaitEvent(st_solve, ev_z[0], 0));
@@ -895,7 +922,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
         sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
-        sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph;
+        sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph; sa.F = Fbuf;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
@@ -1444,7 +1471,7 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
         }
         SolveArgs sa{};
         sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
-        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1;
+        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.F = nullptr;
         const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);
         const bool two = (h->c0 + 2) > 32;
         if (smemc > 48 * 1024) {

@@ -30,6 +30,7 @@ struct SolveArgs {
     int k1p;              // c0+2 rounded up to a multiple of 4 (padding rows are zero)
     int zrows;            // rows per SNP slab: k1p - 1 + number of phenotypes
     int yrow;             // slab row of this launch's phenotype (k1p - 1 + phenotype index)
+    const double* F;      // [m][zrows][kFxCols] x rows of the fixed-lambda evaluations (fixed_xrow_kernel), or nullptr
     Tables2 t2;
     double* out[6];
     int* status;
@@ -49,6 +50,74 @@ __device__ __forceinline__ double rcp_ge1(double t)
     e = fma(-t, r, 1.0);
     r = fma(r, e, r);
     return r;
+}
+
+// ---- x rows of the fixed-lambda evaluations ------------------------------------------------------------------
+// The first kNumFixed evaluations of every SNP (the bracket scan, all of grid mode) sit at lambda_t = 10^(t-5) whatever
+// the optimiser decides later, so their level-0 x rows  sum_k Z[row][k] / (lambda_t d_k + 1)^p,  p = 1, 2,  are one
+// dense contraction per block:  F (slab rows x 22)  =  Z (slab rows x nodes)  .  H (nodes x 22)  on the FP64 tensor
+// pipe (DMMA m8n8k4), instead of kNumFixed x-row passes + butterfly reductions per SNP inside the solver.
+constexpr int kFxCols = 24;   // kNumFixed lambdas x 2 powers = 22 columns, padded to three 8-column DMMA tiles
+
+// H[k][2 t + p] = (lambda_t d_k + 1)^-(p+1)   (the same rcp_ge1 arithmetic as solve_xrow_pass)
+__global__ void build_h_kernel(const double* __restrict__ nodes, int Kcp, double* __restrict__ H)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Kcp * kFxCols) return;
+    const int k = i / kFxCols, c = i - k * kFxCols;
+    double v = 0.0;
+    if (c < 2 * kNumFixed) {
+        const double h = rcp_ge1(fma(fixed_lambda(c >> 1), nodes[k], 1.0));
+        v = (c & 1) ? h * h : h;
+    }
+    H[i] = v;
+}
+
+// One warp contracts 32 slab rows (4 m-tiles) against all 24 columns; H lives in shared memory, Z is read once.
+__global__ void __launch_bounds__(256)
+fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const double* __restrict__ H, double* __restrict__ F)
+{
+    extern __shared__ double Hs[];
+    for (int i = threadIdx.x; i < Kcp * kFxCols; i += 256) Hs[i] = H[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long r0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    if (r0 >= rows) return;
+    const int ar = lane >> 2, ac = lane & 3;
+    double acc[4][3][2];
+    const double* zp[4];
+    bool ok[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const long long row = r0 + mt * 8 + ar;
+        ok[mt] = row < rows;
+        zp[mt] = Z + (size_t)(ok[mt] ? row : 0) * Kcp + ac;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    }
+#pragma unroll 4
+    for (int ks = 0; ks < (Kcp >> 2); ++ks) {
+        double b[3];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) b[nt] = Hs[(ks * 4 + ac) * kFxCols + nt * 8 + ar];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const double av = ok[mt] ? __ldg(zp[mt] + ks * 4) : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                             : "d"(av), "d"(b[nt]));
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        if (!ok[mt]) continue;
+        double* f = F + (size_t)(r0 + mt * 8 + ar) * kFxCols + 2 * ac;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) *reinterpret_cast<double2*>(f + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
 }
 
 // Sum V per-lane values over the warp with V + O(V/8) shuffles instead of 5 V: offsets 16, 8, 4 exchange
@@ -200,14 +269,18 @@ __device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __rest
 // One precompute_mat-equivalent evaluation from the compressed moments (warp-collective).
 // scratch (shared memory, per warp): 3 * k1p doubles for the level-0 x row, then NF2 for an interpolated table-2 row.
 template <int NS>
-__device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const double* __restrict__ Zs, double lam,
-                                                    int fixed_t, int full, int need_ll, double* scratch, EvalOut* e)
+__device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const double* __restrict__ Zs,
+                                                    const double* __restrict__ Fs, double lam, int fixed_t, int full,
+                                                    int need_ll, double* scratch, EvalOut* e)
 {
     const int lane = threadIdx.x & 31, c0 = a.c0, k1 = c0 + 2, k1p = a.k1p, NF2 = a.t2.NF2;
     double* xs = scratch;
     double* rowbuf = scratch + 3 * k1p;
-    if (full) solve_xrow_all<true>(a, Zs, lam, xs);
-    else solve_xrow_all<false>(a, Zs, lam, xs);
+    const bool pre = (fixed_t >= 0) && (Fs != nullptr);   // x row already contracted by fixed_xrow_kernel
+    if (!pre) {
+        if (full) solve_xrow_all<true>(a, Zs, lam, xs);
+        else solve_xrow_all<false>(a, Zs, lam, xs);
+    }
     const double* row2;
     if (fixed_t >= 0) {
         row2 = a.t2.fix2 + (size_t)fixed_t * NF2;
@@ -246,10 +319,17 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
     for (int q = 0; q < NS; ++q) {
         const int j = lane + 32 * q;
         const bool in = j < k1;
-        const int r = j < c0 ? j : (j == c0 ? k1p - 1 : c0);   // Pab column order [W0, y, x] -> slab rows
-        xa[q] = in ? xs[r] : 0.0;
-        xb[q] = in ? xs[k1p + r] : 0.0;
-        xc[q] = (in && full) ? xs[2 * k1p + r] : 0.0;
+        if (pre) {
+            const int r = j < c0 ? j : (j == c0 ? a.yrow : c0);   // Pab column order [W0, y, x] -> slab rows
+            double2 v = make_double2(0.0, 0.0);
+            if (in) v = __ldg(reinterpret_cast<const double2*>(Fs + (size_t)r * kFxCols + 2 * fixed_t));
+            xa[q] = v.x; xb[q] = v.y; xc[q] = 0.0;   // fixed-lambda evaluations are never full (SnpSolver::request_fixed)
+        } else {
+            const int r = j < c0 ? j : (j == c0 ? k1p - 1 : c0);   // ... -> x-row scratch (y sits at k1p - 1)
+            xa[q] = in ? xs[r] : 0.0;
+            xb[q] = in ? xs[k1p + r] : 0.0;
+            xc[q] = (in && full) ? xs[2 * k1p + r] : 0.0;
+        }
     }
     if (full) xrow_recursion_warp<true, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
     else xrow_recursion_warp<false, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
@@ -269,11 +349,12 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= (unsigned long long)a.m) break;
         const double* __restrict__ Zs = a.Z + (size_t)g * a.zrows * a.Kcp;
+        const double* __restrict__ Fs = a.F ? a.F + (size_t)g * a.zrows * kFxCols : nullptr;
         SnpSolver s;
         s.init(a.n, a.c0, a.grid, /*defer_p=*/1);
         while (s.pending()) {
             EvalOut e;
-            eval_snp_compressed<NS>(a, Zs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
+            eval_snp_compressed<NS>(a, Zs, Fs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
             s.feed(e);
         }
         if (lane == 0) {
@@ -314,7 +395,7 @@ __global__ void probe_precompute_compressed_kernel(SolveArgs a, double lam, int 
 {
     extern __shared__ double smem[];
     EvalOut e;
-    eval_snp_compressed<NS>(a, a.Z, lam, fixed_t, full, 1, smem, &e);
+    eval_snp_compressed<NS>(a, a.Z, a.F, lam, fixed_t, full, 1, smem, &e);
     if ((threadIdx.x & 31) == 0) {
         out9[0] = e.yPy; out9[1] = e.yPPy; out9[2] = e.yPPPy; out9[3] = e.trP; out9[4] = e.trPP;
         out9[5] = e.logdetH; out9[6] = e.logdetWHW; out9[7] = e.xPx; out9[8] = e.yPx;
