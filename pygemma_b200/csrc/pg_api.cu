@@ -945,7 +945,11 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         if (lr) return lr;
         CK(cudaGetLastError());
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
-        pvalue_kernel<<<(unsigned)((mb + 63) / 64), 64, 0, st_solve>>>(out[4], out[5], row0, mb, (double)(h->n - h->c0 - 1));
+        {
+            const long double nu = (long double)(h->n - h->c0 - 1);
+            const double lnbeta = (double)(lgammal(0.5L * nu + 0.5L) - lgammal(0.5L * nu) - lgammal(0.5L));
+            pvalue_kernel<<<(unsigned)((mb + 31) / 32), 32, 0, st_solve>>>(out[4], out[5], row0, mb, (double)nu, lnbeta);
+        }
         CK(cudaGetLastError());
         if (split && ph == q - 1) CK(cudaEventRecord(ev_z[1], st_solve));
         return PG_OK;

@@ -212,6 +212,27 @@ PG_HD_NOINLINE double ibeta_xy(double a, double b, double x, double y)
     return 1.0 - exp(lnpre) * betacf(b, a, y) / b;
 }
 
+// the same with lnbeta = lgamma(a + b) - lgamma(a) - lgamma(b) supplied by the caller (one value per scan when a, b are
+// fixed: the difference of two lgammas of ~nu/2 loses 4-5 digits in double, so the host forms it in long double)
+PG_HD_NOINLINE double ibeta_xy_pre(double a, double b, double x, double y, double lnbeta)
+{
+    if (!(x > 0.0)) return 0.0;
+    if (!(y > 0.0)) return 1.0;
+    const double lnpre = lnbeta + a * log(x) + b * log(y);
+    if (x < (a + 1.0) / (a + b + 2.0)) return exp(lnpre) * betacf(a, b, x) / a;
+    return 1.0 - exp(lnpre) * betacf(b, a, y) / b;
+}
+
+PG_HD_NOINLINE double f_sf_1_pre(double F, double nu, double lnbeta)
+{
+    if (isnan(F) || isnan(nu)) return F + nu;
+    if (!(nu > 0.0)) return NAN;
+    if (F <= 0.0) return 1.0;
+    if (isinf(F)) return 0.0;
+    const double x = nu / (nu + F), y = F / (nu + F);
+    return ibeta_xy_pre(0.5 * nu, 0.5, x, y, lnbeta);
+}
+
 PG_HD_NOINLINE double f_sf_1(double F, double nu)
 {
     if (isnan(F) || isnan(nu)) return F + nu;

@@ -370,10 +370,12 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
 
 // p_wald = F(1, n - c0 - 1) survival function of F_wald (scipy.stats.f.sf, reference lmm/lmm.py:482), one thread per SNP:
 // reml_solve_kernel leaves p = NaN (SnpSolver defer_p) so that the continued fraction is not run 32 lanes wide
-__global__ void pvalue_kernel(const double* __restrict__ F, double* __restrict__ p, long long row0, long long m, double nu)
+// lnbeta = lgamma((nu+1)/2) - lgamma(nu/2) - lgamma(1/2), formed once per scan on the host in long double
+__global__ void pvalue_kernel(const double* __restrict__ F, double* __restrict__ p, long long row0, long long m, double nu,
+                              double lnbeta)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) p[row0 + i] = f_sf_1(F[row0 + i], nu);
+    if (i < m) p[row0 + i] = f_sf_1_pre(F[row0 + i], nu, lnbeta);
 }
 
 // table-2 rows: one thread eliminates the covariate levels of one table lambda (pg_eval.cuh: eliminate_w0y_row)
