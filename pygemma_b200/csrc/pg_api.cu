@@ -1261,7 +1261,11 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->rot_engine = last_engine;
         timing->reml_engine = compressed ? PG_REML_COMPRESSED : h->engine;
         timing->n_nodes = compressed ? h->plan.Kc : h->n;
-        if (compressed) timing->reml_launches = (int32_t)(nblocks * (2 + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)));
+        // per block: compress (dmma / copy), fixed-lambda x rows, then solve + p-values per phenotype
+        if (compressed)
+            timing->reml_launches = (int32_t)(nblocks * (1 + 2 * q + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)));
+        else
+            timing->reml_launches = (int32_t)(nblocks * q);
     }
     if (rc != PG_OK) {
         cudaStreamSynchronize(h->compute);
