@@ -291,10 +291,15 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int e = min(eig0 + c * 8 + j, a.n - 1);
-#define PG_PL(P) ((double)(int)r[(j * kSlices + (P)) >> 3][(j * kSlices + (P)) & 7])
-                            const double hi = fma(PG_PL(0), 65536.0, fma(PG_PL(1), 256.0, PG_PL(2)));
-                            const double lo = fma(PG_PL(3), 16777216.0, fma(PG_PL(4), 65536.0, fma(PG_PL(5), 256.0, PG_PL(6))));
+                            // the digit planes are recombined as 64-bit integers (|plane sum| < 2^31, so hi < 2^48 and
+                            // lo < 2^56 never overflow) and converted once each: 2 int -> double conversions per output
+                            // instead of 7.  Same bits as the FP64 Horner form of combine_i8_kernel: both are the exact
+                            // integer, rounded once if it exceeds 2^53 (it does not for dosages: |plane sum| <= 256 n)
+#define PG_PL(P) ((long long)(int)r[(j * kSlices + (P)) >> 3][(j * kSlices + (P)) & 7])
+                            const long long hi_i = (PG_PL(0) << 16) + (PG_PL(1) << 8) + PG_PL(2);
+                            const long long lo_i = (PG_PL(3) << 24) + (PG_PL(4) << 16) + (PG_PL(5) << 8) + PG_PL(6);
 #undef PG_PL
+                            const double hi = (double)hi_i, lo = (double)lo_i;
                             const double v = fma(lo, 2.3283064365386963e-10 /* 2^-32 */, hi);
                             out[j] = v * __ldg(a.scale + e);
                             if (a.info) {
