@@ -1,16 +1,18 @@
 """Randomised parity sweep on the GPU: odd shapes, covariate counts around the kernel's template switches, both
 layouts, all genotype dtypes, grid / Brent+Newton, h2 from 0 (lambda at the lower boundary) to 0.95, against the CPU
-oracle (test infrastructure).  Development tool: the fixed cases that came out of it live in tests/test_gpu_parity.py.
+oracle.  Test infrastructure (not collected by pytest: run by hand on a GPU box); the fixed cases that came out of it
+live in tests/test_gpu_parity.py.
 
-    python tools/fuzz_parity.py [n_cases] [seed] [time_limit_s]
+    python tests/fuzz_parity.py [n_cases] [seed] [time_limit_s]
 """
 import json
+import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import oracle
 from pygemma_b200 import _capi
 from pygemma_b200.synth import make_problem
