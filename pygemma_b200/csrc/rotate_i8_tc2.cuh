@@ -13,7 +13,8 @@
 //             `full[s]` (peer bit of the mbarrier address cleared, as cute::SM100_TMA_2SM_LOAD does)
 //   warp 1    TMEM allocation (both CTAs, cta_group::2); MMA issue by the leader CTA only; tcgen05.commit multicast
 //             to `empty[s]` / `tmem_full` of both CTAs
-//   warps 2-5 epilogue on the CTA's own TMEM; arrival on the leader's `tmem_empty` (remote for the peer CTA)
+//   warps 2-9 epilogue on the CTA's own TMEM (warps 2-5: accumulator 0, warps 6-9: accumulator 1; a warp reads the
+//             TMEM lane quarter warp % 4); arrival on the leader's `tmem_empty` (remote for the peer CTA)
 #pragma once
 
 #include "rotate_i8_tc.cuh"
@@ -43,7 +44,7 @@ constexpr int kStages = 4;
 #define PG_TC2_EIG_GROUP 24
 #endif
 constexpr int kEigGroup = PG_TC2_EIG_GROUP;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // cute::Sm100MmaPeerBitMask: address of the even CTA of the pair
 
@@ -176,7 +177,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 256);   // 128 epilogue threads of each CTA of the pair (only the leader's barrier is used)
+        mbar_init(tmem_empty, 512);   // 256 epilogue threads of each CTA of the pair (only the leader's barrier is used)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -265,6 +266,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
     } else {
         const int quarter = warp & 3;
+        const int acc = (warp - 2) >> 2;   // the two accumulators drain concurrently: half the serial epilogue per tile
         uint32_t acc_phase = 0;
         for (long long t = cluster_id; t < total_tiles; t += num_clusters) {
             int st, et;
@@ -272,8 +274,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             mbar_wait(tmem_full, acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int eig0 = et * kTileEig;
-#pragma unroll 1
-            for (int acc = 0; acc < 2; ++acc) {
+            {
                 const long long snp = (long long)st * kClusterSnps + (long long)rank * kCtaSnps + acc * 128 + quarter * 32 + lane;
                 double lv0 = 0.0, ls = 1.0, leps = 0.0;
                 if (a.info && snp < a.mb) { const LevelInfo li = a.info[snp]; lv0 = li.v0; ls = li.s; leps = li.eps; }
