@@ -44,7 +44,11 @@ constexpr int kStages = 4;
 #define PG_TC2_EIG_GROUP 24
 #endif
 constexpr int kEigGroup = PG_TC2_EIG_GROUP;
-constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
+#ifndef PG_TC2_EPI_WARPS
+#define PG_TC2_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = PG_TC2_EPI_WARPS;              // 8: one warp per accumulator and lane quarter; 16: two (column halves)
+constexpr int kThreads = 64 + 32 * kEpiWarps;           // TMA warp, MMA warp, epilogue warps
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // cute::Sm100MmaPeerBitMask: address of the even CTA of the pair
 
@@ -177,7 +181,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 512);   // 256 epilogue threads of each CTA of the pair (only the leader's barrier is used)
+        mbar_init(tmem_empty, 2 * 32 * kEpiWarps);   // the epilogue threads of both CTAs (only the leader's barrier is used)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -266,7 +270,11 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
     } else {
         const int quarter = warp & 3;
-        const int acc = (warp - 2) >> 2;   // the two accumulators drain concurrently: half the serial epilogue per tile
+        // the accumulators (and, with 16 warps, their column halves) drain concurrently: a short serial chain per tile
+        const int part = (warp - 2) >> 2;
+        const int acc = part & 1;
+        constexpr int kCPer = (kTileEig / 8) / (kEpiWarps / 8);
+        const int c_begin = (part >> 1) * kCPer;
         uint32_t acc_phase = 0;
         for (long long t = cluster_id; t < total_tiles; t += num_clusters) {
             int st, et;
@@ -280,7 +288,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 if (a.info && snp < a.mb) { const LevelInfo li = a.info[snp]; lv0 = li.v0; ls = li.s; leps = li.eps; }
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAcc1Col);
 #pragma unroll 1
-                for (int c = 0; c < kTileEig / 8; ++c) {
+                for (int c = c_begin; c < c_begin + kCPer; ++c) {
                     // eight eigenvectors x seven planes = 56 consecutive columns (eigen-major)
                     uint32_t r[kSlices][8];
 #pragma unroll
