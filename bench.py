@@ -203,16 +203,17 @@ def load_peaks():
 
 
 def ncu_traffic(kernel_substr: str):
-    """DRAM bytes per SNP of a kernel from the committed `ncu --set full` capture (profiles/ncu_r01_hot_kernels_8192snps.json:
-    tools/prof_rot.py 10000 8192 10; the first launch of each kernel covers 3584 SNPs, compress / solve 8192)."""
+    """DRAM bytes per SNP of a kernel from the committed `ncu --set full` captures (cuBLAS engine:
+    profiles/ncu_r01_hot_kernels_8192snps.json, tools/prof_rot.py 10000 8192 10, first launch covers 3584 SNPs)."""
     p = os.path.join(ROOT, "profiles", "ncu_r01_hot_kernels_8192snps.json")
+    snps = {"cutlass": 3584, "combine_i8": 3584, "compress_dmma": 8192, "reml_solve": 8192, "rotate_i8_tc2": 16384}
+    # final-code captures (tools/run_ncu_tc2.sh): prof_tc.py 10000 16384 and prof_reml.py 10000 8192 10
+    if kernel_substr == "rotate_i8_tc2":
+        p = os.path.join(ROOT, "profiles", "ncu_r01_tc2_final_16384snps.json")
+    elif kernel_substr in ("compress_dmma", "reml_solve"):
+        p = os.path.join(ROOT, "profiles", "ncu_r01_reml_final_8192snps.json")
     if not os.path.exists(p):
         return None
-    snps = {"cutlass": 3584, "combine_i8": 3584, "compress_dmma": 8192, "reml_solve": 8192, "rotate_i8_tc2": 16384}
-    if kernel_substr == "rotate_i8_tc2":  # captured separately: tools/prof_tc.py 10000 16384
-        p = os.path.join(ROOT, "profiles", "ncu_r01_tc2_16384snps.json")
-        if not os.path.exists(p):
-            return None
     for e in json.load(open(p)):
         if kernel_substr in e["kernel"] and "dram_traffic_bytes" in e:
             return e["dram_traffic_bytes"] / snps[kernel_substr]
@@ -399,7 +400,7 @@ def run_ours(args):
         per_snp = ncu_traffic("reml_solve")
     roofline["traffic"] = per_snp * res_tm["block_snps"] if per_snp else None
     roofline["traffic_note"] = ("dram__bytes_read+write of the stage's kernels per SNP block (ncu --set full, n=10000, "
-                                "profiles/ncu_r01_tc2_16384snps.json / ncu_r01_hot_kernels_8192snps.json); algorithmic HBM bytes "
+                                "profiles/ncu_r01_tc2_final_16384snps.json / ncu_r01_reml_final_8192snps.json); algorithmic HBM bytes "
                                 "per SNP for the fused rotation: 10 KB int8 in + 80 KB fp64 out (+ the 70 MB digit planes "
                                 "once per eigen-tile group); the cuBLAS form adds 2 x 280 KB of int32 partial products")
     roofline["per_kernel_ms_last_step"] = {"convert": conv_ms, "rotate": rot_ms, "compress": cmp_ms, "solve": solve_ms}
