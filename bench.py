@@ -355,15 +355,15 @@ def run_ours(args):
     nodes = res_tm["n_nodes"]
     i8 = res_tm.get("rot_engine") in (_capi.PG_ROT_I8SPLIT, _capi.PG_ROT_I8TC)
     fused = res_tm.get("rot_engine") == _capi.PG_ROT_I8TC
-    n_planes = 7
+    n_planes = int(_capi.load().pg_rotation_planes())   # 7 unless the library was built with -DPG_SLICES=6
     rot_ops = (n_planes if i8 else 1) * 2.0 * n * n          # int8 (or fp64) multiply-add ops per SNP
     cmp_flops = 2.0 * n * 10 * (c0 + 2)                       # compression: n x kCq x (c0+2) FP64 FMAs per SNP
     stages = {
         "rotation": {"ms": rot_ms, "achieved": rot_ops * m / (rot_ms * 1e-3) / 1e12,
                      "peak": peaks["int8_gemm_tops"] if i8 else peaks["fp64_dmma_tflops"],
-                     "kernel": ("rotation U^T X, exact int8-split (7 base-256 digit planes): rotate_i8_tc2_kernel (hand-written TMA + "
+                     "kernel": (f"rotation U^T X, exact int8-split ({n_planes} base-256 digit planes): rotate_i8_tc2_kernel (hand-written TMA + "
                                 "tcgen05 cta_group::2 kind::i8, recombination fused)") if (i8 and fused) else
-                               ("rotation U^T X, exact int8-split (7 base-256 digit planes): cuBLAS int8 GEMM (cutlass3x sm100 "
+                               (f"rotation U^T X, exact int8-split ({n_planes} base-256 digit planes): cuBLAS int8 GEMM (cutlass3x sm100 "
                                 "tcgen05 2-SM kernel) + combine_i8_kernel") if i8 else
                                "rotation U^T X (cuBLAS DGEMM, FP64 tensor pipe)",
                      "peak_source": ("int8 tensor rate (cuBLAS int8 GEMM 16384x8192x8192) " if i8 else "FP64 DMMA rate ")

@@ -95,6 +95,9 @@ typedef struct {
 } pg_timing;
 
 int pg_abi_version(void);
+/* digit planes of the int8-split rotation this library was built with (7; 6 with -DPG_SLICES=6): the rotation costs
+ * planes * 2 * n^2 int8 operations per SNP */
+int pg_rotation_planes(void);
 int pg_device_count(int* count);
 
 /* last error text of a handle (or of the failed pg_create when h == NULL) */

@@ -21,7 +21,7 @@ PG_MAX_TRAITS = 64  # traits per pass of pg_set_design_multi (include/pygemma_b2
 
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)
 SYMBOLS = [
-    "pg_abi_version", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
+    "pg_abi_version", "pg_rotation_planes", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
     "pg_set_reml_engine", "pg_grm", "pg_set_bed_options",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
@@ -61,6 +61,7 @@ def load():
     L = ctypes.CDLL(LIB_PATH)
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
     L.pg_abi_version.restype = i32
+    L.pg_rotation_planes.restype = i32
     L.pg_device_count.argtypes = [ctypes.POINTER(i32)]
     L.pg_last_error.restype = ctypes.c_char_p
     L.pg_last_error.argtypes = [vp]

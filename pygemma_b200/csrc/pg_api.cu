@@ -153,6 +153,7 @@ static int fail(pg_handle* h, int code, const char* fmt, ...)
     } while (0)
 
 extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
+extern "C" int pg_rotation_planes(void) { return kSlices; }
 
 extern "C" int pg_device_count(int* count)
 {

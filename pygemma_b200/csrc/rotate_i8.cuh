@@ -19,7 +19,17 @@
 
 namespace pg {
 
-constexpr int kSlices = 7;
+// Digit planes per eigenvector: U is held as kSlices balanced base-256 digits of |u| 2^-e < 1/4, i.e. 8 kSlices bits of
+// fixed point below the largest entry of the eigenvector.  7 planes (56 bits) lose nothing an FP64 U carries for its
+// large entries; 6 planes (48 bits, build with -DPG_SLICES=6) round each entry at 2^-50 of the column scale, which is
+// the size of the rounding error an FP64 GEMM commits itself (measured in DESIGN.md) for 6/7 of the tensor work.
+#ifndef PG_SLICES
+#define PG_SLICES 7
+#endif
+constexpr int kSlices = PG_SLICES;
+static_assert(kSlices == 6 || kSlices == 7, "6 or 7 digit planes");
+constexpr double kLoScale = (kSlices == 7) ? 2.3283064365386963e-10 /* 2^-32 */ : 5.9604644775390625e-08 /* 2^-24 */;
+constexpr int kLoShift = 8 * (kSlices - 3);   // value = (hi + lo 2^-kLoShift) 2^(e-24), hi: planes 0..2, lo: planes 3..
 
 // one CTA per eigenvector i: find e_i, write the digit planes
 // U is n x n; eigenvector i is at U + i*n when u_cols_contig (column-major U), else strided (U + i, stride n)
@@ -102,13 +112,13 @@ __global__ void __launch_bounds__(256) combine_i8_kernel(const int32_t* __restri
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || g >= mb) return;
     const int32_t* p = P + (size_t)g * kSlices * npad + i;
-    // sum_t P_t 256^(7-t): planes 0..2 (<= 2^46) and planes 3..6 (<= 2^54) separately, then one fp64 sum
+    // sum_t P_t 256^(kSlices-1-t): planes 0..2 (<= 2^46) and planes 3.. (<= 2^54) separately, then one fp64 sum
     long long hi = 0, lo = 0;
 #pragma unroll
     for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[(size_t)t * npad];
 #pragma unroll
     for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[(size_t)t * npad];
-    const double v = (double)hi + ldexp((double)lo, -32);
+    const double v = (double)hi + ldexp((double)lo, -kLoShift);
     xr[(size_t)g * ldx + i] = ldexp(v, exps[i] - 24);
 }
 
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(256) combine_i8_affine_kernel(const int32_t* _
     for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[(size_t)t * npad];
 #pragma unroll
     for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[(size_t)t * npad];
-    const double r = ldexp((double)hi + ldexp((double)lo, -32), exps[i] - 24);
+    const double r = ldexp((double)hi + ldexp((double)lo, -kLoShift), exps[i] - 24);
     const LevelInfo li = info[g];
     double* dst = xr + (size_t)g * ldx + i;
     if (accumulate) {

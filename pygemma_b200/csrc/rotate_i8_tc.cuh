@@ -254,12 +254,12 @@ rotate_i8_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         for (int j = 0; j < 8; ++j) {
                             const int e = eig0 + c * 8 + j;
                             if (e < a.n) {
-                                // sum_p P_p 256^(6-p): planes 0..2 and 3..6 are exact in fp64, one rounding in the final sum
+                                // sum_p P_p 256^(kSlices-1-p): planes 0..2 and 3.. are exact in fp64, one rounding in the final sum
                                 const double hi = fma((double)(int)r[0][j], 65536.0, fma((double)(int)r[1][j], 256.0, (double)(int)r[2][j]));
-                                const double lo = fma((double)(int)r[3][j], 16777216.0,
-                                                      fma((double)(int)r[4][j], 65536.0,
-                                                          fma((double)(int)r[5][j], 256.0, (double)(int)r[6][j])));
-                                const double v = fma(lo, 2.3283064365386963e-10 /* 2^-32 */, hi);
+                                double lo = (double)(int)r[3][j];
+#pragma unroll
+                                for (int p = 4; p < kSlices; ++p) lo = fma(lo, 256.0, (double)(int)r[p][j]);
+                                const double v = fma(lo, kLoScale, hi);
                                 dst[j] = v * __ldg(a.scale + e);
                             }
                         }

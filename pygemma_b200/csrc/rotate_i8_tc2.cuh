@@ -306,10 +306,12 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                             // integer, rounded once if it exceeds 2^53 (it does not for dosages: |plane sum| <= 256 n)
 #define PG_PL(P) ((long long)(int)r[(j * kSlices + (P)) >> 3][(j * kSlices + (P)) & 7])
                             const long long hi_i = (PG_PL(0) << 16) + (PG_PL(1) << 8) + PG_PL(2);
-                            const long long lo_i = (PG_PL(3) << 24) + (PG_PL(4) << 16) + (PG_PL(5) << 8) + PG_PL(6);
+                            long long lo_i = PG_PL(3);
+#pragma unroll
+                            for (int p = 4; p < kSlices; ++p) lo_i = (lo_i << 8) + PG_PL(p);
 #undef PG_PL
                             const double hi = (double)hi_i, lo = (double)lo_i;
-                            const double v = fma(lo, 2.3283064365386963e-10 /* 2^-32 */, hi);
+                            const double v = fma(lo, kLoScale, hi);
                             out[j] = v * __ldg(a.scale + e);
                             if (a.info) {
                                 if (a.accumulate) out[j] = (leps != 0.0) ? fma(leps, out[j], dst[j]) : dst[j];
