@@ -34,6 +34,11 @@ def test_abi_version(lib):
     assert lib.pg_abi_version() == int(re.search(r"#define PG_ABI_VERSION (\d+)", txt).group(1))
 
 
+def test_default_build_keeps_seven_digit_planes(lib):
+    """The shipped library is the default build: 56-bit fixed-point U (the 6-plane variant is a build option)."""
+    assert lib.pg_rotation_planes() == 7
+
+
 def test_no_cpu_fallback(lib):
     """Without a GPU pg_create must fail loudly (PG_ERR_NO_DEVICE), never compute on the host."""
     import torch
