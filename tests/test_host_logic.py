@@ -155,6 +155,63 @@ def test_pygemma_argument_contract():
     assert lmm._as_genotypes(np.zeros((2, 2), dtype=np.float16)).dtype == np.float32
 
 
+def test_pygemma_multi_groups_traits_and_keeps_order(monkeypatch):
+    """lmm.pygemma_multi on a recording stand-in for the device handle: traits go through in groups of PG_MAX_TRAITS,
+    one genotype pass per group, frames come back in trait order with the reference's columns, failed rows as NaN."""
+    from pygemma_b200 import _capi, lmm
+
+    calls = []
+
+    class FakeHandle:
+        def __init__(self, n, c0, device=0):
+            self.n, self.c0, self.q = n, c0, 1
+
+        def set_kinship(self, K):
+            return 0.0
+
+        def set_eigen(self, U, d):
+            pass
+
+        def set_design(self, W, y, already_rotated=False):
+            y = np.asarray(y)
+            self.q = y.shape[1] if y.ndim == 2 else 1
+            self.first = float(y.reshape(self.n, -1)[0, 0])   # tags the group by its first trait's first value
+            calls.append(("design", self.q))
+            return 1.0
+
+        def scan(self, X, grid=False):
+            m = X.shape[1]
+            calls.append(("scan", self.q))
+            shape = m if self.q == 1 else (self.q, m)
+            base = self.first + np.arange(self.q).reshape(-1, 1) + np.zeros((self.q, m))
+            out = {k: (base + i).reshape(shape) for i, k in enumerate(lmm.COLUMNS)}
+            st = np.zeros(shape, dtype=np.int32)
+            st.reshape(self.q, m)[:, 1] = 1   # second SNP fails for every trait
+            out.update(status=st, n_eval2=np.full(shape, 14, dtype=np.int32), n_eval3=np.full(shape, 3, dtype=np.int32))
+            out["timing"] = {"rotate_ms": 0.0, "reml_ms": 0.0}
+            return out
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_capi, "Handle", FakeHandle)
+    monkeypatch.setattr(multi, "setup_eigen", lambda ctx, h, K: 0.0)
+    n, m = 12, 4
+    q = _capi.PG_MAX_TRAITS + 5
+    Y = np.tile(np.arange(q, dtype=np.float64), (n, 1))      # trait t is the constant t
+    X, W, K = np.zeros((n, m), dtype=np.int8), np.ones((n, 1)), np.eye(n)
+    frames = lmm.pygemma_multi(Y, X, W, K, snps=[f"rs{i}" for i in range(m)])
+    assert calls == [("design", _capi.PG_MAX_TRAITS), ("scan", _capi.PG_MAX_TRAITS), ("design", 5), ("scan", 5)]
+    assert len(frames) == q
+    for t, df in enumerate(frames):
+        assert list(df.columns) == lmm.COLUMNS + ["SNPs"] and len(df) == m
+        assert df["beta"].iloc[0] == float(t) and df["se_beta"].iloc[0] == float(t) + 1
+        assert df.iloc[1][lmm.COLUMNS].isna().all() and not df.iloc[0][lmm.COLUMNS].isna().any()
+    calls.clear()
+    one = lmm.pygemma(Y[:, 3], X, W, K)
+    assert calls == [("design", 1), ("scan", 1)] and one["beta"].iloc[0] == 3.0
+
+
 # ---- eigenvalue-space compression (pygemma_b200/csrc/compress_plan.h) ----------------------------------
 
 def _spectra(rng, n):
