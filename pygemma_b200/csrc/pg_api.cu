@@ -939,10 +939,14 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
             kern<<<grid, warps * 32, smem, st_solve>>>(sa);
             return PG_OK;
         };
-        // 2 CTAs of 8 warps per SM (128 registers): 3 and 4 CTAs/SM and 4-6 warps per CTA were measured slower.
+        // 2 CTAs of 8 warps per SM (128 registers) for x rows of 12 or more entries: 3 and 4 CTAs/SM spill in the x-row
+        // pass and were measured 5-25 % slower (c0 = 10, 11); short x rows (c0 <= 6, 8 entries) run 27 % faster at 4
+        // CTAs/SM (64 registers).  4-6 warps per CTA were measured slower.
         // Under the next block's rotation: 1 CTA per SM (32 K registers + 15 KB shared memory fit beside a rotation CTA).
-        const int per_sm = split ? 1 : 2;
-        const int lr = two ? launch(reml_solve_kernel<2, 2>, per_sm) : launch(reml_solve_kernel<1, 2>, per_sm);
+        const bool small = h->k1p <= 8;
+        const int per_sm = split ? 1 : (small ? 4 : 2);
+        const int lr = two ? launch(reml_solve_kernel<2, 2>, per_sm)
+                           : (small ? launch(reml_solve_kernel<1, 4>, per_sm) : launch(reml_solve_kernel<1, 2>, per_sm));
         if (lr) return lr;
         CK(cudaGetLastError());
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
