@@ -206,9 +206,12 @@ template <bool FULL>
 __device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __restrict__ Zs, double lam, double* xs)
 {
     int jb = 0;
-    while (a.k1p - jb >= 12) {
-        solve_xrow_pass<12, FULL>(a, Zs, lam, jb, xs);
-        jb += 12;
+    // rows per pass: 12 with two powers (24 accumulators per lane), 8 with three (24 again): the 36 accumulators of a
+    // 12-row three-power pass spill at 128 registers (measured: solve stage -7..11 % with the narrower pass)
+    constexpr int kBig = FULL ? 8 : 12;
+    while (a.k1p - jb >= kBig) {
+        solve_xrow_pass<kBig, FULL>(a, Zs, lam, jb, xs);
+        jb += kBig;
     }
     if (a.k1p - jb == 8) solve_xrow_pass<8, FULL>(a, Zs, lam, jb, xs);
     else if (a.k1p - jb == 4) solve_xrow_pass<4, FULL>(a, Zs, lam, jb, xs);
