@@ -38,6 +38,8 @@ struct pg_handle {
     // so that block b's REML stage (FP64 pipes) runs under block b+1's rotation (int8 tensor pipe)
     cudaStream_t aux = nullptr, cmb = nullptr;
     cudaEvent_t ev_xr_ready[2] = {nullptr, nullptr}, ev_xr_free[2] = {nullptr, nullptr}, ev_aux_done = nullptr;
+    cudaEvent_t ev_pv[2] = {nullptr, nullptr};   // brackets the scan's single p-value launch
+    bool defer_pvalues = false;                  // set by pg_scan: one pvalue_kernel launch after the last block
     cudaEvent_t ev_z_ready[2] = {nullptr, nullptr}, ev_z_free[2] = {nullptr, nullptr};
     bool overlap = false;
     // per-call scratch kept across calls (grow-only): device result arrays, pinned host staging, timing events
@@ -198,6 +200,8 @@ static int free_all(pg_handle* h)
         if (h->ev_z_free[s]) cudaEventDestroy(h->ev_z_free[s]);
     }
     if (h->ev_aux_done) cudaEventDestroy(h->ev_aux_done);
+    for (int s = 0; s < 2; ++s)
+        if (h->ev_pv[s]) cudaEventDestroy(h->ev_pv[s]);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     h->ev_pool.clear();
     if (h->res_d) cudaFree(h->res_d);
@@ -949,8 +953,9 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
                            : (small ? launch(reml_solve_kernel<1, 4>, per_sm) : launch(reml_solve_kernel<1, 2>, per_sm));
         if (lr) return lr;
         CK(cudaGetLastError());
-        // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN)
-        {
+        // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN).  The kernel is one long serial chain
+        // per thread (0.18 ms whatever the row count), so a scan launches it once over all rows after its last block.
+        if (!h->defer_pvalues) {
             const long double nu = (long double)(h->n - h->c0 - 1);
             const double lnbeta = (double)(lgammal(0.5L * nu + 0.5L) - lgammal(0.5L * nu) - lgammal(0.5L));
             pvalue_kernel<<<(unsigned)((mb + 31) / 32), 32, 0, st_solve>>>(out[4], out[5], row0, mb, (double)nu, lnbeta);
@@ -1121,6 +1126,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     cudaEvent_t t0 = take(), t1 = take(), t2 = take();
     int n_rot_launch = 0, last_engine = 0;
 
+    h->defer_pvalues = compressed;   // launch_reml leaves p = NaN; one pvalue_kernel launch follows the last block
     rc = [&]() -> int {
         CK(cudaEventRecord(t0, h->compute));
         CK(cudaStreamWaitEvent(h->copy, t0, 0));
@@ -1226,6 +1232,16 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             CK(cudaEventRecord(h->ev_aux_done, h->aux));
             CK(cudaStreamWaitEvent(h->compute, h->ev_aux_done, 0));
         }
+        if (h->defer_pvalues && mq > 0) {
+            const long double nu = (long double)(h->n - h->c0 - 1);
+            const double lnbeta = (double)(lgammal(0.5L * nu + 0.5L) - lgammal(0.5L * nu) - lgammal(0.5L));
+            for (int s = 0; s < 2; ++s)
+                if (!h->ev_pv[s]) CK(cudaEventCreate(&h->ev_pv[s]));
+            CK(cudaEventRecord(h->ev_pv[0], h->compute));
+            pvalue_kernel<<<(unsigned)((mq + 31) / 32), 32, 0, h->compute>>>(dout[4], dout[5], 0, (long long)mq, (double)nu, lnbeta);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h->ev_pv[1], h->compute));
+        }
         CK(cudaEventRecord(t1, h->compute));
         if (!on_device) {
             // two D2H copies into pinned staging, then host memcpy into the caller's (pageable) arrays
@@ -1246,6 +1262,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         }
         return PG_OK;
     }();
+    h->defer_pvalues = false;
 
     if (rc == PG_OK && timing) {
         float v = 0;
@@ -1255,6 +1272,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             cudaEventElapsedTime(&v, ev_conv[b].a, ev_conv[b].b); timing->convert_ms += v;
             cudaEventElapsedTime(&v, ev_rot[b].a, ev_rot[b].b); timing->rotate_ms += v;
             cudaEventElapsedTime(&v, ev_reml[b].a, ev_reml[b].b); timing->reml_ms += v;
+            if (b == 0 && compressed && mq > 0) {   // the scan's single p-value launch cudaEventElapsedTime(&v, h->ev_pv[0], h->ev_pv[1]); timing->reml_ms += v; }
             if (compressed) { cudaEventElapsedTime(&v, ev_cmp[b].a, ev_cmp[b].b); timing->compress_ms += v; }
             if (!on_device) { cudaEventElapsedTime(&v, ev_h2d[b].a, ev_h2d[b].b); timing->h2d_ms += v; }
         }
@@ -1266,9 +1284,9 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->rot_engine = last_engine;
         timing->reml_engine = compressed ? PG_REML_COMPRESSED : h->engine;
         timing->n_nodes = compressed ? h->plan.Kc : h->n;
-        // per block: compress (dmma / copy), fixed-lambda x rows, then solve + p-values per phenotype
+        // per block: compress (dmma / copy), fixed-lambda x rows, one solve per phenotype; one p-value launch per scan
         if (compressed)
-            timing->reml_launches = (int32_t)(nblocks * (1 + 2 * q + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)));
+            timing->reml_launches = (int32_t)(nblocks * (1 + q + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)) + 1);
         else
             timing->reml_launches = (int32_t)(nblocks * q);
     }
