@@ -1272,7 +1272,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             cudaEventElapsedTime(&v, ev_conv[b].a, ev_conv[b].b); timing->convert_ms += v;
             cudaEventElapsedTime(&v, ev_rot[b].a, ev_rot[b].b); timing->rotate_ms += v;
             cudaEventElapsedTime(&v, ev_reml[b].a, ev_reml[b].b); timing->reml_ms += v;
-            if (b == 0 && compressed && mq > 0) {   // the scan's single p-value launch cudaEventElapsedTime(&v, h->ev_pv[0], h->ev_pv[1]); timing->reml_ms += v; }
+            if (b == 0 && compressed && mq > 0) { cudaEventElapsedTime(&v, h->ev_pv[0], h->ev_pv[1]); timing->reml_ms += v; }  // the single p-value launch
             if (compressed) { cudaEventElapsedTime(&v, ev_cmp[b].a, ev_cmp[b].b); timing->compress_ms += v; }
             if (!on_device) { cudaEventElapsedTime(&v, ev_h2d[b].a, ev_h2d[b].b); timing->h2d_ms += v; }
         }
