@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 2
+#define PG_ABI_VERSION 3
 
 typedef struct pg_handle pg_handle;
 
@@ -137,6 +137,14 @@ int pg_set_eigen(pg_handle* h, const double* U_host, int u_row_major, const doub
 int pg_set_eigen_device(pg_handle* h, const double* U_dev, int u_row_major, const double* d_dev);
 /* copy the handle's U (column-major) and d into caller-provided device buffers (multi-GPU broadcast) */
 int pg_get_eigen_device(pg_handle* h, double* U_dev_out, double* d_dev_out);
+
+/*
+ * Take over the eigen-system another handle holds (same n; same or peer device), device to device.  A caller that keeps
+ * one eigendecomposition for many calls -- the reference's callers repeat eigh(K) for every phenotype and covariate set
+ * (lmm/lmm.py:151-162 runs inside every lmm.pygemma call; experiments/animal_gwas/run_gwas.py:167-175 loops it) -- creates
+ * a handle per covariate count c0 and copies U, d instead of decomposing again (pygemma_b200.lmm.factorize).
+ */
+int pg_copy_eigen(pg_handle* h, const pg_handle* src);
 
 /*
  * Covariates and phenotype: W_host is (n, c0) C-order, y_host is n doubles.  Computes U^T W and U^T y

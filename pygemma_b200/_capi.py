@@ -22,7 +22,7 @@ PG_MAX_TRAITS = 64  # traits per pass of pg_set_design_multi (include/pygemma_b2
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)
 SYMBOLS = [
     "pg_abi_version", "pg_rotation_planes", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
-    "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
+    "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_copy_eigen", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
     "pg_set_reml_engine", "pg_grm", "pg_set_bed_options",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
@@ -71,6 +71,7 @@ def load():
     L.pg_set_eigen.argtypes = [vp, vp, i32, vp]
     L.pg_set_eigen_device.argtypes = [vp, vp, i32, vp]
     L.pg_get_eigen_device.argtypes = [vp, vp, vp]
+    L.pg_copy_eigen.argtypes = [vp, vp]
     L.pg_set_design.argtypes = [vp, vp, vp, i32, ctypes.POINTER(ctypes.c_float)]
     L.pg_set_design_multi.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float)]
     L.pg_set_options.argtypes = [vp, i32, i64]
@@ -187,6 +188,10 @@ class Handle:
 
     def get_eigen_device(self, U_ptr: int, d_ptr: int):
         self._ck(self.L.pg_get_eigen_device(self.h, ctypes.c_void_p(U_ptr), ctypes.c_void_p(d_ptr)))
+
+    def copy_eigen_from(self, other: "Handle"):
+        """Take over `other`'s eigen-system (U, d) device to device (pg_copy_eigen)."""
+        self._ck(self.L.pg_copy_eigen(self.h, other.h))
 
     def set_design(self, W, y, already_rotated=False):
         """y: n values, or an (n, q) matrix of q phenotypes scanned together (outputs become (q, m) arrays)."""

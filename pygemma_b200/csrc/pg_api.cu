@@ -576,6 +576,46 @@ extern "C" int pg_get_eigen_device(pg_handle* h, double* U_dev_out, double* d_de
     return PG_OK;
 }
 
+// Hands the eigen-system of `src` (U, clipped d, already in ascending order) to `dst` device-to-device: a caller that
+// keeps one decomposition for many designs (lmm.factorize) re-creates the handle when the covariate count changes.
+extern "C" int pg_copy_eigen(pg_handle* h, const pg_handle* src)
+{
+    if (!h || !src) return fail(h, PG_ERR_ARG, "pg_copy_eigen: NULL argument");
+    if (h == src) return PG_OK;
+    if (h->n != src->n) return fail(h, PG_ERR_ARG, "pg_copy_eigen: n differs (%d vs %d)", h->n, src->n);
+    if (!src->have_d) return fail(h, PG_ERR_ARG, "pg_copy_eigen: the source handle holds no eigen-system");
+    CK(cudaSetDevice(src->device));
+    CK(cudaStreamSynchronize(src->compute));
+    CK(cudaSetDevice(h->device));
+    const int n = h->n;
+    if (src->have_U) {
+        int rc = ensure_U(h);
+        if (rc) return rc;
+        if (h->device == src->device)
+            CK(cudaMemcpyAsync(h->U, src->U, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, h->compute));
+        else
+            CK(cudaMemcpyPeerAsync(h->U, h->device, src->U, src->device, sizeof(double) * (size_t)n * n, h->compute));
+        h->u_op_t = src->u_op_t;
+        h->have_U = true;
+    } else {
+        h->have_U = false;
+    }
+    if (h->device == src->device)
+        CK(cudaMemcpyAsync(h->d, src->d, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->compute));
+    else
+        CK(cudaMemcpyPeerAsync(h->d, h->device, src->d, src->device, sizeof(double) * n, h->compute));
+    CK(cudaStreamSynchronize(h->compute));
+    h->have_d = true; h->have_design = false; h->rotated_inputs = false;
+    rot_invalidate(&h->rot);
+    // src is canonical (ascending); its caller-order permutation is kept so that rotated inputs / probes keep their meaning
+    int rc = canonicalise_eigen(h);
+    if (rc) return rc;
+    h->perm = src->perm;
+    h->perm_identity = src->perm_identity;
+    CK(cudaMemcpy(h->perm_dev, h->perm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    return PG_OK;
+}
+
 static void activate(pg_handle* h, int ph)
 {
     const pg_handle::DesignSlot& S = h->slots[ph];
@@ -912,10 +952,12 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
             {
                 // x rows of the kNumFixed fixed-lambda evaluations of every slab row, all phenotypes at once
                 const long long rows = mb * zrows;
-                const size_t hs = sizeof(double) * (size_t)P.Kcp * kFxCols;
+                // H goes through shared memory in slabs of at most kFxSlabMax nodes (Kcp is a multiple of 32)
+                const int kslab = std::min(P.Kcp, kFxSlabMax);
+                const size_t hs = sizeof(double) * (size_t)kslab * kFxCols;
                 if (hs > 48 * 1024)
                     CK(cudaFuncSetAttribute(fixed_xrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-                fixed_xrow_kernel<<<(unsigned)((rows + 255) / 256), 256, hs, st>>>(Zbuf, rows, P.Kcp, P.H, Fbuf);
+                fixed_xrow_kernel<<<(unsigned)((rows + 255) / 256), 256, hs, st>>>(Zbuf, rows, P.Kcp, P.H, Fbuf, kslab);
                 CK(cudaGetLastError());
             }
             if (split) {

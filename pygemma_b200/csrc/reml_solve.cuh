@@ -73,16 +73,18 @@ __global__ void build_h_kernel(const double* __restrict__ nodes, int Kcp, double
     H[i] = v;
 }
 
-// One warp contracts 32 slab rows (4 m-tiles) against all 24 columns; H lives in shared memory, Z is read once.
+// One warp contracts 32 slab rows (4 m-tiles) against all 24 columns; Z is read once.  H passes through shared memory in
+// slabs of `kslab` nodes (a multiple of 4; the whole table when it fits): a wide spectrum can need more nodes than one
+// CTA's shared memory holds (Kcp * 192 bytes), the accumulators simply stay in registers across slabs.
+constexpr int kFxSlabMax = 960;   // nodes per shared-memory slab: 960 * 24 * 8 = 180 KB
 __global__ void __launch_bounds__(256)
-fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const double* __restrict__ H, double* __restrict__ F)
+fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const double* __restrict__ H, double* __restrict__ F,
+                  int kslab)
 {
     extern __shared__ double Hs[];
-    for (int i = threadIdx.x; i < Kcp * kFxCols; i += 256) Hs[i] = H[i];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long r0 = ((long long)blockIdx.x * 8 + warp) * 32;
-    if (r0 >= rows) return;
+    const bool active = r0 < rows;   // inactive warps still take part in the slab barriers
     const int ar = lane >> 2, ac = lane & 3;
     double acc[4][3][2];
     const double* zp[4];
@@ -90,27 +92,35 @@ fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const d
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
         const long long row = r0 + mt * 8 + ar;
-        ok[mt] = row < rows;
+        ok[mt] = active && row < rows;
         zp[mt] = Z + (size_t)(ok[mt] ? row : 0) * Kcp + ac;
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
     }
+    for (int k0 = 0; k0 < Kcp; k0 += kslab) {
+        const int kn = min(kslab, Kcp - k0);
+        if (k0) __syncthreads();   // everybody is done with the previous slab
+        for (int i = threadIdx.x; i < kn * kFxCols; i += 256) Hs[i] = H[(size_t)k0 * kFxCols + i];
+        __syncthreads();
+        if (!active) continue;
 #pragma unroll 4
-    for (int ks = 0; ks < (Kcp >> 2); ++ks) {
-        double b[3];
+        for (int ks = 0; ks < (kn >> 2); ++ks) {
+            double b[3];
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) b[nt] = Hs[(ks * 4 + ac) * kFxCols + nt * 8 + ar];
+            for (int nt = 0; nt < 3; ++nt) b[nt] = Hs[(ks * 4 + ac) * kFxCols + nt * 8 + ar];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const double av = ok[mt] ? __ldg(zp[mt] + ks * 4) : 0.0;
+            for (int mt = 0; mt < 4; ++mt) {
+                const double av = ok[mt] ? __ldg(zp[mt] + k0 + ks * 4) : 0.0;
 #pragma unroll
-            for (int nt = 0; nt < 3; ++nt) {
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
-                             : "d"(av), "d"(b[nt]));
+                for (int nt = 0; nt < 3; ++nt) {
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                 : "d"(av), "d"(b[nt]));
+                }
             }
         }
     }
+    if (!active) return;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
         if (!ok[mt]) continue;

@@ -11,6 +11,8 @@ libpygemma_b200.so (CUDA, sm_100a) through the C ABI of include/pygemma_b200.h:
     U.T @ {X, Y, W}         lmm/lmm.py:243-246  -> device GEMMs, X in SNP blocks
     Pool.imap(calculate)    lmm/lmm.py:378-403  -> per-SNP REML kernel
 
+Extension: `F = lmm.factorize(K)` decomposes once and `lmm.pygemma(Y, X, W, F)` reuses it (KinshipFactor).
+
 Differences from the reference, all documented in DESIGN.md: arithmetic is float64 throughout (the
 reference mixes float32 storage into a float64 core), so every returned column is float64; `nproc` is
 accepted and ignored (parallelism is the GPU, or several GPUs under torch.distributed); `de=True`
@@ -52,6 +54,82 @@ def _as_genotypes(X):
     if dt == np.float16:
         return X.astype(np.float32)
     return X.astype(np.float64)
+
+
+class KinshipFactor:
+    """The eigendecomposition K = U diag(d) U^T, done once and kept in HBM (extension).
+
+    The reference runs `eigh(K)` inside every `lmm.pygemma` call (lmm/lmm.py:151-162) and its callers loop that call
+    over phenotypes and covariate sets (experiments/animal_gwas/run_gwas.py:167-175, benchmark_pygemma.py:238).  Pass
+    the object returned by `factorize(K)` in the K position instead of the matrix and every call skips the
+    decomposition: U, its int8 digit planes and the eigenvalue-space compression plan stay on the device.
+
+        F = lmm.factorize(K)
+        for y in traits: df = lmm.pygemma(y, X, W, F)
+
+    Under torch.distributed (backend nccl) rank 0 decomposes and U, d are broadcast once; K may be None elsewhere.
+    """
+
+    def __init__(self, K, Z=None, device=None, c0=1, verbose=0):
+        from . import multi
+
+        self.ctx = multi.context(device)
+        multi.check_backend(self.ctx)
+        if K is not None:
+            K = np.asarray(K, dtype=np.float64)
+            if Z is not None:
+                Z = np.asarray(Z, dtype=np.float64)
+                K = Z @ K @ Z.T  # lmm/lmm.py:124-125
+            if K.ndim != 2 or K.shape[0] != K.shape[1]:
+                raise ValueError(f"K must be square, got {K.shape}")
+        elif self.ctx.rank == 0:
+            raise ValueError("K is required on rank 0")
+        n = multi.agree_on_n(self.ctx, None if K is None else K.shape[0])
+        self.n = int(n)
+        self._h = _capi.Handle(self.n, int(c0), self.ctx.device)
+        t0 = time.time()
+        _log(verbose, "Starting eigendecomposition...")
+        self.eig_ms = multi.setup_eigen(self.ctx, self._h, K)
+        self.setup_s = time.time() - t0
+        _log(verbose, f"Eigendecomposition computed - {round(self.setup_s, 3)} s")
+
+    def handle(self, c0: int):
+        """The live handle for designs with c0 covariate columns (re-created device to device when c0 changes)."""
+        if self._h is None:
+            raise ValueError("this KinshipFactor was closed")
+        if self._h.c0 != int(c0):
+            new = _capi.Handle(self.n, int(c0), self.ctx.device)
+            try:
+                new.copy_eigen_from(self._h)
+            except Exception:
+                new.close()
+                raise
+            self._h.close()
+            self._h = new
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._h.close()
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def factorize(K, Z=None, device=None, c0=1, verbose=0) -> KinshipFactor:
+    """eigh(K) once, on the GPU, for any number of later `pygemma(Y, X, W, factor)` calls (see KinshipFactor).
+    `c0` is a hint (the covariate count of the first call) that saves one handle re-creation."""
+    return KinshipFactor(K, Z=Z, device=device, c0=c0, verbose=verbose)
 
 
 def _log(verbose, msg):
@@ -109,14 +187,29 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
     c0 = W.shape[1]
     if Y.shape[0] != n or W.shape[0] != n:
         raise ValueError(f"shape mismatch: X {X.shape}, Y {Y.shape}, W {W.shape}")
-    K = np.asarray(K, dtype=np.float64)
-    if Z is not None:
-        Z = np.asarray(Z, dtype=np.float64)
-        K = Z @ K @ Z.T  # lmm/lmm.py:124-125
-    if eigen and K.shape != (n, n):
-        raise ValueError(f"K must be ({n}, {n}) when eigen=True, got {K.shape}")
-    if not eigen and K.reshape(-1).shape[0] != n:
-        raise ValueError(f"with eigen=False K must be the ({n},) eigenvalue vector, got {K.shape}")
+    factor = K if isinstance(K, KinshipFactor) else None
+    ctx = factor.ctx if factor is not None else multi.context(device)
+    if factor is not None:
+        if not eigen:
+            raise ValueError("a KinshipFactor holds U: it cannot be combined with eigen=False (pre-rotated inputs)")
+        if Z is not None:
+            raise ValueError("apply Z when factorizing: lmm.factorize(K, Z=Z)")
+        if factor.n != n:
+            raise ValueError(f"the KinshipFactor was built for n={factor.n}, X has {n} samples")
+    else:
+        if eigen:
+            multi.check_backend(ctx)
+        if eigen and ctx.rank != 0:
+            K = None  # only rank 0 decomposes (multi.setup_eigen broadcasts U and d): no float64 copy of K elsewhere
+        else:
+            K = np.asarray(K, dtype=np.float64)
+            if Z is not None:
+                Z = np.asarray(Z, dtype=np.float64)
+                K = Z @ K @ Z.T  # lmm/lmm.py:124-125
+            if eigen and K.shape != (n, n):
+                raise ValueError(f"K must be ({n}, {n}) when eigen=True, got {K.shape}")
+            if not eigen and K.reshape(-1).shape[0] != n:
+                raise ValueError(f"with eigen=False K must be the ({n},) eigenvalue vector, got {K.shape}")
 
     if not disable_checks:
         # lmm/lmm.py:253-256 tests the rotated arrays; a NaN survives (and only arises from) the rotation
@@ -124,12 +217,13 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
         if (X.dtype.kind == "f" and np.isnan(X).any()) or np.isnan(Y).any() or np.isnan(W).any():
             raise ValueError("NaNs present in data")
 
-    ctx = multi.context(device)
     timing = {"n": n, "m": m, "c0": c0, "q": q, "world_size": ctx.world_size}
-    h = _capi.Handle(n, c0, ctx.device)
+    h = factor.handle(c0) if factor is not None else _capi.Handle(n, c0, ctx.device)
     try:
         t0 = time.time()
-        if eigen:
+        if factor is not None:
+            timing["eig_ms"] = 0.0  # done once in lmm.factorize
+        elif eigen:
             _log(verbose, "Starting eigendecomposition...")
             timing["eig_ms"] = multi.setup_eigen(ctx, h, K)
             _log(verbose, f"Eigendecomposition computed - {round(time.time() - t0, 3)} s")
@@ -137,7 +231,8 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
             h.set_eigen(None, K.reshape(-1))
         a, b = ctx.shard(m)  # contiguous SNP range of this rank (SampleIter, lmm/lmm.py:427-434)
         outs = []
-        timing["design_ms"], timing["scan_wall_s"] = 0.0, 0.0
+        timing["design_ms"], timing["scan_wall_s"], timing["gather_s"] = 0.0, 0.0, 0.0
+        res = None
         # traits go through in groups of PG_MAX_TRAITS per pass over the genotypes (one group for lmm.pygemma)
         for q0 in range(0, q, _capi.PG_MAX_TRAITS):
             Yg = Y[:, q0:q0 + _capi.PG_MAX_TRAITS]
@@ -149,16 +244,20 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
             t0 = time.time()
             res = h.scan(X[:, a:b], grid=grid)
             timing["scan"] = res["timing"]
+            t1 = time.time()
             if qg == 1:
                 outs.append(multi.gather_results(ctx, res, m))
             else:
                 outs.extend(multi.gather_results(ctx, {k: v[ph] for k, v in res.items() if k != "timing"}, m)
                             for ph in range(qg))
+            timing["gather_s"] += time.time() - t1
             timing["scan_wall_s"] += time.time() - t0
-        _log(verbose, f"Finished testing {m} SNPs in {round(timing['scan_wall_s'], 3)} s "
-                      f"(device: rotate {res['timing']['rotate_ms']:.1f} ms, REML {res['timing']['reml_ms']:.1f} ms)")
+        if res is not None:
+            _log(verbose, f"Finished testing {m} SNPs in {round(timing['scan_wall_s'], 3)} s "
+                          f"(device: rotate {res['timing']['rotate_ms']:.1f} ms, REML {res['timing']['reml_ms']:.1f} ms)")
     finally:
-        h.close()
+        if factor is None:
+            h.close()
 
     frames = []
     for out in outs:

@@ -64,17 +64,42 @@ def _coll_device(ctx: Context):
     return torch.device(f"cuda:{ctx.device}") if ctx.backend == "nccl" else torch.device("cpu")
 
 
+def check_backend(ctx: Context) -> None:
+    """The eigen broadcast is a device collective: refuse any other backend BEFORE handles or K copies are made."""
+    if ctx.world_size > 1 and ctx.backend != "nccl":
+        raise RuntimeError("multi-GPU eigen broadcast needs the nccl backend (device buffers), "
+                           f"the process group uses {ctx.backend!r}")
+
+
+def agree_on_n(ctx: Context, n):
+    """Rank 0 knows n (it holds K); the others may have been given K=None."""
+    if ctx.world_size == 1:
+        return n
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([int(n) if ctx.rank == 0 else 0], dtype=torch.int64, device=_coll_device(ctx))
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
+# seconds spent in the collectives of the most recent call (bench.py reports them)
+last_collective_s = {"broadcast": 0.0, "gather": 0.0}
+
+
 def setup_eigen(ctx: Context, handle, K) -> float:
-    """Eigendecomposition on rank 0, broadcast of U and d to the other ranks' handles.  Returns syevd ms."""
+    """Eigendecomposition on rank 0, broadcast of U and d to the other ranks' handles.  Returns syevd ms.
+    K is only read on rank 0."""
     if ctx.world_size == 1:
         _, ms = handle.set_kinship(K)
         return ms
+    import time
+
     import torch
     import torch.distributed as dist
 
     n = handle.n
-    if ctx.backend != "nccl":
-        raise RuntimeError("multi-GPU eigen broadcast needs the nccl backend (device buffers)")
+    check_backend(ctx)
     dev = _coll_device(ctx)
     U_t = torch.empty(n * n, dtype=torch.float64, device=dev)
     d_t = torch.empty(n, dtype=torch.float64, device=dev)
@@ -83,9 +108,11 @@ def setup_eigen(ctx: Context, handle, K) -> float:
         _, ms = handle.set_kinship(K)
         handle.get_eigen_device(U_t.data_ptr(), d_t.data_ptr())
     torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
     dist.broadcast(U_t, src=0)
     dist.broadcast(d_t, src=0)
     torch.cuda.synchronize(dev)
+    last_collective_s["broadcast"] = time.perf_counter() - t0
     if ctx.rank != 0:
         handle.set_eigen_device(U_t.data_ptr(), False, d_t.data_ptr())
     del U_t, d_t
@@ -119,10 +146,14 @@ def gather_results(ctx: Context, res: dict, m: int) -> dict:
     import torch
     import torch.distributed as dist
 
+    import time
+
     per = -(-m // ctx.world_size)
     dev = _coll_device(ctx)
+    t0 = time.perf_counter()
     mine = torch.from_numpy(pack_results(res, per)).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(ctx.world_size)]
-    dist.all_gather(parts, mine)
-    blocks = [p.cpu().numpy() for p in parts]
+    allb = torch.empty((ctx.world_size * mine.shape[0], mine.shape[1]), dtype=mine.dtype, device=dev)
+    dist.all_gather_into_tensor(allb, mine)  # rank blocks stacked along dim 0
+    blocks = allb.cpu().numpy().reshape(ctx.world_size, mine.shape[0], mine.shape[1])
+    last_collective_s["gather"] = time.perf_counter() - t0
     return unpack_results(blocks, m, ctx.world_size)
