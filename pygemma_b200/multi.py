@@ -31,8 +31,23 @@ class Context:
         return shard_range(m, self.rank, self.world_size)
 
 
-def shard_range(m: int, rank: int, world: int):
+SHARD_ALIGN = 128  # columns: shard starts stay 128-byte aligned inside an int8 row, so device-resident shards of a
+#                    sample-major matrix can be used in place as TMA / GEMM operands
+
+
+def shard_len(m: int, world: int) -> int:
+    """Columns per rank: ceil(m / world) as in the reference's SampleIter (lmm/lmm.py:429), rounded up to SHARD_ALIGN
+    when every rank still gets work (results do not depend on where the chunk boundaries fall)."""
     per = -(-m // world) if world > 0 else m
+    if world > 1 and per >= SHARD_ALIGN:
+        al = -(-per // SHARD_ALIGN) * SHARD_ALIGN
+        if al * (world - 1) < m:
+            per = al
+    return per
+
+
+def shard_range(m: int, rank: int, world: int):
+    per = shard_len(m, world)
     a = min(rank * per, m)
     b = min((rank + 1) * per, m)
     return a, b
@@ -119,6 +134,39 @@ def setup_eigen(ctx: Context, handle, K) -> float:
     return ms
 
 
+def setup_eigen_from(ctx: Context, handle, U_t, d_t) -> None:
+    """An eigen-system computed elsewhere (rank 0's device tensors: U column-major as n*n doubles, d) broadcast to
+    every rank's handle -- the multi-GPU form of pg_set_eigen_device.  Other ranks pass their own empty tensors."""
+    if ctx.world_size > 1:
+        import time
+
+        import torch
+        import torch.distributed as dist
+
+        check_backend(ctx)
+        dev = _coll_device(ctx)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        dist.broadcast(U_t, src=0)
+        dist.broadcast(d_t, src=0)
+        torch.cuda.synchronize(dev)
+        last_collective_s["broadcast"] = time.perf_counter() - t0
+    handle.set_eigen_device(U_t.data_ptr(), False, d_t.data_ptr())
+
+
+def gather_device(ctx: Context, out_dev, st_dev):
+    """Device-resident form of gather_results: out_dev (6, per) float64 and st_dev (3, per) int32 of every rank are
+    all-gathered into (world * 6, per) / (world * 3, per) tensors on the current stream (rank blocks stacked)."""
+    import torch
+    import torch.distributed as dist
+
+    allo = torch.empty((ctx.world_size * out_dev.shape[0], out_dev.shape[1]), dtype=out_dev.dtype, device=out_dev.device)
+    alls = torch.empty((ctx.world_size * st_dev.shape[0], st_dev.shape[1]), dtype=st_dev.dtype, device=st_dev.device)
+    dist.all_gather_into_tensor(allo, out_dev)
+    dist.all_gather_into_tensor(alls, st_dev)
+    return allo, alls
+
+
 def pack_results(res: dict, per: int) -> np.ndarray:
     """(9, per) float64 block of one rank's rows, NaN / 0 padded to the common shard length."""
     k = res["beta"].shape[0]
@@ -148,7 +196,7 @@ def gather_results(ctx: Context, res: dict, m: int) -> dict:
 
     import time
 
-    per = -(-m // ctx.world_size)
+    per = shard_len(m, ctx.world_size)
     dev = _coll_device(ctx)
     t0 = time.perf_counter()
     mine = torch.from_numpy(pack_results(res, per)).to(dev)

@@ -28,7 +28,8 @@ def _worker(rank, world, port, m, tmpdir):
         ctx = multi.context(device=0)
         assert (ctx.rank, ctx.world_size, ctx.backend) == (rank, world, "gloo")
         a, b = ctx.shard(m)
-        per = -(-m // world)
+        per = multi.shard_len(m, world)
+        assert per == (-(-m // world) if m < 256 else 512)  # small inputs: SampleIter's ceil(m / nproc); else 128-aligned
         assert (a, b) == (min(rank * per, m), min((rank + 1) * per, m))
         # every rank fabricates "its" rows of one global, deterministic result table
         rng = np.random.default_rng(123)
@@ -50,7 +51,7 @@ def _worker(rank, world, port, m, tmpdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("m", [11, 64, 1])
+@pytest.mark.parametrize("m", [11, 64, 1, 1000])
 def test_world_size_2_gloo_shard_and_gather(m, tmp_path):
     import torch.multiprocessing as mp
 

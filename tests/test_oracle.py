@@ -124,3 +124,24 @@ def test_oracle_eval_counts_match_survey():
     assert 20 <= tot.mean() <= 32
     og = oracle.scan_rotated(g["d"], g["yr"], g["wr"], xt, grid=True)
     assert (og["n_eval2"] == 13).all() and (og["n_eval3"] == 0).all()
+
+
+def test_oracle_stays_inside_the_float32_reference_noise():
+    """ref32 (the literal float32 reference) vs the float64 oracle on the whole-call goldens: the documented noise of the
+    reference's float32 storage bounds the deviation; p-values rank identically."""
+    import glob
+    import os
+
+    from scipy import stats
+
+    from conftest import COLS, GOLDEN
+    from oracle import oracle
+
+    bounds = {"beta": 5e-3, "se_beta": 1e-4, "tau": 1e-4, "lambda": 1e-3, "F_wald": 1e-2, "p_wald": 2e-3}
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "e2e_*.npz"))):
+        g = np.load(path)
+        o = oracle.pygemma(g["Y"], g["X"], g["W"], g["K"], grid=bool(g["grid"]))
+        for c in COLS:
+            e = np.abs(o[c] - g[f"r32_{c}"]) / np.maximum(np.abs(g[f"r32_{c}"]), 1e-300)
+            assert e.max() < bounds[c], (path, c, float(e.max()))
+        assert stats.spearmanr(o["p_wald"], g["r32_p_wald"]).statistic > 0.9999
