@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 3
+#define PG_ABI_VERSION 4
 
 typedef struct pg_handle pg_handle;
 
@@ -76,6 +76,17 @@ typedef enum {
     PG_REML_STREAM = 2,     /* optimiser streams the full rotated genotype vector on every evaluation (CTA lock step) */
     PG_REML_WARP = 3        /* as STREAM, one independent warp per SNP (cross-check engine) */
 } pg_reml_engine;
+
+/* what a scanned column is (pg_set_scan_mode) */
+typedef enum {
+    PG_SCAN_WALD = 0, /* default: the column is the tested regressor x, the design's y the phenotype (lmm/lmm.py:461 calculate) */
+    PG_SCAN_DE = 1    /* "differential expression": the column is the PHENOTYPE and the design's y the tested regressor --
+                         the reference's de=True / calculate_de (lmm/lmm.py:498-532): lambda from
+                         calc_lambda_restricted(d, X[:, g], [W, Y]), beta / se / tau from
+                         calc_beta_vg_ve_restricted_overload(d, W, Y, lambda, X[:, g]).  (The reference's own driver raises before
+                         reaching it -- SampleIter yields a 5-tuple, lmm/lmm.py:434, calculate_de unpacks 4, :499 -- this is the
+                         computation those lines spell out.) */
+} pg_scan_mode;
 
 /* device-side timings of the last pg_scan call, milliseconds (CUDA events) */
 typedef struct {
@@ -183,6 +194,9 @@ int pg_set_options(pg_handle* h, int rotation, int64_t block_snps);
  * (experiments/wtccc/run_pygemma.py:432).  Default: count_a1 = 0, standardize = 0.
  */
 int pg_set_bed_options(pg_handle* h, int count_a1, int standardize);
+/* Role of the scanned columns for every later pg_scan / pg_scan_device (default PG_SCAN_WALD); PG_SCAN_DE needs the
+ * compressed REML engine.  Outputs keep their names: beta / se_beta are the effect of y on each column. */
+int pg_set_scan_mode(pg_handle* h, int mode);
 /* REML stage engine selection (default PG_REML_AUTO); all engines give the same results to rounding */
 int pg_set_reml_engine(pg_handle* h, int engine);
 

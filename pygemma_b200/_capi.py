@@ -17,13 +17,14 @@ PG_X_I8, PG_X_F32, PG_X_F64, PG_X_BED = 0, 1, 2, 3
 PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1
 PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT, PG_ROT_I8TC = 0, 1, 2, 3
 PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
+PG_SCAN_WALD, PG_SCAN_DE = 0, 1
 PG_MAX_TRAITS = 64  # traits per pass of pg_set_design_multi (include/pygemma_b200.h)
 
 # every symbol include/pygemma_b200.h declares (tests check the library exports each one)
 SYMBOLS = [
     "pg_abi_version", "pg_rotation_planes", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_copy_eigen", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
-    "pg_set_reml_engine", "pg_grm", "pg_set_bed_options",
+    "pg_set_reml_engine", "pg_set_scan_mode", "pg_grm", "pg_set_bed_options",
     "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
 
@@ -77,6 +78,7 @@ def load():
     L.pg_set_options.argtypes = [vp, i32, i64]
     L.pg_set_stream.argtypes = [vp, vp]
     L.pg_set_reml_engine.argtypes = [vp, i32]
+    L.pg_set_scan_mode.argtypes = [vp, i32]
     L.pg_set_bed_options.argtypes = [vp, i32, i32]
     L.pg_grm.argtypes = [vp, vp, i32, i64, i32, i64, vp, i32, vp, ctypes.POINTER(ctypes.c_float),
                          ctypes.POINTER(ctypes.c_float)]
@@ -220,6 +222,10 @@ class Handle:
 
     def set_reml_engine(self, engine=PG_REML_AUTO):
         self._ck(self.L.pg_set_reml_engine(self.h, int(engine)))
+
+    def set_scan_mode(self, mode=PG_SCAN_WALD):
+        """PG_SCAN_DE: scanned columns are phenotypes, the design's y is the tested regressor (reference de=True)."""
+        self._ck(self.L.pg_set_scan_mode(self.h, int(mode)))
 
     # --- scan --------------------------------------------------------------------------------
     def scan(self, X, grid=False, layout=PG_X_SAMPLE_MAJOR, with_counts=True):

@@ -31,6 +31,7 @@ struct pg_handle {
     long long ldw = 0;  // padded leading dimension of d / wy (multiple of kTile, zero-filled)
     long long ldx = 0;  // padded row length of the rotated genotype block (multiple of 16, zero-filled)
     int engine = PG_REML_AUTO;  // REML stage engine (pg_set_reml_engine / env PG_REML_ENGINE)
+    int scan_mode = PG_SCAN_WALD;  // pg_set_scan_mode
     int sm_count = 148;
     std::string err;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -807,6 +808,14 @@ extern "C" int pg_set_bed_options(pg_handle* h, int count_a1, int standardize)
     return PG_OK;
 }
 
+extern "C" int pg_set_scan_mode(pg_handle* h, int mode)
+{
+    if (!h) return PG_ERR_ARG;
+    if (mode != PG_SCAN_WALD && mode != PG_SCAN_DE) return fail(h, PG_ERR_ARG, "pg_set_scan_mode: mode %d", mode);
+    h->scan_mode = mode;
+    return PG_OK;
+}
+
 extern "C" int pg_set_reml_engine(pg_handle* h, int engine)
 {
     if (!h) return PG_ERR_ARG;
@@ -969,7 +978,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
         sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
-        sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph; sa.F = Fbuf;
+        sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph; sa.F = Fbuf; sa.swap = (h->scan_mode == PG_SCAN_DE) ? 1 : 0;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
@@ -1075,6 +1084,8 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     if (xdtype < PG_X_I8 || xdtype > PG_X_BED) return fail(h, PG_ERR_ARG, "pg_scan: xdtype %d", xdtype);
     if (layout != PG_X_SAMPLE_MAJOR && layout != PG_X_SNP_MAJOR) return fail(h, PG_ERR_ARG, "pg_scan: layout %d", layout);
     if (!h->have_design) return fail(h, PG_ERR_ARG, "pg_scan: call pg_set_design first");
+    if (h->scan_mode == PG_SCAN_DE && !(h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED))
+        return fail(h, PG_ERR_ARG, "pg_scan: PG_SCAN_DE runs on the compressed REML engine only");
     const int n = h->n;
     const bool bed = xdtype == PG_X_BED;
     if (bed && layout != PG_X_SNP_MAJOR) return fail(h, PG_ERR_ARG, "pg_scan: PLINK .bed data is SNP-major");
@@ -1544,7 +1555,7 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
         }
         SolveArgs sa{};
         sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
-        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.F = nullptr;
+        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.F = nullptr; sa.swap = 0;
         const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);
         const bool two = (h->c0 + 2) > 32;
         if (smemc > 48 * 1024) {

@@ -290,12 +290,21 @@ PG_HD void xrow_final_level(const double* fin, double app, double bpp, double cp
 }
 
 // scalar form (host tests, probes): xa/xb/xc hold the level-0 x row, entries j < c0: x.w_j, c0: x.y, c0+1: x.x
+// Role swap ("de" mode, reference lmm/lmm.py:498-532 calculate_de): the per-column vector x is the PHENOTYPE and the
+// fixed column y the tested regressor, i.e. the reference's W_star is [W0, y, x].  The covariate levels are the same;
+// the last pivot is (y, y) -- clamped like every pivot diagonal (pyx:953,:961,:1016; only A at c0 = 0, pyx:939) -- and the
+// x diagonal, which is no pivot now, is clamped only after that level (pyx:961 at i = c).  xPx / yPx of EvalOut then hold
+// (y, y) and (x, y) at level c0 and yPy.. the x diagonal at level c0 + 1, so SnpSolver::finish gives the effect of y on x.
+template <bool FULL>
+PG_HD void xrow_final_level_swapped(int c0, const double* fin, double xxa, double xxb, double xxc, double ar, double br,
+                                    double cr, bool need_logdet, EvalOut* out);
+
 template <bool FULL>
 PG_HD_NOINLINE void xrow_recursion_scalar(int c0, const double* row2, double* xa, double* xb, double* xc,
-                                          bool need_logdet, EvalOut* out)
+                                          bool need_logdet, EvalOut* out, bool swap = false)
 {
     const int Tp = t2_pairs(c0), dg = c0 + 1;
-    if (c0 == 0) xa[dg] = cy_max(xa[dg], kMinVal);
+    if (c0 == 0 && !swap) xa[dg] = cy_max(xa[dg], kMinVal);
     for (int p = 0; p < c0; ++p) {
         const double al2 = row2[3 * p], al4 = row2[3 * p + 1], alc = row2[3 * p + 2];
         const double ar = xa[p], br = xb[p], cr = xc[p];
@@ -305,7 +314,7 @@ PG_HD_NOINLINE void xrow_recursion_scalar(int c0, const double* row2, double* xa
                 const int q = t2_col(c0, p, j);
                 as = row2[q]; bs = row2[Tp + q]; cs = row2[2 * Tp + q];
             }
-            const bool clamp = (p == c0 - 1 && j == dg);
+            const bool clamp = (p == c0 - 1 && j == dg) && !swap;
             if (FULL) {
                 double v = (xc[j] + alc * ar * as) + al2 * (ar * cs + cr * as) + al2 * (br * bs) + al4 * (ar * bs + br * as);
                 if (clamp) v = cy_max(v, kMinVal);
@@ -319,8 +328,23 @@ PG_HD_NOINLINE void xrow_recursion_scalar(int c0, const double* row2, double* xa
             xa[j] = v;
         }
     }
-    xrow_final_level<FULL>(row2 + t2_fin(c0), xa[dg], xb[dg], FULL ? xc[dg] : 0.0, xa[c0], xb[c0], FULL ? xc[c0] : 0.0,
-                           need_logdet, out);
+    if (swap)
+        xrow_final_level_swapped<FULL>(c0, row2 + t2_fin(c0), xa[dg], xb[dg], FULL ? xc[dg] : 0.0, xa[c0], xb[c0],
+                                       FULL ? xc[c0] : 0.0, need_logdet, out);
+    else
+        xrow_final_level<FULL>(row2 + t2_fin(c0), xa[dg], xb[dg], FULL ? xc[dg] : 0.0, xa[c0], xb[c0], FULL ? xc[c0] : 0.0,
+                               need_logdet, out);
+}
+
+template <bool FULL>
+PG_HD void xrow_final_level_swapped(int c0, const double* fin, double xxa, double xxb, double xxc, double ar, double br,
+                                    double cr, bool need_logdet, EvalOut* out)
+{
+    const double ya = cy_max(fin[0], kMinVal);
+    const double yb = c0 ? cy_max(fin[1], kMinVal) : fin[1];
+    const double yc = c0 ? cy_max(fin[2], kMinVal) : fin[2];
+    const double fin2[7] = {xxa, xxb, xxc, fin[3], fin[4], fin[5], fin[6]};
+    xrow_final_level<FULL>(fin2, ya, yb, yc, ar, br, cr, need_logdet, out);
 }
 
 // Chebyshev weights L[k] of `lam` inside its table interval (shared by both table kinds)

@@ -31,6 +31,7 @@ struct SolveArgs {
     int zrows;            // rows per SNP slab: k1p - 1 + number of phenotypes
     int yrow;             // slab row of this launch's phenotype (k1p - 1 + phenotype index)
     const double* F;      // [m][zrows][kFxCols] x rows of the fixed-lambda evaluations (fixed_xrow_kernel), or nullptr
+    int swap;             // 1: "de" mode, the genotype column is the phenotype and y the tested regressor (pg_eval.cuh)
     Tables2 t2;
     double* out[6];
     int* status;
@@ -231,10 +232,11 @@ __device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __
 // Pivot values travel by shuffle, pivot columns and level scalars come from the table-2 row (pg_eval.cuh).
 template <bool FULL, int NS>
 __device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __restrict__ row2, double (&xa)[NS],
-                                                    double (&xb)[NS], double (&xc)[NS], bool need_logdet, EvalOut* out)
+                                                    double (&xb)[NS], double (&xc)[NS], bool need_logdet, EvalOut* out,
+                                                    bool swap)
 {
     const int lane = threadIdx.x & 31, Tp = t2_pairs(c0), dg = c0 + 1;
-    if (c0 == 0 && lane == 1) xa[0] = cy_max(xa[0], kMinVal);  // pyx:939 / :993 hits (x,x) without covariates
+    if (c0 == 0 && lane == 1 && !swap) xa[0] = cy_max(xa[0], kMinVal);  // pyx:939 / :993 hits (x,x) without covariates
     auto pick = [&](const double (&x)[NS], int slot) -> double {
         if (NS == 1) return x[0];
         return slot ? x[NS - 1] : x[0];
@@ -255,7 +257,7 @@ __device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __rest
                     as = row2[cb + j]; bs = row2[Tp + cb + j];
                     if (FULL) cs = row2[2 * Tp + cb + j];
                 }
-                const bool clamp = (p == c0 - 1) && (j == dg);
+                const bool clamp = (p == c0 - 1) && (j == dg) && !swap;   // de mode: x is no pivot (pg_eval.cuh)
                 if (FULL) {
                     double v = (xc[q] + alc * ar * as) + al2 * (ar * cs + cr * as) + al2 * (br * bs) + al4 * (ar * bs + br * as);
                     if (clamp) v = cy_max(v, kMinVal);
@@ -276,7 +278,8 @@ __device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __rest
     const double ar = __shfl_sync(0xffffffffu, pick(xa, c0 >> 5), c0 & 31);
     const double br = __shfl_sync(0xffffffffu, pick(xb, c0 >> 5), c0 & 31);
     const double cr = FULL ? __shfl_sync(0xffffffffu, pick(xc, c0 >> 5), c0 & 31) : 0.0;
-    xrow_final_level<FULL>(row2 + t2_fin(c0), app, bpp, cpp, ar, br, cr, need_logdet, out);
+    if (swap) xrow_final_level_swapped<FULL>(c0, row2 + t2_fin(c0), app, bpp, cpp, ar, br, cr, need_logdet, out);
+    else xrow_final_level<FULL>(row2 + t2_fin(c0), app, bpp, cpp, ar, br, cr, need_logdet, out);
 }
 
 // One precompute_mat-equivalent evaluation from the compressed moments (warp-collective).
@@ -344,8 +347,8 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
             xc[q] = (in && full) ? xs[2 * k1p + r] : 0.0;
         }
     }
-    if (full) xrow_recursion_warp<true, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
-    else xrow_recursion_warp<false, NS>(c0, row2, xa, xb, xc, need_ll != 0, e);
+    if (full) xrow_recursion_warp<true, NS>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
+    else xrow_recursion_warp<false, NS>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
     __syncwarp();
 }
 

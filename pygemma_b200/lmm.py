@@ -15,8 +15,9 @@ Extension: `F = lmm.factorize(K)` decomposes once and `lmm.pygemma(Y, X, W, F)` 
 
 Differences from the reference, all documented in DESIGN.md: arithmetic is float64 throughout (the
 reference mixes float32 storage into a float64 core), so every returned column is float64; `nproc` is
-accepted and ignored (parallelism is the GPU, or several GPUs under torch.distributed); `de=True`
-raises (it raises in the reference too: lmm/lmm.py:499 unpacks a 5-tuple into 4 names).
+accepted and ignored (parallelism is the GPU, or several GPUs under torch.distributed); `de=True` runs the
+role-swapped scan that calculate_de spells out (lmm/lmm.py:498-532: each column of X is the outcome, Y the predictor) --
+the reference's own driver raises before reaching it (lmm/lmm.py:499 unpacks SampleIter's 5-tuple into 4 names).
 There is no CPU fallback: without the CUDA library or a GPU the call raises.
 """
 from __future__ import annotations
@@ -33,9 +34,6 @@ COLUMNS = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
 # timings of the most recent call (seconds / milliseconds), for callers that want them without verbose
 last_timing: dict = {}
 
-
-class DifferentialExpressionUnsupported(NotImplementedError, ValueError):
-    """de=True: broken in the reference (ValueError from lmm/lmm.py:499), not provided here."""
 
 
 def _as_genotypes(X):
@@ -146,7 +144,8 @@ def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=Fa
     column supplied by the caller; K (n, n) relatedness matrix, or the (n,) eigenvalue vector when
     eigen=False (then Y, X, W are taken as already rotated, lmm/lmm.py:164-167); Z: K <- Z K Z^T;
     snps: labels for the 'SNPs' column; grid: 12-point grid search for lambda instead of
-    Brent + Newton.  `device` (extension) selects the CUDA device; default 0 or the
+    Brent + Newton; de: differential-expression mode (X columns are outcomes, Y the predictor; grid is not
+    forwarded, as in lmm/lmm.py:504).  `device` (extension) selects the CUDA device; default 0 or the
     torch.distributed local rank.
     """
     Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)  # lmm/lmm.py:115-116
@@ -173,8 +172,11 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
     global last_timing
     t_start = time.time()
     if de:
-        raise DifferentialExpressionUnsupported(
-            "de=True is not supported (the reference's calculate_de raises ValueError at lmm/lmm.py:499)")
+        # calculate_de (lmm/lmm.py:498-532): every column of X is a phenotype, Y the tested regressor; it calls
+        # calc_lambda_restricted without `grid` (:504), i.e. always Brent + Newton
+        if Y.shape[1] != 1:
+            raise ValueError("de=True takes one predictor Y")
+        grid = False
 
     from . import multi  # torch.distributed plumbing, only active when a process group exists
 
@@ -229,6 +231,7 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
             _log(verbose, f"Eigendecomposition computed - {round(time.time() - t0, 3)} s")
         else:
             h.set_eigen(None, K.reshape(-1))
+        h.set_scan_mode(_capi.PG_SCAN_DE if de else _capi.PG_SCAN_WALD)
         a, b = ctx.shard(m)  # contiguous SNP range of this rank (SampleIter, lmm/lmm.py:427-434)
         outs = []
         timing["design_ms"], timing["scan_wall_s"], timing["gather_s"] = 0.0, 0.0, 0.0

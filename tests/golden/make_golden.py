@@ -167,6 +167,42 @@ def make_e2e(lmm32, lmm64):
         print(f"e2e_{name}: lambda med {np.median(r64['lambda']):.4g}")
 
 
+def make_de(lmm32, lmm64):
+    """de=True: calculate_de (lmm/lmm.py:498-532) cannot be run as written -- its driver passes SampleIter's 5-tuple
+    (lmm/lmm.py:499 vs :434) and it hands calc_lambda_restricted a 1-D X[:, g] where the cpdef demands (n, 1) (:504,
+    pyx:61).  The goldens are made with the two cpdefs it calls, in its roles, with that one reshape:
+        lambda = calc_lambda_restricted(d, X[:, g].reshape(-1, 1), np.c_[W, Y])
+        beta, _, se, tau = calc_beta_vg_ve_restricted_overload(d, W, Y, lambda, X[:, g].reshape(-1, 1))
+    and F_wald / p_wald as at lmm/lmm.py:507-519."""
+    from scipy import stats
+
+    from pygemma_b200.synth import make_problem
+    from oracle import oracle
+
+    n, m, c0 = 300, 40, 3
+    p = make_problem(n, m, c0, seed=51, h2=0.5, m_k=100)
+    rng = np.random.default_rng(7)
+    pred = p["X"][:, 4].astype(np.float64)
+    E = rng.standard_normal((n, m)) + 0.2 * pred[:, None] * (np.arange(m) % 2 == 0) + 0.4 * p["Y"]
+    d, U, yr, xr, wr = oracle.eigen_rotate(p["K"], pred, E, p["W"])
+    out = {"d": d, "yr": yr.reshape(-1), "wr": wr, "xr": xr}
+    for tag, lmm, dt in (("r64", lmm64, np.float64), ("r32", lmm32, np.float32)):
+        dd, Y, W, X = d.astype(dt), yr.astype(dt).reshape(-1, 1), np.ascontiguousarray(wr.astype(dt)), np.ascontiguousarray(xr.astype(dt))
+        rows = {c: [] for c in COLS}
+        with np.errstate(all="ignore"):
+            for g in range(m):
+                xg = np.ascontiguousarray(X[:, g].reshape(-1, 1))
+                lam = lmm.calc_lambda_restricted(dd, xg, np.c_[W, Y])
+                beta, _, se, tau = lmm.calc_beta_vg_ve_restricted_overload(dd, W, Y, lam, xg)
+                F = np.float64(beta / se) ** 2.0
+                for c, v in zip(COLS, (beta, se, tau, lam, F, stats.f.sf(x=F, dfn=1, dfd=n - c0 - 1))):
+                    rows[c].append(float(v))
+        for c in COLS:
+            out[f"{tag}_{c}"] = np.array(rows[c])
+    np.savez_compressed(os.path.join(HERE, "de_small.npz"), **out)
+    print("de_small: lambda med", np.median(out["r64_lambda"]), "beta[:4]", out["r64_beta"][:4])
+
+
 if __name__ == "__main__":
     from oracle import build_ref
 
@@ -174,6 +210,7 @@ if __name__ == "__main__":
     from pygemma import lmm as lmm32
     from pygemma64 import lmm as lmm64
 
-    make_kat(lmm32, lmm64)
-    make_scans(lmm32, lmm64)
-    make_e2e(lmm32, lmm64)
+    only = sys.argv[1:]   # e.g. `make_golden.py de` regenerates one family
+    for name, fn in (("kat", make_kat), ("scans", make_scans), ("e2e", make_e2e), ("de", make_de)):
+        if not only or name in only:
+            fn(lmm32, lmm64)

@@ -332,3 +332,44 @@ def test_literal_float32_reference_is_tracked():
             e = rel(df[c].to_numpy(), g[f"r32_{c}"])
             assert e.max() < bounds[c], (path, c, float(e.max()))
         assert stats.spearmanr(df["p_wald"].to_numpy(), g["r32_p_wald"]).statistic > 0.9999
+
+
+def _oracle_de(d, Yr, Wr, Xr):
+    """calculate_de (reference lmm/lmm.py:498-532) on rotated float64 inputs via the oracle: per column g the phenotype is
+    X[:, g] and the tested regressor Y -- calc_lambda_restricted(d, X[:, g], [W, Y]) then
+    calc_beta_vg_ve_restricted_overload(d, W, Y, lambda, X[:, g])."""
+    from oracle import oracle
+
+    out = {c: [] for c in COLS}
+    yrow = np.ascontiguousarray(np.asarray(Yr, float).reshape(1, -1))
+    for g in range(Xr.shape[1]):
+        r = oracle.scan_rotated(d, Xr[:, g], Wr, yrow)
+        for c in COLS:
+            out[c].append(r[c][0])
+    return {c: np.array(v) for c, v in out.items()}
+
+
+def test_de_mode_is_the_role_swapped_scan():
+    """de=True: each column of X is an outcome (real-valued, FP64 rotation), Y the predictor."""
+    from oracle import oracle
+    from pygemma_b200 import lmm
+    from pygemma_b200.synth import make_problem
+
+    n, m, c0 = 700, 96, 4
+    p = make_problem(n, m, c0, seed=44, m_k=1500)
+    rng = np.random.default_rng(3)
+    pred = p["X"][:, 5].astype(np.float64)                      # the predictor: one SNP's dosages
+    E = rng.standard_normal((n, m)) + 0.15 * pred[:, None] * (np.arange(m) % 3 == 0) + p["Y"] * 0.3   # "expression" columns
+    for c0_use in (c0, 0):
+        W = p["W"][:, :c0_use]
+        df = lmm.pygemma(pred, E, W, p["K"], de=True, snps=np.arange(m))
+        assert list(df.columns) == COLS + ["SNPs"] and len(df) == m
+        d, U, yr, xr, wr = oracle.eigen_rotate(p["K"], pred, E, W if c0_use else np.zeros((n, 0)))
+        ref = _oracle_de(d, yr.reshape(-1), wr.reshape(n, c0_use), xr)
+        _check({c: df[c].to_numpy() for c in COLS}, ref, tag=("de", c0_use))
+    # the golden vectors made by the reference's own cpdefs called with swapped roles (tests/golden/make_golden.py)
+    path = os.path.join(GOLDEN, "de_small.npz")
+    if os.path.exists(path):
+        g = np.load(path)
+        df = lmm.pygemma(g["yr"], g["xr"], g["wr"], g["d"], eigen=False, de=True)
+        _check({c: df[c].to_numpy() for c in COLS}, {c: g[f"r64_{c}"] for c in COLS}, tag="de golden")

@@ -106,10 +106,14 @@ def test_brent_state_machine_is_scipy_brentq():
 
 
 def test_shard_range_is_sampleiter():
-    """multi.shard_range reproduces SampleIter's chunking (reference lmm/lmm.py:427-434)."""
-    for m in (1, 7, 100, 101, 12226):
+    """multi.shard_range reproduces SampleIter's chunking (reference lmm/lmm.py:427-434): contiguous chunks of
+    ceil(m / nproc) columns in rank order -- rounded up to 128 columns once chunks are that long, so that device-resident
+    shards start on aligned columns (results do not depend on the chunk boundaries)."""
+    for m in (1, 7, 100, 101, 12226, 100000):
         for world in (1, 2, 3, 8):
-            per = int(np.ceil(m / world))
+            per = multi.shard_len(m, world)
+            ceil = int(np.ceil(m / world))
+            assert per == ceil or (world > 1 and ceil >= 128 and per % 128 == 0 and 0 <= per - ceil < 128)
             cover = []
             for r in range(world):
                 a, b = multi.shard_range(m, r, world)
@@ -138,10 +142,6 @@ def test_pygemma_argument_contract():
 
     n, m = 20, 5
     Y, X, W, K = np.zeros(n), np.zeros((n, m), dtype=np.int8), np.ones((n, 1)), np.eye(n)
-    with pytest.raises(ValueError):
-        lmm.pygemma(Y, X, W, K, de=True)
-    with pytest.raises(NotImplementedError):
-        lmm.pygemma(Y, X, W, K, de=True)
     with pytest.raises(ValueError):
         lmm.pygemma(Y[:-1], X, W, K)
     with pytest.raises(ValueError):
@@ -172,6 +172,9 @@ def test_pygemma_multi_groups_traits_and_keeps_order(monkeypatch):
         def set_eigen(self, U, d):
             pass
 
+        def set_scan_mode(self, mode=0):
+            calls.append(("mode", mode))
+
         def set_design(self, W, y, already_rotated=False):
             y = np.asarray(y)
             self.q = y.shape[1] if y.ndim == 2 else 1
@@ -201,7 +204,7 @@ def test_pygemma_multi_groups_traits_and_keeps_order(monkeypatch):
     Y = np.tile(np.arange(q, dtype=np.float64), (n, 1))      # trait t is the constant t
     X, W, K = np.zeros((n, m), dtype=np.int8), np.ones((n, 1)), np.eye(n)
     frames = lmm.pygemma_multi(Y, X, W, K, snps=[f"rs{i}" for i in range(m)])
-    assert calls == [("design", _capi.PG_MAX_TRAITS), ("scan", _capi.PG_MAX_TRAITS), ("design", 5), ("scan", 5)]
+    assert calls == [("mode", 0), ("design", _capi.PG_MAX_TRAITS), ("scan", _capi.PG_MAX_TRAITS), ("design", 5), ("scan", 5)]
     assert len(frames) == q
     for t, df in enumerate(frames):
         assert list(df.columns) == lmm.COLUMNS + ["SNPs"] and len(df) == m
@@ -209,7 +212,10 @@ def test_pygemma_multi_groups_traits_and_keeps_order(monkeypatch):
         assert df.iloc[1][lmm.COLUMNS].isna().all() and not df.iloc[0][lmm.COLUMNS].isna().any()
     calls.clear()
     one = lmm.pygemma(Y[:, 3], X, W, K)
-    assert calls == [("design", 1), ("scan", 1)] and one["beta"].iloc[0] == 3.0
+    assert calls == [("mode", 0), ("design", 1), ("scan", 1)] and one["beta"].iloc[0] == 3.0
+    calls.clear()
+    lmm.pygemma(Y[:, 3], X, W, K, de=True, grid=True)   # de: role-swapped scan, grid not forwarded (lmm/lmm.py:504)
+    assert calls[0] == ("mode", _capi.PG_SCAN_DE)
 
 
 # ---- eigenvalue-space compression (pygemma_b200/csrc/compress_plan.h) ----------------------------------

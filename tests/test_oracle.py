@@ -145,3 +145,20 @@ def test_oracle_stays_inside_the_float32_reference_noise():
             e = np.abs(o[c] - g[f"r32_{c}"]) / np.maximum(np.abs(g[f"r32_{c}"]), 1e-300)
             assert e.max() < bounds[c], (path, c, float(e.max()))
         assert stats.spearmanr(o["p_wald"], g["r32_p_wald"]).statistic > 0.9999
+
+
+def test_oracle_de_mode_matches_reference_cpdefs():
+    """de=True (lmm/lmm.py:498-532): the oracle with swapped roles against the reference's cpdefs called in calculate_de's
+    roles (tests/golden/de_small.npz, made by make_golden.py de)."""
+    import os
+
+    from conftest import COLS, GOLDEN
+    from oracle import oracle
+
+    g = np.load(os.path.join(GOLDEN, "de_small.npz"))
+    m = g["xr"].shape[1]
+    yrow = np.ascontiguousarray(g["yr"].reshape(1, -1))
+    for j in range(m):
+        r = oracle.scan_rotated(g["d"], g["xr"][:, j], g["wr"], yrow)
+        for c in COLS:
+            assert rel(r[c][0], g[f"r64_{c}"][j]) < (1e-7 if c == "lambda" else 1e-9), (j, c)
