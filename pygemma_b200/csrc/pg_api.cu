@@ -1046,21 +1046,8 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
     return PG_OK;
 }
 
-// Packs the strided host block (rows of `width` bytes, `rows` of them, source pitch `pitch`) into dst, contiguously.
-static void pack_block_threads(char* dst, const char* src, size_t pitch, size_t width, size_t rows)
-{
-    const unsigned hw = std::thread::hardware_concurrency();
-    const size_t nt = std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(hw ? hw : 4), rows}));
-    auto work = [=](size_t t) {
-        const size_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
-        for (size_t r = r0; r < r1; ++r) memcpy(dst + r * width, src + r * pitch, width);
-    };
-    if (nt == 1 || width * rows < (size_t(1) << 22)) { for (size_t t = 0; t < nt; ++t) work(t); return; }
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& x : th) x.join();
-}
+// host_pack.cpp: packs a strided host block into a pinned bounce buffer (host threads, streaming stores)
+namespace pg { void pack_block_threads(char* dst, const char* src, size_t pitch, size_t width, size_t rows); }
 
 static bool host_pointer_is_pinned(const void* p)
 {
