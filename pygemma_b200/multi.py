@@ -187,21 +187,53 @@ def unpack_results(blocks, m: int, world: int) -> dict:
     return out
 
 
+_gather_cache: dict = {}
+
+
+def _gather_buffers(ctx: Context, rows: int, per: int):
+    """Pinned host staging + device buffers of one gather shape, kept across calls (a pageable round trip of the
+    9 x m table costs several ms per call; the scan of an 8-GPU shard takes about as long)."""
+    import torch
+
+    key = (ctx.device, ctx.world_size, rows, per, ctx.backend)
+    buf = _gather_cache.get(key)
+    if buf is None:
+        _gather_cache.clear()
+        dev = _coll_device(ctx)
+        pin = ctx.backend == "nccl"
+        buf = {"mine_h": torch.empty((rows, per), dtype=torch.float64, pin_memory=pin),
+               "all_h": torch.empty((ctx.world_size * rows, per), dtype=torch.float64, pin_memory=pin),
+               "mine_d": torch.empty((rows, per), dtype=torch.float64, device=dev),
+               "all_d": torch.empty((ctx.world_size * rows, per), dtype=torch.float64, device=dev)}
+        _gather_cache[key] = buf
+    return buf
+
+
 def gather_results(ctx: Context, res: dict, m: int) -> dict:
     """All ranks end up with all m rows, in input order."""
     if ctx.world_size == 1:
         return res
+    import time
+
     import torch
     import torch.distributed as dist
 
-    import time
-
     per = shard_len(m, ctx.world_size)
-    dev = _coll_device(ctx)
     t0 = time.perf_counter()
-    mine = torch.from_numpy(pack_results(res, per)).to(dev)
-    allb = torch.empty((ctx.world_size * mine.shape[0], mine.shape[1]), dtype=mine.dtype, device=dev)
-    dist.all_gather_into_tensor(allb, mine)  # rank blocks stacked along dim 0
-    blocks = allb.cpu().numpy().reshape(ctx.world_size, mine.shape[0], mine.shape[1])
+    buf = _gather_buffers(ctx, len(RESULT_KEYS), per)
+    mine = buf["mine_h"].numpy()
+    k = res["beta"].shape[0]
+    mine[:, k:] = np.nan
+    for i, key in enumerate(RESULT_KEYS):
+        mine[i, :k] = res[key] if key in res else 0
+    if ctx.backend == "nccl":
+        buf["mine_d"].copy_(buf["mine_h"], non_blocking=True)
+        dist.all_gather_into_tensor(buf["all_d"], buf["mine_d"])  # rank blocks stacked along dim 0
+        buf["all_h"].copy_(buf["all_d"], non_blocking=True)
+        torch.cuda.current_stream(buf["all_d"].device).synchronize()
+    else:
+        dist.all_gather_into_tensor(buf["all_h"], buf["mine_h"])
+    blocks = buf["all_h"].numpy().reshape(ctx.world_size, len(RESULT_KEYS), per)
+    out = unpack_results(blocks, m, ctx.world_size)
     last_collective_s["gather"] = time.perf_counter() - t0
-    return unpack_results(blocks, m, ctx.world_size)
+    return out

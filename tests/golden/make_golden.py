@@ -203,6 +203,38 @@ def make_de(lmm32, lmm64):
     print("de_small: lambda med", np.median(out["r64_lambda"]), "beta[:4]", out["r64_beta"][:4])
 
 
+def make_lrt(lmm32, lmm64):
+    """Likelihood-ratio outputs (commented out in the reference driver, lmm/lmm.py:137-141,:176-190,:278-300): the live
+    functions those lines call -- lmm.calc_lambda (ML lambda: lmm/lmm.py:22-84), likelihood_lambda (pyx:1542) -- run on
+    rotated inputs for the null model [W] and for every alternative [W, x_g]:
+        D_lrt = 2 (l_alt - l_null),  p_lrt = 1 - chi2.cdf(D_lrt, 1)          (lmm/lmm.py:282,:300)
+    (likelihood(lam, tau = n / yPy, beta_hat, ...) of lmm/lmm.py:189,:281 equals likelihood_lambda(lam, ...) identically.)"""
+    from scipy import stats
+
+    cases = [("lrt_interior", 300, 40, 3, 61, 0.5, 100), ("lrt_low_h2", 260, 32, 2, 62, 0.05, 80), ("lrt_c8", 400, 24, 8, 63, 0.7, 150)]
+    for name, n, m, c0, seed, h2, m_k in cases:
+        d, yr, wr, xr = _rot_problem(n, m, c0, seed, h2, m_k)
+        out = {"d": d, "yr": yr, "wr": wr, "xr": xr}
+        for tag, lmm, dt in (("r64", lmm64, np.float64), ("r32", lmm32, np.float32)):
+            dd, Y, W, X = d.astype(dt), yr.astype(dt).reshape(-1, 1), np.ascontiguousarray(wr.astype(dt)), xr.astype(dt)
+            with np.errstate(all="ignore"):
+                lam0 = lmm.calc_lambda(dd, Y, W)
+                l0 = float(lmm.likelihood_lambda(lam0, dd, Y, W))
+                lam_a, l_a = [], []
+                for g in range(m):
+                    Wx = np.ascontiguousarray(np.c_[W, X[:, g]])
+                    la = lmm.calc_lambda(dd, Y, Wx)
+                    lam_a.append(float(la))
+                    l_a.append(float(lmm.likelihood_lambda(la, dd, Y, Wx)))
+            lam_a, l_a = np.array(lam_a), np.array(l_a)
+            D = 2.0 * (l_a - l0)
+            out.update({f"{tag}_lambda_null": np.array(float(lam0)), f"{tag}_l_null": np.array(l0), f"{tag}_lambda_alt": lam_a,
+                        f"{tag}_l_alt": l_a, f"{tag}_D_lrt": D, f"{tag}_p_lrt": 1.0 - stats.chi2.cdf(D, 1)})
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        print(name, "lambda_null", out["r64_lambda_null"], "l_null", out["r64_l_null"], "D[:4]", out["r64_D_lrt"][:4],
+              "lam_alt[min,max]", out["r64_lambda_alt"].min(), out["r64_lambda_alt"].max())
+
+
 if __name__ == "__main__":
     from oracle import build_ref
 
@@ -211,6 +243,6 @@ if __name__ == "__main__":
     from pygemma64 import lmm as lmm64
 
     only = sys.argv[1:]   # e.g. `make_golden.py de` regenerates one family
-    for name, fn in (("kat", make_kat), ("scans", make_scans), ("e2e", make_e2e), ("de", make_de)):
+    for name, fn in (("kat", make_kat), ("scans", make_scans), ("e2e", make_e2e), ("de", make_de), ("lrt", make_lrt)):
         if not only or name in only:
             fn(lmm32, lmm64)
