@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 4
+#define PG_ABI_VERSION 5
 
 typedef struct pg_handle pg_handle;
 
@@ -214,6 +214,26 @@ int pg_scan(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout, int
 int pg_scan_device(pg_handle* h, const void* X_dev, int xdtype, int64_t ld, int layout, int64_t m, int grid,
                    double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
                    int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing);
+
+/*
+ * Likelihood-ratio outputs next to the Wald scan.  The reference driver carries them as commented-out scaffolding
+ * (result columns 'D_lrt', 'p_lrt', 'likelihood' at lmm/lmm.py:137-141; null model :176-190; per-SNP loop :278-300); the
+ * functions that scaffolding calls are live in the reference and are what is computed here:
+ *   lambda_ml  = lmm.calc_lambda(d, y, [W, x])                    ML lambda of the alternative model (lmm/lmm.py:22-84)
+ *   loglik_ml  = likelihood_lambda(lambda_ml, d, y, [W, x])       (pyx:1542; = likelihood(lam, n / yPy, beta_hat, ..), :1736)
+ *   D_lrt      = 2 (loglik_ml - l_null)                           (lmm/lmm.py:282)
+ *   p_lrt      = chi-square(1) upper tail of D_lrt                (lmm/lmm.py:300, evaluated as a survival function)
+ * with the null model of pg_null_model.  Host pointers, m (x q) doubles each; otherwise exactly pg_scan.
+ */
+int pg_scan_lrt(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+                double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
+                double* lambda_ml, double* loglik_ml, double* D_lrt, double* p_lrt,
+                int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing);
+/*
+ * Null model [W] of phenotype `trait` of the current design (lmm/lmm.py:176-190): lambda_null = lmm.calc_lambda(d, y, W),
+ * tau_null = n / y^T P y, loglik_null = likelihood(lambda_null, tau_null, beta_hat, d, y, W).  Outputs are nullable.
+ */
+int pg_null_model(pg_handle* h, int trait, double* lambda_null, double* tau_null, double* loglik_null);
 
 /*
  * Unit-level probes used by the parity tests (mirrors of the reference's Python-callable cpdefs).

@@ -442,3 +442,217 @@ double pgo_brentq_probe(const double *p5, double a, double b, double xtol, doubl
     return r;
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Likelihood-ratio scaffolding of the reference (commented out in its driver, lmm/lmm.py:137-141,:176-190,:278-300):
+ * the LIVE functions those lines call, restated in their own dense form -- explicit (W^T H^-1 W)^-1 instead of the Pab
+ * recursion -- so that this half of the oracle shares no arithmetic with the product's table / x-row machinery.
+ *   compute_at_Pi_b        pygemma_model.pyx:2045-2095     a^T P b
+ *   compute_at_Pi_Pi_b     pygemma_model.pyx:2120-2173     a^T P P b
+ *   compute_at_Pi_Pi_Pi_b  pygemma_model.pyx:2208-2279     a^T P P P b
+ *   likelihood_lambda / _derivative1_lambda / _derivative2_lambda   pyx:1542-1603
+ *   lmm.calc_lambda        lmm/lmm.py:22-84  (bracket scan, scipy brentq rtol=0.1 maxiter=5000, scipy newton rtol=1e-5
+ *                                             maxiter=10 with fprime, argmax of likelihood_lambda over the candidates)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int n, c;
+    const double *d;
+    const double **cols; /* c column pointers (fixed effects of this model) */
+    const double *y;
+    long evals;
+} ml_ctx;
+
+typedef struct {
+    double yPy, yPPy, yPPPy, trH, trHH, logdetH;
+} ml_eval_t;
+
+/* in-place inverse of a c x c matrix (row-major), Gauss-Jordan with partial pivoting (np.linalg.inv is LU based) */
+static int invert(long double *a, int c)
+{
+    long double *inv = (long double *)calloc((size_t)c * c, sizeof(long double));
+    for (int i = 0; i < c; ++i) inv[i * c + i] = 1.0L;
+    for (int col = 0; col < c; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < c; ++r)
+            if (fabsl(a[r * c + col]) > fabsl(a[piv * c + col])) piv = r;
+        if (a[piv * c + col] == 0.0L) { free(inv); return -1; }
+        if (piv != col)
+            for (int j = 0; j < c; ++j) {
+                long double t = a[col * c + j]; a[col * c + j] = a[piv * c + j]; a[piv * c + j] = t;
+                t = inv[col * c + j]; inv[col * c + j] = inv[piv * c + j]; inv[piv * c + j] = t;
+            }
+        const long double p = a[col * c + col];
+        for (int j = 0; j < c; ++j) { a[col * c + j] /= p; inv[col * c + j] /= p; }
+        for (int r = 0; r < c; ++r) {
+            if (r == col) continue;
+            const long double f = a[r * c + col];
+            if (f == 0.0L) continue;
+            for (int j = 0; j < c; ++j) { a[r * c + j] -= f * a[col * c + j]; inv[r * c + j] -= f * inv[col * c + j]; }
+        }
+    }
+    memcpy(a, inv, sizeof(long double) * (size_t)c * c);
+    free(inv);
+    return 0;
+}
+
+static void ml_evaluate(ml_ctx *m, double lam, ml_eval_t *o)
+{
+    const int n = m->n, c = m->c;
+    m->evals++;
+    long double *A = (long double *)calloc((size_t)c * c + 3 * (size_t)c + 1, sizeof(long double));
+    long double *g = A + (size_t)c * c, *coef = g + c, *q = coef + c;
+    long double yHy = 0, s1 = 0, s2 = 0, sl = 0;
+    for (int l = 0; l < n; ++l) {
+        const double t = lam * m->d[l] + 1.0, h = 1.0 / t;
+        s1 += h; s2 += (long double)h * h; sl += logl((long double)t);
+        yHy += (long double)m->y[l] * m->y[l] * h;
+        for (int r = 0; r < c; ++r) {
+            const long double wr = (long double)m->cols[r][l] * h;
+            g[r] += wr * m->y[l];
+            for (int s = 0; s <= r; ++s) A[r * c + s] += wr * m->cols[s][l];
+        }
+    }
+    for (int r = 0; r < c; ++r)
+        for (int s = r + 1; s < c; ++s) A[r * c + s] = A[s * c + r];
+    if (c > 0 && invert(A, c) != 0) { o->yPy = o->yPPy = o->yPPPy = NAN; o->trH = (double)s1; o->trHH = (double)s2; o->logdetH = (double)sl; free(A); return; }
+    long double gAg = 0;
+    for (int r = 0; r < c; ++r) {
+        long double v = 0;
+        for (int s = 0; s < c; ++s) v += A[r * c + s] * g[s];
+        coef[r] = v;          /* (W^T H^-1 W)^-1 W^T H^-1 y */
+        gAg += g[r] * v;
+    }
+    /* P y = H^-1 (y - W coef)  (pyx:2162-2170) */
+    long double pp = 0, ppp_a = 0;
+    for (int l = 0; l < n; ++l) {
+        const double h = 1.0 / (lam * m->d[l] + 1.0);
+        long double res = m->y[l];
+        for (int r = 0; r < c; ++r) res -= coef[r] * m->cols[r][l];
+        const long double py = res * h;
+        pp += py * py;                 /* a^T P P b   :2171 */
+        ppp_a += py * py * h;          /* :2259 */
+        for (int r = 0; r < c; ++r) q[r] += (long double)m->cols[r][l] * py * h; /* W^T H^-1 P y  :2262-2268 */
+    }
+    long double qAq = 0;
+    for (int r = 0; r < c; ++r) {
+        long double v = 0;
+        for (int s = 0; s < c; ++s) v += A[r * c + s] * q[s];
+        qAq += q[r] * v;
+    }
+    o->yPy = (double)(yHy - gAg);      /* :2093 */
+    o->yPPy = (double)pp;
+    o->yPPPy = (double)(ppp_a - qAq);  /* :2279 */
+    o->trH = (double)s1; o->trHH = (double)s2; o->logdetH = (double)sl;
+    free(A);
+}
+
+/* pyx:1566-1581 */
+static double ml_d1(int n, double lam, const ml_eval_t *e)
+{
+    double r = -0.5 * ((n - e->trH) / lam);
+    const double num = cy_max(e->yPPy, PGO_MIN_VAL), denom = cy_max(e->yPy, PGO_MIN_VAL);
+    return r + (n / 2.0) * (1.0 - num / denom) / lam;
+}
+/* pyx:1586-1603 */
+static double ml_d2(int n, double lam, const ml_eval_t *e)
+{
+    const double yPy = cy_max(e->yPy, PGO_MIN_VAL), yPPy = cy_max(e->yPPy, PGO_MIN_VAL);
+    const double g2 = (yPy + cy_max(e->yPPPy, PGO_MIN_VAL) - 2 * yPPy) / (lam * lam);
+    const double g1 = (yPy - yPPy) / lam;
+    double r = 0.5 * (n + e->trHH - 2 * e->trH) / pow(lam, 2);
+    return r - 0.5 * n * (2 * g2 - g1 * g1 / yPy) / yPy;
+}
+/* pyx:1542-1560 */
+static double ml_ll(int n, const ml_eval_t *e)
+{
+    double r = (n / 2.0) * log(n / (2 * M_PI));
+    r = r - n / 2.0;
+    r = r - 0.5 * e->logdetH;
+    return r - (n / 2.0) * log(cy_max(e->yPy, PGO_MIN_VAL));
+}
+
+static double ml_d1_cb(void *arg, double lam)
+{
+    ml_ctx *m = (ml_ctx *)arg;
+    ml_eval_t e;
+    ml_evaluate(m, lam, &e);
+    return ml_d1(m->n, lam, &e);
+}
+
+/* scipy.optimize.newton, Newton-Raphson branch (fprime given, fprime2 None), tol = 1.48e-8 (default), rtol, maxiter,
+ * disp=False: call site lmm/lmm.py:71-76 */
+static double scipy_newton(ml_ctx *m, double x0, double rtol, int maxiter)
+{
+    const double tol = 1.48e-8;
+    double p0 = x0, p = x0;
+    for (int itr = 0; itr < maxiter; ++itr) {
+        ml_eval_t e;
+        ml_evaluate(m, p0, &e);
+        const double fval = ml_d1(m->n, p0, &e);
+        if (fval == 0) return p0;
+        const double fder = ml_d2(m->n, p0, &e);
+        if (fder == 0) return p0;
+        p = p0 - fval / fder;
+        /* np.isclose(p, p0, rtol=rtol, atol=tol) */
+        if (isfinite(p) && isfinite(p0) ? fabs(p - p0) <= tol + rtol * fabs(p0) : p == p0) return p;
+        p0 = p;
+    }
+    return p;
+}
+
+/* lmm.calc_lambda (lmm/lmm.py:22-84); returns lambda, *ll_out = likelihood_lambda there, *yPy_out = y^T P y there */
+static double ml_calc_lambda(ml_ctx *m, double *ll_out, double *yPy_out)
+{
+    double roots[16], f0 = 0, f1 = 0;
+    int nroots = 0;
+    roots[nroots++] = pow(10.0, -5.0);
+    roots[nroots++] = pow(10.0, 5.0);
+    for (int idx = -5; idx < 5; ++idx) {
+        const double lambda0 = pow(10.0, (double)idx), lambda1 = pow(10.0, (double)idx + 1.0);
+        if (idx == -5) f0 = ml_d1_cb(m, lambda0); else f0 = f1; /* :53-58 */
+        f1 = ml_d1_cb(m, lambda1);
+        if (sgn(f0) * sgn(f1) < 0) { /* :63 */
+            int calls;
+            double lam = pgo_brentq(ml_d1_cb, m, lambda0, lambda1, 2e-12, 0.1, 5000, &calls);
+            lam = scipy_newton(m, lam, 1e-5, 10);
+            if (nroots < 16) roots[nroots++] = lam;
+        }
+    }
+    /* roots[np.argmax(likelihood_list)]: first maximum; a NaN is a maximum */
+    int best = 0;
+    double best_ll = 0, best_yPy = 0;
+    for (int i = 0; i < nroots; ++i) {
+        ml_eval_t e;
+        ml_evaluate(m, roots[i], &e);
+        const double ll = ml_ll(m->n, &e);
+        if (i == 0) { best_ll = ll; best_yPy = e.yPy; continue; }
+        if (isnan(best_ll)) continue;
+        if (isnan(ll) || ll > best_ll) { best = i; best_ll = ll; best_yPy = e.yPy; }
+    }
+    *ll_out = best_ll;
+    if (yPy_out) *yPy_out = best_yPy;
+    return roots[best];
+}
+
+/* null model [W0] -> null3 = {lambda_null, tau_null = n / yPy, l_null}; alternative [W0, x_g] for every SNP row of xr */
+void pgo_ml_scan(int n, int c0, long m, const double *d, const double *w0, const double *y, const double *xr,
+                 double *null3, double *lambda_ml, double *loglik_ml)
+{
+    const double **cols = (const double **)malloc(sizeof(double *) * (size_t)(c0 + 1));
+    for (int j = 0; j < c0; ++j) cols[j] = w0 + (size_t)j * n;
+    ml_ctx mc = {n, c0, d, cols, y, 0};
+    if (null3) {
+        double ll, yPy;
+        null3[0] = ml_calc_lambda(&mc, &ll, &yPy);
+        null3[1] = (double)n / yPy;
+        null3[2] = ll;
+    }
+    mc.c = c0 + 1;
+    for (long g = 0; g < m; ++g) {
+        cols[c0] = xr + (size_t)g * n;
+        double ll;
+        lambda_ml[g] = ml_calc_lambda(&mc, &ll, NULL);
+        loglik_ml[g] = ll;
+    }
+    free(cols);
+}

@@ -25,7 +25,7 @@ SYMBOLS = [
     "pg_abi_version", "pg_rotation_planes", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_copy_eigen", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
     "pg_set_reml_engine", "pg_set_scan_mode", "pg_grm", "pg_set_bed_options",
-    "pg_scan", "pg_scan_device", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
+    "pg_scan", "pg_scan_device", "pg_scan_lrt", "pg_null_model", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
 
 
@@ -85,6 +85,8 @@ def load():
     scan_args = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 9 + [ctypes.POINTER(PgTiming)]
     L.pg_scan.argtypes = scan_args
     L.pg_scan_device.argtypes = scan_args
+    L.pg_scan_lrt.argtypes = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 13 + [ctypes.POINTER(PgTiming)]
+    L.pg_null_model.argtypes = [vp, i32, vp, vp, vp]
     L.pg_probe_precompute.argtypes = [vp, vp, dbl, i32, i32, vp]
     L.pg_probe_f_sf.argtypes = [vp, vp, dbl, i64, vp]
     L.pg_probe_rotated.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
@@ -228,8 +230,15 @@ class Handle:
         self._ck(self.L.pg_set_scan_mode(self.h, int(mode)))
 
     # --- scan --------------------------------------------------------------------------------
-    def scan(self, X, grid=False, layout=PG_X_SAMPLE_MAJOR, with_counts=True):
-        """Host-buffer scan.  X: (n, m) sample-major or (m, n) SNP-major ndarray, any stride along rows."""
+    def null_model(self, trait=0):
+        """ML fit of the null model [W] of one phenotype of the current design: dict(lambda_null, tau_null, l_null)."""
+        v = (ctypes.c_double * 3)()
+        self._ck(self.L.pg_null_model(self.h, int(trait), ctypes.byref(v, 0), ctypes.byref(v, 8), ctypes.byref(v, 16)))
+        return {"lambda_null": v[0], "tau_null": v[1], "l_null": v[2]}
+
+    def scan(self, X, grid=False, layout=PG_X_SAMPLE_MAJOR, with_counts=True, lrt=False):
+        """Host-buffer scan.  X: (n, m) sample-major or (m, n) SNP-major ndarray, any stride along rows.
+        lrt: also return lambda_ml, loglik_ml, D_lrt, p_lrt (pg_scan_lrt)."""
         if X.ndim != 2:
             raise ValueError("X must be 2-D")
         if layout == PG_X_SAMPLE_MAJOR:
@@ -248,10 +257,18 @@ class Handle:
         e2 = np.zeros(shape, dtype=np.int32) if with_counts else None
         e3 = np.zeros(shape, dtype=np.int32) if with_counts else None
         tm = PgTiming()
-        self._ck(self.L.pg_scan(self.h, _ptr(X), xdtype_of(X), ld, layout, m, int(bool(grid)),
-                                _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
-                                _ptr(out["F_wald"]), _ptr(out["p_wald"]), _ptr(st), _ptr(e2), _ptr(e3),
-                                ctypes.byref(tm)))
+        if lrt:
+            out.update({k: np.empty(shape) for k in ("lambda_ml", "loglik_ml", "D_lrt", "p_lrt")})
+            self._ck(self.L.pg_scan_lrt(self.h, _ptr(X), xdtype_of(X), ld, layout, m, int(bool(grid)),
+                                        _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
+                                        _ptr(out["F_wald"]), _ptr(out["p_wald"]), _ptr(out["lambda_ml"]),
+                                        _ptr(out["loglik_ml"]), _ptr(out["D_lrt"]), _ptr(out["p_lrt"]), _ptr(st), _ptr(e2),
+                                        _ptr(e3), ctypes.byref(tm)))
+        else:
+            self._ck(self.L.pg_scan(self.h, _ptr(X), xdtype_of(X), ld, layout, m, int(bool(grid)),
+                                    _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
+                                    _ptr(out["F_wald"]), _ptr(out["p_wald"]), _ptr(st), _ptr(e2), _ptr(e3),
+                                    ctypes.byref(tm)))
         out["status"] = st
         if with_counts:
             out["n_eval2"], out["n_eval3"] = e2, e3

@@ -97,7 +97,12 @@ struct pg_handle {
     // several phenotypes on one eigen-system (pg_set_design_multi): each has its own rotated [W0, y] and lambda tables;
     // slot 0 owns the buffers allocated with the handle, `activate` points the handle's working fields at a slot
     // before its kernels are launched (launches copy the pointers, so slots can alternate per block)
-    struct DesignSlot { double *wy, *fixtab, *itab, *fix2, *itab2; };
+    struct DesignSlot {
+        double *wy, *fixtab, *itab, *fix2, *itab2;
+        bool null_valid = false;                 // null-model ML fit of this phenotype (pg_null_model), cached per design
+        double null_vals[4] = {0, 0, 0, 0};      // lambda_null, tau_null, l_null, status
+    };
+    int active_slot = 0;
     std::vector<DesignSlot> slots;
     int q = 1;
     double* design_raw = nullptr;   // staging of the unrotated [W, y] columns (pg_set_design), n x (c0+1)
@@ -620,6 +625,7 @@ extern "C" int pg_copy_eigen(pg_handle* h, const pg_handle* src)
 static void activate(pg_handle* h, int ph)
 {
     const pg_handle::DesignSlot& S = h->slots[ph];
+    h->active_slot = ph;
     h->wy = S.wy; h->fixtab = S.fixtab; h->itab = S.itab; h->fix2 = S.fix2; h->itab2 = S.itab2;
     h->tab.fixtab = S.fixtab; h->tab.itab = S.itab; h->tab2.fix2 = S.fix2; h->tab2.itab2 = S.itab2;
 }
@@ -767,6 +773,7 @@ static int set_design_active(pg_handle* h, const double* W_host, const double* y
         if (s != CUBLAS_STATUS_SUCCESS) return fail(h, PG_ERR_CUBLAS, "pg_set_design: dgemm status %d", (int)s);
     }
     h->rotated_inputs = already_rotated != 0;
+    h->slots[h->active_slot].null_valid = false;
     int rc = build_tables(h);
     if (rc) return rc;
     CK(cudaEventRecord(e1, h->compute));
@@ -776,6 +783,42 @@ static int set_design_active(pg_handle* h, const double* W_host, const double* y
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms) *ms = t;
+    return PG_OK;
+}
+
+// ML fit of the null model [W0] of phenotype slot `ph` (null_model_kernel), cached until the design changes
+static int ensure_null(pg_handle* h, int ph)
+{
+    if (ph < 0 || ph >= (int)h->slots.size()) return fail(h, PG_ERR_ARG, "null model: phenotype %d of %d", ph, (int)h->slots.size());
+    pg_handle::DesignSlot& S = h->slots[ph];
+    if (S.null_valid) return PG_OK;
+    CK(cudaSetDevice(h->device));
+    double* dout = nullptr;
+    CK(cudaMalloc(&dout, sizeof(double) * 4));
+    Tables2 t2 = h->tab2;
+    t2.fix2 = S.fix2; t2.itab2 = S.itab2;
+    null_model_kernel<<<1, 32, 0, h->compute>>>(h->n, t2, dout);
+    cudaError_t e1 = cudaGetLastError();
+    cudaError_t e2 = cudaMemcpyAsync(S.null_vals, dout, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->compute);
+    cudaError_t e3 = cudaStreamSynchronize(h->compute);
+    cudaFree(dout);
+    for (cudaError_t e : {e1, e2, e3})
+        if (e != cudaSuccess) return fail(h, PG_ERR_CUDA, "null model: %s", cudaGetErrorString(e));
+    S.null_valid = true;
+    return PG_OK;
+}
+
+extern "C" int pg_null_model(pg_handle* h, int trait, double* lambda_null, double* tau_null, double* loglik_null)
+{
+    if (!h) return PG_ERR_ARG;
+    if (!h->have_design) return fail(h, PG_ERR_ARG, "pg_null_model: call pg_set_design first");
+    if (trait < 0 || trait >= h->q) return fail(h, PG_ERR_ARG, "pg_null_model: trait %d of %d", trait, h->q);
+    int rc = ensure_null(h, trait);
+    if (rc) return rc;
+    const double* v = h->slots[trait].null_vals;
+    if (lambda_null) *lambda_null = v[0];
+    if (tau_null) *tau_null = v[1];
+    if (loglik_null) *loglik_null = v[2];
     return PG_OK;
 }
 
@@ -826,7 +869,7 @@ extern "C" int pg_set_reml_engine(pg_handle* h, int engine)
 
 static size_t xdtype_size(int t) { return (t == PG_X_I8 || t == PG_X_BED) ? 1 : (t == PG_X_F32 ? 4 : 8); }
 
-static int ensure_workspace(pg_handle* h, long long m, int xdtype)
+static int ensure_workspace(pg_handle* h, long long m, int xdtype, bool host_input)
 {
     const int n = h->n;
     long long blk = h->block_snps_opt;
@@ -836,6 +879,10 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype)
         blk = std::min<long long>(blk, 32768);
         // keep at least four blocks in flight on large inputs so uploads overlap compute
         if (m >= 4 * 8192) blk = std::min<long long>(blk, std::max<long long>(8192, ((m + 3) / 4 + 255) / 256 * 256));
+        // a host-resident shard that is worth pipelining (>= 64 MB) but shorter than that, e.g. one rank's 12 544 SNPs of a
+        // problem split over 8 GPUs: still about four blocks of whole 512-SNP tiles, so that packing, upload and compute overlap
+        else if (host_input && (size_t)m * n * xdtype_size(xdtype) >= (size_t(64) << 20) && m >= 4 * 2048)
+            blk = std::min<long long>(blk, std::max<long long>(2048, ((m + 3) / 4 + 511) / 512 * 512));
         // compressed moments of a block: at most 2 GiB
         const size_t zrow = sizeof(double) * (size_t)(h->k1p - 1 + h->q) * std::max(h->plan.Kcp, 32);
         blk = std::min<long long>(blk, std::max<long long>(256, (long long)((size_t(1) << 31) / zrow) / 256 * 256));
@@ -923,7 +970,7 @@ static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld,
 static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* Zbuf, long long mb, long long row0,
                        int grid_mode, double* const out[6], int* status, int* e2, int* e3, cudaEvent_t* ev_mid = nullptr,
                        cudaEvent_t ev_xr_done = nullptr, cudaStream_t st_solve = nullptr, cudaEvent_t* ev_z = nullptr,
-                       int parity = 0, int ph = 0)
+                       int parity = 0, int ph = 0, double* const* lrt = nullptr)
 {
     // ph: phenotype slot of this launch (the caller has activated it).  The compressed engine compresses the block for
     // all h->q phenotypes at ph == 0; the direct engines read xr for every phenotype.
@@ -979,6 +1026,8 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
         sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
         sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph; sa.F = Fbuf; sa.swap = (h->scan_mode == PG_SCAN_DE) ? 1 : 0;
+        for (int i = 0; i < 4; ++i) sa.lrt[i] = lrt ? lrt[i] : nullptr;
+        sa.l_null = lrt ? h->slots[ph].null_vals[2] : 0.0;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = counter;
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
@@ -1062,7 +1111,7 @@ struct EvPair {
 
 static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int layout, long long m, int grid_mode,
                      double* const out_user[6], int32_t* status, int32_t* e2, int32_t* e3, pg_timing* timing,
-                     bool on_device)
+                     bool on_device, double* const lrt_user[4] = nullptr)
 {
     if (!h) return PG_ERR_ARG;
     if (!X || m < 0) return fail(h, PG_ERR_ARG, "pg_scan: NULL X or negative m");
@@ -1073,6 +1122,14 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     if (!h->have_design) return fail(h, PG_ERR_ARG, "pg_scan: call pg_set_design first");
     if (h->scan_mode == PG_SCAN_DE && !(h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED))
         return fail(h, PG_ERR_ARG, "pg_scan: PG_SCAN_DE runs on the compressed REML engine only");
+    const bool want_lrt = lrt_user != nullptr;
+    if (want_lrt) {
+        for (int i = 0; i < 4; ++i)
+            if (!lrt_user[i] && m > 0) return fail(h, PG_ERR_ARG, "pg_scan_lrt: NULL likelihood-ratio output %d", i);
+        if (!(h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED))
+            return fail(h, PG_ERR_ARG, "pg_scan_lrt: the likelihood-ratio outputs need the compressed REML engine");
+        if (h->scan_mode == PG_SCAN_DE) return fail(h, PG_ERR_ARG, "pg_scan_lrt: not available in PG_SCAN_DE mode");
+    }
     const int n = h->n;
     const bool bed = xdtype == PG_X_BED;
     if (bed && layout != PG_X_SNP_MAJOR) return fail(h, PG_ERR_ARG, "pg_scan: PLINK .bed data is SNP-major");
@@ -1082,7 +1139,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     if (timing) memset(timing, 0, sizeof *timing);
     if (m == 0) return PG_OK;
     CK(cudaSetDevice(h->device));
-    int rc = ensure_workspace(h, m, xdtype);
+    int rc = ensure_workspace(h, m, xdtype, !on_device);
     if (rc) return rc;
     const long long blk = h->blk;
     // worth it for large pageable inputs only; very wide element types would need multi-GB pinned buffers
@@ -1129,8 +1186,11 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     int* itmp = nullptr;
     const int q = h->q;                       // phenotypes of the current design (pg_set_design_multi)
     const size_t mq = (size_t)m * (size_t)q;  // every output array holds q * m values, phenotype-major
+    double* dlrt[4] = {nullptr, nullptr, nullptr, nullptr};
+    constexpr int kResCols = 10;   // six Wald columns + four likelihood-ratio columns
     if (on_device) {
         for (int i = 0; i < 6; ++i) dout[i] = out_user[i];
+        if (want_lrt) for (int i = 0; i < 4; ++i) dlrt[i] = lrt_user[i];
         dstatus = status; de2 = e2; de3 = e3;
     } else {
         if (mq > h->res_cap) {
@@ -1139,13 +1199,14 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             if (h->res_host) cudaFreeHost(h->res_host);
             h->res_d = nullptr; h->res_i = nullptr; h->res_host = nullptr; h->res_cap = 0;
             const size_t cap = (mq + 1023) / 1024 * 1024;
-            CK(cudaMalloc(&h->res_d, sizeof(double) * 6 * cap));
+            CK(cudaMalloc(&h->res_d, sizeof(double) * kResCols * cap));
             CK(cudaMalloc(&h->res_i, sizeof(int) * 3 * cap));
-            CK(cudaMallocHost(&h->res_host, (sizeof(double) * 6 + sizeof(int) * 3) * cap));
+            CK(cudaMallocHost(&h->res_host, (sizeof(double) * kResCols + sizeof(int) * 3) * cap));
             h->res_cap = cap;
         }
         dtmp = h->res_d; itmp = h->res_i;
         for (int i = 0; i < 6; ++i) dout[i] = dtmp + (size_t)i * mq;
+        if (want_lrt) for (int i = 0; i < 4; ++i) dlrt[i] = dtmp + (size_t)(6 + i) * mq;
         dstatus = itmp; de2 = itmp + mq; de3 = itmp + 2 * mq;
     }
 
@@ -1166,6 +1227,12 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     cudaEvent_t t0 = take(), t1 = take(), t2 = take();
     int n_rot_launch = 0, last_engine = 0;
 
+    if (want_lrt)
+        for (int ph = 0; ph < q; ++ph) {
+            rc = ensure_null(h, ph);
+            if (rc) return rc;
+        }
+    const int ncols = want_lrt ? kResCols : 6;
     h->defer_pvalues = compressed;   // launch_reml leaves p = NaN; one pvalue_kernel launch follows the last block
     rc = [&]() -> int {
         CK(cudaEventRecord(t0, h->compute));
@@ -1257,9 +1324,12 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                 activate(h, ph);
                 double* outp[6];
                 for (int i = 0; i < 6; ++i) outp[i] = dout[i] + (size_t)ph * m;
+                double* lrtp[4];
+                for (int i = 0; i < 4; ++i) lrtp[i] = want_lrt ? dlrt[i] + (size_t)ph * m : nullptr;
                 int r3 = launch_reml(h, st_reml, xr_block, h->Z[s], mb, g0, grid_mode, outp,
                                      dstatus ? dstatus + (size_t)ph * m : nullptr, de2 ? de2 + (size_t)ph * m : nullptr,
-                                     de3 ? de3 + (size_t)ph * m : nullptr, mid, h->ev_xr_free[s], st_solve, evz, s, ph);
+                                     de3 ? de3 + (size_t)ph * m : nullptr, mid, h->ev_xr_free[s], st_solve, evz, s, ph,
+                                     want_lrt ? lrtp : nullptr);
                 if (r3) { activate(h, 0); return r3; }
             }
             activate(h, 0);
@@ -1285,8 +1355,8 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         CK(cudaEventRecord(t1, h->compute));
         if (!on_device) {
             // two D2H copies into pinned staging, then host memcpy into the caller's (pageable) arrays
-            CK(cudaMemcpyAsync(h->res_host, dtmp, sizeof(double) * 6 * mq, cudaMemcpyDeviceToHost, h->compute));
-            CK(cudaMemcpyAsync(h->res_host + sizeof(double) * 6 * mq, itmp, sizeof(int) * 3 * mq,
+            CK(cudaMemcpyAsync(h->res_host, dtmp, sizeof(double) * ncols * mq, cudaMemcpyDeviceToHost, h->compute));
+            CK(cudaMemcpyAsync(h->res_host + sizeof(double) * ncols * mq, itmp, sizeof(int) * 3 * mq,
                                cudaMemcpyDeviceToHost, h->compute));
         }
         CK(cudaEventRecord(t2, h->compute));
@@ -1294,8 +1364,9 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         CK(cudaStreamSynchronize(h->copy));
         if (!on_device) {
             const double* hd = reinterpret_cast<const double*>(h->res_host);
-            const int* hi = reinterpret_cast<const int*>(h->res_host + sizeof(double) * 6 * mq);
+            const int* hi = reinterpret_cast<const int*>(h->res_host + sizeof(double) * ncols * mq);
             for (int i = 0; i < 6; ++i) memcpy(out_user[i], hd + (size_t)i * mq, sizeof(double) * mq);
+            if (want_lrt) for (int i = 0; i < 4; ++i) memcpy(lrt_user[i], hd + (size_t)(6 + i) * mq, sizeof(double) * mq);
             if (status) memcpy(status, hi, sizeof(int) * mq);
             if (e2) memcpy(e2, hi + mq, sizeof(int) * mq);
             if (e3) memcpy(e3, hi + 2 * mq, sizeof(int) * mq);
@@ -1345,6 +1416,16 @@ extern "C" int pg_scan(pg_handle* h, const void* X, int xdtype, int64_t ld, int 
 {
     double* out[6] = {beta, se_beta, tau, lambda, F_wald, p_wald};
     return scan_impl(h, X, xdtype, ld, layout, m, grid, out, status, n_eval2, n_eval3, timing, false);
+}
+
+extern "C" int pg_scan_lrt(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+                           double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
+                           double* lambda_ml, double* loglik_ml, double* D_lrt, double* p_lrt, int32_t* status,
+                           int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing)
+{
+    double* out[6] = {beta, se_beta, tau, lambda, F_wald, p_wald};
+    double* lrt[4] = {lambda_ml, loglik_ml, D_lrt, p_lrt};
+    return scan_impl(h, X, xdtype, ld, layout, m, grid, out, status, n_eval2, n_eval3, timing, false, lrt);
 }
 
 extern "C" int pg_scan_device(pg_handle* h, const void* X_dev, int xdtype, int64_t ld, int layout, int64_t m, int grid,
@@ -1543,6 +1624,8 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
         SolveArgs sa{};
         sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
         sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.F = nullptr; sa.swap = 0;
+        for (int i = 0; i < 4; ++i) sa.lrt[i] = nullptr;
+        sa.l_null = 0.0;
         const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);
         const bool two = (h->c0 + 2) > 32;
         if (smemc > 48 * 1024) {

@@ -183,6 +183,8 @@ PG_HD_NOINLINE void pab_recursion(const Tables& t, double* A, double* B, double*
     out->trPP = FULL ? trPP : NAN;
     out->logdetH = l0.logdetH;
     out->logdetWHW = logdetWHW;
+    out->trH = l0.trP;
+    out->trHH = l0.trPP;
     PG_SYNCWARP();
 }
 
@@ -191,7 +193,8 @@ PG_HD_NOINLINE void pab_recursion(const Tables& t, double* A, double* B, double*
 // do not involve the SNP at all, so that part is run ONCE per table lambda (eliminate_w0y_row) and stored as
 //   per level p:  al2 = -1/a_pp, al4 = b_pp/a_pp^2, alc = c_pp/a_pp^2 - b_pp^2/a_pp^3     (pyx:1011-1031)
 //                 the pivot column of level p: A/B/C[s][p] for s = p+1..c0-1 and s = y
-//   finals:       A/B/C[y][y] after c0 levels, tr_Pi, tr_Pi_Pi, logdet_H, partial logdet_Wt_H_inv_W
+//   finals:       A/B/C[y][y] after c0 levels, tr_Pi, tr_Pi_Pi, logdet_H, partial logdet_Wt_H_inv_W, and the level-0
+//                 traces sum h, sum h^2 (h = 1/(lambda d + 1); the ML derivatives of the LRT outputs use them)
 // ("table-2 row").  Per SNP only the x row (x.w_j, x.y, x.x at the three powers) is carried through the c0
 // levels -- O(c0^2) fused multiply-adds without a division -- followed by the one SNP-dependent pivot (x itself).
 // Arithmetic per entry is the expression of pab_recursion above, so both forms agree to rounding.
@@ -200,14 +203,14 @@ PG_HD_NOINLINE void pab_recursion(const Tables& t, double* A, double* B, double*
 // |Im log(lambda)| < pi/2, which still gives rho ~ 22 per 1/8-decade interval and 22^-12 ~ 1e-16.
 // ------------------------------------------------------------------------------------------------
 struct Tables2 {
-    int c0, Tp, NF2;       // Tp = c0(c0+1)/2 pivot-column entries per power; NF2 = 3 c0 + 3 Tp + 7
+    int c0, Tp, NF2;       // Tp = c0(c0+1)/2 pivot-column entries per power; NF2 = 3 c0 + 3 Tp + 9
     const double* fix2;    // [kNumFixed][NF2]
     const double* itab2;   // [kNumIntervals][kNodes][NF2]
     const double* basis;   // as Tables::basis
 };
 
 PG_HD int t2_pairs(int c0) { return c0 * (c0 + 1) / 2; }
-PG_HD int t2_nf(int c0) { return 3 * c0 + 3 * t2_pairs(c0) + 7; }
+PG_HD int t2_nf(int c0) { return 3 * c0 + 3 * t2_pairs(c0) + 9; }
 // column entry (s, p), p < s <= c0 (s == c0 is y), power 0: index; powers 1, 2 follow at +Tp, +2Tp
 PG_HD int t2_col(int c0, int p, int s) { return 3 * c0 + p * c0 - p * (p - 1) / 2 + (s - p - 1); }
 PG_HD int t2_fin(int c0) { return 3 * c0 + 3 * t2_pairs(c0); }
@@ -255,6 +258,16 @@ PG_HD_NOINLINE void eliminate_w0y_row(int c0, const double* row0, double* work, 
     const int f = t2_fin(c0), yy = tri(c0, c0);
     out[f] = A[yy]; out[f + 1] = B[yy]; out[f + 2] = C[yy];
     out[f + 3] = trP; out[f + 4] = trPP; out[f + 5] = row0[3 * T0 + 2]; out[f + 6] = logdet;
+    out[f + 7] = row0[3 * T0]; out[f + 8] = row0[3 * T0 + 1];
+}
+
+// The model without any x ("null model", lmm/lmm.py:176-190): level c0 of the [W0, y] block is all there is.
+PG_HD void null_eval_from_row(const double* fin, EvalOut* out)
+{
+    out->yPy = fin[0]; out->yPPy = fin[1]; out->yPPPy = fin[2];
+    out->trP = fin[3]; out->trPP = fin[4]; out->logdetH = fin[5]; out->logdetWHW = fin[6];
+    out->trH = fin[7]; out->trHH = fin[8];
+    out->xPx = NAN; out->yPx = NAN;
 }
 
 // last level: pivot on x itself.  (app, bpp, cpp) = x diagonal after the covariate levels (clamped), (ar, br, cr) = the
@@ -287,6 +300,7 @@ PG_HD void xrow_final_level(const double* fin, double app, double bpp, double cp
     out->yPy = va; out->yPPy = vb; out->yPPPy = vc;
     out->trP = trP; out->trPP = FULL ? trPP : NAN;
     out->logdetH = fin[5]; out->logdetWHW = logdet;
+    out->trH = fin[7]; out->trHH = fin[8];
 }
 
 // scalar form (host tests, probes): xa/xb/xc hold the level-0 x row, entries j < c0: x.w_j, c0: x.y, c0+1: x.x
@@ -343,7 +357,7 @@ PG_HD void xrow_final_level_swapped(int c0, const double* fin, double xxa, doubl
     const double ya = cy_max(fin[0], kMinVal);
     const double yb = c0 ? cy_max(fin[1], kMinVal) : fin[1];
     const double yc = c0 ? cy_max(fin[2], kMinVal) : fin[2];
-    const double fin2[7] = {xxa, xxb, xxc, fin[3], fin[4], fin[5], fin[6]};
+    const double fin2[9] = {xxa, xxb, xxc, fin[3], fin[4], fin[5], fin[6], fin[7], fin[8]};
     xrow_final_level<FULL>(fin2, ya, yb, yc, ar, br, cr, need_logdet, out);
 }
 

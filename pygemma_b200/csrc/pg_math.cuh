@@ -66,6 +66,7 @@ struct EvalOut {
     double trP, trPP;         // level c_f
     double logdetH, logdetWHW;
     double xPx, yPx;          // level c0 (Wald numerator / denominator)
+    double trH, trHH;         // level 0: sum 1/(lam d + 1), sum 1/(lam d + 1)^2 (the ML derivatives use these)
 };
 
 // pyx:1656-1669 (c = number of fixed effects including the SNP)
@@ -101,6 +102,40 @@ PG_HD double reml_loglik(int n, int c, double yPy, double logdetH, double logdet
     r = r - 0.5 * logdetH;
     r = r - 0.5 * logdetWHW;
     r = r - 0.5 * df * log(yPy);
+    return r;
+}
+
+// ---- unrestricted (ML) log-likelihood in lambda: the functions behind the reference's likelihood-ratio scaffolding
+// (lmm/lmm.py:22-84 calc_lambda, commented call sites :177,:189,:278-282).  c = all fixed effects of the model.
+// pyx:1566-1581 likelihood_derivative1_lambda
+PG_HD double ml_d1(double lam, int n, double yPy_in, double yPPy_in, double trH)
+{
+    double r = -0.5 * (((double)n - trH) / lam);
+    const double num = cy_max(yPPy_in, kMinVal), denom = cy_max(yPy_in, kMinVal);
+    r = r + (0.5 * (double)n) * (1.0 - num / denom) / lam;
+    return r;
+}
+
+// pyx:1586-1603 likelihood_derivative2_lambda
+PG_HD double ml_d2(double lam, int n, double yPy_in, double yPPy_in, double yPPPy_in, double trH, double trHH)
+{
+    const double yPy = cy_max(yPy_in, kMinVal), yPPy = cy_max(yPPy_in, kMinVal);
+    const double g2 = (yPy + cy_max(yPPPy_in, kMinVal) - 2 * yPPy) / (lam * lam);
+    const double g1 = (yPy - yPPy) / lam;
+    double r = 0.5 * ((double)n + trHH - 2 * trH) / (lam * lam);
+    r = r - 0.5 * (double)n * (2 * g2 - g1 * g1 / yPy) / yPy;
+    return r;
+}
+
+// pyx:1542-1560 likelihood_lambda; identical to likelihood(lam, tau = n / yPy, beta_hat, ...) (pyx:1736-1755), which is
+// what the commented LRT lines evaluate (lmm/lmm.py:189,:281)
+PG_HD double ml_loglik(int n, double yPy_in, double logdetH)
+{
+    const double hn = 0.5 * (double)n;
+    double r = hn * log((double)n / (2 * 3.14159265358979323846));
+    r = r - hn;
+    r = r - 0.5 * logdetH;
+    r = r - hn * log(cy_max(yPy_in, kMinVal));
     return r;
 }
 
@@ -231,6 +266,15 @@ PG_HD_NOINLINE double f_sf_1_pre(double F, double nu, double lnbeta)
     if (isinf(F)) return 0.0;
     const double x = nu / (nu + F), y = F / (nu + F);
     return ibeta_xy_pre(0.5 * nu, 0.5, x, y, lnbeta);
+}
+
+// chi-square(1) upper tail of the LRT statistic, p = 1 - chi2.cdf(D, 1) (reference lmm/lmm.py:300) = erfc(sqrt(D/2)),
+// evaluated as the survival function so that small p-values keep their relative accuracy; D <= 0 gives 1
+PG_HD double chi2_sf_1(double D)
+{
+    if (isnan(D)) return D;
+    if (D <= 0.0) return 1.0;
+    return erfc(sqrt(0.5 * D));
 }
 
 PG_HD_NOINLINE double f_sf_1(double F, double nu)
@@ -481,6 +525,127 @@ struct SnpSolver {
     // grid-mode bookkeeping (lower boundary and running interior argmax)
     double grid_ll0, grid_in_ll, grid_in_lam;
     double grid_w0[3], grid_in_w[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+// The ML lambda of one model as lmm.calc_lambda finds it (reference lmm/lmm.py:22-84), resumable like SnpSolver:
+//   * d1 = likelihood_derivative1_lambda at lambda = 10^-5 .. 10^5, reused between neighbouring brackets (:47-61);
+//   * a bracket counts when np.sign(d1_lo) * np.sign(d1_hi) < 0 (:63) -- NaN never does;
+//   * scipy.optimize.brentq(rtol = 0.1, maxiter = 5000) (:64-69), then scipy.optimize.newton with fprime = d2,
+//     rtol = 1e-5, tol = 1.48e-8 (SciPy default), maxiter = 10, disp = False (:71-76): at most ten steps
+//     p <- p - d1/d2, stopping when d1 == 0, d2 == 0 or np.isclose(p_new, p_old, rtol, atol = tol), no bracket clamp;
+//   * roots = [1e-5, 1e5, newton results...]; the answer is roots[np.argmax(likelihood_lambda(roots))] (:81-84): the
+//     first maximum wins, and a NaN likelihood counts as a maximum (np.argmax returns the first NaN).
+// One deviation: the reference evaluates its closed forms at whatever lambda Newton produces; the tables here span
+// [1e-5, 1e5], so an iterate outside that range (or not finite) ends Newton at the last iterate inside it and sets
+// status bit 1.  It does not happen after a 10 %-accurate Brent start on the test problems.
+// The same machine serves the null model (its evaluator has no x) and every alternative model [W0, x].
+// ------------------------------------------------------------------------------------------------
+struct MlSolver {
+    enum Phase { kFixed = 0, kBrent = 1, kNewton = 2, kRootLL = 3, kDone = 4 };
+    int n, phase, t_req, idx;
+    double d1_fixed[kNumFixed];
+    double best_lambda, best_ll, best_yPy;
+    Brent br;
+    double nt_p0;
+    int nt_iter;
+    double rq_lambda;
+    int rq_fixed, rq_full;
+    int status, n_eval2, n_eval3;
+
+    PG_HD int pending() const { return phase != kDone; }
+    PG_HD double req_lambda() const { return rq_lambda; }
+    PG_HD int req_fixed() const { return rq_fixed; }
+    PG_HD int req_full() const { return rq_full; }
+
+    PG_HD void request_fixed(int t) { phase = kFixed; t_req = t; rq_fixed = t; rq_lambda = fixed_lambda(t); rq_full = 0; }
+    PG_HD void request(double lam, int full) { rq_fixed = -1; rq_lambda = lam; rq_full = full; }
+
+    PG_HD void init(int n_)
+    {
+        n = n_; idx = 0; status = 0; n_eval2 = 0; n_eval3 = 0;
+        best_lambda = 0; best_ll = 0; best_yPy = 0; nt_p0 = 0; nt_iter = 0; br.done = 0;
+        for (int k = 0; k < kNumFixed; ++k) d1_fixed[k] = 0;
+        request_fixed(0);
+    }
+
+    // np.argmax over the growing list: first maximum, NaN beats everything and the first NaN stays
+    PG_HD void candidate(double ll, double lam, double yPy)
+    {
+        if (isnan(best_ll)) return;
+        if (isnan(ll) || ll > best_ll) { best_ll = ll; best_lambda = lam; best_yPy = yPy; }
+    }
+
+    PG_HD void next_bracket()
+    {
+        for (; idx < kNumFixed - 1; ++idx) {
+            const double f0 = d1_fixed[idx], f1 = d1_fixed[idx + 1];
+            if (np_sign(f0) * np_sign(f1) < 0) {  // lmm.py:63
+                br.start(fixed_lambda(idx), f0, fixed_lambda(idx + 1), f1, 2e-12, 0.1, 5000);
+                if (br.done) { start_newton(br.root); return; }
+                phase = kBrent;
+                request(br.query(), 0);
+                return;
+            }
+        }
+        phase = kDone;
+    }
+
+    PG_HD void start_newton(double lam0) { nt_p0 = lam0; nt_iter = 0; phase = kNewton; request(nt_p0, 1); }
+
+    PG_HD static bool in_tables(double lam) { return lam >= fixed_lambda(0) && lam <= fixed_lambda(kNumFixed - 1); }
+
+    PG_HD void feed(const EvalOut& e)
+    {
+        if (rq_full) n_eval3++; else n_eval2++;
+        if (phase == kFixed) {
+            const int t = t_req;
+            d1_fixed[t] = ml_d1(rq_lambda, n, e.yPy, e.yPPy, e.trH);
+            if (t == 0) {
+                best_ll = ml_loglik(n, e.yPy, e.logdetH); best_lambda = rq_lambda; best_yPy = e.yPy;   // roots[0]
+            } else if (t == kNumFixed - 1) {
+                candidate(ml_loglik(n, e.yPy, e.logdetH), rq_lambda, e.yPy);                          // roots[1]
+            }
+            if (t + 1 < kNumFixed) { request_fixed(t + 1); return; }
+            idx = 0;
+            next_bracket();
+            return;
+        }
+        if (phase == kBrent) {
+            br.feed(ml_d1(rq_lambda, n, e.yPy, e.yPPy, e.trH));
+            if (br.done) { start_newton(br.root); return; }
+            request(br.query(), 0);
+            return;
+        }
+        if (phase == kNewton) {
+            // scipy.optimize.newton, Newton-Raphson branch
+            const double fval = ml_d1(nt_p0, n, e.yPy, e.yPPy, e.trH);
+            const double fder = ml_d2(nt_p0, n, e.yPy, e.yPPy, e.yPPPy, e.trH, e.trHH);
+            double root = nt_p0;
+            bool stop = (fval == 0) || (fder == 0);
+            if (!stop) {
+                const double p = nt_p0 - fval / fder;
+                const bool fin = isfinite(p) && isfinite(nt_p0);
+                const bool close = fin ? (fabs(p - nt_p0) <= 1.48e-8 + 1e-5 * fabs(nt_p0)) : (p == nt_p0);
+                if (!(isfinite(p) && in_tables(p))) { status |= 2; stop = true; }   // deviation, see above
+                else {
+                    root = p;
+                    if (close || nt_iter + 1 >= 10) stop = true;
+                    else { nt_p0 = p; nt_iter++; }
+                }
+            }
+            if (!stop) { request(nt_p0, 1); return; }
+            phase = kRootLL;
+            request(root, 0);
+            return;
+        }
+        if (phase == kRootLL) {
+            candidate(ml_loglik(n, e.yPy, e.logdetH), rq_lambda, e.yPy);
+            idx++;
+            next_bracket();
+            return;
+        }
+    }
 };
 
 }  // namespace pg

@@ -32,6 +32,10 @@ struct SolveArgs {
     int yrow;             // slab row of this launch's phenotype (k1p - 1 + phenotype index)
     const double* F;      // [m][zrows][kFxCols] x rows of the fixed-lambda evaluations (fixed_xrow_kernel), or nullptr
     int swap;             // 1: "de" mode, the genotype column is the phenotype and y the tested regressor (pg_eval.cuh)
+    // likelihood-ratio outputs (nullable, all four or none): ML lambda and log-likelihood of the model [W0, x],
+    // D_lrt = 2 (l_alt - l_null), p_lrt = chi2(1) upper tail (reference lmm/lmm.py:278-282,:300, commented there)
+    double* lrt[4];
+    double l_null;        // ML log-likelihood of the null model [W0] of this launch's phenotype (null_model_kernel)
     Tables2 t2;
     double* out[6];
     int* status;
@@ -377,14 +381,75 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
             eval_snp_compressed<NS>(a, Zs, Fs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
             s.feed(e);
         }
+        int st_bits = s.status;
         if (lane == 0) {
             const long long row = a.row0 + (long long)g;
             a.out[0][row] = s.beta; a.out[1][row] = s.se; a.out[2][row] = s.tau;
             a.out[3][row] = s.lambda; a.out[4][row] = s.F; a.out[5][row] = s.p;
-            if (a.status) a.status[row] = s.status;
             if (a.n_eval2) a.n_eval2[row] = s.n_eval2;
             if (a.n_eval3) a.n_eval3[row] = s.n_eval3;
         }
+        if (a.lrt[0]) {
+            // the ML optimisation of the alternative model on the same moments; its state takes over the REML solver's
+            // shared-memory slot (the Wald row has been written)
+            __syncwarp();
+            static_assert(sizeof(MlSolver) <= sizeof(SnpSolver), "MlSolver must fit the solver slot");
+            MlSolver& ms = *reinterpret_cast<MlSolver*>(solver_mem[warp]);
+            ms.init(a.n);
+            while (ms.pending()) {
+                EvalOut e;
+                eval_snp_compressed<NS>(a, Zs, Fs, ms.req_lambda(), ms.req_fixed(), ms.req_full(), 0, scratch, &e);
+                ms.feed(e);
+            }
+            if (lane == 0) {
+                const long long row = a.row0 + (long long)g;
+                const double D = 2.0 * (ms.best_ll - a.l_null);
+                a.lrt[0][row] = ms.best_lambda; a.lrt[1][row] = ms.best_ll; a.lrt[2][row] = D;
+                a.lrt[3][row] = chi2_sf_1(D);
+            }
+            st_bits |= ms.status;
+        }
+        if (lane == 0 && a.status) a.status[a.row0 + (long long)g] = st_bits;
+    }
+}
+
+// The null model [W0] of one phenotype (reference lmm/lmm.py:176-190, commented there): ML lambda as lmm.calc_lambda
+// finds it, tau = n / y^T P y, and the log-likelihood the LRT subtracts.  No genotype is involved: every evaluation
+// is a table-2 row (level c0 of the [W0, y] block).  One warp; out4 = {lambda_null, tau_null, l_null, status}.
+__global__ void null_model_kernel(int n, Tables2 t2, double* out4)
+{
+    __shared__ double rowbuf[16];
+    __shared__ MlSolver ms;
+    const int lane = threadIdx.x & 31, NF2 = t2.NF2, c0 = t2.c0;
+    ms.init(n);
+    __syncwarp();
+    while (ms.pending()) {
+        EvalOut e;
+        const double lam = ms.req_lambda();
+        const int fixed_t = ms.req_fixed();
+        const double* fin;
+        if (fixed_t >= 0) {
+            fin = t2.fix2 + (size_t)fixed_t * NF2 + t2_fin(c0);
+        } else {
+            int iv;
+            double L[kNodes];
+            table_weights(t2.basis, lam, &iv, L);
+            const double* base = t2.itab2 + (size_t)iv * kNodes * NF2 + t2_fin(c0);
+            if (lane < 9) {
+                double v = 0.0;
+                for (int k = 0; k < kNodes; ++k) v += L[k] * base[(size_t)k * NF2 + lane];
+                rowbuf[lane] = v;
+            }
+            __syncwarp();
+            fin = rowbuf;
+        }
+        null_eval_from_row(fin, &e);
+        __syncwarp();
+        ms.feed(e);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        out4[0] = ms.best_lambda; out4[1] = (double)n / ms.best_yPy; out4[2] = ms.best_ll; out4[3] = (double)ms.status;
     }
 }
 

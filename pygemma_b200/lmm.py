@@ -30,6 +30,11 @@ import pandas as pd
 from . import _capi
 
 COLUMNS = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
+# opt-in likelihood-ratio columns, named as the reference's commented-out result keys (lmm/lmm.py:137-141)
+LRT_COLUMNS = ["D_lrt", "p_lrt", "likelihood"]
+
+# null model of the most recent lrt=True call: one dict(lambda_null, tau_null, l_null) per trait (lmm/lmm.py:176-190)
+last_null_model: list = []
 
 # timings of the most recent call (seconds / milliseconds), for callers that want them without verbose
 last_timing: dict = {}
@@ -136,7 +141,7 @@ def _log(verbose, msg):
 
 
 def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=False, grid=False, eigen=True,
-            nproc=1, device=None):
+            nproc=1, device=None, lrt=False):
     """Per-SNP LMM association scan (GEMMA Wald test) on a B200.
 
     Args mirror the reference (lmm/lmm.py:87-103): Y (n,) or (n, 1) phenotype; X (n, m) genotypes
@@ -146,13 +151,51 @@ def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=Fa
     snps: labels for the 'SNPs' column; grid: 12-point grid search for lambda instead of
     Brent + Newton; de: differential-expression mode (X columns are outcomes, Y the predictor; grid is not
     forwarded, as in lmm/lmm.py:504).  `device` (extension) selects the CUDA device; default 0 or the
-    torch.distributed local rank.
+    torch.distributed local rank.  `lrt=True` (extension) adds the likelihood-ratio columns the reference keeps as
+    commented-out scaffolding (lmm/lmm.py:137-141,:176-190,:278-300): 'D_lrt' = 2 (l_alt - l_null) with the ML fits of
+    lmm.calc_lambda, 'p_lrt' = its chi-square(1) tail, 'likelihood' = l_alt; the null fit is left in `last_null_model`.
     """
     Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)  # lmm/lmm.py:115-116
-    return _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device)[0]
+    return _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device, lrt)[0]
 
 
-def pygemma_multi(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, grid=False, eigen=True, device=None):
+def null_model(Y, W, K, Z=None, eigen=True, device=None):
+    """The null model of the reference's likelihood-ratio scaffolding (lmm/lmm.py:176-190): ML lambda as lmm.calc_lambda
+    finds it for y ~ W, tau_null = n / y^T P y and the log-likelihood.  K may be a KinshipFactor.  Returns a dict."""
+    from . import multi
+
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1)
+    W = np.asarray(W, dtype=np.float64)
+    if W.ndim == 1:
+        W = W.reshape(-1, 1)
+    n, c0 = W.shape
+    if Y.shape[0] != n:
+        raise ValueError(f"shape mismatch: Y {Y.shape}, W {W.shape}")
+    if isinstance(K, KinshipFactor):
+        if not eigen or Z is not None:
+            raise ValueError("a KinshipFactor already holds U (apply Z in lmm.factorize; eigen=False does not apply)")
+        h = K.handle(c0)
+        h.set_design(W, Y)
+        return h.null_model(0)
+    ctx = multi.context(device)
+    with _capi.Handle(n, c0, ctx.device) as h:
+        if eigen:
+            multi.check_backend(ctx)
+            Km = None
+            if ctx.rank == 0:
+                Km = np.asarray(K, dtype=np.float64)
+                if Z is not None:
+                    Zm = np.asarray(Z, dtype=np.float64)
+                    Km = Zm @ Km @ Zm.T
+            multi.setup_eigen(ctx, h, Km)
+        else:
+            h.set_eigen(None, np.asarray(K, dtype=np.float64).reshape(-1))
+        h.set_design(W, Y, already_rotated=not eigen)
+        return h.null_model(0)
+
+
+def pygemma_multi(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, grid=False, eigen=True, device=None,
+                  lrt=False):
     """Several phenotypes in one pass (extension; the reference is called once per trait, e.g.
     experiments/benchmarks/benchmarks.py loops lmm.pygemma over simulated phenotypes).
 
@@ -165,17 +208,19 @@ def pygemma_multi(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True,
         Y = Y.reshape(-1, 1)
     if Y.ndim != 2:
         raise ValueError("Y must be (n, q)")
-    return _run(Y, X, W, K, Z, snps, verbose, disable_checks, False, grid, eigen, device)
+    return _run(Y, X, W, K, Z, snps, verbose, disable_checks, False, grid, eigen, device, lrt)
 
 
-def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
-    global last_timing
+def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device, lrt=False):
+    global last_timing, last_null_model
     t_start = time.time()
     if de:
         # calculate_de (lmm/lmm.py:498-532): every column of X is a phenotype, Y the tested regressor; it calls
         # calc_lambda_restricted without `grid` (:504), i.e. always Brent + Newton
         if Y.shape[1] != 1:
             raise ValueError("de=True takes one predictor Y")
+        if lrt:
+            raise ValueError("lrt=True is not available with de=True")
         grid = False
 
     from . import multi  # torch.distributed plumbing, only active when a process group exists
@@ -234,6 +279,7 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
         h.set_scan_mode(_capi.PG_SCAN_DE if de else _capi.PG_SCAN_WALD)
         a, b = ctx.shard(m)  # contiguous SNP range of this rank (SampleIter, lmm/lmm.py:427-434)
         outs = []
+        nulls = []
         timing["design_ms"], timing["scan_wall_s"], timing["gather_s"] = 0.0, 0.0, 0.0
         res = None
         # traits go through in groups of PG_MAX_TRAITS per pass over the genotypes (one group for lmm.pygemma)
@@ -245,7 +291,9 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
             _log(verbose, f"Rotated Y, W and built lambda tables - {round(time.time() - t0, 3)} s")
             _log(verbose, f"Running {m} SNPs with {n} individuals...")
             t0 = time.time()
-            res = h.scan(X[:, a:b], grid=grid)
+            res = h.scan(X[:, a:b], grid=grid, lrt=lrt)
+            if lrt:
+                nulls.extend(h.null_model(ph) for ph in range(qg))
             timing["scan"] = res["timing"]
             t1 = time.time()
             if qg == 1:
@@ -272,7 +320,16 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
                 col = col.copy()
                 col[bad] = np.nan  # lmm/lmm.py:484-493
             data[c] = col
-        results_df = pd.DataFrame(data, columns=COLUMNS)
+        cols = list(COLUMNS)
+        if lrt:
+            for c, k in zip(LRT_COLUMNS, ("D_lrt", "p_lrt", "loglik_ml")):
+                col = out[k]
+                if bad.any():
+                    col = col.copy()
+                    col[bad] = np.nan
+                data[c] = col
+            cols += LRT_COLUMNS
+        results_df = pd.DataFrame(data, columns=cols)
         if snps is not None:
             results_df["SNPs"] = snps  # lmm/lmm.py:408-409 (same statement: pandas alignment semantics preserved)
         frames.append(results_df)
@@ -280,4 +337,6 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device):
     timing["n_eval2_mean"] = float(np.mean([o["n_eval2"].mean() for o in outs])) if m else 0.0
     timing["n_eval3_mean"] = float(np.mean([o["n_eval3"].mean() for o in outs])) if m else 0.0
     last_timing = timing
+    if lrt:
+        last_null_model = nulls
     return frames

@@ -17,6 +17,12 @@ from dataclasses import dataclass
 import numpy as np
 
 RESULT_KEYS = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald", "status", "n_eval2", "n_eval3"]
+LRT_KEYS = ["lambda_ml", "loglik_ml", "D_lrt", "p_lrt"]   # present when the scan was asked for the likelihood-ratio outputs
+_INT_KEYS = {"status", "n_eval2", "n_eval3"}
+
+
+def _keys_of(res: dict):
+    return RESULT_KEYS + (LRT_KEYS if "D_lrt" in res else [])
 
 
 @dataclass
@@ -167,23 +173,25 @@ def gather_device(ctx: Context, out_dev, st_dev):
     return allo, alls
 
 
-def pack_results(res: dict, per: int) -> np.ndarray:
-    """(9, per) float64 block of one rank's rows, NaN / 0 padded to the common shard length."""
+def pack_results(res: dict, per: int, keys=None) -> np.ndarray:
+    """(len(keys), per) float64 block of one rank's rows, NaN / 0 padded to the common shard length."""
+    keys = keys or RESULT_KEYS
     k = res["beta"].shape[0]
-    blk = np.full((len(RESULT_KEYS), per), np.nan)
-    for i, key in enumerate(RESULT_KEYS):
+    blk = np.full((len(keys), per), np.nan)
+    for i, key in enumerate(keys):
         blk[i, :k] = res[key] if key in res else 0
     return blk
 
 
-def unpack_results(blocks, m: int, world: int) -> dict:
+def unpack_results(blocks, m: int, world: int, keys=None) -> dict:
     """Concatenate rank blocks in rank order (= input column order) and trim the padding."""
-    out = {key: np.empty(m, dtype=np.float64 if i < 6 else np.int32) for i, key in enumerate(RESULT_KEYS)}
+    keys = keys or RESULT_KEYS
+    out = {key: np.empty(m, dtype=np.int32 if key in _INT_KEYS else np.float64) for key in keys}
     for r, blk in enumerate(blocks):
         a, b = shard_range(m, r, world)
-        for i, key in enumerate(RESULT_KEYS):
+        for i, key in enumerate(keys):
             vals = blk[i, : b - a]
-            out[key][a:b] = vals if i < 6 else np.nan_to_num(vals).astype(np.int32)
+            out[key][a:b] = np.nan_to_num(vals).astype(np.int32) if key in _INT_KEYS else vals
     return out
 
 
@@ -220,11 +228,12 @@ def gather_results(ctx: Context, res: dict, m: int) -> dict:
 
     per = shard_len(m, ctx.world_size)
     t0 = time.perf_counter()
-    buf = _gather_buffers(ctx, len(RESULT_KEYS), per)
+    keys = _keys_of(res)
+    buf = _gather_buffers(ctx, len(keys), per)
     mine = buf["mine_h"].numpy()
     k = res["beta"].shape[0]
     mine[:, k:] = np.nan
-    for i, key in enumerate(RESULT_KEYS):
+    for i, key in enumerate(keys):
         mine[i, :k] = res[key] if key in res else 0
     if ctx.backend == "nccl":
         buf["mine_d"].copy_(buf["mine_h"], non_blocking=True)
@@ -233,7 +242,7 @@ def gather_results(ctx: Context, res: dict, m: int) -> dict:
         torch.cuda.current_stream(buf["all_d"].device).synchronize()
     else:
         dist.all_gather_into_tensor(buf["all_h"], buf["mine_h"])
-    blocks = buf["all_h"].numpy().reshape(ctx.world_size, len(RESULT_KEYS), per)
-    out = unpack_results(blocks, m, ctx.world_size)
+    blocks = buf["all_h"].numpy().reshape(ctx.world_size, len(keys), per)
+    out = unpack_results(blocks, m, ctx.world_size, keys)
     last_collective_s["gather"] = time.perf_counter() - t0
     return out

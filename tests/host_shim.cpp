@@ -149,7 +149,7 @@ void build_tables2(const HostTables& H, HostTables2& H2)
 
 // evaluation through the x-row recursion + table-2 rows (what reml_solve_kernel does)
 void eval_snp_xrow(const HostTables2& H2, const CompressPlan& P, const double* z, double lam, int fixed_t, int full,
-                   int need_ll, EvalOut* out)
+                   int need_ll, EvalOut* out, bool swap = false)
 {
     const int c0 = H2.t.c0, k1 = c0 + 2, Kc = P.Kc, NF2 = H2.t.NF2;
     std::vector<double> xa(k1), xb(k1), xc(k1), row(NF2);
@@ -175,8 +175,28 @@ void eval_snp_xrow(const HostTables2& H2, const CompressPlan& P, const double* z
         }
         row2 = row.data();
     }
-    if (full) xrow_recursion_scalar<true>(c0, row2, xa.data(), xb.data(), xc.data(), need_ll, out);
-    else xrow_recursion_scalar<false>(c0, row2, xa.data(), xb.data(), xc.data(), need_ll, out);
+    if (full) xrow_recursion_scalar<true>(c0, row2, xa.data(), xb.data(), xc.data(), need_ll, out, swap);
+    else xrow_recursion_scalar<false>(c0, row2, xa.data(), xb.data(), xc.data(), need_ll, out, swap);
+}
+
+// table-2 finals at lambda (null model: no x anywhere)
+void eval_null(const HostTables2& H2, double lam, int fixed_t, EvalOut* out)
+{
+    const int c0 = H2.t.c0, NF2 = H2.t.NF2;
+    double fin[9];
+    if (fixed_t >= 0) {
+        for (int f = 0; f < 9; ++f) fin[f] = H2.fix2[(size_t)fixed_t * NF2 + t2_fin(c0) + f];
+    } else {
+        int iv;
+        double L[kNodes];
+        table_weights(H2.t.basis, lam, &iv, L);
+        for (int f = 0; f < 9; ++f) {
+            double v = 0.0;
+            for (int k = 0; k < kNodes; ++k) v += L[k] * H2.itab2[((size_t)iv * kNodes + k) * NF2 + t2_fin(c0) + f];
+            fin[f] = v;
+        }
+    }
+    null_eval_from_row(fin, out);
 }
 }  // namespace
 
@@ -217,8 +237,21 @@ double pgh_compress_error(int n, const double* d_sorted, const double* a, int po
 }
 
 // the scan on compressed moments: d / wy / xr in any eigenvalue order (sorted here)
+void pgh_scan_compressed_ex(int n, int c0, long m, const double* d, const double* wy, const double* xr, int grid,
+                            int xrow_form, double* out6, int32_t* status, int32_t* evals, int32_t* kc_out, int swap,
+                            double* null3, double* lrt2);
+
 void pgh_scan_compressed(int n, int c0, long m, const double* d, const double* wy, const double* xr, int grid,
                          int xrow_form, double* out6, int32_t* status, int32_t* evals, int32_t* kc_out)
+{
+    pgh_scan_compressed_ex(n, c0, m, d, wy, xr, grid, xrow_form, out6, status, evals, kc_out, 0, nullptr, nullptr);
+}
+
+// swap != 0: "de" mode (x-row form only).  null3 / lrt2 (nullable, x-row form only): the product's MlSolver on the null
+// model -> {lambda_null, tau_null, l_null} and on every alternative model -> lrt2[2 g] = lambda_ml, lrt2[2 g + 1] = loglik_ml
+void pgh_scan_compressed_ex(int n, int c0, long m, const double* d, const double* wy, const double* xr, int grid,
+                            int xrow_form, double* out6, int32_t* status, int32_t* evals, int32_t* kc_out, int swap,
+                            double* null3, double* lrt2)
 {
     std::vector<int> perm(n);
     for (int l = 0; l < n; ++l) perm[l] = l;
@@ -236,6 +269,16 @@ void pgh_scan_compressed(int n, int c0, long m, const double* d, const double* w
     CompressPlan P;
     build_compress_plan(ds.data(), n, &P);
     if (kc_out) *kc_out = P.Kc;
+    if (null3 && xrow_form) {
+        MlSolver ms;
+        ms.init(n);
+        while (ms.pending()) {
+            EvalOut e;
+            eval_null(H2, ms.req_lambda(), ms.req_fixed(), &e);
+            ms.feed(e);
+        }
+        null3[0] = ms.best_lambda; null3[1] = (double)n / ms.best_yPy; null3[2] = ms.best_ll;
+    }
     std::vector<double> z((size_t)k1 * P.Kc);
     for (long g = 0; g < m; ++g) {
         std::fill(z.begin(), z.end(), 0.0);
@@ -253,13 +296,24 @@ void pgh_scan_compressed(int n, int c0, long m, const double* d, const double* w
         s.init(n, c0, grid);
         while (s.pending()) {
             EvalOut e;
-            if (xrow_form) eval_snp_xrow(H2, P, z.data(), s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), &e);
+            if (xrow_form) eval_snp_xrow(H2, P, z.data(), s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), &e, swap != 0);
             else eval_snp_compressed(H, P, z.data(), s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), &e);
             s.feed(e);
         }
         double* o = out6 + g * 6;
         o[0] = s.beta; o[1] = s.se; o[2] = s.tau; o[3] = s.lambda; o[4] = s.F; o[5] = s.p;
         status[g] = s.status; evals[2 * g] = s.n_eval2; evals[2 * g + 1] = s.n_eval3;
+        if (lrt2 && xrow_form) {
+            MlSolver ms;
+            ms.init(n);
+            while (ms.pending()) {
+                EvalOut e;
+                eval_snp_xrow(H2, P, z.data(), ms.req_lambda(), ms.req_fixed(), ms.req_full(), 0, &e);
+                ms.feed(e);
+            }
+            lrt2[2 * g] = ms.best_lambda; lrt2[2 * g + 1] = ms.best_ll;
+            status[g] |= ms.status;
+        }
     }
 }
 }

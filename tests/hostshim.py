@@ -42,6 +42,9 @@ def lib():
     L.pgh_scan_compressed.restype = None
     L.pgh_scan_compressed.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long, _dp, _dp, _dp, ctypes.c_int,
                                       ctypes.c_int, _dp, _ip, _ip, _ip]
+    L.pgh_scan_compressed_ex.restype = None
+    L.pgh_scan_compressed_ex.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long, _dp, _dp, _dp, ctypes.c_int,
+                                         ctypes.c_int, _dp, _ip, _ip, _ip, ctypes.c_int, _dp, _dp]
     _lib = L
     return L
 
@@ -89,4 +92,30 @@ def scan_compressed(d, y, w0, xr_snp_major, grid=False, xrow_form=True):
     r["n_eval2"] = ev[:, 0].copy()
     r["n_eval3"] = ev[:, 1].copy()
     r["nodes"] = int(kc[0])
+    return r
+
+
+def scan_compressed_ex(d, y, w0, xr_snp_major, swap=False, lrt=False):
+    """x-row form of the compressed scan with the product's optional modes: swap = "de" role swap (PG_SCAN_DE),
+    lrt = the ML optimiser of the likelihood-ratio outputs (pg::MlSolver) on the null and every alternative model."""
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    w0 = np.asarray(w0, dtype=np.float64)
+    wy = np.asfortranarray(np.concatenate([w0, np.asarray(y, dtype=np.float64).reshape(-1, 1)], axis=1))
+    xr = np.ascontiguousarray(xr_snp_major, dtype=np.float64)
+    n, c0, m = d.shape[0], w0.shape[1], xr.shape[0]
+    out = np.empty((m, 6))
+    st = np.zeros(m, dtype=np.int32)
+    ev = np.zeros((m, 2), dtype=np.int32)
+    kc = np.zeros(1, dtype=np.int32)
+    null3 = np.empty(3)
+    lrt2 = np.empty((m, 2))
+    lib().pgh_scan_compressed_ex(n, c0, m, _p(d), _p(wy), _p(xr), 0, 1, _p(out), st.ctypes.data_as(_ip),
+                                 ev.ctypes.data_as(_ip), kc.ctypes.data_as(_ip), int(swap), _p(null3) if lrt else None,
+                                 _p(lrt2) if lrt else None)
+    cols = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
+    r = {c: out[:, i].copy() for i, c in enumerate(cols)}
+    r["status"] = st
+    if lrt:
+        r.update(lambda_null=null3[0], tau_null=null3[1], l_null=null3[2], lambda_ml=lrt2[:, 0].copy(),
+                 loglik_ml=lrt2[:, 1].copy())
     return r

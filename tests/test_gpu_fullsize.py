@@ -373,3 +373,101 @@ def test_de_mode_is_the_role_swapped_scan():
         g = np.load(path)
         df = lmm.pygemma(g["yr"], g["xr"], g["wr"], g["d"], eigen=False, de=True)
         _check({c: df[c].to_numpy() for c in COLS}, {c: g[f"r64_{c}"] for c in COLS}, tag="de golden")
+
+
+@pytest.mark.parametrize("name", ["lrt_interior", "lrt_low_h2", "lrt_c8"])
+def test_lrt_outputs_match_reference_functions(name):
+    """lrt=True: null model and per-SNP ML fits on the device (null_model_kernel, MlSolver in reml_solve_kernel) against
+    the reference's live lmm.calc_lambda / likelihood_lambda (tests/golden/lrt_*.npz) and the dense oracle; the Wald
+    columns must not change a bit when the LRT columns are requested."""
+    from oracle import oracle
+    from pygemma_b200 import lmm
+
+    capi = _capi()
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    d, yr, wr, xr = g["d"], g["yr"], g["wr"], g["xr"]
+    n, m = xr.shape
+    with capi.Handle(n, wr.shape[1]) as h:
+        h.set_eigen(None, d)
+        h.set_design(wr, yr, already_rotated=True)
+        h.set_options(block_snps=16)   # several blocks
+        o = h.scan(np.ascontiguousarray(xr), lrt=True)
+        o0 = h.scan(np.ascontiguousarray(xr))
+        nm = h.null_model(0)
+    for c in COLS:
+        assert np.array_equal(o[c], o0[c], equal_nan=True), c
+    assert (o["status"] == 0).all()
+    assert rel(nm["lambda_null"], g["r64_lambda_null"]) < TOL and rel(nm["l_null"], g["r64_l_null"]) < 1e-9
+    assert rel(o["lambda_ml"], g["r64_lambda_alt"]).max() < TOL
+    assert rel(o["loglik_ml"], g["r64_l_alt"]).max() < 1e-9
+    assert np.abs(o["D_lrt"] - g["r64_D_lrt"]).max() < 1e-7
+    ok = g["r64_p_lrt"] > 1e-9
+    assert rel(o["p_lrt"][ok], g["r64_p_lrt"][ok]).max() < TOL
+    ref = oracle.lrt_rotated(d, yr, wr, np.ascontiguousarray(xr.T))
+    assert rel(nm["tau_null"], ref["tau_null"]) < 1e-9
+    assert rel(o["p_lrt"], ref["p_lrt"]).max() < TOL   # accurate tail on both sides
+    # the public call: three more columns, named as the reference's commented-out keys
+    df = lmm.pygemma(yr, xr, wr, d, eigen=False, lrt=True, snps=np.arange(m))
+    assert list(df.columns) == COLS + ["D_lrt", "p_lrt", "likelihood", "SNPs"]
+    assert np.array_equal(df["D_lrt"].to_numpy(), o["D_lrt"]) and np.array_equal(df["likelihood"].to_numpy(), o["loglik_ml"])
+    assert rel(lmm.last_null_model[0]["l_null"], g["r64_l_null"]) < 1e-9
+    assert rel(lmm.null_model(yr, wr, d, eigen=False)["lambda_null"], g["r64_lambda_null"]) < TOL
+
+
+def test_lrt_through_kinship_and_multi_trait():
+    """lrt=True end to end (syevd, int8 rotation) vs the dense oracle on LAPACK-rotated inputs, single- and multi-trait."""
+    from oracle import oracle
+    from pygemma_b200 import lmm
+    from pygemma_b200.synth import make_problem
+
+    n, m, c0 = 500, 120, 3
+    p = make_problem(n, m, c0, seed=71, m_k=1200)
+    rng = np.random.default_rng(2)
+    Y = np.stack([p["Y"].reshape(-1), 0.4 * p["Y"].reshape(-1) + rng.standard_normal(n)], axis=1)
+    frames = lmm.pygemma_multi(Y, p["X"], p["W"], p["K"], lrt=True)
+    d, U, _, xr, wr = oracle.eigen_rotate(p["K"], Y[:, 0], p["X"], p["W"])
+    for ph in range(2):
+        ref = oracle.lrt_rotated(d, U.T @ Y[:, ph], wr, np.ascontiguousarray(xr.T))
+        df = frames[ph]
+        assert np.abs(df["D_lrt"].to_numpy() - ref["D_lrt"]).max() < 1e-6
+        assert rel(df["likelihood"].to_numpy(), ref["loglik_ml"]).max() < 1e-8
+        assert rel(df["p_lrt"].to_numpy(), ref["p_lrt"]).max() < 1e-5
+        assert rel(lmm.last_null_model[ph]["l_null"], ref["l_null"]) < 1e-9
+        one = lmm.pygemma(Y[:, ph], p["X"], p["W"], p["K"], lrt=True)
+        for c in COLS + ["D_lrt", "p_lrt", "likelihood"]:
+            assert np.array_equal(one[c].to_numpy(), df[c].to_numpy(), equal_nan=True), (ph, c)
+
+
+def test_traw_ingest_with_std_filter_matches_oracle(tmp_path):
+    """PLINK .traw -> packed 2-bit block -> device decode / mean imputation / int8 rotation, with the callers' std > 0
+    filter (experiments/wtccc/run_pygemma.py:407-410): against the oracle on the NumPy-imputed kept columns."""
+    from oracle import oracle
+    from pygemma_b200 import traw
+    from pygemma_b200.synth import make_problem
+
+    n, m, c0 = 401, 90, 3
+    p = make_problem(n, m, c0, seed=13, m_k=900)
+    rng = np.random.default_rng(6)
+    G = p["X"].astype(np.float64)
+    G[rng.random(G.shape) < 0.02] = np.nan
+    G[:, 7] = 0.0       # monomorphic -> filtered
+    G[:, 8] = np.nan    # all missing -> filtered
+    G[:, 30] = p["X"][:, 30]   # complete column
+    path = str(tmp_path / "toy.traw.gz")
+    traw.write_traw(path, G)
+    for policy in ("omit", "propagate"):
+        for std in (False, True):
+            df, keep = traw.pygemma_traw(p["Y"], path, p["W"], p["K"], filter_std=True, nan_policy=policy, standardize=std)
+            with np.errstate(invalid="ignore"):
+                want = (np.nan_to_num(np.nanstd(np.where(np.isnan(G).all(0), 0.0, G), axis=0)) > 0) if policy == "omit" \
+                    else (np.nan_to_num(G.std(axis=0)) > 0)
+            assert np.array_equal(keep, want) and not keep[7] and not keep[8] and keep[30]
+            assert len(df) == int(keep.sum()) and list(df["SNPs"]) == [f"rs{i}" for i in np.where(keep)[0]]
+            Xk = G[:, keep]
+            Xi = np.where(np.isnan(Xk), np.nanmean(Xk, axis=0), Xk)   # SimpleImputer(strategy='mean')
+            if std:
+                Xi = (Xi - Xi.mean(axis=0)) / Xi.std(axis=0)
+            ref = oracle.pygemma(p["Y"], Xi, p["W"], p["K"])
+            _check({c: df[c].to_numpy() for c in COLS}, ref, tag=("traw", policy, std))
+    df_all, keep_all = traw.pygemma_traw(p["Y"], path, p["W"], p["K"])
+    assert keep_all.all() and len(df_all) == m

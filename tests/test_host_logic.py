@@ -13,6 +13,9 @@ from oracle import oracle
 from pygemma_b200 import multi
 
 
+TOL = 1e-6  # north star: lambda, beta, se, p within 1e-6 relative
+
+
 def rel(a, b):
     a = np.asarray(a, float)
     b = np.asarray(b, float)
@@ -182,7 +185,7 @@ def test_pygemma_multi_groups_traits_and_keeps_order(monkeypatch):
             calls.append(("design", self.q))
             return 1.0
 
-        def scan(self, X, grid=False):
+        def scan(self, X, grid=False, lrt=False):
             m = X.shape[1]
             calls.append(("scan", self.q))
             shape = m if self.q == 1 else (self.q, m)
@@ -313,3 +316,61 @@ def test_bed_pack_unpack_and_files(tmp_path):
     open(prefix + ".bed", "r+b").write(b"\x00")
     with pytest.raises(ValueError):
         bed.read_packed(prefix)
+
+
+def test_de_mode_solver_matches_reference_cpdefs():
+    """The role-swapped final level (pg_eval.cuh: xrow_final_level_swapped, PG_SCAN_DE) through the product's scalar
+    headers on the CPU, against the reference's cpdefs called in calculate_de's roles (tests/golden/de_small.npz)."""
+    g = np.load(os.path.join(GOLDEN, "de_small.npz"))
+    o = hostshim.scan_compressed_ex(g["d"], g["yr"], g["wr"], np.ascontiguousarray(g["xr"].T), swap=True)
+    assert (o["status"] == 0).all()
+    for c in COLS:
+        assert rel(o[c], g[f"r64_{c}"]).max() < TOL, c
+
+
+@pytest.mark.parametrize("name", ["lrt_interior", "lrt_low_h2", "lrt_c8"])
+def test_ml_solver_matches_reference_functions(name):
+    """pg::MlSolver (pg_math.cuh) + table-2 finals on the CPU against the reference's lmm.calc_lambda / likelihood_lambda
+    (tests/golden/lrt_*.npz): null model and every alternative model."""
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    o = hostshim.scan_compressed_ex(g["d"], g["yr"], g["wr"], np.ascontiguousarray(g["xr"].T), lrt=True)
+    assert (o["status"] == 0).all()
+    assert rel(o["lambda_null"], g["r64_lambda_null"]) < TOL and rel(o["l_null"], g["r64_l_null"]) < 1e-9
+    assert rel(o["lambda_ml"], g["r64_lambda_alt"]).max() < TOL
+    assert rel(o["loglik_ml"], g["r64_l_alt"]).max() < 1e-9
+    assert np.abs(2 * (o["loglik_ml"] - o["l_null"]) - g["r64_D_lrt"]).max() < 1e-7
+
+
+def test_traw_reader_and_std_filter(tmp_path):
+    """.traw text ingest (host) and the callers' `X.std(axis=0) > 0` filter (experiments/wtccc/run_pygemma.py:407-410)
+    computed from packed genotype counts: round trip, NA handling, gz, ragged n, both NaN policies against NumPy."""
+    from pygemma_b200 import bed, traw
+
+    rng = np.random.default_rng(3)
+    n, m = 37, 60   # n % 4 != 0
+    G = rng.binomial(2, rng.uniform(0.05, 0.5, m), size=(n, m)).astype(np.float64)
+    G[rng.random(G.shape) < 0.03] = np.nan
+    G[:, 4] = 1.0                       # monomorphic
+    G[:, 9] = np.nan                    # all missing
+    G[:, 11] = 2.0; G[3, 11] = np.nan   # monomorphic among the observed calls
+    G[:, 20] = rng.integers(0, 3, n)    # complete, polymorphic
+    for name in ("toy.traw", "toy.traw.gz"):
+        path = str(tmp_path / name)
+        traw.write_traw(path, G, snp_ids=[f"snp{i}" for i in range(m)])
+        packed, n2, info, samples = traw.read_traw(path, chunk_snps=17)
+        assert n2 == n and packed.shape == (m, (n + 3) // 4) and len(samples) == n
+        assert list(info.columns) == traw.INFO_COLUMNS and list(info["SNP"][:2]) == ["snp0", "snp1"]
+        D = bed.decode_packed(packed, n)
+        assert np.array_equal(D, G, equal_nan=True)
+    c = traw.genotype_counts(packed, n)
+    assert (c.sum(axis=1) == n).all() and c[9, 1] == n and c[4, 2] == n
+    with np.errstate(invalid="ignore"):
+        ref_prop = np.nan_to_num(G.std(axis=0), nan=0.0) > 0           # NaN > 0 is False
+        ref_omit = np.nan_to_num(np.nanstd(np.where(np.isnan(G).all(0), 0.0, G), axis=0), nan=0.0) > 0
+    assert np.array_equal(traw.std_filter(packed, n), ref_prop)
+    assert np.array_equal(traw.std_filter(packed, n, nan_policy="omit"), ref_omit)
+    assert not traw.std_filter(packed, n, "omit")[[4, 9, 11]].any() and traw.std_filter(packed, n)[20]
+    bad = str(tmp_path / "bad.traw")
+    open(bad, "w").write("CHR\tSNP\t(C)M\tPOS\tCOUNTED\tALT\ta_a\tb_b\n1\trs1\t0\t1\tA\tG\t0.5\t1\n")
+    with pytest.raises(ValueError, match="0, 1, 2 or NA"):
+        traw.read_traw(bad)

@@ -162,3 +162,22 @@ def test_oracle_de_mode_matches_reference_cpdefs():
         r = oracle.scan_rotated(g["d"], g["xr"][:, j], g["wr"], yrow)
         for c in COLS:
             assert rel(r[c][0], g[f"r64_{c}"][j]) < (1e-7 if c == "lambda" else 1e-9), (j, c)
+
+
+@pytest.mark.parametrize("name", ["lrt_interior", "lrt_low_h2", "lrt_c8"])
+def test_oracle_lrt_matches_reference_functions(name):
+    """LRT scaffolding (lmm/lmm.py:176-190,:278-300): the oracle's dense restatement against the reference's live
+    lmm.calc_lambda / likelihood_lambda (tests/golden/lrt_*.npz, made by make_golden.py lrt)."""
+    import os
+
+    from conftest import GOLDEN
+    from oracle import oracle
+
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    o = oracle.lrt_rotated(g["d"], g["yr"], g["wr"], np.ascontiguousarray(g["xr"].T))
+    assert rel(o["lambda_null"], g["r64_lambda_null"]) < 1e-7 and rel(o["l_null"], g["r64_l_null"]) < 1e-10
+    assert rel(o["lambda_ml"], g["r64_lambda_alt"]).max() < 1e-6
+    assert rel(o["loglik_ml"], g["r64_l_alt"]).max() < 1e-10
+    assert np.abs(o["D_lrt"] - g["r64_D_lrt"]).max() < 1e-8
+    ok = g["r64_p_lrt"] > 1e-9   # the reference's 1 - cdf loses the tail
+    assert rel(o["p_lrt"][ok], g["r64_p_lrt"][ok]).max() < 1e-6
