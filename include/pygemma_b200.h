@@ -20,8 +20,10 @@
  *   - all pointers are caller-owned; host entry points are synchronous at return.
  *   - a handle is bound to one CUDA device and is not thread-safe.
  *   - there is no CPU fallback: without a usable CUDA device pg_create fails.
- *   - per-SNP failure (status[g] != 0) yields a NaN row, never an error return,
- *     like the reference's LinAlgError branch (lmm/lmm.py:484-493).
+ *   - per-SNP failure (status[g] & 1) yields a NaN row, never an error return,
+ *     like the reference's LinAlgError branch (lmm/lmm.py:484-493).  Bits 1 and 2 of status are notes, not
+ *     failures: 2 = the ML Newton iteration of the LRT outputs was stopped at the edge of the tabulated lambda range,
+ *     4 = a bracket with a NaN derivative at one end was skipped (the other candidates still competed).
  */
 #ifndef PYGEMMA_B200_H
 #define PYGEMMA_B200_H

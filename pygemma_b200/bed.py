@@ -108,7 +108,7 @@ def pygemma_bed(Y, prefix: str, W, K, count_A1: bool = False, standardize: bool 
         out = h.scan_bed(packed, grid=grid, count_A1=count_A1, standardize=standardize)
     if verbose > 0:
         print(f"[pygemma_b200] {packed.shape[0]} SNPs from {os.path.basename(prefix)}.bed: {out['timing']}", flush=True)
-    bad = out["status"] != 0
+    bad = (out["status"] & 1) != 0
     data = {}
     for c in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"):
         col = out[c]

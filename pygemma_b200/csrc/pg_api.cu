@@ -160,6 +160,28 @@ static int fail(pg_handle* h, int code, const char* fmt, ...)
             return fail(h, PG_ERR_CUSOLVER, "%s:%d %s -> cusolver status %d", __FILE__, __LINE__, #call, (int)s_); \
     } while (0)
 
+// Scope guards for temporaries of one call: error paths return through the CK macros, the destructors release.
+struct DevMem {
+    void* p = nullptr;
+    DevMem() = default;
+    DevMem(const DevMem&) = delete;
+    DevMem& operator=(const DevMem&) = delete;
+    ~DevMem() { if (p) cudaFree(p); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    void* release() { void* q = p; p = nullptr; return q; }
+};
+struct EventGuard {
+    cudaEvent_t e = nullptr;
+    EventGuard() = default;
+    EventGuard(const EventGuard&) = delete;
+    EventGuard& operator=(const EventGuard&) = delete;
+    ~EventGuard() { if (e) cudaEventDestroy(e); }
+};
+struct SolverParamsGuard {
+    cusolverDnParams_t p = nullptr;
+    ~SolverParamsGuard() { if (p) cusolverDnDestroyParams(p); }
+};
+
 extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
 extern "C" int pg_rotation_planes(void) { return kSlices; }
 
@@ -459,14 +481,14 @@ static int canonicalise_eigen(pg_handle* h)
     if (!h->perm_identity) {
         CK(cudaMemcpy(h->d, ds.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
         if (h->have_U) {
-            double* tmp = nullptr;
-            CK(cudaMalloc(&tmp, sizeof(double) * (size_t)n * n));
+            DevMem tmp;
+            CK(cudaMalloc(&tmp.p, sizeof(double) * (size_t)n * n));
             const size_t total = (size_t)n * n;
-            permute_u_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->compute>>>(h->U, tmp, n, h->perm_dev, h->u_op_t);
+            permute_u_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->compute>>>(h->U, tmp.as<double>(), n, h->perm_dev, h->u_op_t);
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(h->compute));
             cudaFree(h->U);
-            h->U = tmp;
+            h->U = static_cast<double*>(tmp.release());
         }
     }
     return upload_plan(h, ds);
@@ -493,18 +515,21 @@ static int set_kinship_common(pg_handle* h, const double* K_host, cudaMemcpyKind
     int rc = ensure_U(h);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->U, K_host, sizeof(double) * (size_t)n * n, kind, h->compute));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    cusolverDnParams_t params;
-    CKS(cusolverDnCreateParams(&params));
+    EventGuard g0, g1;
+    CK(cudaEventCreate(&g0.e));
+    CK(cudaEventCreate(&g1.e));
+    const cudaEvent_t e0 = g0.e, e1 = g1.e;
+    SolverParamsGuard pg;
+    CKS(cusolverDnCreateParams(&pg.p));
+    cusolverDnParams_t params = pg.p;
     size_t wdev = 0, whost = 0;
     CKS(cusolverDnXsyevd_bufferSize(h->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F,
                                     h->U, n, CUDA_R_64F, h->d, CUDA_R_64F, &wdev, &whost));
-    void* dwork = nullptr;
-    int* info = nullptr;
-    CK(cudaMalloc(&dwork, wdev ? wdev : 8));
-    CK(cudaMalloc(&info, sizeof(int)));
+    DevMem dwork_g, info_g;
+    CK(cudaMalloc(&dwork_g.p, wdev ? wdev : 8));
+    CK(cudaMalloc(&info_g.p, sizeof(int)));
+    void* dwork = dwork_g.p;
+    int* info = info_g.as<int>();
     std::vector<char> hwork(whost ? whost : 8);
     CK(cudaEventRecord(e0, h->compute));
     cusolverStatus_t st = cusolverDnXsyevd(h->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
@@ -514,17 +539,12 @@ static int set_kinship_common(pg_handle* h, const double* K_host, cudaMemcpyKind
     int hinfo = -1;
     cudaError_t ce = cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->compute);
     cudaError_t se = cudaStreamSynchronize(h->compute);
-    cudaFree(dwork);
-    cudaFree(info);
-    cusolverDnDestroyParams(params);
     if (st != CUSOLVER_STATUS_SUCCESS) return fail(h, PG_ERR_CUSOLVER, "cusolverDnXsyevd status %d", (int)st);
     if (ce != cudaSuccess || se != cudaSuccess)
         return fail(h, PG_ERR_CUDA, "syevd: %s", cudaGetErrorString(ce != cudaSuccess ? ce : se));
     if (hinfo != 0) return fail(h, PG_ERR_CUSOLVER, "syevd did not converge (info=%d)", hinfo);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (eig_ms) *eig_ms = ms;
     clip_nonneg_kernel<<<(n + 255) / 256, 256, 0, h->compute>>>(h->d, n);
     CK(cudaGetLastError());
@@ -754,9 +774,10 @@ static int set_design_active(pg_handle* h, const double* W_host, const double* y
     for (int j = 0; j < c0; ++j)
         for (int l = 0; l < n; ++l) col[(size_t)j * n + l] = W_host[(size_t)(gather ? h->perm[l] : l) * c0 + j];
     for (int l = 0; l < n; ++l) col[(size_t)c0 * n + l] = y_host[gather ? h->perm[l] : l];
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    EventGuard g0, g1;
+    CK(cudaEventCreate(&g0.e));
+    CK(cudaEventCreate(&g1.e));
+    const cudaEvent_t e0 = g0.e, e1 = g1.e;
     CK(cudaEventRecord(e0, h->compute));
     if (already_rotated) {
         CK(cudaMemcpy2DAsync(h->wy, sizeof(double) * h->ldw, col.data(), sizeof(double) * n, sizeof(double) * n, k0,
@@ -780,8 +801,6 @@ static int set_design_active(pg_handle* h, const double* W_host, const double* y
     CK(cudaStreamSynchronize(h->compute));
     float t = 0;
     cudaEventElapsedTime(&t, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (ms) *ms = t;
     return PG_OK;
 }
@@ -1212,10 +1231,11 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
 
     // timing events come from a pool owned by the handle (creating / destroying ~40 events per call costs host time)
     size_t ev_next = 0;
+    bool ev_ok = true;
     auto take = [&]() -> cudaEvent_t {
         if (ev_next == h->ev_pool.size()) {
             cudaEvent_t e = nullptr;
-            cudaEventCreate(&e);
+            if (cudaEventCreate(&e) != cudaSuccess) { ev_ok = false; return nullptr; }
             h->ev_pool.push_back(e);
         }
         return h->ev_pool[ev_next++];
@@ -1225,6 +1245,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     for (long long b = 0; b < nblocks; ++b) { mk(ev_conv[b]); mk(ev_rot[b]); mk(ev_reml[b]); mk(ev_cmp[b]); if (!on_device) mk(ev_h2d[b]); }
     const bool compressed = (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED);
     cudaEvent_t t0 = take(), t1 = take(), t2 = take();
+    if (!ev_ok) return fail(h, PG_ERR_CUDA, "pg_scan: cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
     int n_rot_launch = 0, last_engine = 0;
 
     if (want_lrt)
@@ -1596,9 +1617,10 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     if (!h->have_design) return fail(h, PG_ERR_ARG, "pg_probe_precompute: call pg_set_design first");
     CK(cudaSetDevice(h->device));
     const int n = h->n;
-    double *dx = nullptr, *dout = nullptr;
-    CK(cudaMalloc(&dx, sizeof(double) * h->ldx));
-    CK(cudaMalloc(&dout, sizeof(double) * 9));
+    DevMem dx_g, dout_g, dz_g;
+    CK(cudaMalloc(&dx_g.p, sizeof(double) * h->ldx));
+    CK(cudaMalloc(&dout_g.p, sizeof(double) * 9));
+    double *dx = dx_g.as<double>(), *dout = dout_g.as<double>();
     CK(cudaMemsetAsync(dx, 0, sizeof(double) * h->ldx, h->compute));
     std::vector<double> xs(n);
     for (int l = 0; l < n; ++l) xs[l] = x_rot_host[h->perm_identity ? l : h->perm[l]];
@@ -1606,8 +1628,8 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     if (h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) {
         const DevPlan& P = h->plan;
         const int k1p = h->k1p, zrows = k1p - 1 + h->q;   // probes phenotype 0
-        double* dz = nullptr;
-        CK(cudaMalloc(&dz, sizeof(double) * (size_t)zrows * P.Kcp));
+        CK(cudaMalloc(&dz_g.p, sizeof(double) * (size_t)zrows * P.Kcp));
+        double* dz = dz_g.as<double>();
         CK(cudaMemsetAsync(dz, 0, sizeof(double) * (size_t)zrows * P.Kcp, h->compute));
         if (P.nitems) {
             CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
@@ -1637,7 +1659,6 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out9, dout, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->compute));
         CK(cudaStreamSynchronize(h->compute));
-        cudaFree(dx); cudaFree(dout); cudaFree(dz);
         return PG_OK;
     }
     ScanArgs a{};
@@ -1650,8 +1671,6 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out9, dout, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->compute));
     CK(cudaStreamSynchronize(h->compute));
-    cudaFree(dx);
-    cudaFree(dout);
     return PG_OK;
 }
 
@@ -1660,16 +1679,15 @@ extern "C" int pg_probe_f_sf(pg_handle* h, const double* F_host, double nu, int6
     if (!h || !F_host || !p_host || k < 0) return fail(h, PG_ERR_ARG, "pg_probe_f_sf: bad argument");
     if (k == 0) return PG_OK;
     CK(cudaSetDevice(h->device));
-    double *dF = nullptr, *dp = nullptr;
-    CK(cudaMalloc(&dF, sizeof(double) * k));
-    CK(cudaMalloc(&dp, sizeof(double) * k));
+    DevMem dF_g, dp_g;
+    CK(cudaMalloc(&dF_g.p, sizeof(double) * k));
+    CK(cudaMalloc(&dp_g.p, sizeof(double) * k));
+    double *dF = dF_g.as<double>(), *dp = dp_g.as<double>();
     CK(cudaMemcpyAsync(dF, F_host, sizeof(double) * k, cudaMemcpyHostToDevice, h->compute));
     probe_f_sf_kernel<<<(unsigned)((k + 127) / 128), 128, 0, h->compute>>>(dF, nu, k, dp);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(p_host, dp, sizeof(double) * k, cudaMemcpyDeviceToHost, h->compute));
     CK(cudaStreamSynchronize(h->compute));
-    cudaFree(dF);
-    cudaFree(dp);
     return PG_OK;
 }
 

@@ -403,7 +403,7 @@ struct SnpSolver {
         const double z = beta / se;
         F = z * z;
         p = defer_p ? NAN : f_sf_1(F, (double)df);
-        if (status != 0) { lambda = beta = se = tau = F = p = NAN; }
+        if (status & 1) { lambda = beta = se = tau = F = p = NAN; }   // bit 0: fatal; bits 1, 2: notes (MlSolver / skipped bracket)
     }
 
     PG_HD void start_newton(double lam0)
@@ -419,7 +419,9 @@ struct SnpSolver {
         for (; idx < kNumFixed - 1; ++idx) {
             const double f0 = d1_fixed[idx], f1 = d1_fixed[idx + 1];
             if (copysign(1.0, f0) * copysign(1.0, f1) < 0) {  // pyx:174
-                if (isnan(f0) || isnan(f1)) { status = 1; continue; }  // SciPy's brentq raises on NaN: row -> NaN
+                // a NaN derivative at a bracket end: the bracket is skipped and noted (status bit 2, not fatal) -- the other
+                // brackets and the two boundary candidates still compete; only rows without any finite candidate end as NaN
+                if (isnan(f0) || isnan(f1)) { status |= 4; continue; }
                 br.start(fixed_lambda(idx), f0, fixed_lambda(idx + 1), f1, 2e-12, 0.1, 100);
                 if (br.done) { start_newton(br.root); return; }
                 phase = kBrent;
@@ -483,7 +485,7 @@ struct SnpSolver {
         }
         if (phase == kBrent) {
             const double f = reml_d1(rq_lambda, n, cf, e.yPy, e.yPPy, e.trP);
-            if (isnan(f)) { status = 1; idx++; next_bracket(); return; }
+            if (isnan(f)) { status |= 4; idx++; next_bracket(); return; }   // as above: give up on this bracket only
             br.feed(f);
             if (br.done) { start_newton(br.root); return; }
             request(br.query(), 0, 0);

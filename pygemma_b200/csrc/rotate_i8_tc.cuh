@@ -1,22 +1,10 @@
-// rotate_i8_tc.cuh -- the exact int8-split rotation as ONE hand-written sm_100a kernel: TMA-staged operands,
-// tcgen05.mma kind::i8 with the accumulators of all seven digit planes in tensor memory, and the exact
-// recombination (int32 planes -> fp64, rounded once) fused into the epilogue.  Replaces the cuBLAS int8 GEMM +
-// combine_i8_kernel pair of rotate_kernels.cuh: the int32 partial products (280 KB per SNP at n = 10 000) never
-// touch HBM.  Reference: `X = U.T @ X`, lmm/lmm.py:244.
+// rotate_i8_tc.cuh -- shared pieces of the fused int8-split rotation (rotate_i8_tc2.cuh): tile constants, mbarrier /
+// TMA / tcgen05 inline-PTX helpers with watchdog waits, the UMMA shared-memory descriptor, the per-eigenvector scale
+// kernel and the driver entry point for tensor-map encoding.  Reference: `X = U.T @ X`, lmm/lmm.py:244.
 //
-// Tile: 256 SNPs x 32 eigenvectors x 7 planes.  Per k-step (32 samples) two MMAs of shape M = 128 (SNPs) x
-// N = 224 (plane-major: column p*32 + e) x K = 32 share the same B operand; accumulators live in TMEM columns
-// [0, 224) and [256, 480).  Shared-memory stage = 128 samples: A0, A1 (128 SNP rows x 128 B each) and B (224 rows x
-// 128 B), all K-major with the 128-byte swizzle TMA writes and the UMMA descriptor reads.  Arithmetic intensity
-// 122 MAC per L2 byte, the same regime as cuBLAS's 2-SM 256x256 tile.
-//
-// Warp roles (192 threads, persistent CTAs, static tile schedule):
-//   warp 0    TMA producer (one elected lane): waits `empty[s]`, issues 2 + 1 bulk tensor loads onto `full[s]`
-//   warp 1    TMEM allocator + MMA issuer (one elected lane): waits `full[s]`, issues 8 tcgen05.mma, commits to `empty[s]`;
-//             after the last k-step commits to `tmem_full`; waits `tmem_empty` before overwriting the accumulators
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 bit x 8 columns per plane), exact recombination in fp64 FMAs,
-//             64-byte stores of 8 rotated values per SNP row; arrive on `tmem_empty`
-// Every mbarrier wait carries a watchdog that traps instead of hanging the GPU.
+// Tile: per k-step (32 samples) MMAs of shape M = 128 (SNPs) x N = 224 (32 eigenvectors x 7 digit planes) x K = 32;
+// accumulators live in TMEM columns [0, 224) and [256, 480).  Operands are K-major (or MN-major for the caller's
+// sample-major block) with the 128-byte swizzle TMA writes and the UMMA descriptor reads.
 #pragma once
 
 #include <cuda.h>
@@ -126,158 +114,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
                  : "r"(taddr));
 }
 
-struct Args {
-    long long mb;          // SNPs in the block
-    int n;                 // eigenvectors / samples
-    int snp_tiles, eig_tiles;
-    const double* scale;   // [n] 2^(e_i - 24)
-    double* xr;            // [mb][ldx]
-    long long ldx;
-};
+// (the single-CTA kernel that used to live here -- 14.4 ms per 25 k SNPs against 10.0 for the CTA-pair kernel -- was
+// removed in round 2; rotate_i8_tc2.cuh is the only fused engine and this header keeps the shared helpers)
 
-__global__ void __launch_bounds__(kThreads, 1)
-rotate_i8_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_p, Args a)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
-    uint64_t* full = bars;                   // [kStages]
-    uint64_t* empty = bars + kStages;        // [kStages]
-    uint64_t* tmem_full = bars + 2 * kStages;
-    uint64_t* tmem_empty = tmem_full + 1;
-    uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long total_tiles = (long long)a.snp_tiles * a.eig_tiles;
-    const int ksteps = (a.n + kStageK - 1) / kStageK;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 128);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_base_slot;
-
-    // tile t -> (snp tile, eigen tile): eigen tiles in groups of kEigGroup, SNP tiles swept inside a group
-    auto decode = [&](long long t, int& st, int& et) {
-        const long long per_group = (long long)kEigGroup * a.snp_tiles;
-        const int g = (int)(t / per_group);
-        const long long r = t - (long long)g * per_group;
-        const int e0 = g * kEigGroup;
-        const int ecount = min(kEigGroup, a.eig_tiles - e0);
-        st = (int)(r / ecount);
-        et = e0 + (int)(r % ecount);
-    };
-    // the last eigen group may hold fewer than kEigGroup tiles: recompute the tile count it really has
-    const int full_groups = a.eig_tiles / kEigGroup, tail = a.eig_tiles - full_groups * kEigGroup;
-    (void)tail;
-
-    if (warp == 0) {
-        // whole warp walks the schedule (keeps the warp convergent for the final barrier); lane 0 issues
-        int stage = 0;
-        uint32_t phase = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            int st, et;
-            decode(t, st, et);
-            for (int k = 0; k < ksteps; ++k) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                if (lane == 0) {
-                    uint8_t* sA = smem + (size_t)stage * kStageBytes;
-                    mbar_expect_tx(&full[stage], kStageBytes);
-                    tma_load_2d(sA, &map_x, &full[stage], k * kStageK, st * kTileSnps);
-                    tma_load_2d(sA + kABytes, &map_x, &full[stage], k * kStageK, st * kTileSnps + 128);
-                    tma_load_3d(sA + 2 * kABytes, &map_p, &full[stage], k * kStageK, et * kTileEig, 0);
-                }
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        int stage = 0;
-        uint32_t phase = 0, acc_phase = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators of the previous tile
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int k = 0; k < ksteps; ++k) {
-                mbar_wait(&full[stage], phase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t sA = smem_u32(smem + (size_t)stage * kStageBytes);
-                    const uint64_t da0 = umma_desc_sw128(sA), da1 = umma_desc_sw128(sA + kABytes);
-                    const uint64_t db = umma_desc_sw128(sA + 2 * kABytes);
-#pragma unroll
-                    for (int kk = 0; kk < kStageK / 32; ++kk) {
-                        const uint32_t accum = (k | kk) ? 1u : 0u;
-                        const uint64_t adv = (uint64_t)((kk * 32) >> 4);  // 32 bytes along K inside the swizzle atom
-                        umma_i8(tmem_base, da0 + adv, db + adv, accum);
-                        umma_i8(tmem_base + kAcc1Col, da1 + adv, db + adv, accum);
-                    }
-                    umma_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
-                    if (k == ksteps - 1) umma_commit(tmem_full);
-                }
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-            acc_phase ^= 1;
-        }
-    } else {
-        // epilogue warps 2..5 own TMEM lanes 32*(warp%4) .. +31
-        const int quarter = warp & 3;
-        uint32_t acc_phase = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            int st, et;
-            decode(t, st, et);
-            mbar_wait(tmem_full, acc_phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int eig0 = et * kTileEig;
-#pragma unroll 1
-            for (int acc = 0; acc < 2; ++acc) {
-                const long long snp = (long long)st * kTileSnps + acc * 128 + quarter * 32 + lane;
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAcc1Col);
-#pragma unroll 1
-                for (int c = 0; c < kTileEig / 8; ++c) {
-                    uint32_t r[kSlices][8];
-#pragma unroll
-                    for (int p = 0; p < kSlices; ++p) tmem_ld8(tbase + (uint32_t)(p * kTileEig + c * 8), r[p]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (snp < a.mb) {
-                        double* dst = a.xr + (size_t)snp * a.ldx + eig0 + c * 8;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int e = eig0 + c * 8 + j;
-                            if (e < a.n) {
-                                // sum_p P_p 256^(kSlices-1-p): planes 0..2 and 3.. are exact in fp64, one rounding in the final sum
-                                const double hi = fma((double)(int)r[0][j], 65536.0, fma((double)(int)r[1][j], 256.0, (double)(int)r[2][j]));
-                                double lo = (double)(int)r[3][j];
-#pragma unroll
-                                for (int p = 4; p < kSlices; ++p) lo = fma(lo, 256.0, (double)(int)r[p][j]);
-                                const double v = fma(lo, kLoScale, hi);
-                                dst[j] = v * __ldg(a.scale + e);
-                            }
-                        }
-                    }
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tmem_empty);
-            acc_phase ^= 1;
-        }
-    }
-
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
-    }
-}
 
 // 2^(e_i - 24): exact power-of-two scale of eigenvector i's fixed-point representation
 __global__ void plane_scale_kernel(const int* __restrict__ exps, int n, double* __restrict__ scale)
@@ -304,44 +143,6 @@ inline EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-// x8: [rows][ldk] int8 (SNP-major, K contiguous); planes: [kSlices][npad][ldk] int8
-inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long x8_rows, const int8_t* planes, int npad,
-                  int ldk, int n, long long mb, const double* scale, double* xr, long long ldx)
-{
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return -1;
-    CUtensorMap mx, mp;
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)ldk, (cuuint64_t)x8_rows};
-        cuuint64_t strides[1] = {(cuuint64_t)ldk};
-        cuuint32_t box[2] = {(cuuint32_t)kStageK, 128};
-        cuuint32_t es[2] = {1, 1};
-        if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)x8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                (kStageK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return -2;
-    }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)ldk, (cuuint64_t)npad, (cuuint64_t)kSlices};
-        cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)ldk * (cuuint64_t)npad};
-        cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)kTileEig, (cuuint32_t)kSlices};
-        cuuint32_t es[3] = {1, 1, 1};
-        if (enc(&mp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                (kStageK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return -3;
-    }
-    Args a;
-    a.mb = mb; a.n = n;
-    a.snp_tiles = (int)((mb + kTileSnps - 1) / kTileSnps);
-    a.eig_tiles = (n + kTileEig - 1) / kTileEig;
-    a.scale = scale; a.xr = xr; a.ldx = ldx;
-    // per call: the attribute is per device, and a process may hold handles on several devices
-    if (cudaFuncSetAttribute(rotate_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-        return -4;
-    const long long tiles = (long long)a.snp_tiles * a.eig_tiles;
-    const int grid = (int)std::min<long long>(tiles, sm_count);
-    rotate_i8_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mx, mp, a);
-    return cudaGetLastError() == cudaSuccess ? 0 : -5;
-}
 
 }  // namespace tc
 }  // namespace pg

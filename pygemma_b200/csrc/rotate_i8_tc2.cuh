@@ -145,7 +145,7 @@ struct Args {
     int n;
     int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors
     int eig_group;              // eigen tiles swept together (L2 residency of the B panels)
-    int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes (default 0)
+    int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes (default 2, see launch)
     const double* scale;
     double* xr;
     long long ldx;

@@ -321,10 +321,9 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
     // PG_ROT_AUTO on int8 dosages: the hand-written fused tcgen05 kernel (PG_ROT_DEFAULT=cublas selects the library GEMM
     // + recombination pair, which level-coded float blocks always use: their affine fix-up lives in the recombination)
     static const bool default_tc = !(getenv("PG_ROT_DEFAULT") && !strcmp(getenv("PG_ROT_DEFAULT"), "cublas"));
-    static const bool tc_single = getenv("PG_TC_SINGLE") != nullptr;
-    const bool fused_tc = (rotation == PG_ROT_I8TC || (rotation == PG_ROT_AUTO && default_tc)) && !(affine && tc_single);
+    const bool fused_tc = (rotation == PG_ROT_I8TC || (rotation == PG_ROT_AUTO && default_tc));
     (void)forced_i8;
-    const bool direct = !pre_staged && (!fused_tc || !tc_single) && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
+    const bool direct = !pre_staged && gemm_tt && layout == PG_X_SAMPLE_MAJOR && (ld % 16 == 0) && (((uintptr_t)src) % 16 == 0) &&
                         (n % 16 == 0) && (mb % 16 == 0);
     if (!direct && !pre_staged) {
         rc = stage_block();
@@ -338,22 +337,17 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // CTA-pair kernel (cta_group::2) unless PG_TC_SINGLE is set
-        int r;
-        if (tc_single) {
-            r = tc::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx);
-        } else {
-            r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+        // CTA-pair kernel (cta_group::2)
+        int r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
                             direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 0);
-            if (r == 0 && affine && need_eps) {
-                // second component (unequally spaced levels / an outlier level): the indicator, accumulated with weight eps
-                rc = encode_block(1);
-                if (rc == 0 && !direct && !pre_staged) rc = stage_block();
-                if (rc) return rc;
-                r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
-                                direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 1);
-                (*n_launch)++;
-            }
+        if (r == 0 && affine && need_eps) {
+            // second component (unequally spaced levels / an outlier level): the indicator, accumulated with weight eps
+            rc = encode_block(1);
+            if (rc == 0 && !direct && !pre_staged) rc = stage_block();
+            if (rc) return rc;
+            r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                            direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 1);
+            (*n_launch)++;
         }
         if (r) { w->err = "fused tcgen05 rotation launch failed, code " + std::to_string(r); return PG_ERR_CUDA; }
         (*n_launch)++;

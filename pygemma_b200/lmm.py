@@ -312,7 +312,7 @@ def _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device, 
 
     frames = []
     for out in outs:
-        bad = out["status"] != 0
+        bad = (out["status"] & 1) != 0   # bit 0 = failed row; higher bits are notes (include/pygemma_b200.h)
         data = {}
         for c in COLUMNS:
             col = out[c]

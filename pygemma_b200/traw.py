@@ -119,7 +119,7 @@ def pygemma_traw(Y, path: str, W, K, filter_std: bool = False, nan_policy: str =
         out = h.scan_bed(sel, grid=grid, count_A1=False, standardize=standardize)
     if verbose > 0:
         print(f"[pygemma_b200] {sel.shape[0]} of {packed.shape[0]} SNPs from {path}: {out['timing']}", flush=True)
-    bad = out["status"] != 0
+    bad = (out["status"] & 1) != 0
     data = {}
     for c in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"):
         col = out[c]
