@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpygemma_b200.so")
+# PYGEMMA_B200_LIB selects another build of the same library (the bounds-checked debug build, csrc/pg_debug.cuh)
+LIB_PATH = os.environ.get("PYGEMMA_B200_LIB") or os.path.join(_HERE, "libpygemma_b200.so")
 
 PG_X_I8, PG_X_F32, PG_X_F64, PG_X_BED = 0, 1, 2, 3
 PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1

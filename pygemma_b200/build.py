@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpygemma_b200.so")
+LIB = os.environ.get("PG_LIB_OUT") or os.path.join(HERE, "libpygemma_b200.so")   # PG_LIB_OUT: e.g. a -DPG_DEBUG_BOUNDS build
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "compress_plan.h"
+#include "pg_debug.cuh"
 
 namespace pg {
 
@@ -141,11 +142,13 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
             const int r = c / (kCtL / 2), o = (c % (kCtL / 2)) * 2;
             const long long snp = snp0 + r;
             const bool valid = snp < mb;
+            PG_BOUNDS(lbase >= 0 && lbase + o + 2 <= ldx && r < kCtSnps && o + 2 <= kCtL, "compress: X tile load");
             cpa16_zfill(Xs + r * kXsPitch + o, xr + (size_t)(valid ? snp : 0) * ldx + lbase + o, valid ? 16 : 0);
         }
 #pragma unroll
         for (int c = tid; c < kCtL * (kGroupCols / 2); c += 256) {
             const int r = c >> 6, o = (c & 63) * 2;
+            PG_BOUNDS(r < kCtL && o + 2 <= kGroupCols && it.vcol0 + o + 2 <= vpitch, "compress: V tile load");
             cpa16(Vs + r * kVsPitch + o, V + (size_t)(lbase + r) * vpitch + it.vcol0 + o);
         }
     };
@@ -214,6 +217,7 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
                     const int col = 8 * t + 2 * (lane & 3) + e;
                     if (col < ncol_lin) {
                         const int jl = col / it.kq, k = col - jl * it.kq;
+                        PG_BOUNDS(z_row(it.j0 + jl, c0, k1p) < zrows && it.kb + k < Kcp, "compress: linear moment store");
                         Zs[(size_t)z_row(it.j0 + jl, c0, k1p) * Kcp + it.kb + k] = acc[b][t][e];
                     }
                 }
@@ -225,6 +229,7 @@ compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb,
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int col = 8 * t + 2 * (lane & 3) + e;
+                    PG_BOUNDS(col >= it.kq || (c0 < zrows && it.kb + col < Kcp), "compress: x^2 moment store");
                     if (col < it.kq) Zs[(size_t)c0 * Kcp + it.kb + col] = acc[b][kLinTiles + t][e];
                 }
             }

@@ -91,8 +91,10 @@ struct pg_handle {
     DevPlan plan;
     double* Z[2] = {nullptr, nullptr};  // [blk][k1p][Kcp], double-buffered like xr
     size_t z_elems = 0;
-    double* F[2] = {nullptr, nullptr};  // [blk][zrows][kFxCols] x rows of the fixed-lambda evaluations, per Z buffer
-    size_t f_elems = 0;
+    double* F[2] = {nullptr, nullptr};  // [kNumFixed][zrows][ldF] double2: x rows of the fixed-lambda evaluations, per Z buffer
+    double* FX[2] = {nullptr, nullptr}; // [kNumFixed][kFxOut][ldF] results of the fixed-lambda evaluations (fixed_phase_kernel)
+    size_t f_elems = 0, fx_elems = 0;
+    long long ldF = 0;                  // SNP stride of F / FX: the block size rounded up to 32
     int k1p = 0;          // c0+2 rounded up to a multiple of 4
     // several phenotypes on one eigen-system (pg_set_design_multi): each has its own rotated [W0, y] and lambda tables;
     // slot 0 owns the buffers allocated with the handle, `activate` points the handle's working fields at a slot
@@ -119,12 +121,15 @@ static void activate(pg_handle* h, int ph);
 static void free_plan(pg_handle* h)
 {
     DevPlan& P = h->plan;
-    void* bufs[] = {P.nodes, P.H, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z[0], h->Z[1], h->F[0], h->F[1]};
+    void* bufs[] = {P.nodes, P.H, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z[0], h->Z[1], h->F[0], h->F[1],
+                    h->FX[0], h->FX[1]};
     for (void* b : bufs)
         if (b) cudaFree(b);
     P = DevPlan{};
     h->Z[0] = h->Z[1] = nullptr;
     h->F[0] = h->F[1] = nullptr;
+    h->FX[0] = h->FX[1] = nullptr;
+    h->fx_elems = 0;
     h->z_elems = 0;
     h->f_elems = 0;
     h->z_rows = 0;
@@ -945,7 +950,8 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype, bool host_inp
             }
             h->z_elems = zneed;
         }
-        const size_t fneed = (size_t)blk * zrows * kFxCols;
+        h->ldF = (blk + 31) / 32 * 32;
+        const size_t fneed = (size_t)2 * kNumFixed * zrows * h->ldF;   // double2 per (lambda, slab row, SNP)
         if (fneed > h->f_elems) {
             for (int s = 0; s < 2; ++s) {
                 if (h->F[s]) cudaFree(h->F[s]);
@@ -954,6 +960,16 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype, bool host_inp
             h->f_elems = 0;
             for (int s = 0; s < 2; ++s) CK(cudaMalloc(&h->F[s], sizeof(double) * fneed));
             h->f_elems = fneed;
+        }
+        const size_t fxneed = (size_t)kNumFixed * kFxOut * h->ldF;
+        if (fxneed > h->fx_elems) {
+            for (int s = 0; s < 2; ++s) {
+                if (h->FX[s]) cudaFree(h->FX[s]);
+                h->FX[s] = nullptr;
+            }
+            h->fx_elems = 0;
+            for (int s = 0; s < 2; ++s) CK(cudaMalloc(&h->FX[s], sizeof(double) * fxneed));
+            h->fx_elems = fxneed;
         }
     }
     const size_t sbytes = need * xdtype_size(xdtype);
@@ -998,6 +1014,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
     const bool split = st_solve != st;
     unsigned long long* counter = h->counter + (parity & 1);
     double* Fbuf = Zbuf == h->Z[1] ? h->F[1] : h->F[0];
+    double* FXbuf = Zbuf == h->Z[1] ? h->FX[1] : h->FX[0];
     ScanArgs a;
     a.n = h->n; a.c0 = h->c0; a.grid = grid_mode; a.m = mb; a.row0 = row0;
     a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = xr; a.ldx = h->ldx; a.tab = h->tab;
@@ -1032,7 +1049,9 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
                 const size_t hs = sizeof(double) * (size_t)kslab * kFxCols;
                 if (hs > 48 * 1024)
                     CK(cudaFuncSetAttribute(fixed_xrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-                fixed_xrow_kernel<<<(unsigned)((rows + 255) / 256), 256, hs, st>>>(Zbuf, rows, P.Kcp, P.H, Fbuf, kslab);
+                fixed_xrow_kernel<<<(unsigned)((rows + 255) / 256), 256, hs, st>>>(Zbuf, rows, P.Kcp, P.H,
+                                                                                    reinterpret_cast<double2*>(Fbuf), kslab, zrows,
+                                                                                    h->ldF);
                 CK(cudaGetLastError());
             }
             if (split) {
@@ -1041,10 +1060,21 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
             }
         }
         CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st_solve));
+        {
+            // the kNumFixed fixed-lambda evaluations of this phenotype, one thread per SNP (reml_solve.cuh)
+            FixedArgs fa;
+            fa.c0 = h->c0; fa.zrows = zrows; fa.yrow = h->k1p - 1 + ph; fa.swap = (h->scan_mode == PG_SCAN_DE) ? 1 : 0;
+            fa.m = mb; fa.ldF = h->ldF; fa.F2 = reinterpret_cast<const double2*>(Fbuf); fa.t2 = h->tab2; fa.FX = FXbuf;
+            const size_t fsm = sizeof(double) * ((size_t)((h->tab2.NF2 + 1) & ~1) + (size_t)2 * (h->c0 + 2) * 128);
+            if (fsm > 48 * 1024)
+                CK(cudaFuncSetAttribute(fixed_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            fixed_phase_kernel<<<(unsigned)((mb + 127) / 128), 128, fsm, st_solve>>>(fa);
+            CK(cudaGetLastError());
+        }
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
         sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
-        sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph; sa.F = Fbuf; sa.swap = (h->scan_mode == PG_SCAN_DE) ? 1 : 0;
+        sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph; sa.FX = FXbuf; sa.ldF = h->ldF; sa.swap = (h->scan_mode == PG_SCAN_DE) ? 1 : 0;
         for (int i = 0; i < 4; ++i) sa.lrt[i] = lrt ? lrt[i] : nullptr;
         sa.l_null = lrt ? h->slots[ph].null_vals[2] : 0.0;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
@@ -1416,9 +1446,10 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->rot_engine = last_engine;
         timing->reml_engine = compressed ? PG_REML_COMPRESSED : h->engine;
         timing->n_nodes = compressed ? h->plan.Kc : h->n;
-        // per block: compress (dmma / copy), fixed-lambda x rows, one solve per phenotype; one p-value launch per scan
+        // per block: compress (dmma / copy), fixed-lambda x rows, fixed-lambda evaluations + solve per phenotype; one
+        // p-value launch per scan
         if (compressed)
-            timing->reml_launches = (int32_t)(nblocks * (1 + q + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)) + 1);
+            timing->reml_launches = (int32_t)(nblocks * (1 + 2 * q + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)) + 1);
         else
             timing->reml_launches = (int32_t)(nblocks * q);
     }
@@ -1645,7 +1676,7 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
         }
         SolveArgs sa{};
         sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
-        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.F = nullptr; sa.swap = 0;
+        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.FX = nullptr; sa.ldF = 0; sa.swap = 0;
         for (int i = 0; i < 4; ++i) sa.lrt[i] = nullptr;
         sa.l_null = 0.0;
         const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);

@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h>
 
+#include "pg_debug.cuh"
 #include "reml_kernels.cuh"
 
 namespace pg {
@@ -30,7 +31,8 @@ struct SolveArgs {
     int k1p;              // c0+2 rounded up to a multiple of 4 (padding rows are zero)
     int zrows;            // rows per SNP slab: k1p - 1 + number of phenotypes
     int yrow;             // slab row of this launch's phenotype (k1p - 1 + phenotype index)
-    const double* F;      // [m][zrows][kFxCols] x rows of the fixed-lambda evaluations (fixed_xrow_kernel), or nullptr
+    const double* FX;     // [kNumFixed][kFxOut][ldF] results of the fixed-lambda evaluations (fixed_phase_kernel), or nullptr
+    long long ldF;        // SNP stride of FX
     int swap;             // 1: "de" mode, the genotype column is the phenotype and y the tested regressor (pg_eval.cuh)
     // likelihood-ratio outputs (nullable, all four or none): ML lambda and log-likelihood of the model [W0, x],
     // D_lrt = 2 (l_alt - l_null), p_lrt = chi2(1) upper tail (reference lmm/lmm.py:278-282,:300, commented there)
@@ -78,13 +80,15 @@ __global__ void build_h_kernel(const double* __restrict__ nodes, int Kcp, double
     H[i] = v;
 }
 
+// Output layout: F2[(t * zrows + j) * ldF + snp] = (power 1, power 2) of slab row j of the SNP at lambda_t -- SNP-fastest,
+// so that fixed_phase_kernel (one THREAD per SNP) reads it coalesced.
 // One warp contracts 32 slab rows (4 m-tiles) against all 24 columns; Z is read once.  H passes through shared memory in
 // slabs of `kslab` nodes (a multiple of 4; the whole table when it fits): a wide spectrum can need more nodes than one
 // CTA's shared memory holds (Kcp * 192 bytes), the accumulators simply stay in registers across slabs.
 constexpr int kFxSlabMax = 960;   // nodes per shared-memory slab: 960 * 24 * 8 = 180 KB
 __global__ void __launch_bounds__(256)
-fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const double* __restrict__ H, double* __restrict__ F,
-                  int kslab)
+fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const double* __restrict__ H, double2* __restrict__ F2,
+                  int kslab, int zrows, long long ldF)
 {
     extern __shared__ double Hs[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -115,6 +119,7 @@ fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const d
             for (int nt = 0; nt < 3; ++nt) b[nt] = Hs[(ks * 4 + ac) * kFxCols + nt * 8 + ar];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
+                PG_BOUNDS(k0 + ks * 4 + ac < Kcp && (ks * 4 + ac) < kslab, "fixed x rows: node index");
                 const double av = ok[mt] ? __ldg(zp[mt] + k0 + ks * 4) : 0.0;
 #pragma unroll
                 for (int nt = 0; nt < 3; ++nt) {
@@ -129,9 +134,88 @@ fixed_xrow_kernel(const double* __restrict__ Z, long long rows, int Kcp, const d
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
         if (!ok[mt]) continue;
-        double* f = F + (size_t)(r0 + mt * 8 + ar) * kFxCols + 2 * ac;
+        const long long row = r0 + mt * 8 + ar;
+        const long long snp = row / zrows;
+        const int j = (int)(row - snp * zrows);
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) *reinterpret_cast<double2*>(f + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        for (int nt = 0; nt < 3; ++nt) {
+            const int t = nt * 4 + ac;   // accumulator columns 2t, 2t+1 = the two powers at lambda_t
+            if (t < kNumFixed) F2[((size_t)t * zrows + j) * ldF + snp] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        }
+    }
+}
+
+// ---- the fixed-lambda evaluations, one THREAD per SNP -----------------------------------------------------------
+// The first kNumFixed evaluations of every SNP (bracket scan; all of grid mode; the same for the ML optimiser of the LRT
+// outputs) share their lambda across SNPs, so the covariate levels of the Pab recursion read the SAME table-2 row for
+// every SNP.  Here a CTA stages that row in shared memory once per lambda and each thread carries its own SNP's x row
+// (shared memory, SNP-fastest: conflict-free) through the c0 levels: no shuffles, no dependent global loads, all 32
+// lanes busy -- against 12 of 32 lanes, two shuffles and two L2 loads per level in the warp-per-SNP form
+// (xrow_recursion_warp), which remains for the SNP-specific lambdas of Brent / Newton.  Arithmetic per entry is the
+// expression of pab_recursion (pg_eval.cuh).  Output FX[(t * kFxOut + f) * ldF + snp], f = yPy, yPPy, trP, logdetWHW,
+// xPx, yPx (level c_f / c0 as in EvalOut).
+constexpr int kFxOut = 6;
+
+struct FixedArgs {
+    int c0, zrows, yrow, swap;
+    long long m, ldF;
+    const double2* F2;
+    Tables2 t2;
+    double* FX;
+};
+
+__global__ void __launch_bounds__(128) fixed_phase_kernel(FixedArgs a)
+{
+    extern __shared__ double fsm[];
+    const int c0 = a.c0, k1 = c0 + 2, dg = c0 + 1, NF2 = a.t2.NF2, Tp = a.t2.Tp;
+    const int NF2p = (NF2 + 1) & ~1;
+    double* row2 = fsm;                 // the table-2 row of lambda_t
+    double* xa = fsm + NF2p;            // [k1][128]
+    double* xb = xa + (size_t)k1 * 128;
+    const int tid = threadIdx.x;
+    const long long snp = (long long)blockIdx.x * 128 + tid;
+    const bool ok = snp < a.m;
+    const bool swap = a.swap != 0;
+    for (int t = 0; t < kNumFixed; ++t) {
+        __syncthreads();   // everybody is done with the previous lambda's row
+        for (int i = tid; i < NF2; i += 128) row2[i] = __ldg(a.t2.fix2 + (size_t)t * NF2 + i);
+        for (int j = 0; j < k1; ++j) {
+            const int r = j < c0 ? j : (j == c0 ? a.yrow : c0);   // Pab column order [W0, y, x] -> slab rows
+            const double2 v = ok ? __ldg(a.F2 + ((size_t)t * a.zrows + r) * a.ldF + snp) : make_double2(0.0, 0.0);
+            xa[j * 128 + tid] = v.x;
+            xb[j * 128 + tid] = v.y;
+        }
+        __syncthreads();
+        if (c0 == 0 && !swap) xa[dg * 128 + tid] = cy_max(xa[dg * 128 + tid], kMinVal);   // pyx:939 / :993
+        for (int p = 0; p < c0; ++p) {
+            const double al2 = row2[3 * p], al4 = row2[3 * p + 1];
+            const double ar = xa[p * 128 + tid], br = xb[p * 128 + tid];
+            const int cb = t2_col(c0, p, p + 1) - (p + 1);
+            for (int j = p + 1; j <= dg; ++j) {
+                double as = ar, bs = br;
+                if (j <= c0) { as = row2[cb + j]; bs = row2[Tp + cb + j]; }
+                const bool clamp = (p == c0 - 1) && (j == dg) && !swap;
+                double v = (xb[j * 128 + tid] + al4 * ar * as) + al2 * (ar * bs + br * as);
+                if (clamp) v = cy_max(v, kMinVal);
+                xb[j * 128 + tid] = v;
+                v = xa[j * 128 + tid] + al2 * ar * as;
+                if (clamp) v = cy_max(v, kMinVal);
+                xa[j * 128 + tid] = v;
+            }
+        }
+        EvalOut e;
+        const double* fin = row2 + t2_fin(c0);
+        if (swap)
+            xrow_final_level_swapped<false>(c0, fin, xa[dg * 128 + tid], xb[dg * 128 + tid], 0.0, xa[c0 * 128 + tid],
+                                            xb[c0 * 128 + tid], 0.0, true, &e);
+        else
+            xrow_final_level<false>(fin, xa[dg * 128 + tid], xb[dg * 128 + tid], 0.0, xa[c0 * 128 + tid], xb[c0 * 128 + tid],
+                                    0.0, true, &e);
+        if (ok) {
+            double* fx = a.FX + (size_t)t * kFxOut * a.ldF + snp;
+            fx[0] = e.yPy; fx[a.ldF] = e.yPPy; fx[2 * a.ldF] = e.trP; fx[3 * a.ldF] = e.logdetWHW;
+            fx[4 * a.ldF] = e.xPx; fx[5 * a.ldF] = e.yPx;
+        }
     }
 }
 
@@ -211,6 +295,7 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
             const int o = base + i;
             if (o < NP * NC) {
                 const int p = o / NC, j = jb + (o - p * NC);
+                PG_BOUNDS(p < 3 && j < a.k1p, "solver: x-row scratch");
                 xs[p * a.k1p + j] = v[i];
             }
         }
@@ -289,18 +374,14 @@ __device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __rest
 // One precompute_mat-equivalent evaluation from the compressed moments (warp-collective).
 // scratch (shared memory, per warp): 3 * k1p doubles for the level-0 x row, then NF2 for an interpolated table-2 row.
 template <int NS>
-__device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const double* __restrict__ Zs,
-                                                    const double* __restrict__ Fs, double lam, int fixed_t, int full,
-                                                    int need_ll, double* scratch, EvalOut* e)
+__device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const double* __restrict__ Zs, double lam,
+                                                    int fixed_t, int full, int need_ll, double* scratch, EvalOut* e)
 {
     const int lane = threadIdx.x & 31, c0 = a.c0, k1 = c0 + 2, k1p = a.k1p, NF2 = a.t2.NF2;
     double* xs = scratch;
     double* rowbuf = scratch + 3 * k1p;
-    const bool pre = (fixed_t >= 0) && (Fs != nullptr);   // x row already contracted by fixed_xrow_kernel
-    if (!pre) {
-        if (full) solve_xrow_all<true>(a, Zs, lam, xs);
-        else solve_xrow_all<false>(a, Zs, lam, xs);
-    }
+    if (full) solve_xrow_all<true>(a, Zs, lam, xs);
+    else solve_xrow_all<false>(a, Zs, lam, xs);
     const double* row2;
     if (fixed_t >= 0) {
         row2 = a.t2.fix2 + (size_t)fixed_t * NF2;
@@ -339,21 +420,25 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
     for (int q = 0; q < NS; ++q) {
         const int j = lane + 32 * q;
         const bool in = j < k1;
-        if (pre) {
-            const int r = j < c0 ? j : (j == c0 ? a.yrow : c0);   // Pab column order [W0, y, x] -> slab rows
-            double2 v = make_double2(0.0, 0.0);
-            if (in) v = __ldg(reinterpret_cast<const double2*>(Fs + (size_t)r * kFxCols + 2 * fixed_t));
-            xa[q] = v.x; xb[q] = v.y; xc[q] = 0.0;   // fixed-lambda evaluations are never full (SnpSolver::request_fixed)
-        } else {
-            const int r = j < c0 ? j : (j == c0 ? k1p - 1 : c0);   // ... -> x-row scratch (y sits at k1p - 1)
-            xa[q] = in ? xs[r] : 0.0;
-            xb[q] = in ? xs[k1p + r] : 0.0;
-            xc[q] = (in && full) ? xs[2 * k1p + r] : 0.0;
-        }
+        const int r = j < c0 ? j : (j == c0 ? k1p - 1 : c0);   // Pab column order [W0, y, x] -> x-row scratch (y at k1p - 1)
+        xa[q] = in ? xs[r] : 0.0;
+        xb[q] = in ? xs[k1p + r] : 0.0;
+        xc[q] = (in && full) ? xs[2 * k1p + r] : 0.0;
     }
     if (full) xrow_recursion_warp<true, NS>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
     else xrow_recursion_warp<false, NS>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
     __syncwarp();
+}
+
+// one fixed-lambda evaluation of SNP g as fixed_phase_kernel left it (every lane reads the same words)
+__device__ __forceinline__ void load_fixed(const SolveArgs& a, long long g, int t, EvalOut* e)
+{
+    const double* __restrict__ fx = a.FX + (size_t)t * kFxOut * a.ldF + g;
+    e->yPy = __ldg(fx); e->yPPy = __ldg(fx + a.ldF); e->trP = __ldg(fx + 2 * a.ldF); e->logdetWHW = __ldg(fx + 3 * a.ldF);
+    e->xPx = __ldg(fx + 4 * a.ldF); e->yPx = __ldg(fx + 5 * a.ldF);
+    const double* __restrict__ fin = a.t2.fix2 + (size_t)t * a.t2.NF2 + t2_fin(a.c0);
+    e->logdetH = __ldg(fin + 5); e->trH = __ldg(fin + 7); e->trHH = __ldg(fin + 8);
+    e->yPPPy = NAN; e->trPP = NAN;   // fixed-lambda evaluations are never full (SnpSolver::request_fixed)
 }
 
 template <int NS, int MINB>
@@ -369,8 +454,8 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         if (lane == 0) g = atomicAdd(a.counter, 1ULL);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= (unsigned long long)a.m) break;
+        PG_BOUNDS(a.yrow < a.zrows && a.k1p - 1 <= a.zrows, "solver: slab rows");
         const double* __restrict__ Zs = a.Z + (size_t)g * a.zrows * a.Kcp;
-        const double* __restrict__ Fs = a.F ? a.F + (size_t)g * a.zrows * kFxCols : nullptr;
         // The optimiser state (448 bytes, identical in every lane) lives in shared memory, one copy per warp: all lanes
         // run the state machine in lock step and store the same values, and the ~50 registers it would pin per thread
         // go to the evaluation instead (solve stage -10 %; with c0 <= 6 the kernel then fits 4 CTAs per SM: -27 %).
@@ -378,7 +463,8 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         s.init(a.n, a.c0, a.grid, /*defer_p=*/1);
         while (s.pending()) {
             EvalOut e;
-            eval_snp_compressed<NS>(a, Zs, Fs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
+            if (s.req_fixed() >= 0 && a.FX) load_fixed(a, (long long)g, s.req_fixed(), &e);   // fixed_phase_kernel did it
+            else eval_snp_compressed<NS>(a, Zs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
             s.feed(e);
         }
         int st_bits = s.status;
@@ -398,7 +484,8 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
             ms.init(a.n);
             while (ms.pending()) {
                 EvalOut e;
-                eval_snp_compressed<NS>(a, Zs, Fs, ms.req_lambda(), ms.req_fixed(), ms.req_full(), 0, scratch, &e);
+                if (ms.req_fixed() >= 0 && a.FX) load_fixed(a, (long long)g, ms.req_fixed(), &e);
+                else eval_snp_compressed<NS>(a, Zs, ms.req_lambda(), ms.req_fixed(), ms.req_full(), 0, scratch, &e);
                 ms.feed(e);
             }
             if (lane == 0) {
@@ -482,7 +569,7 @@ __global__ void probe_precompute_compressed_kernel(SolveArgs a, double lam, int 
 {
     extern __shared__ double smem[];
     EvalOut e;
-    eval_snp_compressed<NS>(a, a.Z, a.F, lam, fixed_t, full, 1, smem, &e);
+    eval_snp_compressed<NS>(a, a.Z, lam, fixed_t, full, 1, smem, &e);
     if ((threadIdx.x & 31) == 0) {
         out9[0] = e.yPy; out9[1] = e.yPPy; out9[2] = e.yPPPy; out9[3] = e.trP; out9[4] = e.trPP;
         out9[5] = e.logdetH; out9[6] = e.logdetWHW; out9[7] = e.xPx; out9[8] = e.yPx;

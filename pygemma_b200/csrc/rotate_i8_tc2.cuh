@@ -17,6 +17,7 @@
 //             TMEM lane quarter warp % 4); arrival on the leader's `tmem_empty` (remote for the peer CTA)
 #pragma once
 
+#include "pg_debug.cuh"
 #include "rotate_i8_tc.cuh"
 
 namespace pg {
@@ -292,10 +293,13 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     // eight eigenvectors x seven planes = 56 consecutive columns (eigen-major)
                     uint32_t r[kSlices][8];
 #pragma unroll
+                    PG_BOUNDS(c * 8 * kSlices + kSlices * 8 <= kTileN, "TMEM column range of an accumulator");
                     for (int q = 0; q < kSlices; ++q) tmem_ld8(tbase + (uint32_t)(c * 8 * kSlices + q * 8), r[q]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (snp < a.mb) {
                         double* dst = a.xr + (size_t)snp * a.ldx + eig0 + c * 8;
+                        PG_BOUNDS(snp >= 0 && snp < a.mb && eig0 + c * 8 < a.ldx && (eig0 + c * 8 + 8 <= a.n ? eig0 + c * 8 + 8 <= a.ldx : true),
+                                  "rotated-genotype store outside the block");
                         double out[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {

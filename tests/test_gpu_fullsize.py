@@ -425,6 +425,7 @@ def test_lrt_through_kinship_and_multi_trait():
     rng = np.random.default_rng(2)
     Y = np.stack([p["Y"].reshape(-1), 0.4 * p["Y"].reshape(-1) + rng.standard_normal(n)], axis=1)
     frames = lmm.pygemma_multi(Y, p["X"], p["W"], p["K"], lrt=True)
+    nulls = list(lmm.last_null_model)   # one per trait; a later single-trait call replaces the list
     d, U, _, xr, wr = oracle.eigen_rotate(p["K"], Y[:, 0], p["X"], p["W"])
     for ph in range(2):
         ref = oracle.lrt_rotated(d, U.T @ Y[:, ph], wr, np.ascontiguousarray(xr.T))
@@ -432,7 +433,7 @@ def test_lrt_through_kinship_and_multi_trait():
         assert np.abs(df["D_lrt"].to_numpy() - ref["D_lrt"]).max() < 1e-6
         assert rel(df["likelihood"].to_numpy(), ref["loglik_ml"]).max() < 1e-8
         assert rel(df["p_lrt"].to_numpy(), ref["p_lrt"]).max() < 1e-5
-        assert rel(lmm.last_null_model[ph]["l_null"], ref["l_null"]) < 1e-9
+        assert rel(nulls[ph]["l_null"], ref["l_null"]) < 1e-9
         one = lmm.pygemma(Y[:, ph], p["X"], p["W"], p["K"], lrt=True)
         for c in COLS + ["D_lrt", "p_lrt", "likelihood"]:
             assert np.array_equal(one[c].to_numpy(), df[c].to_numpy(), equal_nan=True), (ph, c)
