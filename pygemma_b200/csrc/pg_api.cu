@@ -1082,6 +1082,10 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
         int warps = 8;
         while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
+        // under the next block's rotation (PG_OVERLAP): the rotation CTA leaves 10 K registers and ~37 KB of shared memory
+        // per SM, i.e. room for two solver warps (128 registers each) beside it
+        static const int ov_warps = getenv("PG_OVERLAP_WARPS") ? std::max(1, atoi(getenv("PG_OVERLAP_WARPS"))) : 2;
+        if (split) warps = std::min(warps, ov_warps);
         const size_t smem = per_warp * warps;
         const bool two = (h->c0 + 2) > 32;
         auto launch = [&](auto kern, int ctas) -> int {

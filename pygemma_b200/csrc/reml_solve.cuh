@@ -406,7 +406,10 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
 #pragma unroll
         for (int k = 0; k < kNodes; ++k) L[k] = __shfl_sync(0xffffffffu, Lk, k);
         const double* __restrict__ base = a.t2.itab2 + (size_t)iv * kNodes * NF2;
-        for (int f = lane; f < NF2; f += 32) {
+        // two-power evaluations never read the third-power pivot columns: skip that third of the row
+        const int skip0 = full ? NF2 : 3 * c0 + 2 * a.t2.Tp, skip1 = full ? NF2 : t2_fin(c0);
+        for (int f0 = lane; f0 < NF2 - (skip1 - skip0); f0 += 32) {
+            const int f = f0 < skip0 ? f0 : f0 + (skip1 - skip0);
             double v = 0.0;
 #pragma unroll
             for (int k = 0; k < kNodes; ++k) v += L[k] * __ldg(base + (size_t)k * NF2 + f);
