@@ -1079,18 +1079,35 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         sa.l_null = lrt ? h->slots[ph].null_vals[2] : 0.0;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = counter;
-        const size_t per_warp = sizeof(double) * (3 * (size_t)h->k1p + h->tab2.NF2);
-        int warps = 8;
-        while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
+        // per-warp shared memory: x-row scratch + an interpolated table-2 row, and -- when it fits -- the SNP's whole moment
+        // slab (k1p rows x Kcp nodes), staged once per SNP instead of ~7 passes over it through L2
+        const size_t scratch_d = (size_t)((3 * h->k1p + h->tab2.NF2 + 1) & ~1);
+        const size_t slab_d = (size_t)h->k1p * P.Kcp;
+        static const bool zsm_env = !(getenv("PG_SOLVE_ZSM") && atoi(getenv("PG_SOLVE_ZSM")) == 0);
+        const size_t budget = 200 * 1024;   // per SM
+        int warps = 8, ctas_fit = 2;
+        bool zsm = false;
+        if (zsm_env && !split && (!grid_mode || lrt)) {   // grid mode without LRT has no SNP-specific evaluation at all
+            const size_t pw = sizeof(double) * (scratch_d + slab_d);
+            const int fit = (int)(budget / pw);          // warps per SM with the slab resident
+            if (fit >= 16) { warps = 8; ctas_fit = 2; zsm = true; }
+            else if (fit >= 12) { warps = 6; ctas_fit = 2; zsm = true; }
+            else if (fit >= 10) { warps = 5; ctas_fit = 2; zsm = true; }
+            else if (fit >= 8) { warps = 8; ctas_fit = 1; zsm = true; }
+            else if (fit >= 6) { warps = 6; ctas_fit = 1; zsm = true; }
+        }
+        const size_t per_warp = sizeof(double) * (scratch_d + (zsm ? slab_d : 0));
+        if (!zsm) while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
         // under the next block's rotation (PG_OVERLAP): the rotation CTA leaves 10 K registers and ~37 KB of shared memory
         // per SM, i.e. room for two solver warps (128 registers each) beside it
         static const int ov_warps = getenv("PG_OVERLAP_WARPS") ? std::max(1, atoi(getenv("PG_OVERLAP_WARPS"))) : 2;
         if (split) warps = std::min(warps, ov_warps);
         const size_t smem = per_warp * warps;
+        sa.zsm = zsm ? 1 : 0;
         const bool two = (h->c0 + 2) > 32;
         auto launch = [&](auto kern, int ctas) -> int {
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(ctas, (200 * 1024) / std::max<size_t>(smem, 1)));
+            const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(ctas, budget / std::max<size_t>(smem, 1)));
             long long want = (mb + warps - 1) / warps;
             int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
             kern<<<grid, warps * 32, smem, st_solve>>>(sa);
@@ -1099,11 +1116,12 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         // 2 CTAs of 8 warps per SM (128 registers) for x rows of 12 or more entries: 3 and 4 CTAs/SM spill in the x-row
         // pass and were measured 5-25 % slower (c0 = 10, 11); short x rows (c0 <= 6, 8 entries) run 27 % faster at 4
         // CTAs/SM (64 registers).  4-6 warps per CTA were measured slower.
-        // Under the next block's rotation: 1 CTA per SM (32 K registers + 15 KB shared memory fit beside a rotation CTA).
+        // Under the next block's rotation: 1 CTA per SM.
         const bool small = h->k1p <= 8;
-        const int per_sm = split ? 1 : (small ? 4 : 2);
+        const int per_sm = split ? 1 : (zsm ? ctas_fit : (small ? 4 : 2));
+        // with the slab resident the shared memory caps the SM at two CTAs anyway: the 128-register variant (no spills)
         const int lr = two ? launch(reml_solve_kernel<2, 2>, per_sm)
-                           : (small ? launch(reml_solve_kernel<1, 4>, per_sm) : launch(reml_solve_kernel<1, 2>, per_sm));
+                           : ((small && !zsm) ? launch(reml_solve_kernel<1, 4>, per_sm) : launch(reml_solve_kernel<1, 2>, per_sm));
         if (lr) return lr;
         CK(cudaGetLastError());
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN).  The kernel is one long serial chain
@@ -1680,7 +1698,7 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
         }
         SolveArgs sa{};
         sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
-        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.FX = nullptr; sa.ldF = 0; sa.swap = 0;
+        sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.FX = nullptr; sa.ldF = 0; sa.swap = 0; sa.zsm = 0;
         for (int i = 0; i < 4; ++i) sa.lrt[i] = nullptr;
         sa.l_null = 0.0;
         const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);

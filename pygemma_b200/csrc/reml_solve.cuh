@@ -33,6 +33,8 @@ struct SolveArgs {
     int yrow;             // slab row of this launch's phenotype (k1p - 1 + phenotype index)
     const double* FX;     // [kNumFixed][kFxOut][ldF] results of the fixed-lambda evaluations (fixed_phase_kernel), or nullptr
     long long ldF;        // SNP stride of FX
+    int zsm;              // 1: every warp stages its SNP's slab (k1p rows x Kcp) in shared memory once and the ~7 SNP-specific
+                          //    evaluations read it from there (ncu r02: 28 % of the solver's stall samples sat on these loads)
     int swap;             // 1: "de" mode, the genotype column is the phenotype and y the tested regressor (pg_eval.cuh)
     // likelihood-ratio outputs (nullable, all four or none): ML lambda and log-likelihood of the model [W0, x],
     // D_lrt = 2 (l_alt - l_null), p_lrt = chi2(1) upper tail (reference lmm/lmm.py:278-282,:300, commented there)
@@ -262,7 +264,9 @@ __device__ __forceinline__ void warp_reduce_halving(double (&v)[V], int lane)
 
 // level-0 x row for slab rows [jb, jb+NC) -> xs[p * k1p + j] (p = power index; row j < c0: x.w_j, c0: x.x, k1p-1: x.y,
 // the last one read from the launch's own phenotype row a.yrow)
-template <int NC, bool FULL>
+// ZSM: Zs is the warp's shared-memory copy of the slab (rows 0..k1p-2, then the phenotype row at k1p-1), else the slab
+// in global memory (phenotype row a.yrow, read-only cache path).
+template <int NC, bool FULL, bool ZSM>
 __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double* __restrict__ Zs, double lam, int jb,
                                                 double* xs)
 {
@@ -273,14 +277,15 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = 0.0;
     const double* __restrict__ z = Zs + (size_t)jb * Kcp;
-    const double* __restrict__ zl = Zs + (size_t)(jb + NC == a.k1p ? a.yrow : jb + NC - 1) * Kcp;
+    const double* __restrict__ zl = Zs + (size_t)(jb + NC == a.k1p ? (ZSM ? a.k1p - 1 : a.yrow) : jb + NC - 1) * Kcp;
 #pragma unroll 2
     for (int k = lane; k < Kcp; k += 32) {
         const double h = rcp_ge1(fma(lam, __ldg(a.nodes + k), 1.0));
         const double h2 = h * h, h3 = h2 * h;
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-            const double zz = (j == NC - 1) ? __ldg(zl + k) : __ldg(z + (size_t)j * Kcp + k);
+            const double zz = ZSM ? ((j == NC - 1) ? zl[k] : z[(size_t)j * Kcp + k])
+                                  : ((j == NC - 1) ? __ldg(zl + k) : __ldg(z + (size_t)j * Kcp + k));
             v[j] = fma(h, zz, v[j]);
             v[NC + j] = fma(h2, zz, v[NC + j]);
             if (FULL) v[2 * NC + j] = fma(h3, zz, v[2 * NC + j]);
@@ -302,7 +307,7 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
     }
 }
 
-template <bool FULL>
+template <bool FULL, bool ZSM>
 __device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __restrict__ Zs, double lam, double* xs)
 {
     int jb = 0;
@@ -310,11 +315,11 @@ __device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __
     // 12-row three-power pass spill at 128 registers (measured: solve stage -7..11 % with the narrower pass)
     constexpr int kBig = FULL ? 8 : 12;
     while (a.k1p - jb >= kBig) {
-        solve_xrow_pass<kBig, FULL>(a, Zs, lam, jb, xs);
+        solve_xrow_pass<kBig, FULL, ZSM>(a, Zs, lam, jb, xs);
         jb += kBig;
     }
-    if (a.k1p - jb == 8) solve_xrow_pass<8, FULL>(a, Zs, lam, jb, xs);
-    else if (a.k1p - jb == 4) solve_xrow_pass<4, FULL>(a, Zs, lam, jb, xs);
+    if (a.k1p - jb == 8) solve_xrow_pass<8, FULL, ZSM>(a, Zs, lam, jb, xs);
+    else if (a.k1p - jb == 4) solve_xrow_pass<4, FULL, ZSM>(a, Zs, lam, jb, xs);
 }
 
 // The covariate levels applied to the x row held in registers: lane (j & 31), slot (j >> 5) owns entry j.
@@ -380,8 +385,13 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
     const int lane = threadIdx.x & 31, c0 = a.c0, k1 = c0 + 2, k1p = a.k1p, NF2 = a.t2.NF2;
     double* xs = scratch;
     double* rowbuf = scratch + 3 * k1p;
-    if (full) solve_xrow_all<true>(a, Zs, lam, xs);
-    else solve_xrow_all<false>(a, Zs, lam, xs);
+    if (a.zsm) {
+        if (full) solve_xrow_all<true, true>(a, Zs, lam, xs);
+        else solve_xrow_all<false, true>(a, Zs, lam, xs);
+    } else {
+        if (full) solve_xrow_all<true, false>(a, Zs, lam, xs);
+        else solve_xrow_all<false, false>(a, Zs, lam, xs);
+    }
     const double* row2;
     if (fixed_t >= 0) {
         row2 = a.t2.fix2 + (size_t)fixed_t * NF2;
@@ -451,7 +461,9 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
     __shared__ __align__(16) unsigned char solver_mem[8][(sizeof(SnpSolver) + 15) / 16 * 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k1p = a.k1p;
-    double* scratch = smem + (size_t)warp * (3 * k1p + a.t2.NF2);
+    const size_t per_warp = (size_t)((3 * k1p + a.t2.NF2 + 1) & ~1) + (a.zsm ? (size_t)k1p * a.Kcp : 0);
+    double* scratch = smem + (size_t)warp * per_warp;
+    double* zcopy = scratch + ((3 * k1p + a.t2.NF2 + 1) & ~1);
     for (;;) {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(a.counter, 1ULL);
@@ -459,6 +471,18 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         if (g >= (unsigned long long)a.m) break;
         PG_BOUNDS(a.yrow < a.zrows && a.k1p - 1 <= a.zrows, "solver: slab rows");
         const double* __restrict__ Zs = a.Z + (size_t)g * a.zrows * a.Kcp;
+        if (a.zsm) {
+            // rows 0..k1p-2 are contiguous in the slab; the phenotype row follows them in the copy
+            __syncwarp();
+            const int half_row = a.Kcp >> 1, total = k1p * half_row;
+            const double2* __restrict__ src = reinterpret_cast<const double2*>(Zs);
+            const double2* __restrict__ srcy = reinterpret_cast<const double2*>(Zs + (size_t)a.yrow * a.Kcp);
+            double2* dst = reinterpret_cast<double2*>(zcopy);
+            const int body = (k1p - 1) * half_row;
+            for (int i = lane; i < total; i += 32) dst[i] = i < body ? __ldg(src + i) : __ldg(srcy + (i - body));
+            __syncwarp();
+            Zs = zcopy;
+        }
         // The optimiser state (448 bytes, identical in every lane) lives in shared memory, one copy per warp: all lanes
         // run the state machine in lock step and store the same values, and the ~50 registers it would pin per thread
         // go to the evaluation instead (solve stage -10 %; with c0 <= 6 the kernel then fits 4 CTAs per SM: -27 %).
@@ -572,7 +596,7 @@ __global__ void probe_precompute_compressed_kernel(SolveArgs a, double lam, int 
 {
     extern __shared__ double smem[];
     EvalOut e;
-    eval_snp_compressed<NS>(a, a.Z, lam, fixed_t, full, 1, smem, &e);
+    eval_snp_compressed<NS>(a, a.Z, lam, fixed_t, full, 1, smem, &e);   // a.zsm == 0: the probe reads the slab in place
     if ((threadIdx.x & 31) == 0) {
         out9[0] = e.yPy; out9[1] = e.yPPy; out9[2] = e.yPPPy; out9[3] = e.trP; out9[4] = e.trPP;
         out9[5] = e.logdetH; out9[6] = e.logdetWHW; out9[7] = e.xPx; out9[8] = e.yPx;

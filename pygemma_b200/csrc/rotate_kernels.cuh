@@ -22,6 +22,7 @@
 #include "rotate_i8.cuh"
 #include "rotate_i8_tc.cuh"
 #include "rotate_i8_tc2.cuh"
+#include "rotate_i8_tc4.cuh"
 
 namespace pg {
 
@@ -337,16 +338,22 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // CTA-pair kernel (cta_group::2)
-        int r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
-                            direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 0);
+        // CTA-pair kernel (cta_group::2), or two pairs per cluster sharing the genotype tiles by TMA multicast (PG_TC_CLUSTER=4)
+        static const int tc_cluster = getenv("PG_TC_CLUSTER") ? atoi(getenv("PG_TC_CLUSTER")) : 2;
+        auto tc_launch = [&](int accumulate) -> int {
+            if (tc_cluster == 4)
+                return tc4::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                                   direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, accumulate);
+            return tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                               direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, accumulate);
+        };
+        int r = tc_launch(0);
         if (r == 0 && affine && need_eps) {
             // second component (unequally spaced levels / an outlier level): the indicator, accumulated with weight eps
             rc = encode_block(1);
             if (rc == 0 && !direct && !pre_staged) rc = stage_block();
             if (rc) return rc;
-            r = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
-                            direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 1);
+            r = tc_launch(1);
             (*n_launch)++;
         }
         if (r) { w->err = "fused tcgen05 rotation launch failed, code " + std::to_string(r); return PG_ERR_CUDA; }

@@ -472,3 +472,29 @@ def test_traw_ingest_with_std_filter_matches_oracle(tmp_path):
             _check({c: df[c].to_numpy() for c in COLS}, ref, tag=("traw", policy, std))
     df_all, keep_all = traw.pygemma_traw(p["Y"], path, p["W"], p["K"])
     assert keep_all.all() and len(df_all) == m
+
+
+def test_four_cta_cluster_rotation_is_bit_identical():
+    """PG_TC_CLUSTER=4 (rotate_i8_tc4.cuh: two CTA pairs per cluster, genotype tiles TMA-multicast to both pairs; kept as a
+    measured alternative, not the default) against the default CTA-pair kernel: exact integer arithmetic, so every output
+    bit must agree -- odd eigen-tile count (phantom tile of the second pair), ragged SNP tail, several waves of units."""
+    import subprocess
+    import sys
+    import tempfile
+
+    code = ("import numpy as np, sys; sys.path.insert(0, '.');"
+            "from pygemma_b200 import _capi; from pygemma_b200.synth import make_problem;"
+            "n, m = 2080, 9000 + 37;"   # 65 eigen tiles (odd), 18 SNP tiles -> 594 units over <= 37 clusters
+            "p = make_problem(n, 64, 3, seed=12, m_k=2 * n);"
+            "X = np.random.default_rng(4).integers(0, 3, size=(n, m), dtype=np.int8);"
+            "h = _capi.Handle(n, 3); h.set_kinship(p['K']); h.set_design(p['W'], p['Y']);"
+            "h.set_options(rotation=_capi.PG_ROT_I8TC, block_snps=0);"
+            "o = h.scan(X); xr, _ = h.probe_rotated(64);"
+            "np.save(sys.argv[1], np.concatenate([np.stack([o[c] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]).ravel(), xr.ravel()]))")
+    outs = []
+    for cl in ("2", "4"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            env = dict(os.environ, PG_TC_CLUSTER=cl)
+            subprocess.check_call([sys.executable, "-c", code, f.name], env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+            outs.append(np.load(f.name))
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
