@@ -1087,7 +1087,11 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         const size_t budget = 200 * 1024;   // per SM
         int warps = 8, ctas_fit = 2;
         bool zsm = false;
-        if (zsm_env && !split && (!grid_mode || lrt)) {   // grid mode without LRT has no SNP-specific evaluation at all
+        // Measured (profiles/bench_r02_solver_slab_ab.txt): with short x rows (k1p <= 8, e.g. the GD449 shape, c0 = 6) the slab is
+        // 8 KB and 16 warps per SM keep it resident: solve stage 5.9 -> 5.0 ms per 100 k SNPs; for k1p = 12 / 16 only 10-11
+        // warps fit and the lost occupancy costs more than the L2 latency saved (c0 = 10: 6.6 -> 8.9 ms), so those stay on
+        // the read-only cache path.  Grid mode without LRT has no SNP-specific evaluation at all.
+        if (zsm_env && !split && h->k1p <= 8 && (!grid_mode || lrt)) {
             const size_t pw = sizeof(double) * (scratch_d + slab_d);
             const int fit = (int)(budget / pw);          // warps per SM with the slab resident
             if (fit >= 16) { warps = 8; ctas_fit = 2; zsm = true; }
