@@ -53,7 +53,11 @@ static void copy_row(char* dst, const char* src, size_t bytes)
 void pack_block_threads(char* dst, const char* src, size_t pitch, size_t width, size_t rows)
 {
     const unsigned hw = std::thread::hardware_concurrency();
-    static const size_t max_threads = getenv("PG_PACK_THREADS") ? (size_t)std::max(1, atoi(getenv("PG_PACK_THREADS"))) : 16;
+    // one process per GPU (torchrun sets LOCAL_WORLD_SIZE): the ranks of a node share its cores -- 8 x 16 packing threads on
+    // 32 cores were measured slower than the upload they feed
+    static const size_t local_world = getenv("LOCAL_WORLD_SIZE") ? (size_t)std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+    static const size_t max_threads = getenv("PG_PACK_THREADS") ? (size_t)std::max(1, atoi(getenv("PG_PACK_THREADS")))
+                                                                : std::max<size_t>(2, std::min<size_t>(16, (hw ? hw : 4) / local_world));
     const size_t nt = std::max<size_t>(1, std::min<size_t>({max_threads, (size_t)(hw ? hw : 4), rows}));
     auto work = [=](size_t t) {
         const size_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
