@@ -111,6 +111,11 @@ struct pg_handle {
     double* wy_all = nullptr;   // q > 1: rotated [W0, y_0 .. y_{q-1}], the linear columns of the shared compression
     int wy_all_cols = 0;
     int z_rows = 0;             // slab rows per SNP the Z buffers were last laid out for (k1p - 1 + q)
+    // tables as one DGEMM per design (reml_kernels.cuh): powers of 1/(lambda d + 1) per eigen-system, pair products and the
+    // product matrix per design
+    double *hpow = nullptr, *hscal = nullptr, *pairp = nullptr, *tabc = nullptr;
+    long long ldh = 0;
+    bool hpow_valid = false;
     // table-2 rows (covariate levels eliminated per table lambda, pg_eval.cuh)
     double *fix2 = nullptr, *itab2 = nullptr, *t2work = nullptr;
     Tables2 tab2{};
@@ -247,7 +252,7 @@ static int free_all(pg_handle* h)
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->cmb) cudaStreamDestroy(h->cmb);
     void* bufs[] = {h->U, h->d, h->wy, h->fixtab, h->itab, h->basis, h->lambdas, h->tri_ab, h->xf, h->xr[0], h->xr[1], h->counter,
-                    h->perm_dev, h->fix2, h->itab2, h->t2work};
+                    h->perm_dev, h->fix2, h->itab2, h->t2work, h->hpow, h->hscal, h->pairp, h->tabc};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->blas) cublasDestroy(h->blas);
@@ -470,6 +475,7 @@ static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
 static int canonicalise_eigen(pg_handle* h)
 {
     const int n = h->n;
+    h->hpow_valid = false;   // the table powers belong to the eigenvalues
     std::vector<double> dh(n);
     CK(cudaMemcpyAsync(dh.data(), h->d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->compute));
     CK(cudaStreamSynchronize(h->compute));
@@ -673,9 +679,47 @@ static int ensure_slots(pg_handle* h, int q)
     return PG_OK;
 }
 
+// powers of 1/(lambda d + 1) for every table lambda and the design-independent scalars: once per eigen-system
+static int ensure_hpow(pg_handle* h)
+{
+    if (h->hpow_valid) return PG_OK;
+    const int n = h->n, R3 = 3 * kNumTableRows, T0 = h->tab.T0;
+    h->ldh = h->ldw;
+    if (!h->hpow) CK(cudaMalloc(&h->hpow, sizeof(double) * (size_t)h->ldh * R3));
+    if (!h->hscal) CK(cudaMalloc(&h->hscal, sizeof(double) * 3 * kNumTableRows));
+    if (!h->pairp) CK(cudaMalloc(&h->pairp, sizeof(double) * (size_t)h->ldh * T0));
+    if (!h->tabc) CK(cudaMalloc(&h->tabc, sizeof(double) * (size_t)R3 * T0));
+    build_hpow_kernel<<<dim3((unsigned)((h->ldh + 255) / 256), kNumTableRows), 256, 0, h->compute>>>(n, h->ldh, h->d, h->lambdas, h->hpow);
+    CK(cudaGetLastError());
+    build_hscal_kernel<<<kNumTableRows, 256, 0, h->compute>>>(n, h->d, h->lambdas, h->hscal);
+    CK(cudaGetLastError());
+    h->hpow_valid = true;
+    return PG_OK;
+}
+
 static int build_tables(pg_handle* h)
 {
     const int T0 = h->tab.T0;
+    // PG_TABLES_GEMM=0: the per-row reduction kernel of round 1 (cross-check); memory: 24 n x 971 bytes for the powers
+    static const bool use_gemm = !(getenv("PG_TABLES_GEMM") && atoi(getenv("PG_TABLES_GEMM")) == 0);
+    if (use_gemm) {
+        int rc = ensure_hpow(h);
+        if (rc) return rc;
+        const int n = h->n, R3 = 3 * kNumTableRows;
+        pair_products_kernel<<<dim3((unsigned)((h->ldh + 255) / 256), T0), 256, 0, h->compute>>>(n, h->ldh, T0, h->wy, h->ldw,
+                                                                                              h->tri_ab, h->pairp);
+        CK(cudaGetLastError());
+        const double one = 1.0, zero = 0.0;
+        // C (R3 x T0) = Hpow^T (R3 x n) . P (n x T0), all column-major
+        CKB(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, R3, T0, n, &one, h->hpow, (int)h->ldh, h->pairp, (int)h->ldh, &zero,
+                        h->tabc, R3));
+        scatter_tables_kernel<<<kNumTableRows, 128, 0, h->compute>>>(T0, h->tab.NF, R3, h->tabc, h->hscal, h->fixtab, h->itab);
+        CK(cudaGetLastError());
+        eliminate_tables_kernel<<<(kNumTableRows + 63) / 64, 64, 0, h->compute>>>(h->c0, h->tab.NF, h->tab2.NF2, h->fixtab, h->itab,
+                                                                                  h->fix2, h->itab2, h->t2work);
+        CK(cudaGetLastError());
+        return PG_OK;
+    }
     const int nchunks = (T0 + kTablePairs - 1) / kTablePairs;
     dim3 grid(nchunks + 1, kNumTableRows);
     build_tables_kernel<<<grid, 256, 0, h->compute>>>(h->n, h->c0, h->d, h->wy, h->ldw, h->lambdas, h->fixtab, h->itab,

@@ -498,3 +498,32 @@ def test_four_cta_cluster_rotation_is_bit_identical():
             subprocess.check_call([sys.executable, "-c", code, f.name], env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
             outs.append(np.load(f.name))
     assert np.array_equal(outs[0], outs[1], equal_nan=True)
+
+
+def test_tables_by_gemm_agree_with_row_reductions():
+    """The SNP-independent lambda tables come from one DGEMM per design (powers of 1/(lambda d + 1) kept per eigen-system);
+    PG_TABLES_GEMM=0 selects the per-row reduction kernel of round 1.  Both must give the same scan to summation rounding --
+    single- and multi-trait, a second design on the same handle, c0 = 0."""
+    import subprocess
+    import sys
+    import tempfile
+
+    code = ("import numpy as np, sys; sys.path.insert(0, '.');"
+            "from pygemma_b200 import _capi; from pygemma_b200.synth import make_problem;"
+            "p = make_problem(1500, 400, 7, seed=5, m_k=3000); rng = np.random.default_rng(1);"
+            "Y2 = np.stack([p['Y'].reshape(-1), rng.standard_normal(1500)], axis=1);"
+            "h = _capi.Handle(1500, 7); h.set_kinship(p['K']); outs = [];"
+            "h.set_design(p['W'], p['Y']); o = h.scan(p['X']); outs.append(np.stack([o[c] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]));"
+            "h.set_design(p['W'], Y2); o = h.scan(p['X'], grid=True); outs.append(np.stack([o[c][1] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]));"
+            "h.close(); h = _capi.Handle(1500, 0); h.set_kinship(p['K']); h.set_design(np.zeros((1500, 0)), p['Y']); o = h.scan(p['X']);"
+            "outs.append(np.stack([o[c] for c in ['beta','se_beta','tau','lambda','F_wald','p_wald']]));"
+            "np.save(sys.argv[1], np.stack(outs))")
+    res = []
+    for g in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            env = dict(os.environ, PG_TABLES_GEMM=g)
+            subprocess.check_call([sys.executable, "-c", code, f.name], env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+            res.append(np.load(f.name))
+    assert np.array_equal(np.isnan(res[0]), np.isnan(res[1]))
+    e = rel(res[0], res[1])
+    assert np.nanmax(e[:, [0, 1, 2, 4, 5]]) < 1e-9 and np.nanmax(e[:, 3]) < 1e-7, (float(np.nanmax(e)),)
