@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 5
+#define PG_ABI_VERSION 6
 
 typedef struct pg_handle pg_handle;
 
@@ -236,6 +236,31 @@ int pg_scan_lrt(pg_handle* h, const void* X, int xdtype, int64_t ld, int layout,
  * tau_null = n / y^T P y, loglik_null = likelihood(lambda_null, tau_null, beta_hat, d, y, W).  Outputs are nullable.
  */
 int pg_null_model(pg_handle* h, int trait, double* lambda_null, double* tau_null, double* loglik_null);
+
+/*
+ * Several GPUs of one node driven by ONE process (SURVEY 8b's pg_create_multi): a pg_multi owns one handle per device.
+ * The eigendecomposition runs on the first device and U, d travel to the others peer to peer (cudaMemcpyPeer: NVLink /
+ * NVSwitch where the devices are connected), the design goes to every device, and pg_multi_scan cuts the m columns into
+ * contiguous shards -- SampleIter's chunks (lmm/lmm.py:427-434), chunk length rounded up to 128 columns -- scanned
+ * concurrently by one host thread per device; every shard writes its rows of the caller's output arrays directly, so the
+ * result is in input order and bit-identical to a single-GPU scan.  One phenotype per pass (pg_set_design semantics).
+ * The one-process-per-GPU route (torch.distributed + NCCL, pygemma_b200/multi.py) is the other way to use several GPUs.
+ */
+typedef struct pg_multi pg_multi;
+/* devices: ngpu CUDA device ordinals, or NULL for 0 .. ngpu-1 */
+int pg_multi_create(int n, int c0, int ngpu, const int* devices, pg_multi** out);
+int pg_multi_destroy(pg_multi* mh);
+const char* pg_multi_last_error(const pg_multi* mh);
+int pg_multi_count(const pg_multi* mh);
+pg_handle* pg_multi_handle(pg_multi* mh, int i);   /* the i-th device's handle (options, probes); owned by mh */
+/* as pg_set_kinship on the first device + peer copies; bcast_ms (nullable): wall time of the copies */
+int pg_multi_set_kinship(pg_multi* mh, const double* K_host, double* d_out_host, float* eig_ms, float* bcast_ms);
+int pg_multi_set_eigen(pg_multi* mh, const double* U_host, int u_row_major, const double* d_host);
+int pg_multi_set_design(pg_multi* mh, const double* W_host, const double* y_host, int already_rotated, float* ms);
+/* as pg_scan; timing (nullable) receives pg_multi_count(mh) entries, one per device */
+int pg_multi_scan(pg_multi* mh, const void* X, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+                  double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
+                  int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing);
 
 /*
  * Unit-level probes used by the parity tests (mirrors of the reference's Python-callable cpdefs).

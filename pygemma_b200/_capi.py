@@ -26,7 +26,9 @@ SYMBOLS = [
     "pg_abi_version", "pg_rotation_planes", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_copy_eigen", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
     "pg_set_reml_engine", "pg_set_scan_mode", "pg_grm", "pg_set_bed_options",
-    "pg_scan", "pg_scan_device", "pg_scan_lrt", "pg_null_model", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
+    "pg_scan", "pg_scan_device", "pg_scan_lrt", "pg_null_model",
+    "pg_multi_create", "pg_multi_destroy", "pg_multi_last_error", "pg_multi_count", "pg_multi_handle", "pg_multi_set_kinship",
+    "pg_multi_set_eigen", "pg_multi_set_design", "pg_multi_scan", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
 ]
 
 
@@ -91,10 +93,22 @@ def load():
     L.pg_probe_precompute.argtypes = [vp, vp, dbl, i32, i32, vp]
     L.pg_probe_f_sf.argtypes = [vp, vp, dbl, i64, vp]
     L.pg_probe_rotated.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.pg_multi_create.argtypes = [i32, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(vp)]
+    L.pg_multi_destroy.argtypes = [vp]
+    L.pg_multi_last_error.argtypes = [vp]
+    L.pg_multi_count.argtypes = [vp]
+    L.pg_multi_handle.argtypes = [vp, i32]
+    L.pg_multi_set_kinship.argtypes = [vp, vp, vp, fp, fp]
+    L.pg_multi_set_eigen.argtypes = [vp, vp, i32, vp]
+    L.pg_multi_set_design.argtypes = [vp, vp, vp, i32, fp]
+    L.pg_multi_scan.argtypes = [vp, vp, i32, i64, i32, i64, i32] + [vp] * 9 + [ctypes.POINTER(PgTiming)]
     for name in SYMBOLS:
-        if name not in ("pg_last_error",):
+        if name not in ("pg_last_error", "pg_multi_last_error", "pg_multi_handle"):
             getattr(L, name).restype = i32
     L.pg_last_error.restype = ctypes.c_char_p
+    L.pg_multi_last_error.restype = ctypes.c_char_p
+    L.pg_multi_handle.restype = vp
     _lib = L
     return L
 
@@ -328,6 +342,107 @@ class Handle:
         row0 = ctypes.c_int64(0)
         self._ck(self.L.pg_probe_rotated(self.h, _ptr(xr), count, ctypes.byref(row0)))
         return xr, int(row0.value)
+
+
+class MultiHandle:
+    """Several GPUs of one node driven by this process (pg_multi_*): one pg_handle per device, U and d copied peer to peer,
+    contiguous SNP shards scanned concurrently, rows written in input order.  One phenotype per pass."""
+
+    def __init__(self, n: int, c0: int, devices):
+        self.L = load()
+        devices = list(range(int(devices))) if isinstance(devices, (int, np.integer)) else [int(d) for d in devices]
+        if not devices:
+            raise ValueError("MultiHandle needs at least one device")
+        self.n, self.c0, self.devices, self.q = int(n), int(c0), devices, 1
+        arr = (ctypes.c_int * len(devices))(*devices)
+        h = ctypes.c_void_p()
+        rc = self.L.pg_multi_create(self.n, self.c0, len(devices), arr, ctypes.byref(h))
+        if rc != 0:
+            raise PgError(rc, self.L.pg_multi_last_error(None).decode())
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PgError(rc, self.L.pg_multi_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pg_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_kinship(self, K):
+        K = np.ascontiguousarray(K, dtype=np.float64)
+        assert K.shape == (self.n, self.n)
+        d = np.empty(self.n)
+        ms, bms = ctypes.c_float(0), ctypes.c_float(0)
+        self._ck(self.L.pg_multi_set_kinship(self.h, _ptr(K), _ptr(d), ctypes.byref(ms), ctypes.byref(bms)))
+        self.bcast_ms = float(bms.value)
+        return d, float(ms.value)
+
+    def set_eigen(self, U, d):
+        d = np.ascontiguousarray(d, dtype=np.float64).reshape(-1)
+        if U is None:
+            self._ck(self.L.pg_multi_set_eigen(self.h, None, 0, _ptr(d)))
+            return
+        U = np.asarray(U, dtype=np.float64)
+        if U.flags.f_contiguous and not U.flags.c_contiguous:
+            self._ck(self.L.pg_multi_set_eigen(self.h, _ptr(U), 0, _ptr(d)))
+        else:
+            U = np.ascontiguousarray(U)
+            self._ck(self.L.pg_multi_set_eigen(self.h, _ptr(U), 1, _ptr(d)))
+
+    def set_design(self, W, y, already_rotated=False):
+        W = np.ascontiguousarray(W, dtype=np.float64).reshape(self.n, self.c0)
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        assert y.shape[0] == self.n
+        ms = ctypes.c_float(0)
+        self._ck(self.L.pg_multi_set_design(self.h, _ptr(W) if self.c0 else None, _ptr(y), int(already_rotated), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def set_scan_mode(self, mode=PG_SCAN_WALD):
+        for i in range(len(self.devices)):
+            rc = self.L.pg_set_scan_mode(ctypes.c_void_p(self.L.pg_multi_handle(self.h, i)), int(mode))
+            if rc != 0:
+                raise PgError(rc, "pg_set_scan_mode")
+
+    def scan(self, X, grid=False, layout=PG_X_SAMPLE_MAJOR, with_counts=True, lrt=False):
+        if lrt:
+            raise ValueError("the likelihood-ratio outputs are not available through MultiHandle")
+        if X.ndim != 2:
+            raise ValueError("X must be 2-D")
+        n, m = X.shape if layout == PG_X_SAMPLE_MAJOR else X.shape[::-1]
+        if n != self.n:
+            raise ValueError(f"X has {n} samples, handle was created for {self.n}")
+        if X.strides[1] != X.itemsize or (X.shape[0] > 1 and X.strides[0] % X.itemsize) or X.strides[0] < 0:
+            X = np.ascontiguousarray(X)
+        ld = max(X.strides[0] // X.itemsize if X.shape[0] > 1 else X.shape[1], X.shape[1])
+        out = {k: np.empty(m) for k in ("beta", "se_beta", "tau", "lambda", "F_wald", "p_wald")}
+        st = np.zeros(m, dtype=np.int32)
+        e2 = np.zeros(m, dtype=np.int32) if with_counts else None
+        e3 = np.zeros(m, dtype=np.int32) if with_counts else None
+        tms = (PgTiming * len(self.devices))()
+        self._ck(self.L.pg_multi_scan(self.h, _ptr(X), xdtype_of(X), ld, layout, m, int(bool(grid)),
+                                      _ptr(out["beta"]), _ptr(out["se_beta"]), _ptr(out["tau"]), _ptr(out["lambda"]),
+                                      _ptr(out["F_wald"]), _ptr(out["p_wald"]), _ptr(st), _ptr(e2), _ptr(e3), tms))
+        out["status"] = st
+        if with_counts:
+            out["n_eval2"], out["n_eval3"] = e2, e3
+        per = [t.as_dict() for t in tms]
+        out["timing_per_device"] = per
+        out["timing"] = max(per, key=lambda t: t["total_ms"])   # the slowest device is the step
+        return out
 
 
 def device_count() -> int:

@@ -8,6 +8,7 @@
 #include <cusolverDn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1810,4 +1811,129 @@ extern "C" int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, in
     }
     if (row0) *row0 = h->last_block_row0;
     return PG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs, one process (include/pygemma_b200.h: pg_multi_*).  SNP shards are independent units: one host thread per
+// device runs the ordinary blocked scan on its contiguous column range and writes straight into the caller's arrays.
+// ------------------------------------------------------------------------------------------------
+struct pg_multi {
+    std::vector<pg_handle*> hs;
+    std::string err;
+};
+
+static int mfail(pg_multi* mh, int code, const std::string& msg)
+{
+    if (mh) mh->err = msg; else g_create_error = msg;
+    return code;
+}
+
+extern "C" const char* pg_multi_last_error(const pg_multi* mh) { return mh ? mh->err.c_str() : g_create_error.c_str(); }
+extern "C" int pg_multi_count(const pg_multi* mh) { return mh ? (int)mh->hs.size() : 0; }
+extern "C" pg_handle* pg_multi_handle(pg_multi* mh, int i) { return (mh && i >= 0 && i < (int)mh->hs.size()) ? mh->hs[i] : nullptr; }
+
+extern "C" int pg_multi_destroy(pg_multi* mh)
+{
+    if (!mh) return PG_OK;
+    for (pg_handle* h : mh->hs) pg_destroy(h);
+    delete mh;
+    return PG_OK;
+}
+
+extern "C" int pg_multi_create(int n, int c0, int ngpu, const int* devices, pg_multi** out)
+{
+    if (!out) return mfail(nullptr, PG_ERR_ARG, "pg_multi_create: out is NULL");
+    *out = nullptr;
+    if (ngpu < 1) return mfail(nullptr, PG_ERR_ARG, "pg_multi_create: ngpu must be >= 1");
+    pg_multi* mh = new pg_multi;
+    for (int i = 0; i < ngpu; ++i) {
+        pg_handle* h = nullptr;
+        const int rc = pg_create(n, c0, devices ? devices[i] : i, &h);
+        if (rc != PG_OK) {
+            const std::string msg = g_create_error;
+            pg_multi_destroy(mh);
+            return mfail(nullptr, rc, "pg_multi_create: device " + std::to_string(devices ? devices[i] : i) + ": " + msg);
+        }
+        mh->hs.push_back(h);
+    }
+    *out = mh;
+    return PG_OK;
+}
+
+// runs fn(i) for every handle on its own host thread; the first failure is reported
+template <typename F>
+static int for_each_device(pg_multi* mh, F fn)
+{
+    const int g = (int)mh->hs.size();
+    std::vector<int> rcs(g, PG_OK);
+    std::vector<std::thread> th;
+    for (int i = 1; i < g; ++i) th.emplace_back([&, i] { rcs[i] = fn(i); });
+    rcs[0] = fn(0);
+    for (auto& t : th) t.join();
+    for (int i = 0; i < g; ++i)
+        if (rcs[i] != PG_OK) return mfail(mh, rcs[i], "device " + std::to_string(mh->hs[i]->device) + ": " + mh->hs[i]->err);
+    return PG_OK;
+}
+
+static int multi_share_eigen(pg_multi* mh, float* bcast_ms)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    // U (8 n^2 bytes) and d from the first device to every other one, peer to peer, concurrently
+    const int rc = for_each_device(mh, [&](int i) { return i == 0 ? PG_OK : pg_copy_eigen(mh->hs[i], mh->hs[0]); });
+    if (bcast_ms) *bcast_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+extern "C" int pg_multi_set_kinship(pg_multi* mh, const double* K_host, double* d_out_host, float* eig_ms, float* bcast_ms)
+{
+    if (!mh) return PG_ERR_ARG;
+    const int rc = pg_set_kinship(mh->hs[0], K_host, d_out_host, eig_ms);
+    if (rc != PG_OK) return mfail(mh, rc, mh->hs[0]->err);
+    return multi_share_eigen(mh, bcast_ms);
+}
+
+extern "C" int pg_multi_set_eigen(pg_multi* mh, const double* U_host, int u_row_major, const double* d_host)
+{
+    if (!mh) return PG_ERR_ARG;
+    const int rc = pg_set_eigen(mh->hs[0], U_host, u_row_major, d_host);
+    if (rc != PG_OK) return mfail(mh, rc, mh->hs[0]->err);
+    return multi_share_eigen(mh, nullptr);
+}
+
+extern "C" int pg_multi_set_design(pg_multi* mh, const double* W_host, const double* y_host, int already_rotated, float* ms)
+{
+    if (!mh) return PG_ERR_ARG;
+    std::vector<float> t(mh->hs.size(), 0.f);
+    const int rc = for_each_device(mh, [&](int i) { return pg_set_design(mh->hs[i], W_host, y_host, already_rotated, &t[i]); });
+    if (ms) *ms = *std::max_element(t.begin(), t.end());
+    return rc;
+}
+
+extern "C" int pg_multi_scan(pg_multi* mh, const void* X, int xdtype, int64_t ld, int layout, int64_t m, int grid,
+                             double* beta, double* se_beta, double* tau, double* lambda, double* F_wald, double* p_wald,
+                             int32_t* status, int32_t* n_eval2, int32_t* n_eval3, pg_timing* timing)
+{
+    if (!mh) return PG_ERR_ARG;
+    if (!X || m < 0) return mfail(mh, PG_ERR_ARG, "pg_multi_scan: NULL X or negative m");
+    if (xdtype < PG_X_I8 || xdtype > PG_X_BED) return mfail(mh, PG_ERR_ARG, "pg_multi_scan: xdtype");
+    const int g = (int)mh->hs.size();
+    for (pg_handle* h : mh->hs)
+        if (h->q != 1) return mfail(mh, PG_ERR_ARG, "pg_multi_scan: one phenotype per pass");
+    // contiguous shards, ceil(m / g) columns each (SampleIter), rounded up to 128 columns once shards are that long
+    long long per = (m + g - 1) / g;
+    if (g > 1 && per >= 128) {
+        const long long al = (per + 127) / 128 * 128;
+        if (al * (g - 1) < m) per = al;
+    }
+    const size_t esz = xdtype_size(xdtype);
+    return for_each_device(mh, [&](int i) -> int {
+        const long long a = std::min<long long>((long long)i * per, m), b = std::min<long long>((long long)(i + 1) * per, m);
+        if (timing) memset(&timing[i], 0, sizeof(pg_timing));
+        if (b <= a) return PG_OK;
+        const char* Xi = layout == PG_X_SAMPLE_MAJOR ? (const char*)X + (size_t)a * esz : (const char*)X + (size_t)a * (size_t)ld * esz;
+        double* out[6] = {beta + a, se_beta + a, tau + a, lambda + a, F_wald + a, p_wald + a};
+        return scan_impl(mh->hs[i], Xi, xdtype, ld, layout, b - a, grid, out, status ? status + a : nullptr,
+                         n_eval2 ? n_eval2 + a : nullptr, n_eval3 ? n_eval3 + a : nullptr, timing ? &timing[i] : nullptr, false);
+    });
 }

@@ -141,7 +141,7 @@ def _log(verbose, msg):
 
 
 def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=False, grid=False, eigen=True,
-            nproc=1, device=None, lrt=False):
+            nproc=1, device=None, lrt=False, gpus=None):
     """Per-SNP LMM association scan (GEMMA Wald test) on a B200.
 
     Args mirror the reference (lmm/lmm.py:87-103): Y (n,) or (n, 1) phenotype; X (n, m) genotypes
@@ -154,9 +154,80 @@ def pygemma(Y, X, W, K, Z=None, snps=None, verbose=0, disable_checks=True, de=Fa
     torch.distributed local rank.  `lrt=True` (extension) adds the likelihood-ratio columns the reference keeps as
     commented-out scaffolding (lmm/lmm.py:137-141,:176-190,:278-300): 'D_lrt' = 2 (l_alt - l_null) with the ML fits of
     lmm.calc_lambda, 'p_lrt' = its chi-square(1) tail, 'likelihood' = l_alt; the null fit is left in `last_null_model`.
+    `gpus` (extension): an int or a list of CUDA devices to be driven by THIS process (pg_multi_*: U and d copied peer to
+    peer, contiguous SNP shards scanned concurrently, same rows in the same order); the one-process-per-GPU route under
+    torchrun needs no argument.
     """
     Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)  # lmm/lmm.py:115-116
+    if gpus is not None and not (isinstance(gpus, (int, np.integer)) and int(gpus) <= 1):
+        return _run_multi_device(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, gpus, lrt)
     return _run(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, device, lrt)[0]
+
+
+def _run_multi_device(Y, X, W, K, Z, snps, verbose, disable_checks, de, grid, eigen, gpus, lrt):
+    """lmm.pygemma on several GPUs of one node from one process (include/pygemma_b200.h: pg_multi_*)."""
+    global last_timing
+    t_start = time.time()
+    if lrt or isinstance(K, KinshipFactor):
+        raise ValueError("gpus=... takes a kinship matrix (or eigenvalues with eigen=False) and has no lrt=True")
+    if _dist_active():
+        raise ValueError("gpus=... drives several devices from one process; under torch.distributed every rank owns one GPU")
+    X = _as_genotypes(X)
+    W = np.asarray(W, dtype=np.float64)
+    if W.ndim == 1:
+        W = W.reshape(-1, 1)
+    n, m = X.shape
+    c0 = W.shape[1]
+    if Y.shape[0] != n or W.shape[0] != n:
+        raise ValueError(f"shape mismatch: X {X.shape}, Y {Y.shape}, W {W.shape}")
+    K = np.asarray(K, dtype=np.float64)
+    if Z is not None:
+        Zm = np.asarray(Z, dtype=np.float64)
+        K = Zm @ K @ Zm.T  # lmm/lmm.py:124-125
+    if eigen and K.shape != (n, n):
+        raise ValueError(f"K must be ({n}, {n}) when eigen=True, got {K.shape}")
+    if not disable_checks:
+        if (X.dtype.kind == "f" and np.isnan(X).any()) or np.isnan(Y).any() or np.isnan(W).any():
+            raise ValueError("NaNs present in data")
+    if de:
+        grid = False
+    timing = {"n": n, "m": m, "c0": c0, "q": 1}
+    with _capi.MultiHandle(n, c0, gpus) as mh:
+        timing["devices"] = mh.devices
+        if eigen:
+            _log(verbose, "Starting eigendecomposition...")
+            _, timing["eig_ms"] = mh.set_kinship(K)
+            timing["bcast_ms"] = mh.bcast_ms
+            _log(verbose, f"Eigendecomposition computed, U and d on {len(mh.devices)} devices - {round(time.time() - t_start, 3)} s")
+        else:
+            mh.set_eigen(None, K.reshape(-1))
+        mh.set_scan_mode(_capi.PG_SCAN_DE if de else _capi.PG_SCAN_WALD)
+        timing["design_ms"] = mh.set_design(W, Y.reshape(-1), already_rotated=not eigen)
+        _log(verbose, f"Running {m} SNPs with {n} individuals on {len(mh.devices)} GPUs...")
+        t0 = time.time()
+        out = mh.scan(X, grid=grid)
+        timing["scan_wall_s"] = time.time() - t0
+        timing["scan"] = out["timing"]
+    bad = (out["status"] & 1) != 0
+    data = {}
+    for c in COLUMNS:
+        col = out[c]
+        if bad.any():
+            col = col.copy()
+            col[bad] = np.nan
+        data[c] = col
+    df = pd.DataFrame(data, columns=COLUMNS)
+    if snps is not None:
+        df["SNPs"] = snps  # lmm/lmm.py:408-409
+    timing["total_s"] = time.time() - t_start
+    last_timing = timing
+    return df
+
+
+def _dist_active() -> bool:
+    from . import multi
+
+    return multi._dist() is not None
 
 
 def null_model(Y, W, K, Z=None, eigen=True, device=None):
