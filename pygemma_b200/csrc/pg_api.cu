@@ -625,6 +625,16 @@ extern "C" int pg_copy_eigen(pg_handle* h, const pg_handle* src)
     CK(cudaSetDevice(src->device));
     CK(cudaStreamSynchronize(src->compute));
     CK(cudaSetDevice(h->device));
+    if (h->device != src->device) {
+        // direct peer-to-peer copies (NVLink / NVSwitch) instead of staging through host memory, where the devices allow it
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, h->device, src->device) == cudaSuccess && can) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (pe != cudaSuccess) cudaGetLastError();   // cudaErrorPeerAccessAlreadyEnabled is fine; anything else falls back to staging
+        } else {
+            cudaGetLastError();
+        }
+    }
     const int n = h->n;
     if (src->have_U) {
         int rc = ensure_U(h);
