@@ -1134,11 +1134,18 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         sa.l_null = lrt ? h->slots[ph].null_vals[2] : 0.0;
         for (int i = 0; i < 6; ++i) sa.out[i] = out[i];
         sa.status = status; sa.n_eval2 = e2; sa.n_eval3 = e3; sa.counter = counter;
-        // per-warp shared memory: x-row scratch + an interpolated table-2 row, and -- when it fits -- the SNP's whole moment
-        // slab (k1p rows x Kcp nodes), staged once per SNP instead of ~7 passes over it through L2
+        // per-tile shared memory (a tile = the 32 or 16 lanes that own one SNP): x-row scratch + an interpolated table-2 row,
+        // and -- when it pays -- the SNP's whole moment slab (k1p rows x Kcp nodes), staged once per SNP
         const size_t scratch_d = (size_t)((3 * h->k1p + h->tab2.NF2 + 1) & ~1);
         const size_t slab_d = (size_t)h->k1p * P.Kcp;
         static const bool zsm_env = !(getenv("PG_SOLVE_ZSM") && atoi(getenv("PG_SOLVE_ZSM")) == 0);
+        // two SNPs per warp when the x row has 9..16 entries (7 <= c0 <= 14): the covariate recursion and the optimiser's
+        // scalar code never use more lanes.  Measured (profiles/bench_r02_solver_tile_ab.txt): c0 = 10 solve stage 6.5 -> 5.7 ms
+        // per 100 k SNPs, c0 = 11 unchanged, c0 = 6 (8 entries, slab staged in shared memory) 4.9 -> 5.3 ms, so short rows keep
+        // a warp per SNP.  PG_SOLVE_TILE=32 forces a warp per SNP everywhere.
+        static const int tile_env = getenv("PG_SOLVE_TILE") ? atoi(getenv("PG_SOLVE_TILE")) : 16;
+        const int T = (tile_env == 16 && h->c0 + 2 <= 16 && h->k1p > 8 && !split) ? 16 : 32;
+        const int tpw = 32 / T;   // tiles per warp
         const size_t budget = 200 * 1024;   // per SM
         int warps = 8, ctas_fit = 2;
         bool zsm = false;
@@ -1147,15 +1154,15 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         // warps fit and the lost occupancy costs more than the L2 latency saved (c0 = 10: 6.6 -> 8.9 ms), so those stay on
         // the read-only cache path.  Grid mode without LRT has no SNP-specific evaluation at all.
         if (zsm_env && !split && h->k1p <= 8 && (!grid_mode || lrt)) {
-            const size_t pw = sizeof(double) * (scratch_d + slab_d);
-            const int fit = (int)(budget / pw);          // warps per SM with the slab resident
+            const size_t pw = sizeof(double) * (scratch_d + slab_d) * tpw;
+            const int fit = (int)(budget / pw);          // warps per SM with the slabs resident
             if (fit >= 16) { warps = 8; ctas_fit = 2; zsm = true; }
             else if (fit >= 12) { warps = 6; ctas_fit = 2; zsm = true; }
             else if (fit >= 10) { warps = 5; ctas_fit = 2; zsm = true; }
             else if (fit >= 8) { warps = 8; ctas_fit = 1; zsm = true; }
             else if (fit >= 6) { warps = 6; ctas_fit = 1; zsm = true; }
         }
-        const size_t per_warp = sizeof(double) * (scratch_d + (zsm ? slab_d : 0));
+        const size_t per_warp = sizeof(double) * (scratch_d + (zsm ? slab_d : 0)) * tpw;
         if (!zsm) while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
         // under the next block's rotation (PG_OVERLAP): the rotation CTA leaves 10 K registers and ~37 KB of shared memory
         // per SM, i.e. room for two solver warps (128 registers each) beside it
@@ -1167,7 +1174,8 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         auto launch = [&](auto kern, int ctas) -> int {
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(ctas, budget / std::max<size_t>(smem, 1)));
-            long long want = (mb + warps - 1) / warps;
+            const long long per_cta = (long long)warps * tpw;   // SNPs in flight per CTA
+            long long want = (mb + per_cta - 1) / per_cta;
             int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
             kern<<<grid, warps * 32, smem, st_solve>>>(sa);
             return PG_OK;
@@ -1179,8 +1187,10 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         const bool small = h->k1p <= 8;
         const int per_sm = split ? 1 : (zsm ? ctas_fit : (small ? 4 : 2));
         // with the slab resident the shared memory caps the SM at two CTAs anyway: the 128-register variant (no spills)
-        const int lr = two ? launch(reml_solve_kernel<2, 2>, per_sm)
-                           : ((small && !zsm) ? launch(reml_solve_kernel<1, 4>, per_sm) : launch(reml_solve_kernel<1, 2>, per_sm));
+        int lr;
+        if (two) lr = launch(reml_solve_kernel<2, 2, 32>, per_sm);
+        else if (T == 16) lr = (small && !zsm) ? launch(reml_solve_kernel<1, 4, 16>, per_sm) : launch(reml_solve_kernel<1, 2, 16>, per_sm);
+        else lr = (small && !zsm) ? launch(reml_solve_kernel<1, 4, 32>, per_sm) : launch(reml_solve_kernel<1, 2, 32>, per_sm);
         if (lr) return lr;
         CK(cudaGetLastError());
         // p-values, one thread per SNP (NaN F -> NaN p, so failed rows stay NaN).  The kernel is one long serial chain

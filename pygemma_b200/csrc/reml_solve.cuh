@@ -221,44 +221,56 @@ __global__ void __launch_bounds__(128) fixed_phase_kernel(FixedArgs a)
     }
 }
 
-// Sum V per-lane values over the warp with V + O(V/8) shuffles instead of 5 V: offsets 16, 8, 4 exchange
+// Sum V per-lane values over the tile with V + O(V/8) shuffles instead of 5 V: offsets 16, 8, 4 exchange
 // halves of the array, offsets 2 and 1 finish.  Afterwards lane group g = lane >> 2 holds in v[i], i < V/8,
-// the warp total of the original entry  ((g>>2)&1) V/2 + ((g>>1)&1) V/4 + (g&1) V/8 + i.
-template <int V>
+// the warp total of the original entry  ((g>>2)&1) V/2 + ((g>>1)&1) V/4 + (g&1) V/8 + i   (T = 16: g = (lane & 15) >> 2,
+// i < V/4, entry ((g>>1)&1) V/2 + (g&1) V/4 + i).
+// T lanes own one SNP: T = 32 (a warp) or 16 (two SNPs per warp, for x rows of at most 16 entries: the covariate recursion
+// and the optimiser's scalar code keep at most 16 lanes busy, so a half warp per SNP doubles their throughput).  Every
+// collective below names only the lanes of its own tile, the two tiles of a warp are free to diverge.
+template <int T>
+__device__ __forceinline__ unsigned tile_mask()
+{
+    return T == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+}
+
+template <int V, int T>
 __device__ __forceinline__ void warp_reduce_halving(double (&v)[V], int lane)
 {
     static_assert(V % 8 == 0, "V must be a multiple of 8");
-    {
+    const unsigned tm = tile_mask<T>();
+    constexpr int S0 = (T == 32) ? 2 : 1;   // the array half exchanged with offset 16 exists only for a whole warp
+    if (T == 32) {
         constexpr int H = V / 2;
         const bool up = (lane & 16) != 0;
 #pragma unroll
         for (int i = 0; i < H; ++i) {
             const double keep = up ? v[i + H] : v[i], send = up ? v[i] : v[i + H];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            v[i] = keep + __shfl_xor_sync(tm, send, 16);
         }
     }
     {
-        constexpr int H = V / 4;
+        constexpr int H = V / (2 * S0);
         const bool up = (lane & 8) != 0;
 #pragma unroll
         for (int i = 0; i < H; ++i) {
             const double keep = up ? v[i + H] : v[i], send = up ? v[i] : v[i + H];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            v[i] = keep + __shfl_xor_sync(tm, send, 8);
         }
     }
     {
-        constexpr int H = V / 8;
+        constexpr int H = V / (4 * S0);
         const bool up = (lane & 4) != 0;
 #pragma unroll
         for (int i = 0; i < H; ++i) {
             const double keep = up ? v[i + H] : v[i], send = up ? v[i] : v[i + H];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            v[i] = keep + __shfl_xor_sync(tm, send, 4);
         }
     }
 #pragma unroll
-    for (int i = 0; i < V / 8; ++i) {
-        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
-        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+    for (int i = 0; i < V / (4 * S0); ++i) {
+        v[i] += __shfl_xor_sync(tm, v[i], 2);
+        v[i] += __shfl_xor_sync(tm, v[i], 1);
     }
 }
 
@@ -266,20 +278,20 @@ __device__ __forceinline__ void warp_reduce_halving(double (&v)[V], int lane)
 // the last one read from the launch's own phenotype row a.yrow)
 // ZSM: Zs is the warp's shared-memory copy of the slab (rows 0..k1p-2, then the phenotype row at k1p-1), else the slab
 // in global memory (phenotype row a.yrow, read-only cache path).
-template <int NC, bool FULL, bool ZSM>
+template <int NC, bool FULL, bool ZSM, int T>
 __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double* __restrict__ Zs, double lam, int jb,
                                                 double* xs)
 {
     constexpr int NP = FULL ? 3 : 2;
     constexpr int V = ((NP * NC + 7) / 8) * 8;
-    const int lane = threadIdx.x & 31, Kcp = a.Kcp;
+    const int lane = threadIdx.x & (T - 1), Kcp = a.Kcp;
     double v[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = 0.0;
     const double* __restrict__ z = Zs + (size_t)jb * Kcp;
     const double* __restrict__ zl = Zs + (size_t)(jb + NC == a.k1p ? (ZSM ? a.k1p - 1 : a.yrow) : jb + NC - 1) * Kcp;
 #pragma unroll 2
-    for (int k = lane; k < Kcp; k += 32) {
+    for (int k = lane; k < Kcp; k += T) {
         const double h = rcp_ge1(fma(lam, __ldg(a.nodes + k), 1.0));
         const double h2 = h * h, h3 = h2 * h;
 #pragma unroll
@@ -291,12 +303,13 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
             if (FULL) v[2 * NC + j] = fma(h3, zz, v[2 * NC + j]);
         }
     }
-    warp_reduce_halving<V>(v, lane);
+    warp_reduce_halving<V, T>(v, lane);
     if ((lane & 3) == 0) {
         const int g = lane >> 2;
-        const int base = ((g >> 2) & 1) * (V / 2) + ((g >> 1) & 1) * (V / 4) + (g & 1) * (V / 8);
+        const int base = T == 32 ? ((g >> 2) & 1) * (V / 2) + ((g >> 1) & 1) * (V / 4) + (g & 1) * (V / 8)
+                                 : ((g >> 1) & 1) * (V / 2) + (g & 1) * (V / 4);
 #pragma unroll
-        for (int i = 0; i < V / 8; ++i) {
+        for (int i = 0; i < (T == 32 ? V / 8 : V / 4); ++i) {
             const int o = base + i;
             if (o < NP * NC) {
                 const int p = o / NC, j = jb + (o - p * NC);
@@ -307,7 +320,7 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
     }
 }
 
-template <bool FULL, bool ZSM>
+template <bool FULL, bool ZSM, int T>
 __device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __restrict__ Zs, double lam, double* xs)
 {
     int jb = 0;
@@ -315,31 +328,34 @@ __device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __
     // 12-row three-power pass spill at 128 registers (measured: solve stage -7..11 % with the narrower pass)
     constexpr int kBig = FULL ? 8 : 12;
     while (a.k1p - jb >= kBig) {
-        solve_xrow_pass<kBig, FULL, ZSM>(a, Zs, lam, jb, xs);
+        solve_xrow_pass<kBig, FULL, ZSM, T>(a, Zs, lam, jb, xs);
         jb += kBig;
     }
-    if (a.k1p - jb == 8) solve_xrow_pass<8, FULL, ZSM>(a, Zs, lam, jb, xs);
-    else if (a.k1p - jb == 4) solve_xrow_pass<4, FULL, ZSM>(a, Zs, lam, jb, xs);
+    if (a.k1p - jb == 8) solve_xrow_pass<8, FULL, ZSM, T>(a, Zs, lam, jb, xs);
+    else if (a.k1p - jb == 4) solve_xrow_pass<4, FULL, ZSM, T>(a, Zs, lam, jb, xs);
 }
 
 // The covariate levels applied to the x row held in registers: lane (j & 31), slot (j >> 5) owns entry j.
 // Pivot values travel by shuffle, pivot columns and level scalars come from the table-2 row (pg_eval.cuh).
-template <bool FULL, int NS>
+template <bool FULL, int NS, int T>
 __device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __restrict__ row2, double (&xa)[NS],
                                                     double (&xb)[NS], double (&xc)[NS], bool need_logdet, EvalOut* out,
                                                     bool swap)
 {
-    const int lane = threadIdx.x & 31, Tp = t2_pairs(c0), dg = c0 + 1;
+    static_assert(T == 32 || NS == 1, "a half warp holds x rows of at most 16 entries");
+    const int lane = threadIdx.x & (T - 1), Tp = t2_pairs(c0), dg = c0 + 1;
+    const int tb = (threadIdx.x & 31) & ~(T - 1);   // first lane of this tile inside the warp
+    const unsigned tm = tile_mask<T>();
     if (c0 == 0 && lane == 1 && !swap) xa[0] = cy_max(xa[0], kMinVal);  // pyx:939 / :993 hits (x,x) without covariates
     auto pick = [&](const double (&x)[NS], int slot) -> double {
         if (NS == 1) return x[0];
         return slot ? x[NS - 1] : x[0];
     };
     for (int p = 0; p < c0; ++p) {
-        const int src = p & 31, sl = p >> 5;
-        const double ar = __shfl_sync(0xffffffffu, pick(xa, sl), src);
-        const double br = __shfl_sync(0xffffffffu, pick(xb, sl), src);
-        const double cr = FULL ? __shfl_sync(0xffffffffu, pick(xc, sl), src) : 0.0;
+        const int src = tb | (p & (T - 1)), sl = p >> 5;
+        const double ar = __shfl_sync(tm, pick(xa, sl), src);
+        const double br = __shfl_sync(tm, pick(xb, sl), src);
+        const double cr = FULL ? __shfl_sync(tm, pick(xc, sl), src) : 0.0;
         const double al2 = row2[3 * p], al4 = row2[3 * p + 1], alc = FULL ? row2[3 * p + 2] : 0.0;
         const int cb = t2_col(c0, p, p + 1) - (p + 1);
 #pragma unroll
@@ -366,31 +382,33 @@ __device__ __forceinline__ void xrow_recursion_warp(int c0, const double* __rest
             }
         }
     }
-    const double app = __shfl_sync(0xffffffffu, pick(xa, dg >> 5), dg & 31);
-    const double bpp = __shfl_sync(0xffffffffu, pick(xb, dg >> 5), dg & 31);
-    const double cpp = FULL ? __shfl_sync(0xffffffffu, pick(xc, dg >> 5), dg & 31) : 0.0;
-    const double ar = __shfl_sync(0xffffffffu, pick(xa, c0 >> 5), c0 & 31);
-    const double br = __shfl_sync(0xffffffffu, pick(xb, c0 >> 5), c0 & 31);
-    const double cr = FULL ? __shfl_sync(0xffffffffu, pick(xc, c0 >> 5), c0 & 31) : 0.0;
+    const double app = __shfl_sync(tm, pick(xa, dg >> 5), tb | (dg & (T - 1)));
+    const double bpp = __shfl_sync(tm, pick(xb, dg >> 5), tb | (dg & (T - 1)));
+    const double cpp = FULL ? __shfl_sync(tm, pick(xc, dg >> 5), tb | (dg & (T - 1))) : 0.0;
+    const double ar = __shfl_sync(tm, pick(xa, c0 >> 5), tb | (c0 & (T - 1)));
+    const double br = __shfl_sync(tm, pick(xb, c0 >> 5), tb | (c0 & (T - 1)));
+    const double cr = FULL ? __shfl_sync(tm, pick(xc, c0 >> 5), tb | (c0 & (T - 1))) : 0.0;
     if (swap) xrow_final_level_swapped<FULL>(c0, row2 + t2_fin(c0), app, bpp, cpp, ar, br, cr, need_logdet, out);
     else xrow_final_level<FULL>(row2 + t2_fin(c0), app, bpp, cpp, ar, br, cr, need_logdet, out);
 }
 
 // One precompute_mat-equivalent evaluation from the compressed moments (warp-collective).
 // scratch (shared memory, per warp): 3 * k1p doubles for the level-0 x row, then NF2 for an interpolated table-2 row.
-template <int NS>
+template <int NS, int T = 32>
 __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const double* __restrict__ Zs, double lam,
                                                     int fixed_t, int full, int need_ll, double* scratch, EvalOut* e)
 {
-    const int lane = threadIdx.x & 31, c0 = a.c0, k1 = c0 + 2, k1p = a.k1p, NF2 = a.t2.NF2;
+    const int lane = threadIdx.x & (T - 1), c0 = a.c0, k1 = c0 + 2, k1p = a.k1p, NF2 = a.t2.NF2;
+    const int tb = (threadIdx.x & 31) & ~(T - 1);
+    const unsigned tm = tile_mask<T>();
     double* xs = scratch;
     double* rowbuf = scratch + 3 * k1p;
     if (a.zsm) {
-        if (full) solve_xrow_all<true, true>(a, Zs, lam, xs);
-        else solve_xrow_all<false, true>(a, Zs, lam, xs);
+        if (full) solve_xrow_all<true, true, T>(a, Zs, lam, xs);
+        else solve_xrow_all<false, true, T>(a, Zs, lam, xs);
     } else {
-        if (full) solve_xrow_all<true, false>(a, Zs, lam, xs);
-        else solve_xrow_all<false, false>(a, Zs, lam, xs);
+        if (full) solve_xrow_all<true, false, T>(a, Zs, lam, xs);
+        else solve_xrow_all<false, false, T>(a, Zs, lam, xs);
     }
     const double* row2;
     if (fixed_t >= 0) {
@@ -414,11 +432,11 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
         }
         double L[kNodes];
 #pragma unroll
-        for (int k = 0; k < kNodes; ++k) L[k] = __shfl_sync(0xffffffffu, Lk, k);
+        for (int k = 0; k < kNodes; ++k) L[k] = __shfl_sync(tm, Lk, tb | k);
         const double* __restrict__ base = a.t2.itab2 + (size_t)iv * kNodes * NF2;
         // two-power evaluations never read the third-power pivot columns: skip that third of the row
         const int skip0 = full ? NF2 : 3 * c0 + 2 * a.t2.Tp, skip1 = full ? NF2 : t2_fin(c0);
-        for (int f0 = lane; f0 < NF2 - (skip1 - skip0); f0 += 32) {
+        for (int f0 = lane; f0 < NF2 - (skip1 - skip0); f0 += T) {
             const int f = f0 < skip0 ? f0 : f0 + (skip1 - skip0);
             double v = 0.0;
 #pragma unroll
@@ -427,7 +445,7 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
         }
         row2 = rowbuf;
     }
-    __syncwarp();
+    __syncwarp(tm);
     double xa[NS], xb[NS], xc[NS];
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
@@ -438,9 +456,9 @@ __device__ __forceinline__ void eval_snp_compressed(const SolveArgs& a, const do
         xb[q] = in ? xs[k1p + r] : 0.0;
         xc[q] = (in && full) ? xs[2 * k1p + r] : 0.0;
     }
-    if (full) xrow_recursion_warp<true, NS>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
-    else xrow_recursion_warp<false, NS>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
-    __syncwarp();
+    if (full) xrow_recursion_warp<true, NS, T>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
+    else xrow_recursion_warp<false, NS, T>(c0, row2, xa, xb, xc, need_ll != 0, e, a.swap != 0);
+    __syncwarp(tm);
 }
 
 // one fixed-lambda evaluation of SNP g as fixed_phase_kernel left it (every lane reads the same words)
@@ -454,12 +472,14 @@ __device__ __forceinline__ void load_fixed(const SolveArgs& a, long long g, int 
     e->yPPPy = NAN; e->trPP = NAN;   // fixed-lambda evaluations are never full (SnpSolver::request_fixed)
 }
 
-template <int NS, int MINB>
+template <int NS, int MINB, int T = 32>
 __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
 {
     extern __shared__ double smem[];
-    __shared__ __align__(16) unsigned char solver_mem[8][(sizeof(SnpSolver) + 15) / 16 * 16];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ __align__(16) unsigned char solver_mem[256 / T][(sizeof(SnpSolver) + 15) / 16 * 16];
+    const int lane = threadIdx.x & (T - 1), warp = threadIdx.x / T;   // `warp` = this tile's index inside the CTA
+    const int tb = (threadIdx.x & 31) & ~(T - 1);
+    const unsigned tm = tile_mask<T>();
     const int k1p = a.k1p;
     const size_t per_warp = (size_t)((3 * k1p + a.t2.NF2 + 1) & ~1) + (a.zsm ? (size_t)k1p * a.Kcp : 0);
     double* scratch = smem + (size_t)warp * per_warp;
@@ -467,20 +487,20 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
     for (;;) {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(a.counter, 1ULL);
-        g = __shfl_sync(0xffffffffu, g, 0);
+        g = __shfl_sync(tm, g, tb);
         if (g >= (unsigned long long)a.m) break;
         PG_BOUNDS(a.yrow < a.zrows && a.k1p - 1 <= a.zrows, "solver: slab rows");
         const double* __restrict__ Zs = a.Z + (size_t)g * a.zrows * a.Kcp;
         if (a.zsm) {
             // rows 0..k1p-2 are contiguous in the slab; the phenotype row follows them in the copy
-            __syncwarp();
+            __syncwarp(tm);
             const int half_row = a.Kcp >> 1, total = k1p * half_row;
             const double2* __restrict__ src = reinterpret_cast<const double2*>(Zs);
             const double2* __restrict__ srcy = reinterpret_cast<const double2*>(Zs + (size_t)a.yrow * a.Kcp);
             double2* dst = reinterpret_cast<double2*>(zcopy);
             const int body = (k1p - 1) * half_row;
-            for (int i = lane; i < total; i += 32) dst[i] = i < body ? __ldg(src + i) : __ldg(srcy + (i - body));
-            __syncwarp();
+            for (int i = lane; i < total; i += T) dst[i] = i < body ? __ldg(src + i) : __ldg(srcy + (i - body));
+            __syncwarp(tm);
             Zs = zcopy;
         }
         // The optimiser state (448 bytes, identical in every lane) lives in shared memory, one copy per warp: all lanes
@@ -491,7 +511,7 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         while (s.pending()) {
             EvalOut e;
             if (s.req_fixed() >= 0 && a.FX) load_fixed(a, (long long)g, s.req_fixed(), &e);   // fixed_phase_kernel did it
-            else eval_snp_compressed<NS>(a, Zs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
+            else eval_snp_compressed<NS, T>(a, Zs, s.req_lambda(), s.req_fixed(), s.req_full(), s.req_ll(), scratch, &e);
             s.feed(e);
         }
         int st_bits = s.status;
@@ -505,14 +525,14 @@ __global__ void __launch_bounds__(256, MINB) reml_solve_kernel(SolveArgs a)
         if (a.lrt[0]) {
             // the ML optimisation of the alternative model on the same moments; its state takes over the REML solver's
             // shared-memory slot (the Wald row has been written)
-            __syncwarp();
+            __syncwarp(tm);
             static_assert(sizeof(MlSolver) <= sizeof(SnpSolver), "MlSolver must fit the solver slot");
             MlSolver& ms = *reinterpret_cast<MlSolver*>(solver_mem[warp]);
             ms.init(a.n);
             while (ms.pending()) {
                 EvalOut e;
                 if (ms.req_fixed() >= 0 && a.FX) load_fixed(a, (long long)g, ms.req_fixed(), &e);
-                else eval_snp_compressed<NS>(a, Zs, ms.req_lambda(), ms.req_fixed(), ms.req_full(), 0, scratch, &e);
+                else eval_snp_compressed<NS, T>(a, Zs, ms.req_lambda(), ms.req_fixed(), ms.req_full(), 0, scratch, &e);
                 ms.feed(e);
             }
             if (lane == 0) {
