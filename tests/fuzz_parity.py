@@ -49,23 +49,47 @@ def one_case(rng, idx):
     elif xkind == "f64real":
         X = X.astype(np.float64) + rng.uniform(-0.3, 0.3, size=X.shape)
     q = int(rng.choice([1, 1, 3]))   # a third of the cases scan three traits in one pass and check the last one
+    # round 2: a quarter of the compressed-engine cases exercise de=True (role swap) or the likelihood-ratio columns
+    mode = str(rng.choice(["wald", "wald", "wald", "de", "lrt"])) if engine == _capi.PG_REML_AUTO else "wald"
+    if mode == "de":
+        q, grid = 1, False
     Y = p["Y"]
     if q > 1:
         Y = np.concatenate([p["Y"].reshape(-1, 1), rng.standard_normal((n, q - 1)) + 0.3 * p["Y"].reshape(-1, 1)], axis=1)
-    cfg = dict(idx=idx, n=n, c0=c0, m=m, grid=grid, h2=h2, xkind=xkind, layout=layout, blk=blk, engine=engine, q=q)
+    cfg = dict(idx=idx, n=n, c0=c0, m=m, grid=grid, h2=h2, xkind=xkind, layout=layout, blk=blk, engine=engine, q=q, mode=mode)
     with _capi.Handle(n, c0) as h:
         h.set_options(block_snps=blk)
         h.set_reml_engine(engine)
         h.set_kinship(p["K"])
         h.set_design(p["W"], Y)
+        h.set_scan_mode(_capi.PG_SCAN_DE if mode == "de" else _capi.PG_SCAN_WALD)
         if layout == 0:
-            o = h.scan(np.ascontiguousarray(X), grid=grid)
+            o = h.scan(np.ascontiguousarray(X), grid=grid, lrt=(mode == "lrt"))
         else:
-            o = h.scan(np.ascontiguousarray(X.T), grid=grid, layout=_capi.PG_X_SNP_MAJOR)
+            o = h.scan(np.ascontiguousarray(X.T), grid=grid, layout=_capi.PG_X_SNP_MAJOR, lrt=(mode == "lrt"))
     if q > 1:
         o = {k: (v[q - 1] if k != "timing" else v) for k, v in o.items()}
-    ref = oracle.pygemma(Y.reshape(n, -1)[:, q - 1], np.asarray(X, dtype=np.float64), p["W"], p["K"], grid=grid)
+    yq = Y.reshape(n, -1)[:, q - 1]
     worst = 0.0
+    if mode == "de":
+        # calculate_de (lmm/lmm.py:498-532): every column is the outcome, y the predictor
+        d, U, yr, xr, wr = oracle.eigen_rotate(p["K"], yq, np.asarray(X, dtype=np.float64), p["W"] if c0 else np.zeros((n, 0)))
+        yrow = np.ascontiguousarray(yr.reshape(1, -1))
+        ref = {c: np.empty(m) for c in COLS}
+        for g in range(m):
+            r1 = oracle.scan_rotated(d, xr[:, g], wr.reshape(n, c0), yrow)
+            for c in COLS:
+                ref[c][g] = r1[c][0]
+    else:
+        ref = oracle.pygemma(yq, np.asarray(X, dtype=np.float64), p["W"], p["K"], grid=grid)
+    if mode == "lrt":
+        d, U, yr, xr, wr = oracle.eigen_rotate(p["K"], yq, np.asarray(X, dtype=np.float64), p["W"] if c0 else np.zeros((n, 0)))
+        lref = oracle.lrt_rotated(d, yr.reshape(-1), wr.reshape(n, c0), np.ascontiguousarray(xr.T))
+        ok = ~np.isnan(lref["D_lrt"]) & ~np.isnan(o["D_lrt"])
+        # D is a difference of two log-likelihoods of size ~n: compare on that scale
+        cfg["D_lrt"] = float((np.abs(o["D_lrt"][ok] - lref["D_lrt"][ok]) / (1.0 + np.abs(lref["loglik_ml"][ok]))).max()) if ok.any() else 0.0
+        cfg["loglik_ml"] = float(rel(o["loglik_ml"][ok], lref["loglik_ml"][ok]).max()) if ok.any() else 0.0
+        worst = max(worst, cfg["D_lrt"], cfg["loglik_ml"])
     for c in COLS:
         a, b = np.asarray(o[c]), np.asarray(ref[c])
         nan_mismatch = int((np.isnan(a) != np.isnan(b)).sum())
