@@ -11,7 +11,10 @@ libpygemma_b200.so (CUDA, sm_100a) through the C ABI of include/pygemma_b200.h:
     U.T @ {X, Y, W}         lmm/lmm.py:243-246  -> device GEMMs, X in SNP blocks
     Pool.imap(calculate)    lmm/lmm.py:378-403  -> per-SNP REML kernel
 
-Extension: `F = lmm.factorize(K)` decomposes once and `lmm.pygemma(Y, X, W, F)` reuses it (KinshipFactor).
+Extensions (all opt-in): `F = lmm.factorize(K)` decomposes once and `lmm.pygemma(Y, X, W, F)` reuses it (KinshipFactor);
+`lmm.pygemma_multi` scans several traits per pass; `lrt=True` adds the likelihood-ratio columns of the reference's
+commented-out scaffolding; `gpus=N` drives several GPUs from this one process (under torchrun every rank owns one GPU and
+the call shards by itself); `lmm.null_model` returns the null-model fit.
 
 Differences from the reference, all documented in DESIGN.md: arithmetic is float64 throughout (the
 reference mixes float32 storage into a float64 core), so every returned column is float64; `nproc` is
@@ -38,7 +41,6 @@ last_null_model: list = []
 
 # timings of the most recent call (seconds / milliseconds), for callers that want them without verbose
 last_timing: dict = {}
-
 
 
 def _as_genotypes(X):
