@@ -27,6 +27,11 @@ using namespace pg;
 
 static thread_local std::string g_create_error;
 
+// Dynamic shared memory above which a launch opts in with cudaFuncAttributeMaxDynamicSharedMemorySize.  The 48 KB default
+// limit counts STATIC + dynamic bytes and the solver kernels carry up to ~10 KB of static state (one SnpSolver per tile), so
+// the opt-in starts well below 48 KB (found by the round-2 fuzz sweep: c0 = 13 asked for 46.3 KB dynamic + static > 48 KB).
+static constexpr size_t kDynSmemOptIn = 16 * 1024;
+
 struct pg_handle {
     int n = 0, c0 = 0, device = 0;
     long long ldw = 0;  // padded leading dimension of d / wy (multiple of kTile, zero-filled)
@@ -1102,7 +1107,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
                 // H goes through shared memory in slabs of at most kFxSlabMax nodes (Kcp is a multiple of 32)
                 const int kslab = std::min(P.Kcp, kFxSlabMax);
                 const size_t hs = sizeof(double) * (size_t)kslab * kFxCols;
-                if (hs > 48 * 1024)
+                if (hs > kDynSmemOptIn)
                     CK(cudaFuncSetAttribute(fixed_xrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
                 fixed_xrow_kernel<<<(unsigned)((rows + 255) / 256), 256, hs, st>>>(Zbuf, rows, P.Kcp, P.H,
                                                                                     reinterpret_cast<double2*>(Fbuf), kslab, zrows,
@@ -1121,7 +1126,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
             fa.c0 = h->c0; fa.zrows = zrows; fa.yrow = h->k1p - 1 + ph; fa.swap = (h->scan_mode == PG_SCAN_DE) ? 1 : 0;
             fa.m = mb; fa.ldF = h->ldF; fa.F2 = reinterpret_cast<const double2*>(Fbuf); fa.t2 = h->tab2; fa.FX = FXbuf;
             const size_t fsm = sizeof(double) * ((size_t)((h->tab2.NF2 + 1) & ~1) + (size_t)2 * (h->c0 + 2) * 128);
-            if (fsm > 48 * 1024)
+            if (fsm > kDynSmemOptIn)
                 CK(cudaFuncSetAttribute(fixed_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             fixed_phase_kernel<<<(unsigned)((mb + 127) / 128), 128, fsm, st_solve>>>(fa);
             CK(cudaGetLastError());
@@ -1172,7 +1177,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         sa.zsm = zsm ? 1 : 0;
         const bool two = (h->c0 + 2) > 32;
         auto launch = [&](auto kern, int ctas) -> int {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > kDynSmemOptIn) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(ctas, budget / std::max<size_t>(smem, 1)));
             const long long per_cta = (long long)warps * tpw;   // SNPs in flight per CTA
             long long want = (mb + per_cta - 1) / per_cta;
@@ -1223,7 +1228,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
     int warps = 8;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps;
-    if (smem > 48 * 1024)
+    if (smem > kDynSmemOptIn)
         CK(cudaFuncSetAttribute(reml_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
     long long want = (mb + warps - 1) / warps;
@@ -1772,7 +1777,7 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
         sa.l_null = 0.0;
         const size_t smemc = sizeof(double) * (3 * (size_t)k1p + h->tab2.NF2);
         const bool two = (h->c0 + 2) > 32;
-        if (smemc > 48 * 1024) {
+        if (smemc > kDynSmemOptIn) {
             if (two) CK(cudaFuncSetAttribute(probe_precompute_compressed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
             else CK(cudaFuncSetAttribute(probe_precompute_compressed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
         }
@@ -1787,7 +1792,7 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
     a.n = n; a.c0 = h->c0; a.grid = 0; a.m = 1; a.row0 = 0; a.d = h->d; a.wy = h->wy; a.ldw = h->ldw; a.xr = dx; a.ldx = h->ldx; a.tab = h->tab;
     const int k = h->c0 + 2, TT = k * (k + 1) / 2;
     const size_t smem = sizeof(double) * 3 * TT;
-    if (smem > 48 * 1024)
+    if (smem > kDynSmemOptIn)
         CK(cudaFuncSetAttribute(probe_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     probe_precompute_kernel<<<1, 32, smem, h->compute>>>(a, lam, fixed_index, full, dout);
     CK(cudaGetLastError());

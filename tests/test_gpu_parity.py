@@ -167,6 +167,27 @@ def test_seeded_vs_oracle(n, m, c0, grid, h2):
     assert (o["status"] == 0).all()
 
 
+def test_every_covariate_count_launches_and_matches():
+    """c0 = 0..46 one by one: every x-row width walks through the solver's template and launch-shape switches (warp or
+    half-warp tiles, one or two x rows per lane, slab staging, the shared-memory opt-in).  The round-2 fuzz sweep found
+    c0 = 13 failing to LAUNCH (static + dynamic shared memory just over the 48 KB default limit) while 12 and 14 ran."""
+    from oracle import oracle
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    n, m = 160, 40
+    for c0 in range(0, 47):
+        p = make_problem(n, m, c0, seed=900 + c0, h2=0.4, m_k=300)
+        with capi.Handle(n, c0) as h:
+            h.set_kinship(p["K"])
+            h.set_design(p["W"], p["Y"])
+            for grid in (False, True):
+                o = h.scan(p["X"], grid=grid, lrt=not grid)
+                ref = oracle.pygemma(p["Y"], p["X"], p["W"], p["K"], grid=grid)
+                _check(o, ref, tag=(c0, grid))
+                assert (o["status"] & 1 == 0).all(), (c0, grid)
+
+
 def test_rotation_matches_lapack_rotation():
     """U^T X from the device against float64 LAPACK eigh + matmul, up to eigenvector signs (via |.|)
     and through rotation-invariant sums."""
