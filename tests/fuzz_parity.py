@@ -18,10 +18,31 @@ from pygemma_b200 import _capi
 from pygemma_b200.synth import make_problem
 
 COLS = ["beta", "se_beta", "tau", "lambda", "F_wald", "p_wald"]
+LAST_CFG = {}
 
 
 def rel(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def flat_likelihood_rows(ref, o, rows, d, yr, wr, xr, n, c0):
+    """Rows whose lambda differs from the oracle's by more than the tolerance although BOTH values maximise the REML
+    log-likelihood equally well at fp64 resolution (|ll(lambda_gpu) - ll(lambda_ref)| <= 8 ulp): with d2 ~ 1e-11 the root of
+    d1 is not determined to 1e-6 by fp64 arithmetic (tiny n - c0 - 1, h2 = 0).  Such rows are reported, not failed."""
+    import ctypes
+
+    L = oracle.lib()
+    L.pgo_loglik.restype = ctypes.c_double
+    L.pgo_loglik.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 3
+    flat = []
+    for j in rows:
+        ll = []
+        for lam in (ref["lambda"][j], o["lambda"][j]):
+            _, sc = oracle.precompute_probe(float(lam), d, wr, np.ascontiguousarray(xr[:, j]), yr, full=False)
+            ll.append(L.pgo_loglik(n, c0 + 1, sc[0], sc[5], sc[6]))
+        if abs(ll[0] - ll[1]) <= 8 * np.finfo(float).eps * max(1.0, abs(ll[0])):
+            flat.append(int(j))
+    return flat
 
 
 def one_case(rng, idx):
@@ -57,6 +78,8 @@ def one_case(rng, idx):
     if q > 1:
         Y = np.concatenate([p["Y"].reshape(-1, 1), rng.standard_normal((n, q - 1)) + 0.3 * p["Y"].reshape(-1, 1)], axis=1)
     cfg = dict(idx=idx, n=n, c0=c0, m=m, grid=grid, h2=h2, xkind=xkind, layout=layout, blk=blk, engine=engine, q=q, mode=mode)
+    LAST_CFG.clear()
+    LAST_CFG.update(cfg)   # an exception below is reported with the configuration that raised it
     with _capi.Handle(n, c0) as h:
         h.set_options(block_snps=blk)
         h.set_reml_engine(engine)
@@ -98,6 +121,25 @@ def one_case(rng, idx):
         cfg[c] = e
         cfg[c + "_nan_mismatch"] = nan_mismatch
         worst = max(worst, e, 1.0 if nan_mismatch else 0.0)
+    if worst >= 1e-6 and mode != "de" and not grid and not any(cfg[c + "_nan_mismatch"] for c in COLS):
+        # lambda (and tau = (n - c0 - 1) / yPy(lambda)) beyond the tolerance on a flat likelihood?
+        with np.errstate(invalid="ignore"):
+            bad = np.nonzero(rel(np.asarray(o["lambda"]), np.asarray(ref["lambda"])) >= 1e-6)[0]
+        d, U, yr, xr, wr = oracle.eigen_rotate(p["K"], yq, np.asarray(X, dtype=np.float64), p["W"] if c0 else np.zeros((n, 0)))
+        flat = flat_likelihood_rows(ref, o, bad, d, yr.reshape(-1), wr.reshape(n, c0), xr, n, c0)
+        if len(flat) == len(bad) and len(bad):
+            keep = np.ones(len(np.asarray(ref["lambda"])), dtype=bool)
+            keep[bad] = False
+            worst = 0.0
+            for c in COLS:
+                a, b = np.asarray(o[c]), np.asarray(ref[c])
+                ok = ~np.isnan(b) & ~np.isnan(a) & (keep if c in ("lambda", "tau") else True)
+                # the other columns of a flat row move with lambda only in second order: held to 1e-6 as everywhere
+                e = float(rel(a[ok], b[ok]).max()) if ok.any() else 0.0
+                cfg[c] = e
+                worst = max(worst, e)
+            worst = max(worst, cfg.get("D_lrt", 0.0), cfg.get("loglik_ml", 0.0))
+            cfg["flat_likelihood_rows"] = flat
     cfg["bad_status"] = int((o["status"] != 0).sum())
     cfg["worst"] = worst
     return cfg
@@ -117,11 +159,11 @@ def main():
         try:
             r = one_case(rng, seed * 1000 + i)
         except Exception as ex:  # noqa: BLE001 - report and go on
-            r = {"idx": i, "error": repr(ex), "worst": 1.0}
+            r = dict(LAST_CFG, error=repr(ex), worst=1.0)
         done += 1
         flag = r["worst"] >= 1e-6
         fails += flag
-        if flag or i % 10 == 0:
+        if flag or i % 10 == 0 or r.get("flat_likelihood_rows"):
             print(("FAIL " if flag else "ok   ") + json.dumps(r), flush=True)
     print(json.dumps({"cases": done, "fails": fails, "seconds": time.time() - t0}))
 

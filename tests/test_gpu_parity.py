@@ -168,7 +168,7 @@ def test_seeded_vs_oracle(n, m, c0, grid, h2):
 
 
 def test_every_covariate_count_launches_and_matches():
-    """c0 = 0..46 one by one: every x-row width walks through the solver's template and launch-shape switches (warp or
+    """c0 = 0..62 (the ABI's maximum) one by one: every x-row width walks through the solver's template and launch-shape switches (warp or
     half-warp tiles, one or two x rows per lane, slab staging, the shared-memory opt-in).  The round-2 fuzz sweep found
     c0 = 13 failing to LAUNCH (static + dynamic shared memory just over the 48 KB default limit) while 12 and 14 ran."""
     from oracle import oracle
@@ -176,7 +176,7 @@ def test_every_covariate_count_launches_and_matches():
 
     capi = _capi()
     n, m = 160, 40
-    for c0 in range(0, 47):
+    for c0 in range(0, 63):
         p = make_problem(n, m, c0, seed=900 + c0, h2=0.4, m_k=300)
         with capi.Handle(n, c0) as h:
             h.set_kinship(p["K"])
