@@ -1133,7 +1133,7 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         }
         SolveArgs sa;
         sa.n = h->n; sa.c0 = h->c0; sa.grid = grid_mode; sa.m = mb; sa.row0 = row0;
-        sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
+        sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Kc = P.Kc; sa.Z = Zbuf; sa.k1p = h->k1p; sa.t2 = h->tab2;
         sa.zrows = zrows; sa.yrow = h->k1p - 1 + ph; sa.FX = FXbuf; sa.ldF = h->ldF; sa.swap = (h->scan_mode == PG_SCAN_DE) ? 1 : 0;
         for (int i = 0; i < 4; ++i) sa.lrt[i] = lrt ? lrt[i] : nullptr;
         sa.l_null = lrt ? h->slots[ph].null_vals[2] : 0.0;
@@ -1771,7 +1771,7 @@ extern "C" int pg_probe_precompute(pg_handle* h, const double* x_rot_host, doubl
             CK(cudaGetLastError());
         }
         SolveArgs sa{};
-        sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Z = dz;
+        sa.n = n; sa.c0 = h->c0; sa.grid = 0; sa.m = 1; sa.row0 = 0; sa.nodes = P.nodes; sa.Kcp = P.Kcp; sa.Kc = P.Kc; sa.Z = dz;
         sa.k1p = k1p; sa.t2 = h->tab2; sa.zrows = zrows; sa.yrow = k1p - 1; sa.FX = nullptr; sa.ldF = 0; sa.swap = 0; sa.zsm = 0;
         for (int i = 0; i < 4; ++i) sa.lrt[i] = nullptr;
         sa.l_null = 0.0;

@@ -27,6 +27,7 @@ struct SolveArgs {
     long long m, row0;
     const double* nodes;  // [Kcp] node eigenvalues (padding: 0)
     int Kcp;
+    int Kc;               // nodes really in use (<= Kcp): the padding nodes carry zero moments and are not read by the solver
     const double* Z;      // [m][zrows][Kcp], slab rows as laid out in compress.cuh
     int k1p;              // c0+2 rounded up to a multiple of 4 (padding rows are zero)
     int zrows;            // rows per SNP slab: k1p - 1 + number of phenotypes
@@ -290,8 +291,11 @@ __device__ __forceinline__ void solve_xrow_pass(const SolveArgs& a, const double
     for (int i = 0; i < V; ++i) v[i] = 0.0;
     const double* __restrict__ z = Zs + (size_t)jb * Kcp;
     const double* __restrict__ zl = Zs + (size_t)(jb + NC == a.k1p ? (ZSM ? a.k1p - 1 : a.yrow) : jb + NC - 1) * Kcp;
+    // Global-memory slabs: the padding nodes (>= Kc) carry zero moments and are not fetched (adding 0 is exact); see
+    // solve_xrow_all for the padding rows.
+    const int kend = ZSM ? Kcp : a.Kc;
 #pragma unroll 2
-    for (int k = lane; k < Kcp; k += T) {
+    for (int k = lane; k < kend; k += T) {
         const double h = rcp_ge1(fma(lam, __ldg(a.nodes + k), 1.0));
         const double h2 = h * h, h3 = h2 * h;
 #pragma unroll
@@ -332,7 +336,13 @@ __device__ __noinline__ void solve_xrow_all(const SolveArgs& a, const double* __
         jb += kBig;
     }
     if (a.k1p - jb == 8) solve_xrow_pass<8, FULL, ZSM, T>(a, Zs, lam, jb, xs);
-    else if (a.k1p - jb == 4) solve_xrow_pass<4, FULL, ZSM, T>(a, Zs, lam, jb, xs);
+    else if (a.k1p - jb == 4) {
+        // rows c0+1 .. k1p-2 are padding (all zero): when only the phenotype row is left (c0 = 11: rows 12-14 padding, 15 = y)
+        // a one-row pass reads 13 instead of 16 rows per evaluation -- with the node bound above the slabs of the SNPs in
+        // flight (re-read from the L2 by every evaluation) shrink from 95 MB to 71 MB at the mouse shape (Kc = 129)
+        if (!ZSM && a.c0 < jb) solve_xrow_pass<1, FULL, ZSM, T>(a, Zs, lam, a.k1p - 1, xs);
+        else solve_xrow_pass<4, FULL, ZSM, T>(a, Zs, lam, jb, xs);
+    }
 }
 
 // The covariate levels applied to the x row held in registers: lane (j & 31), slot (j >> 5) owns entry j.
