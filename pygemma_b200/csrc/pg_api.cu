@@ -1305,15 +1305,19 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         for (int s = 0; s < 2; ++s)
             if (!h->ev_bounce_done[s]) CK(cudaEventCreateWithFlags(&h->ev_bounce_done[s], cudaEventDisableTiming));
     }
-    // Block boundaries.  Host input with automatic blocking: the first two blocks are short (1/16 and 1/4 of a block) so
-    // that compute starts after ~0.4 ms of upload instead of a whole block's worth; every later upload hides behind
-    // the previous block's compute.
+    // Block boundaries.  Host input with automatic blocking: the blocks grow geometrically (x 1.6 from 1 536 SNPs) up to the
+    // full block, so that compute starts after ~0.6 ms of packing + upload instead of a whole block's worth and every later
+    // block is packed and uploaded in less time than the block before it computes (n = 10 000: 0.35 us per SNP to pack and
+    // upload, 0.6 us to compute; the ratio is >= 1.6 at every n measured).  Round 1 used two short blocks (1/16, 1/4): the
+    // third, full-sized block then waited ~4 ms for its 250 MB while the GPU had 5 ms of work.  PG_RAMP=0: no short blocks.
     std::vector<long long> bstart;
     {
         long long g = 0;
-        if (!on_device && h->block_snps_opt <= 0 && m >= 2 * blk) {
-            for (long long first : {std::max<long long>(1024, blk / 16 / 256 * 256), std::max<long long>(4096, blk / 4 / 256 * 256)}) {
-                if (first < blk && g + first < m) { bstart.push_back(g); g += first; }
+        static const bool ramp = !(getenv("PG_RAMP") && atoi(getenv("PG_RAMP")) == 0);
+        if (ramp && !on_device && h->block_snps_opt <= 0 && m >= 2 * blk) {
+            for (long long cur = 1536; cur < blk && g + cur + 1024 < m; cur = (cur * 8 / 5 + 255) / 256 * 256) {
+                bstart.push_back(g);
+                g += cur;
             }
         }
         for (; g < m; g += blk) bstart.push_back(g);
