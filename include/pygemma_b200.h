@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 6
+#define PG_ABI_VERSION 7
 
 typedef struct pg_handle pg_handle;
 
@@ -275,6 +275,11 @@ int pg_probe_f_sf(pg_handle* h, const double* F_host, double nu, int64_t k, doub
 /* rotated genotypes of the last SNP block pg_scan processed: copies min(count, block) * n doubles
  * (SNP-major) and reports the global index of the block's first SNP in *row0 (nullable) */
 int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, int64_t* row0);
+/* The SNP-block boundaries pg_scan uses for m SNPs when one block holds at most `blk` SNPs (pure host arithmetic, needs
+ * no device): host_input != 0 -> the geometric ramp of short first blocks that lets packing / upload of block b+1 hide
+ * under the compute of block b; on-device input and a caller-fixed block size (pg_set_options) -> plain blocks.
+ * Writes min(count + 1, cap) boundaries (first = 0, last = m) and returns the block count, or PG_ERR_ARG. */
+int pg_probe_block_plan(int64_t m, int64_t blk, int host_input, int fixed_block, int64_t* starts, int cap);
 
 #ifdef __cplusplus
 }

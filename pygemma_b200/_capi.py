@@ -29,6 +29,7 @@ SYMBOLS = [
     "pg_scan", "pg_scan_device", "pg_scan_lrt", "pg_null_model",
     "pg_multi_create", "pg_multi_destroy", "pg_multi_last_error", "pg_multi_count", "pg_multi_handle", "pg_multi_set_kinship",
     "pg_multi_set_eigen", "pg_multi_set_design", "pg_multi_scan", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
+    "pg_probe_block_plan",
 ]
 
 
@@ -93,6 +94,7 @@ def load():
     L.pg_probe_precompute.argtypes = [vp, vp, dbl, i32, i32, vp]
     L.pg_probe_f_sf.argtypes = [vp, vp, dbl, i64, vp]
     L.pg_probe_rotated.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
+    L.pg_probe_block_plan.argtypes = [i64, i64, i32, i32, ctypes.POINTER(i64), i32]
     fp = ctypes.POINTER(ctypes.c_float)
     L.pg_multi_create.argtypes = [i32, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(vp)]
     L.pg_multi_destroy.argtypes = [vp]
@@ -111,6 +113,17 @@ def load():
     L.pg_multi_handle.restype = vp
     _lib = L
     return L
+
+
+def block_plan(m: int, blk: int, host_input: bool = True, fixed_block: bool = False):
+    """SNP-block boundaries pg_scan uses (pg_probe_block_plan; host arithmetic, no device needed)."""
+    L = load()
+    cap = 4096
+    buf = (ctypes.c_int64 * cap)()
+    nb = L.pg_probe_block_plan(int(m), int(blk), int(bool(host_input)), int(bool(fixed_block)), buf, cap)
+    if nb < 0:
+        raise PgError(nb, "pg_probe_block_plan: bad arguments")
+    return [int(buf[i]) for i in range(min(nb + 1, cap))] if m else []
 
 
 def _ptr(a):

@@ -32,6 +32,33 @@ static thread_local std::string g_create_error;
 // the opt-in starts well below 48 KB (found by the round-2 fuzz sweep: c0 = 13 asked for 46.3 KB dynamic + static > 48 KB).
 static constexpr size_t kDynSmemOptIn = 16 * 1024;
 
+// SNP-block boundaries of a scan (see scan_impl, "Block boundaries"): plain blocks of `blk`, preceded for host-resident
+// genotypes with automatic blocking by short blocks growing x 1.6 from 1 536 SNPs (multiples of 256).  PG_RAMP=0: none.
+static std::vector<long long> plan_blocks(long long m, long long blk, bool host_input, bool fixed_block)
+{
+    std::vector<long long> bstart;
+    long long g = 0;
+    static const bool ramp = !(getenv("PG_RAMP") && atoi(getenv("PG_RAMP")) == 0);
+    if (ramp && host_input && !fixed_block && m >= 2 * blk) {
+        for (long long cur = 1536; cur < blk && g + cur + 1024 < m; cur = (cur * 8 / 5 + 255) / 256 * 256) {
+            bstart.push_back(g);
+            g += cur;
+        }
+    }
+    for (; g < m; g += blk) bstart.push_back(g);
+    bstart.push_back(m);
+    return bstart;
+}
+
+extern "C" int pg_probe_block_plan(int64_t m, int64_t blk, int host_input, int fixed_block, int64_t* starts, int cap)
+{
+    if (m < 0 || blk <= 0 || (!starts && cap > 0)) return PG_ERR_ARG;
+    if (m == 0) return 0;
+    const std::vector<long long> b = plan_blocks(m, blk, host_input != 0, fixed_block != 0);
+    for (int i = 0; i < (int)b.size() && i < cap; ++i) starts[i] = b[i];
+    return (int)b.size() - 1;
+}
+
 struct pg_handle {
     int n = 0, c0 = 0, device = 0;
     long long ldw = 0;  // padded leading dimension of d / wy (multiple of kTile, zero-filled)
@@ -1310,19 +1337,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     // block is packed and uploaded in less time than the block before it computes (n = 10 000: 0.35 us per SNP to pack and
     // upload, 0.6 us to compute; the ratio is >= 1.6 at every n measured).  Round 1 used two short blocks (1/16, 1/4): the
     // third, full-sized block then waited ~4 ms for its 250 MB while the GPU had 5 ms of work.  PG_RAMP=0: no short blocks.
-    std::vector<long long> bstart;
-    {
-        long long g = 0;
-        static const bool ramp = !(getenv("PG_RAMP") && atoi(getenv("PG_RAMP")) == 0);
-        if (ramp && !on_device && h->block_snps_opt <= 0 && m >= 2 * blk) {
-            for (long long cur = 1536; cur < blk && g + cur + 1024 < m; cur = (cur * 8 / 5 + 255) / 256 * 256) {
-                bstart.push_back(g);
-                g += cur;
-            }
-        }
-        for (; g < m; g += blk) bstart.push_back(g);
-        bstart.push_back(m);
-    }
+    const std::vector<long long> bstart = plan_blocks(m, blk, !on_device, h->block_snps_opt > 0);
     const long long nblocks = (long long)bstart.size() - 1;
     const size_t esz = xdtype_size(xdtype);
     const size_t snp_row_bytes = bed ? (size_t)((n + 3) / 4) : (size_t)n * esz;   // one SNP of an SNP-major block

@@ -69,3 +69,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU or oracle", ""), os.path.join(dirpath, f)
+
+
+def test_block_plan_covers_every_snp_once(lib):
+    """pg_scan's SNP blocks (pg_probe_block_plan): contiguous, complete, none above the block size; host-resident
+    genotypes start with short blocks growing by at most x 1.6 (+ rounding to 256), on whole 256-SNP boundaries, so
+    that upload of block b+1 hides under the compute of block b."""
+    for m, blk in [(100000, 25088), (12544, 3584), (1_000_000, 5120), (50177, 25088), (50176, 25088), (2 * 1536 + 1025, 1536),
+                   (7, 32), (1, 32), (100000, 32768), (3000, 1024), (125056, 5120)]:
+        for host in (True, False):
+            for fixed in (True, False):
+                b = _capi.block_plan(m, blk, host, fixed)
+                assert b[0] == 0 and b[-1] == m and all(x < y for x, y in zip(b, b[1:])), (m, blk, b)
+                sizes = [y - x for x, y in zip(b, b[1:])]
+                assert max(sizes) <= blk
+                if not host or fixed or m < 2 * blk:
+                    assert sizes[:-1] == [blk] * (len(sizes) - 1)       # plain blocks
+                    continue
+                if blk > 1536:
+                    assert sizes[0] == 1536
+                for s0, s1 in zip(sizes, sizes[1:-1]):
+                    assert s1 <= max(blk, s0 * 8 // 5 + 256) and s1 >= min(s0, blk), (m, blk, sizes)
+                assert all(x % 256 == 0 for x in b[:-1]) or blk % 256, (m, blk, b)
+    assert _capi.block_plan(0, 1024) == []
+    assert lib.pg_probe_block_plan(-1, 1024, 1, 0, None, 0) == -1
