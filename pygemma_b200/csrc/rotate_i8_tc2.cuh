@@ -292,8 +292,8 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 for (int c = c_begin; c < c_begin + kCPer; ++c) {
                     // eight eigenvectors x seven planes = 56 consecutive columns (eigen-major)
                     uint32_t r[kSlices][8];
-#pragma unroll
                     PG_BOUNDS(c * 8 * kSlices + kSlices * 8 <= kTileN, "TMEM column range of an accumulator");
+#pragma unroll
                     for (int q = 0; q < kSlices; ++q) tmem_ld8(tbase + (uint32_t)(c * 8 * kSlices + q * 8), r[q]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (snp < a.mb) {
