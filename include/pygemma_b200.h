@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 7
+#define PG_ABI_VERSION 8
 
 typedef struct pg_handle pg_handle;
 
@@ -68,7 +68,9 @@ typedef enum {
     PG_ROT_AUTO = 0,  /* integer dosages -> exact int8-split tensor-core path when available, else FP64 */
     PG_ROT_FP64 = 1,  /* FP64 GEMM */
     PG_ROT_I8SPLIT = 2, /* exact int8 split: cuBLAS int8 GEMM + recombination kernel */
-    PG_ROT_I8TC = 3     /* exact int8 split as one hand-written TMA + tcgen05 kernel with the recombination fused in */
+    PG_ROT_I8TC = 3,    /* exact int8 split as one hand-written TMA + tcgen05 kernel with the recombination fused in */
+    PG_ROT_I8TC_MOMENTS = 4 /* reported in pg_timing.rot_engine only (not selectable): the PG_ROT_I8TC kernel with the
+                               eigenvalue-space moments fused in -- see pg_set_moment_fusion */
 } pg_rotation;
 
 /* REML stage engine (stage 2 of pg_scan) */
@@ -201,6 +203,23 @@ int pg_set_bed_options(pg_handle* h, int count_a1, int standardize);
 int pg_set_scan_mode(pg_handle* h, int mode);
 /* REML stage engine selection (default PG_REML_AUTO); all engines give the same results to rounding */
 int pg_set_reml_engine(pg_handle* h, int engine);
+/*
+ * Moment fusion.  The rotated genotypes U^T x (lmm/lmm.py:244) are consumed only by the per-SNP moment sums the reference
+ * forms in precompute_mat (pyx:938-943, :1002); on the compressed REML engine those are linear (x.w_j, x.y) or quadratic
+ * (x.x) in U^T x.  With fusion the PG_ROT_I8TC kernel produces them itself: the linear moments as extra exact int8 tiles
+ * against G = U V (V = the compression operand, built once per design), the x^2 moments in its epilogue; rotated genotypes
+ * are never written and the compression kernels do not run.  Results agree with the unfused path to rounding (different
+ * summation order), and are deterministic.  mode: -1 (default) = where it pays (PG_ROT_AUTO, int8 / level-coded
+ * genotypes, n >= 2048, <= 160 compression nodes, extra tiles <= half of the rotation); 0 = never; 1 = wherever the
+ * engine allows it (also with PG_ROT_I8TC selected).  Blocks that need the second, eps-weighted rotation pass (unequally
+ * spaced levels, missing .bed calls), the FP64 rotation or another engine are compressed as before.
+ * pg_probe_rotated is not available after a fused scan.
+ */
+int pg_set_moment_fusion(pg_handle* h, int mode);
+/* What the next scan of the current design would do (host-only probe, all outputs nullable): *fused != 0 when the moments
+ * come from the fused rotation; *g_columns = columns of G = U V appended to the rotation (COMPRESS nodes x linear columns),
+ * *pieces = x^2 partial sums per SNP, *build_ms = device time of the last build of G and its digit planes (0 before it). */
+int pg_probe_fusion(pg_handle* h, int32_t* fused, int32_t* g_columns, int32_t* pieces, float* build_ms);
 
 /*
  * The scan: for each of the m genotype columns, rotate (unless the handle holds rotated inputs),

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("PYGEMMA_B200_LIB") or os.path.join(_HERE, "libpygemma
 PG_X_I8, PG_X_F32, PG_X_F64, PG_X_BED = 0, 1, 2, 3
 PG_X_SAMPLE_MAJOR, PG_X_SNP_MAJOR = 0, 1
 PG_ROT_AUTO, PG_ROT_FP64, PG_ROT_I8SPLIT, PG_ROT_I8TC = 0, 1, 2, 3
+PG_ROT_I8TC_MOMENTS = 4   # reported by pg_timing.rot_engine only: the fused kernel also produced the moments
 PG_REML_AUTO, PG_REML_COMPRESSED, PG_REML_STREAM, PG_REML_WARP = 0, 1, 2, 3
 PG_SCAN_WALD, PG_SCAN_DE = 0, 1
 PG_MAX_TRAITS = 64  # traits per pass of pg_set_design_multi (include/pygemma_b200.h)
@@ -25,7 +26,7 @@ PG_MAX_TRAITS = 64  # traits per pass of pg_set_design_multi (include/pygemma_b2
 SYMBOLS = [
     "pg_abi_version", "pg_rotation_planes", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_copy_eigen", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
-    "pg_set_reml_engine", "pg_set_scan_mode", "pg_grm", "pg_set_bed_options",
+    "pg_set_reml_engine", "pg_set_scan_mode", "pg_grm", "pg_set_bed_options", "pg_set_moment_fusion", "pg_probe_fusion",
     "pg_scan", "pg_scan_device", "pg_scan_lrt", "pg_null_model",
     "pg_multi_create", "pg_multi_destroy", "pg_multi_last_error", "pg_multi_count", "pg_multi_handle", "pg_multi_set_kinship",
     "pg_multi_set_eigen", "pg_multi_set_design", "pg_multi_scan", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
@@ -83,6 +84,8 @@ def load():
     L.pg_set_stream.argtypes = [vp, vp]
     L.pg_set_reml_engine.argtypes = [vp, i32]
     L.pg_set_scan_mode.argtypes = [vp, i32]
+    L.pg_set_moment_fusion.argtypes = [vp, i32]
+    L.pg_probe_fusion.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_float)]
     L.pg_set_bed_options.argtypes = [vp, i32, i32]
     L.pg_grm.argtypes = [vp, vp, i32, i64, i32, i64, vp, i32, vp, ctypes.POINTER(ctypes.c_float),
                          ctypes.POINTER(ctypes.c_float)]
@@ -252,6 +255,17 @@ class Handle:
 
     def set_reml_engine(self, engine=PG_REML_AUTO):
         self._ck(self.L.pg_set_reml_engine(self.h, int(engine)))
+
+    def set_moment_fusion(self, mode=-1):
+        """-1: the fused rotation also produces the moments where that pays; 0: never; 1: wherever the engine allows."""
+        self._ck(self.L.pg_set_moment_fusion(self.h, int(mode)))
+
+    def fusion_info(self):
+        """What the next scan of the current design would do: {'fused', 'g_columns', 'pieces', 'build_ms'}."""
+        a, b, c = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        ms = ctypes.c_float(0)
+        self._ck(self.L.pg_probe_fusion(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(ms)))
+        return {"fused": bool(a.value), "g_columns": b.value, "pieces": c.value, "build_ms": ms.value}
 
     def set_scan_mode(self, mode=PG_SCAN_WALD):
         """PG_SCAN_DE: scanned columns are phenotypes, the design's y is the tested regressor (reference de=True)."""
@@ -423,6 +437,17 @@ class MultiHandle:
         ms = ctypes.c_float(0)
         self._ck(self.L.pg_multi_set_design(self.h, _ptr(W) if self.c0 else None, _ptr(y), int(already_rotated), ctypes.byref(ms)))
         return float(ms.value)
+
+    def set_moment_fusion(self, mode=-1):
+        """-1: the fused rotation also produces the moments where that pays; 0: never; 1: wherever the engine allows."""
+        self._ck(self.L.pg_set_moment_fusion(self.h, int(mode)))
+
+    def fusion_info(self):
+        """What the next scan of the current design would do: {'fused', 'g_columns', 'pieces', 'build_ms'}."""
+        a, b, c = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        ms = ctypes.c_float(0)
+        self._ck(self.L.pg_probe_fusion(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(ms)))
+        return {"fused": bool(a.value), "g_columns": b.value, "pieces": c.value, "build_ms": ms.value}
 
     def set_scan_mode(self, mode=PG_SCAN_WALD):
         for i in range(len(self.devices)):

@@ -118,6 +118,19 @@ __global__ void build_v_kernel(int n, int klin, const double* __restrict__ Lw, c
     (void)ngroups;
 }
 
+// Fused moments (rotate_i8_tc2.cuh, FUSE): the compact right-hand operand of G = U V.  Column k * klin + j holds
+// L_k(log d_l) w_jl for the rows l of COMPRESS segments (zero on COPY rows); segment s then contributes the n x (kq klin)
+// block  G_s = U[:, l0:l1] . Vc[l0:l1, 0 : kq klin]  (one DGEMM per segment).
+__global__ void build_vc_kernel(int n, int klin, const double* __restrict__ Lw, const int* __restrict__ seg_kq,
+                                const double* __restrict__ wy, long long ldw, double* __restrict__ Vc)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const int col = blockIdx.y;            // k * klin + j
+    const int k = col / klin, j = col - k * klin;
+    Vc[(size_t)col * n + l] = seg_kq[l] > 0 ? Lw[(size_t)l * kCq + k] * wy[(size_t)j * ldw + l] : 0.0;
+}
+
 __global__ void __launch_bounds__(256, 1)
 compress_dmma_kernel(const double* __restrict__ xr, long long ldx, long long mb, const CompItem* __restrict__ items,
                      const double* __restrict__ V, int vpitch, int c0, int k1p, int zrows, int Kcp, double* __restrict__ Z,

@@ -152,12 +152,44 @@ struct pg_handle {
     // table-2 rows (covariate levels eliminated per table lambda, pg_eval.cuh)
     double *fix2 = nullptr, *itab2 = nullptr, *t2work = nullptr;
     Tables2 tab2{};
+    // Moments straight from the fused rotation (rotate_i8_tc2.cuh, FUSE).  Per eigen-system: which x^2 piece / node every
+    // eigen-index feeds and the piece ranges of the segments.  Per design: G = U V (one column per COMPRESS node and linear
+    // column), its digit planes, scales, column sums and slab offsets.
+    int fuse_mode = -1;   // pg_set_moment_fusion: -1 automatic, 0 never, 1 wherever the engine allows it
+    struct Fused {
+        int2* einfo = nullptr;
+        tc2::SegRed* segs = nullptr;
+        int nsegs = 0, npieces = 0, cnodes = 0;       // cnodes: nodes of COMPRESS segments
+        std::vector<Segment> csegs;                   // the COMPRESS segments, eigen order
+        bool valid = false;                           // the per-design part below matches the current design
+        int klin = 0, gcols = 0, g_tiles = 0;
+        double *G = nullptr, *vdc = nullptr, *gscale = nullptr, *g1 = nullptr;
+        size_t g_elems = 0, vdc_elems = 0;
+        int8_t* planes_g = nullptr;
+        size_t planes_bytes = 0;
+        int *exps_g = nullptr, *goff = nullptr, *jrow = nullptr;
+        int col_cap = 0, jrow_cap = 0;
+        double* P2 = nullptr;
+        size_t p2_elems = 0;
+        long long ldp = 0;
+        float build_ms = 0.f;
+    } fz;
 };
 
 static void activate(pg_handle* h, int ph);
 
+static void free_fused(pg_handle* h)
+{
+    pg_handle::Fused& F = h->fz;
+    void* bufs[] = {F.einfo, F.segs, F.G, F.vdc, F.gscale, F.g1, F.planes_g, F.exps_g, F.goff, F.jrow, F.P2};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    F = pg_handle::Fused{};
+}
+
 static void free_plan(pg_handle* h)
 {
+    free_fused(h);
     DevPlan& P = h->plan;
     void* bufs[] = {P.nodes, P.H, P.Lw, P.seg_kq, P.V, P.items, P.copy_l, P.copy_node, h->Z[0], h->Z[1], h->F[0], h->F[1],
                     h->FX[0], h->FX[1]};
@@ -389,6 +421,7 @@ extern "C" int pg_create(int n, int c0, int device, pg_handle** out)
         h->tab2.c0 = c0; h->tab2.Tp = t2_pairs(c0); h->tab2.NF2 = NF2;
         h->tab2.fix2 = h->fix2; h->tab2.itab2 = h->itab2; h->tab2.basis = h->basis;
         h->k1p = (c0 + 2 + 3) / 4 * 4;
+        if (getenv("PG_FUSE_MOMENTS")) h->fuse_mode = std::max(-1, std::min(1, atoi(getenv("PG_FUSE_MOMENTS"))));   // pg_set_moment_fusion
         h->tab.c0 = c0; h->tab.k0 = k0; h->tab.T0 = T0; h->tab.NF = NF;
         h->tab.fixtab = h->fixtab; h->tab.itab = h->itab; h->tab.basis = h->basis; h->tab.tri_ab = h->tri_ab;
         return PG_OK;
@@ -491,6 +524,39 @@ static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
     }
     CK(cudaMalloc(&P.seg_kq, sizeof(int) * n));
     CK(cudaMemcpy(P.seg_kq, seg_kq.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    {
+        // fused moments: x^2 piece (COMPRESS rows) or node (COPY rows) of every eigen-index, piece ranges per segment
+        pg_handle::Fused& F = h->fz;
+        const int e32 = (n + tc2::kTileEig - 1) / tc2::kTileEig * tc2::kTileEig;
+        std::vector<int2> einfo(e32, make_int2(0, -1));
+        std::vector<tc2::SegRed> segred;
+        F.csegs.clear();
+        F.npieces = 0; F.cnodes = 0;
+        for (const Segment& sg : H.segs) {
+            if (sg.type == kSegCompress) {
+                tc2::SegRed sr{F.npieces, 0, sg.kb, sg.kq};
+                int last = -1;
+                for (int l = sg.l0; l < sg.l1; ++l) {
+                    if (l / tc2::kPieceEig != last) { last = l / tc2::kPieceEig; ++F.npieces; }
+                    einfo[l] = make_int2(F.npieces - 1, sg.kq);
+                }
+                sr.pe = F.npieces;
+                segred.push_back(sr);
+                F.csegs.push_back(sg);
+                F.cnodes += sg.kq;
+            } else {
+                for (int l = sg.l0; l < sg.l1; ++l) einfo[l] = make_int2(sg.kb + (l - sg.l0), 0);
+            }
+        }
+        F.nsegs = (int)segred.size();
+        CK(cudaMalloc(&F.einfo, sizeof(int2) * e32));
+        CK(cudaMemcpy(F.einfo, einfo.data(), sizeof(int2) * e32, cudaMemcpyHostToDevice));
+        if (F.nsegs) {
+            CK(cudaMalloc(&F.segs, sizeof(tc2::SegRed) * F.nsegs));
+            CK(cudaMemcpy(F.segs, segred.data(), sizeof(tc2::SegRed) * F.nsegs, cudaMemcpyHostToDevice));
+        }
+        F.valid = false;
+    }
     int rcg = build_groups(h, k0);
     if (rcg) return rcg;
     P.ncopy = (int)copy_l.size();
@@ -780,6 +846,7 @@ static int set_design_active(pg_handle* h, const double* W_host, const double* y
 static int build_v(pg_handle* h, int q)
 {
     const int n = h->n, c0 = h->c0, klin = c0 + q;
+    h->fz.valid = false;   // G = U V belongs to the design
     if (h->plan.klin != klin) {
         int rc = build_groups(h, klin);
         if (rc) return rc;
@@ -805,6 +872,140 @@ static int build_v(pg_handle* h, int q)
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(h->compute));
+    return PG_OK;
+}
+
+// ---- moments straight from the fused rotation -------------------------------------------------------------------
+static bool fuse_env_tc2()
+{
+    static const bool ok = !(getenv("PG_ROT_DEFAULT") && !strcmp(getenv("PG_ROT_DEFAULT"), "cublas")) &&
+                           !(getenv("PG_TC_CLUSTER") && atoi(getenv("PG_TC_CLUSTER")) != 2);
+    return ok;
+}
+
+// Whether scans of the current design take the linear moments from tiles of G = U V and the x^2 moments from the rotation
+// epilogue (rotate_i8_tc2.cuh) instead of writing the rotated genotypes and compressing them.  The extra tensor work is
+// (COMPRESS nodes x linear columns) / n of the rotation; the compression it replaces costs ~196 / nodes times that (FP64
+// tensor pipe vs int8 tensor pipe), so the automatic mode asks for <= 160 nodes, and for n >= 2048: below that
+// the rotation is a few per cent of the step and the solver decides.
+static bool fuse_wanted(const pg_handle* h)
+{
+    if (h->fuse_mode == 0 || !fuse_env_tc2()) return false;
+    if (!(h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) || h->overlap) return false;
+    if (!h->have_U || h->rotated_inputs || h->fz.nsegs == 0) return false;
+    if (!(h->rotation == PG_ROT_AUTO || (h->fuse_mode == 1 && h->rotation == PG_ROT_I8TC))) return false;
+    const long long gcols = (long long)h->fz.cnodes * (h->c0 + h->q);
+    if (h->fuse_mode == 1) return gcols <= 4LL * h->n + 4096;
+    static const int n_min = getenv("PG_FUSE_MIN_N") ? atoi(getenv("PG_FUSE_MIN_N")) : 2048;
+    return h->n >= n_min && h->fz.cnodes <= 160 && gcols <= h->n / 2;
+}
+
+// G = U V for the current design, sliced into digit planes like U^T (slice_u_kernel), with its scales, column sums
+// and the slab offset of every column.  Built lazily by the first scan that fuses; pg_set_design* invalidates it.
+static int ensure_fused_operand(pg_handle* h)
+{
+    pg_handle::Fused& F = h->fz;
+    if (F.valid) return PG_OK;
+    CK(cudaSetDevice(h->device));
+    const int n = h->n, c0 = h->c0, q = h->q, klin = c0 + q, Kcp = h->plan.Kcp;
+    const int gcols = F.cnodes * klin, g_tiles = (gcols + tc2::kTileEig - 1) / tc2::kTileEig, npad_g = g_tiles * tc2::kTileEig;
+    const int ldk = (n + 127) / 128 * 128;   // row pitch of the digit planes: rot_prepare_i8's
+    const double* cols = q > 1 ? h->wy_all : h->slots[0].wy;
+    EventGuard g0, g1;
+    CK(cudaEventCreate(&g0.e));
+    CK(cudaEventCreate(&g1.e));
+    CK(cudaEventRecord(g0.e, h->compute));
+    const size_t g_need = (size_t)n * std::max(gcols, 1), vdc_need = (size_t)n * kCq * klin;
+    if (g_need > F.g_elems) {
+        if (F.G) cudaFree(F.G);
+        F.G = nullptr; F.g_elems = 0;
+        CK(cudaMalloc(&F.G, sizeof(double) * g_need));
+        F.g_elems = g_need;
+    }
+    if (vdc_need > F.vdc_elems) {
+        if (F.vdc) cudaFree(F.vdc);
+        F.vdc = nullptr; F.vdc_elems = 0;
+        CK(cudaMalloc(&F.vdc, sizeof(double) * vdc_need));
+        F.vdc_elems = vdc_need;
+    }
+    const size_t pl_need = (size_t)kSlices * npad_g * ldk;
+    if (pl_need > F.planes_bytes) {
+        if (F.planes_g) cudaFree(F.planes_g);
+        F.planes_g = nullptr; F.planes_bytes = 0;
+        CK(cudaMalloc(&F.planes_g, pl_need));
+        F.planes_bytes = pl_need;
+    }
+    if (npad_g > F.col_cap) {
+        void* old[] = {F.gscale, F.g1, F.exps_g, F.goff};
+        for (void* b : old)
+            if (b) cudaFree(b);
+        F.gscale = F.g1 = nullptr; F.exps_g = F.goff = nullptr; F.col_cap = 0;
+        CK(cudaMalloc(&F.gscale, sizeof(double) * npad_g));
+        CK(cudaMalloc(&F.g1, sizeof(double) * npad_g));
+        CK(cudaMalloc(&F.exps_g, sizeof(int) * npad_g));
+        CK(cudaMalloc(&F.goff, sizeof(int) * npad_g));
+        F.col_cap = npad_g;
+    }
+    if (klin > F.jrow_cap) {
+        if (F.jrow) cudaFree(F.jrow);
+        F.jrow = nullptr; F.jrow_cap = 0;
+        CK(cudaMalloc(&F.jrow, sizeof(int) * klin));
+        F.jrow_cap = klin;
+    }
+    build_vc_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)(kCq * klin)), 256, 0, h->compute>>>(
+        n, klin, h->plan.Lw, h->plan.seg_kq, cols, h->ldw, F.vdc);
+    CK(cudaGetLastError());
+    std::vector<int> goff(npad_g, -1), jrow(klin);
+    for (int j = 0; j < klin; ++j) jrow[j] = z_row(j, c0, h->k1p) * Kcp;
+    const double one = 1.0, zero = 0.0;
+    int col0 = 0;
+    for (const Segment& sg : F.csegs) {
+        const int len = sg.l1 - sg.l0, ncs = sg.kq * klin;
+        // G[:, col0 : col0 + ncs] = U[:, l0:l1] . Vc[l0:l1, 0:ncs]   (all column-major, leading dimension n)
+        if (h->u_op_t)
+            CKB(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, n, ncs, len, &one, h->U + (size_t)sg.l0 * n, n, F.vdc + sg.l0, n,
+                            &zero, F.G + (size_t)col0 * n, n));
+        else
+            CKB(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, n, ncs, len, &one, h->U + sg.l0, n, F.vdc + sg.l0, n, &zero,
+                            F.G + (size_t)col0 * n, n));
+        for (int k = 0; k < sg.kq; ++k)
+            for (int j = 0; j < klin; ++j) goff[col0 + k * klin + j] = jrow[j] + sg.kb + k;
+        col0 += ncs;
+    }
+    CK(cudaMemsetAsync(F.gscale, 0, sizeof(double) * npad_g, h->compute));
+    CK(cudaMemsetAsync(F.g1, 0, sizeof(double) * npad_g, h->compute));
+    if (gcols) {
+        slice_u_kernel<<<npad_g, 256, 0, h->compute>>>(F.G, 1, n, npad_g, ldk, F.planes_g, F.exps_g, gcols);
+        CK(cudaGetLastError());
+        tc::plane_scale_kernel<<<(gcols + 255) / 256, 256, 0, h->compute>>>(F.exps_g, gcols, F.gscale);
+        CK(cudaGetLastError());
+        column_sums_kernel<<<gcols, 256, 0, h->compute>>>(F.G, 1, n, F.g1);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(F.goff, goff.data(), sizeof(int) * npad_g, cudaMemcpyHostToDevice, h->compute));
+    CK(cudaMemcpyAsync(F.jrow, jrow.data(), sizeof(int) * klin, cudaMemcpyHostToDevice, h->compute));
+    CK(cudaEventRecord(g1.e, h->compute));
+    CK(cudaStreamSynchronize(h->compute));   // goff / jrow are local buffers
+    cudaEventElapsedTime(&F.build_ms, g0.e, g1.e);
+    F.klin = klin; F.gcols = gcols; F.g_tiles = g_tiles;
+    F.valid = true;
+    return PG_OK;
+}
+
+extern "C" int pg_set_moment_fusion(pg_handle* h, int mode)
+{
+    if (!h || mode < -1 || mode > 1) return fail(h, PG_ERR_ARG, "pg_set_moment_fusion: mode %d", mode);
+    h->fuse_mode = mode;
+    return PG_OK;
+}
+
+extern "C" int pg_probe_fusion(pg_handle* h, int32_t* fused, int32_t* g_columns, int32_t* pieces, float* build_ms)
+{
+    if (!h) return PG_ERR_ARG;
+    if (fused) *fused = (h->have_design && fuse_wanted(h)) ? 1 : 0;
+    if (g_columns) *g_columns = h->fz.cnodes * (h->c0 + h->q);
+    if (pieces) *pieces = h->fz.npieces;
+    if (build_ms) *build_ms = h->fz.build_ms;
     return PG_OK;
 }
 
@@ -1092,8 +1293,9 @@ static int launch_stage(pg_handle* h, const void* src, int xdtype, long long ld,
 static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* Zbuf, long long mb, long long row0,
                        int grid_mode, double* const out[6], int* status, int* e2, int* e3, cudaEvent_t* ev_mid = nullptr,
                        cudaEvent_t ev_xr_done = nullptr, cudaStream_t st_solve = nullptr, cudaEvent_t* ev_z = nullptr,
-                       int parity = 0, int ph = 0, double* const* lrt = nullptr)
+                       int parity = 0, int ph = 0, double* const* lrt = nullptr, bool have_moments = false)
 {
+    // have_moments: the fused rotation already wrote this block's moments into Zbuf (no compression, xr is not read)
     // ph: phenotype slot of this launch (the caller has activated it).  The compressed engine compresses the block for
     // all h->q phenotypes at ph == 0; the direct engines read xr for every phenotype.
     const int q = h->q;
@@ -1113,13 +1315,13 @@ static int launch_reml(pg_handle* h, cudaStream_t st, const double* xr, double* 
         const int zrows = h->k1p - 1 + q;
         if (ph == 0) {
             if (ev_mid) CK(cudaEventRecord(ev_mid[0], st));
-            if (P.nitems) {
+            if (P.nitems && !have_moments) {
                 CK(cudaFuncSetAttribute(compress_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemBytes));
                 compress_dmma_kernel<<<(unsigned)((long long)P.nitems * ntiles), 256, kCtSmemBytes, st>>>(
                     xr, h->ldx, mb, P.items, P.V, P.vpitch, h->c0, h->k1p, zrows, P.Kcp, Zbuf, ntiles);
                 CK(cudaGetLastError());
             }
-            if (P.ncopy) {
+            if (P.ncopy && !have_moments) {
                 dim3 grid((unsigned)((P.ncopy + 127) / 128), (unsigned)((mb + 7) / 8));
                 compress_copy_kernel<<<grid, 128, 0, st>>>(xr, h->ldx, mb, P.copy_l, P.copy_node, P.ncopy,
                                                            q > 1 ? h->wy_all : h->wy, h->ldw, h->c0, P.klin, h->k1p, zrows,
@@ -1398,6 +1600,23 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
             rc = ensure_null(h, ph);
             if (rc) return rc;
         }
+    // moments straight from the fused rotation where it pays (fuse_wanted); rot_run still decides per block
+    const bool want_fuse = rotate && fuse_wanted(h);
+    if (want_fuse) {
+        rc = ensure_fused_operand(h);
+        if (rc) return rc;
+        pg_handle::Fused& F = h->fz;
+        const long long ldp = (blk + 511) / 512 * 512;
+        const size_t need_p = (size_t)std::max(F.npieces, 1) * kCq * ldp;
+        if (need_p > F.p2_elems) {
+            if (F.P2) cudaFree(F.P2);
+            F.P2 = nullptr; F.p2_elems = 0;
+            CK(cudaMalloc(&F.P2, sizeof(double) * need_p));
+            F.p2_elems = need_p;
+        }
+        F.ldp = ldp;
+    }
+    int n_fused_blocks = 0;
     const int ncols = want_lrt ? kResCols : 6;
     h->defer_pvalues = compressed;   // launch_reml leaves p = NaN; one pvalue_kernel launch follows the last block
     rc = [&]() -> int {
@@ -1462,12 +1681,23 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                 CK(cudaStreamWaitEvent(st_cmb, h->ev_xr_free[s], 0));
             }
             CK(cudaEventRecord(ev_conv[b].a, h->compute));
-            int used_i8 = 0;
+            int used_i8 = 0, moments_done = 0;
             if (rotate) {
+                FuseLaunch fl;
+                if (want_fuse) {
+                    const pg_handle::Fused& F = h->fz;
+                    tc2::FuseArgs& fa = fl.args;
+                    fa.g_tiles = F.g_tiles; fa.gscale = F.gscale; fa.g1 = F.g1; fa.goff = F.goff; fa.einfo = F.einfo;
+                    fa.Lw = h->plan.Lw; fa.wy = q > 1 ? h->wy_all : h->slots[0].wy; fa.ldw = h->ldw; fa.klin = F.klin;
+                    fa.jrow = F.jrow; fa.Z = h->Z[s]; fa.ldz = (long long)(h->k1p - 1 + q) * h->plan.Kcp;
+                    fa.x2row = h->c0 * h->plan.Kcp; fa.P2 = F.P2; fa.ldp = F.ldp;
+                    fl.planes_g = F.planes_g; fl.segs = F.segs; fl.nsegs = F.nsegs;
+                }
                 int r2 = rot_run(&h->rot, h->blas, h->compute, st_cmb, h->rotation, h->U, h->u_op_t, n, src_dev, xdtype,
                                  ld_dev, layout, mb, blk, h->xf, xr_block, h->ldx, &used_i8, &n_rot_launch, ev_conv[b].b,
-                                 ev_rot[b].a, ev_rot[b].b);
+                                 ev_rot[b].a, ev_rot[b].b, want_fuse ? &fl : nullptr, &moments_done);
                 if (r2 != 0) return fail(h, r2, "rotation failed: %s", rot_error(&h->rot));
+                n_fused_blocks += moments_done;
                 last_engine = used_i8;  // rot_run reports PG_ROT_I8SPLIT / PG_ROT_I8TC, 0 for the FP64 GEMM
                 if (!last_engine) last_engine = PG_ROT_FP64;
                 CK(cudaEventRecord(h->ev_xr_ready[s], (used_i8 == PG_ROT_I8SPLIT) ? st_cmb : h->compute));
@@ -1495,14 +1725,14 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
                 int r3 = launch_reml(h, st_reml, xr_block, h->Z[s], mb, g0, grid_mode, outp,
                                      dstatus ? dstatus + (size_t)ph * m : nullptr, de2 ? de2 + (size_t)ph * m : nullptr,
                                      de3 ? de3 + (size_t)ph * m : nullptr, mid, h->ev_xr_free[s], st_solve, evz, s, ph,
-                                     want_lrt ? lrtp : nullptr);
+                                     want_lrt ? lrtp : nullptr, moments_done != 0);
                 if (r3) { activate(h, 0); return r3; }
             }
             activate(h, 0);
             CK(cudaEventRecord(ev_reml[b].b, st_solve));
             h->last_block_count = mb;
             h->last_block_row0 = g0;
-            h->last_xr = xr_block;
+            h->last_xr = moments_done ? nullptr : xr_block;   // a fused block leaves no rotated genotypes behind
         }
         if (h->overlap) {
             CK(cudaEventRecord(h->ev_aux_done, h->aux));
@@ -1558,7 +1788,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         timing->reml_launches = (int32_t)nblocks;
         timing->rotate_launches = n_rot_launch;
         timing->convert_launches = rotate ? 0 : (int32_t)nblocks;  // staging kernels of the rotation are in rotate_launches
-        timing->rot_engine = last_engine;
+        timing->rot_engine = (n_fused_blocks == nblocks && nblocks > 0) ? PG_ROT_I8TC_MOMENTS : last_engine;
         timing->reml_engine = compressed ? PG_REML_COMPRESSED : h->engine;
         timing->n_nodes = compressed ? h->plan.Kc : h->n;
         // per block: compress (dmma / copy), fixed-lambda x rows, fixed-lambda evaluations + solve per phenotype; one

@@ -31,19 +31,20 @@ static_assert(kSlices == 6 || kSlices == 7, "6 or 7 digit planes");
 constexpr double kLoScale = (kSlices == 7) ? 2.3283064365386963e-10 /* 2^-32 */ : 5.9604644775390625e-08 /* 2^-24 */;
 constexpr int kLoShift = 8 * (kSlices - 3);   // value = (hi + lo 2^-kLoShift) 2^(e-24), hi: planes 0..2, lo: planes 3..
 
-// one CTA per eigenvector i: find e_i, write the digit planes
-// U is n x n; eigenvector i is at U + i*n when u_cols_contig (column-major U), else strided (U + i, stride n)
+// one CTA per vector i: find e_i, write the digit planes
+// U holds nvec vectors of n entries (the n eigenvectors; the columns of G = U V for the fused moments, rotate_i8_tc2.cuh);
+// vector i is at U + i*n when u_cols_contig (column-major), else strided (U + i, stride nvec)
 __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__ U, int u_cols_contig, int n, int npad,
                                                        int ldk, int8_t* __restrict__ planes /* [kSlices][npad][ldk] */,
-                                                       int* __restrict__ exps)
+                                                       int* __restrict__ exps, int nvec)
 {
     const int i = blockIdx.x;
     __shared__ double red[8];
     __shared__ int e_sh;
-    const size_t stride = u_cols_contig ? 1 : (size_t)n;
+    const size_t stride = u_cols_contig ? 1 : (size_t)nvec;
     const double* u = u_cols_contig ? U + (size_t)i * n : U + i;
     double mx = 0.0;
-    if (i < n)
+    if (i < nvec)
         for (int j = threadIdx.x; j < n; j += blockDim.x) mx = fmax(mx, fabs(u[(size_t)j * stride]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -54,14 +55,14 @@ __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
         // |u| * 2^-e < 0.25 for every entry
         e_sh = (m > 0.0 && isfinite(m)) ? ilogb(m) + 3 : 0;
-        if (i < n) exps[i] = e_sh;
+        if (i < nvec) exps[i] = e_sh;
     }
     __syncthreads();
     const int e = e_sh;
     const size_t plane = (size_t)npad * ldk;
     for (int j = threadIdx.x; j < ldk; j += blockDim.x) {
         long long Q = 0;
-        if (i < n && j < n) Q = llrint(ldexp(u[(size_t)j * stride], 8 * kSlices - e));
+        if (i < nvec && j < n) Q = llrint(ldexp(u[(size_t)j * stride], 8 * kSlices - e));
         int8_t dig[kSlices];
 #pragma unroll
         for (int t = kSlices - 1; t >= 1; --t) {

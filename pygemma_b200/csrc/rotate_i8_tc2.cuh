@@ -15,8 +15,18 @@
 //             to `empty[s]` / `tmem_full` of both CTAs
 //   warps 2-9 epilogue on the CTA's own TMEM (warps 2-5: accumulator 0, warps 6-9: accumulator 1; a warp reads the
 //             TMEM lane quarter warp % 4); arrival on the leader's `tmem_empty` (remote for the peer CTA)
+//
+// MOMENT FUSION (template flag FUSE, round 2): the rotated genotypes are only ever consumed by the eigenvalue-space
+// compression (compress.cuh), whose linear moments  z_jk = sum_l L_k(d_l) w_jl (U^T x)_l = x^T (U V)_{jk}  are linear in
+// the RAW genotypes.  G = U V (n x klin * nodes, built once per design) is sliced into digit planes exactly like U^T and
+// its 32-column tiles are appended to the eigen tiles of this kernel: their epilogue writes the moments straight into the
+// SNP's slab.  On the eigen tiles the epilogue squares the rotated value in registers and accumulates the x^2 moments of
+// its 16 eigenvectors per (half tile, segment) "piece" (moments_reduce_kernel sums the pieces in a fixed order); isolated
+// eigenvalues (COPY rows) store x_l w_jl and x_l^2 directly.  The rotated genotypes never reach HBM: -160 KB per SNP of
+// traffic and the whole compress_dmma_kernel (17 % of the step) for +10-14 % tensor work.
 #pragma once
 
+#include "compress_plan.h"
 #include "pg_debug.cuh"
 #include "rotate_i8_tc.cuh"
 
@@ -141,6 +151,27 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr)
     return d;
 }
 
+// eigen-indices per x^2 piece: what one epilogue thread holds of a tile
+constexpr int kPieceEig = kTileEig / (kEpiWarps / 8);
+
+struct FuseArgs {
+    int g_tiles = 0;                 // tiles of 32 columns of G = U V that follow the eigen tiles
+    const double* gscale = nullptr;  // [32 g_tiles] power-of-two scale of each G column's fixed-point form
+    const double* g1 = nullptr;      // [32 g_tiles] column sums of G (level-coded genotypes: x = v0 + s code)
+    const int* goff = nullptr;       // [32 g_tiles] offset of the column's moment inside an SNP slab, -1 for padding columns
+    const int2* einfo = nullptr;     // [32 eig_tiles] {piece, kq > 0}: COMPRESS row; {node, 0}: COPY row; {_, -1}: padding
+    const double* Lw = nullptr;      // [n][kCq] interpolation weights (compress_plan.h)
+    const double* wy = nullptr;      // rotated [W0, y..] columns, column j at wy + j * ldw (COPY rows: x_l w_jl)
+    long long ldw = 0;
+    int klin = 0;
+    const int* jrow = nullptr;       // [klin] slab offset of linear column j: z_row(j) * Kcp
+    double* Z = nullptr;             // moment slabs of the block
+    long long ldz = 0;               // doubles per SNP slab (zrows * Kcp)
+    int x2row = 0;                   // slab offset of the x.x row (c0 * Kcp)
+    double* P2 = nullptr;            // x^2 partial sums [piece][kCq][ldp]
+    long long ldp = 0;
+};
+
 struct Args {
     long long mb;
     int n;
@@ -154,13 +185,42 @@ struct Args {
     const LevelInfo* info;   // nullable
     const double* u1;
     int accumulate;
+    FuseArgs f;                 // FUSE kernels only
 };
+
+// x^2 moments: node k of segment s = sum over the segment's pieces, in eigen order (deterministic)
+struct SegRed {
+    int pb, pe;   // piece range
+    int kb, kq;   // first node, node count
+};
+__global__ void __launch_bounds__(128) moments_reduce_kernel(const double* __restrict__ P2, long long ldp, long long mb,
+                                                             const SegRed* __restrict__ segs, double* __restrict__ Z,
+                                                             long long ldz, int x2row)
+{
+    const long long snp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (snp >= mb) return;
+    const SegRed sr = segs[blockIdx.y];
+    double acc[kCq];
+#pragma unroll
+    for (int k = 0; k < kCq; ++k) acc[k] = 0.0;
+    for (int p = sr.pb; p < sr.pe; ++p) {
+        const double* src = P2 + (size_t)p * kCq * ldp + snp;
+#pragma unroll
+        for (int k = 0; k < kCq; ++k)
+            if (k < sr.kq) acc[k] += src[(size_t)k * ldp];
+    }
+    double* dst = Z + (size_t)snp * ldz + x2row + sr.kb;
+#pragma unroll
+    for (int k = 0; k < kCq; ++k)
+        if (k < sr.kq) dst[k] = acc[k];
+}
 
 // A_MN: the A tensor map walks the caller's sample-major block (SNP, sample) and A is an MN-major operand;
 // otherwise it walks the staged SNP-major copy (sample, SNP) and A is K-major.
-template <bool A_MN>
+template <bool A_MN, bool FUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_p, Args a)
+rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_p,
+                     const __grid_constant__ CUtensorMap map_g, Args a)
 {
     constexpr uint32_t idesc = kInstrDesc2 | (A_MN ? (1u << 15) : 0u);
     extern __shared__ uint8_t smem_raw[];
@@ -176,7 +236,8 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const long long total_tiles = (long long)a.snp_tiles * a.eig_tiles;
+    const int all_tiles = a.eig_tiles + (FUSE ? a.f.g_tiles : 0);   // eigen tiles, then the tiles of G
+    const long long total_tiles = (long long)a.snp_tiles * all_tiles;
     const int ksteps = (a.n + kStageK - 1) / kStageK;
 
     if (threadIdx.x == 0) {
@@ -200,7 +261,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int g = (int)(t / per_group);
         const long long r = t - (long long)g * per_group;
         const int e0 = g * a.eig_group;
-        const int ecount = min(a.eig_group, a.eig_tiles - e0);
+        const int ecount = min(a.eig_group, all_tiles - e0);
         st = (int)(r / ecount);
         et = e0 + (int)(r % ecount);
     };
@@ -231,7 +292,11 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         tma2_load_2d(sA, &map_x, &full[stage], k * kStageK, snp0, pol_a);
                         tma2_load_2d(sA + kABytes, &map_x, &full[stage], k * kStageK, snp0 + 128, pol_a);
                     }
-                    tma2_load_3d(sA + 2 * kABytes, &map_p, &full[stage], k * kStageK, 0, et * kTileEig + (int)rank * (kTileEig / 2), pol_b);
+                    if (FUSE && et >= a.eig_tiles)
+                        tma2_load_3d(sA + 2 * kABytes, &map_g, &full[stage], k * kStageK, 0,
+                                     (et - a.eig_tiles) * kTileEig + (int)rank * (kTileEig / 2), pol_b);
+                    else
+                        tma2_load_3d(sA + 2 * kABytes, &map_p, &full[stage], k * kStageK, 0, et * kTileEig + (int)rank * (kTileEig / 2), pol_b);
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -282,12 +347,35 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             decode(t, st, et);
             mbar_wait(tmem_full, acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int eig0 = et * kTileEig;
+            const bool g_tile = FUSE && et >= a.eig_tiles;          // a tile of G = U V: its values ARE linear moments
+            const int eig0 = (g_tile ? et - a.eig_tiles : et) * kTileEig;   // first eigenvector / first column of G
+            const double* sc_tab = g_tile ? a.f.gscale : a.scale;
+            const double* u1_tab = g_tile ? a.f.g1 : a.u1;
+            const int idx_max = g_tile ? a.f.g_tiles * kTileEig - 1 : a.n - 1;
             {
                 const long long snp = (long long)st * kClusterSnps + (long long)rank * kCtaSnps + acc * 128 + quarter * 32 + lane;
                 double lv0 = 0.0, ls = 1.0, leps = 0.0;
                 if (a.info && snp < a.mb) { const LevelInfo li = a.info[snp]; lv0 = li.v0; ls = li.s; leps = li.eps; }
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAcc1Col);
+                // FUSE, eigen tiles: x^2 moments of the current piece (one segment inside this thread's kPieceEig eigenvectors)
+                double m2[FUSE ? kCq : 1];
+                int piece = -1;
+                if (FUSE) {
+#pragma unroll
+                    for (int k = 0; k < (FUSE ? kCq : 1); ++k) m2[k] = 0.0;
+                }
+                auto flush_piece = [&]() {
+                    if (FUSE) {
+                        if (piece >= 0 && snp < a.mb) {
+                            PG_BOUNDS(snp < a.f.ldp, "x^2 partial store outside the piece buffer");
+                            double* pp = a.f.P2 + (size_t)piece * kCq * a.f.ldp + snp;
+#pragma unroll
+                            for (int k = 0; k < (FUSE ? kCq : 1); ++k) pp[(size_t)k * a.f.ldp] = m2[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < (FUSE ? kCq : 1); ++k) m2[k] = 0.0;
+                    }
+                };
 #pragma unroll 1
                 for (int c = c_begin; c < c_begin + kCPer; ++c) {
                     // eight eigenvectors x seven planes = 56 consecutive columns (eigen-major)
@@ -296,14 +384,16 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
                     for (int q = 0; q < kSlices; ++q) tmem_ld8(tbase + (uint32_t)(c * 8 * kSlices + q * 8), r[q]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (snp < a.mb) {
-                        double* dst = a.xr + (size_t)snp * a.ldx + eig0 + c * 8;
-                        PG_BOUNDS(snp >= 0 && snp < a.mb && eig0 + c * 8 < a.ldx && (eig0 + c * 8 + 8 <= a.n ? eig0 + c * 8 + 8 <= a.ldx : true),
-                                  "rotated-genotype store outside the block");
+                    if (FUSE || snp < a.mb) {
+                        double* dst = FUSE ? nullptr : a.xr + (size_t)snp * a.ldx + eig0 + c * 8;
+                        double* Zs = FUSE ? a.f.Z + (size_t)(snp < a.mb ? snp : 0) * a.f.ldz : nullptr;
+                        if (!FUSE)
+                            PG_BOUNDS(snp >= 0 && snp < a.mb && eig0 + c * 8 < a.ldx && (eig0 + c * 8 + 8 <= a.n ? eig0 + c * 8 + 8 <= a.ldx : true),
+                                      "rotated-genotype store outside the block");
                         double out[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int e = min(eig0 + c * 8 + j, a.n - 1);
+                            const int e = min(eig0 + c * 8 + j, idx_max);
                             // the digit planes are recombined as 64-bit integers (|plane sum| < 2^31, so hi < 2^48 and
                             // lo < 2^56 never overflow) and converted once each: 2 int -> double conversions per output
                             // instead of 7.  Same bits as the FP64 Horner form of combine_i8_kernel: both are the exact
@@ -316,22 +406,47 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #undef PG_PL
                             const double hi = (double)hi_i, lo = (double)lo_i;
                             const double v = fma(lo, kLoScale, hi);
-                            out[j] = v * __ldg(a.scale + e);
+                            out[j] = v * __ldg(sc_tab + e);
                             if (a.info) {
-                                if (a.accumulate) out[j] = (leps != 0.0) ? fma(leps, out[j], dst[j]) : dst[j];
-                                else out[j] = fma(ls, out[j], lv0 * __ldg(a.u1 + e));
+                                if (!FUSE && a.accumulate) out[j] = (leps != 0.0) ? fma(leps, out[j], dst[j]) : dst[j];
+                                else out[j] = fma(ls, out[j], lv0 * __ldg(u1_tab + e));
+                            }
+                            if (FUSE) {
+                                if (g_tile) {
+                                    const int off = __ldg(a.f.goff + e);
+                                    PG_BOUNDS(off < a.f.ldz, "linear-moment store outside the slab");
+                                    if (off >= 0 && snp < a.mb) Zs[off] = out[j];
+                                } else {
+                                    const int2 ei = __ldg(a.f.einfo + eig0 + c * 8 + j);   // the same for every lane
+                                    if (ei.y > 0) {
+                                        if (ei.x != piece) { flush_piece(); piece = ei.x; }
+                                        const double sq = out[j] * out[j];
+                                        const double* lw = a.f.Lw + (size_t)e * kCq;
+#pragma unroll
+                                        for (int k = 0; k < (FUSE ? kCq : 1); ++k) m2[k] = fma(__ldg(lw + k), sq, m2[k]);
+                                    } else if (ei.y == 0 && snp < a.mb) {
+                                        // isolated eigenvalue, its own node: x_l w_jl and x_l^2 (compress_copy_kernel)
+                                        PG_BOUNDS(a.f.x2row + ei.x < a.f.ldz, "COPY-row moment store outside the slab");
+                                        for (int jj = 0; jj < a.f.klin; ++jj)
+                                            Zs[__ldg(a.f.jrow + jj) + ei.x] = out[j] * __ldg(a.f.wy + (size_t)jj * a.f.ldw + e);
+                                        Zs[a.f.x2row + ei.x] = out[j] * out[j];
+                                    }
+                                }
                             }
                         }
-                        if (eig0 + c * 8 + 8 <= a.n) {   // rows are 128-byte aligned (ldx % 16 == 0): four 16-byte stores
+                        if (!FUSE) {
+                            if (eig0 + c * 8 + 8 <= a.n) {   // rows are 128-byte aligned (ldx % 16 == 0): four 16-byte stores
 #pragma unroll
-                            for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
-                        } else {
+                                for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (eig0 + c * 8 + j < a.n) dst[j] = out[j];
+                                for (int j = 0; j < 8; ++j)
+                                    if (eig0 + c * 8 + j < a.n) dst[j] = out[j];
+                            }
                         }
                     }
                 }
+                flush_piece();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_on_cta(tmem_empty, 0);   // the leader's barrier gates the next tile's first MMA
@@ -352,11 +467,13 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long x8_rows, const int8_t* planes, int npad,
                   int ldk, int n, long long mb, const double* scale, double* xr, long long ldx,
                   const int8_t* xsm = nullptr, long long ld_sm = 0, const LevelInfo* info = nullptr,
-                  const double* u1 = nullptr, int accumulate = 0)
+                  const double* u1 = nullptr, int accumulate = 0, const FuseArgs* fuse = nullptr,
+                  const int8_t* planes_g = nullptr)
 {
     tc::EncodeTiledFn enc = tc::encode_tiled_fn();
     if (!enc) return -1;
-    CUtensorMap mx, mp;
+    if (fuse && (accumulate || !planes_g)) return -6;
+    CUtensorMap mx, mp, mg;
     if (xsm) {
         cuuint64_t dims[2] = {(cuuint64_t)mb, (cuuint64_t)n};
         cuuint64_t strides[1] = {(cuuint64_t)ld_sm};
@@ -383,6 +500,15 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
         if (enc(&mp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return -3;
+        mg = mp;
+        if (fuse) {   // the digit planes of G: [kSlices][32 g_tiles][ldk]
+            const int npad_g = fuse->g_tiles * kTileEig;
+            dims[2] = (cuuint64_t)npad_g;
+            strides[0] = (cuuint64_t)ldk * (cuuint64_t)npad_g;
+            if (enc(&mg, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes_g, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return -3;
+        }
     }
     Args a;
     a.mb = mb; a.n = n;
@@ -390,19 +516,27 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     a.eig_tiles = (n + kTileEig - 1) / kTileEig;
     a.scale = scale; a.xr = xr; a.ldx = ldx;
     a.info = info; a.u1 = u1; a.accumulate = accumulate;
+    if (fuse) a.f = *fuse;
     static const int eg_env = getenv("PG_TC2_EG") ? atoi(getenv("PG_TC2_EG")) : 0;
     a.eig_group = eg_env > 0 ? eg_env : kEigGroup;
     // measured at n = 10 000 per 25 088 SNPs: no hint 10.17 ms, evict_last(B) 10.13, evict_first(A) 10.86, both 10.81
     static const int hints_env = getenv("PG_TC2_HINTS") ? atoi(getenv("PG_TC2_HINTS")) : 2;
     a.hints = hints_env;
     // per call: the attribute is per device, and a process may hold handles on several devices
-    if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(rotate_i8_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rotate_i8_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rotate_i8_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(rotate_i8_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
         return -4;
-    const long long tiles = (long long)a.snp_tiles * a.eig_tiles;
+    const long long tiles = (long long)a.snp_tiles * (a.eig_tiles + (fuse ? fuse->g_tiles : 0));
     const int clusters = (int)std::min<long long>(tiles, sm_count / 2);
-    if (xsm) rotate_i8_tc2_kernel<true><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, a);
-    else rotate_i8_tc2_kernel<false><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, a);
+    if (fuse) {
+        if (xsm) rotate_i8_tc2_kernel<true, true><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
+        else rotate_i8_tc2_kernel<false, true><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
+    } else {
+        if (xsm) rotate_i8_tc2_kernel<true, false><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
+        else rotate_i8_tc2_kernel<false, false><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 

@@ -158,7 +158,7 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
-        slice_u_kernel<<<npad, 256, 0, stream>>>(U, u_op_t ? 1 : 0, n, npad, ldk, w->planes, w->exps);
+        slice_u_kernel<<<npad, 256, 0, stream>>>(U, u_op_t ? 1 : 0, n, npad, ldk, w->planes, w->exps, n);
         PG_ROT_CK(cudaGetLastError());
         tc::plane_scale_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w->exps, n, w->scale);
         PG_ROT_CK(cudaGetLastError());
@@ -173,14 +173,28 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
     return 0;
 }
 
+// Moments straight from the fused rotation (rotate_i8_tc2.cuh, FUSE): what the handle prepared for the current design.
+// args.Z is the block's moment buffer; planes_g shares the row pitch ldk of the eigenvector planes.
+struct FuseLaunch {
+    tc2::FuseArgs args;
+    const int8_t* planes_g = nullptr;     // [kSlices][32 g_tiles][ldk]
+    const tc2::SegRed* segs = nullptr;    // x^2 reduction: one entry per COMPRESS segment
+    int nsegs = 0;
+};
+
 // Rotates one block.  xf: staging buffer (mb x n fp64), xr: output (mb x n fp64, SNP-major).
 // `stream` carries staging and the GEMMs, `cmb` the int8 recombination kernels; the block's rotated vectors are
 // complete when `ev_rot_end` (recorded on the stream that wrote them last) has fired.
 inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cudaStream_t cmb, int rotation,
                    const double* U, int u_op_t, int n, const void* src, int xdtype, long long ld, int layout, long long mb,
                    long long blk, double* xf, double* xr, long long ldx, int* used_i8, int* n_launch,
-                   cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin, cudaEvent_t ev_rot_end)
+                   cudaEvent_t ev_conv_end, cudaEvent_t ev_rot_begin, cudaEvent_t ev_rot_end,
+                   const FuseLaunch* fuse = nullptr, int* moments_done = nullptr)
 {
+    // fuse: the fused tcgen05 engine may write the block's compressed moments (fuse->args.Z) instead of the rotated
+    // genotypes; *moments_done says whether it did (it does not for blocks that need the second, eps-weighted pass or
+    // that fall back to another engine: the caller then runs the compression on xr as usual)
+    if (moments_done) *moments_done = 0;
     const bool i8 = (xdtype == PG_X_I8) && (rotation == PG_ROT_AUTO || rotation == PG_ROT_I8SPLIT || rotation == PG_ROT_I8TC);
     const bool forced_i8 = (rotation == PG_ROT_I8SPLIT || rotation == PG_ROT_I8TC);
     *used_i8 = i8 ? PG_ROT_I8SPLIT : 0;   // engine actually used (refined below)
@@ -340,7 +354,11 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         // CTA-pair kernel (cta_group::2), or two pairs per cluster sharing the genotype tiles by TMA multicast (PG_TC_CLUSTER=4)
         static const int tc_cluster = getenv("PG_TC_CLUSTER") ? atoi(getenv("PG_TC_CLUSTER")) : 2;
+        const bool fuse_now = fuse && tc_cluster == 2 && !(affine && need_eps);
         auto tc_launch = [&](int accumulate) -> int {
+            if (fuse_now)
+                return tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                                   direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, 0, &fuse->args, fuse->planes_g);
             if (tc_cluster == 4)
                 return tc4::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
                                    direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, accumulate);
@@ -358,6 +376,15 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
         }
         if (r) { w->err = "fused tcgen05 rotation launch failed, code " + std::to_string(r); return PG_ERR_CUDA; }
         (*n_launch)++;
+        if (fuse_now) {
+            if (fuse->nsegs) {
+                tc2::moments_reduce_kernel<<<dim3((unsigned)((mb + 127) / 128), (unsigned)fuse->nsegs), 128, 0, stream>>>(
+                    fuse->args.P2, fuse->args.ldp, mb, fuse->segs, fuse->args.Z, fuse->args.ldz, fuse->args.x2row);
+                PG_ROT_CK(cudaGetLastError());
+                (*n_launch)++;
+            }
+            if (moments_done) *moments_done = 1;
+        }
         cudaEventRecord(ev_rot_end, stream);
         return 0;
     }
