@@ -620,10 +620,13 @@ def run_ours(args):
     solve_ms = reml_ms - cmp_ms
     step_ms = max(res_tm["total_ms"], 1e-9)
     nodes = res_tm["n_nodes"]
-    i8 = res_tm.get("rot_engine") in (_capi.PG_ROT_I8SPLIT, _capi.PG_ROT_I8TC)
-    fused = res_tm.get("rot_engine") == _capi.PG_ROT_I8TC
+    i8 = res_tm.get("rot_engine") in (_capi.PG_ROT_I8SPLIT, _capi.PG_ROT_I8TC, _capi.PG_ROT_I8TC_MOMENTS)
+    fused = res_tm.get("rot_engine") in (_capi.PG_ROT_I8TC, _capi.PG_ROT_I8TC_MOMENTS)
+    # PG_FUSE_MOMENTS=1 (opt-in, pg_set_moment_fusion): the rotation kernel also contracts against the columns of G = U V
+    moments_fused = res_tm.get("rot_engine") == _capi.PG_ROT_I8TC_MOMENTS
+    g_cols = h.fusion_info()["g_columns"] if moments_fused else 0
     n_planes = int(_capi.load().pg_rotation_planes())   # 7 unless the library was built with -DPG_SLICES=6
-    rot_ops = (n_planes if i8 else 1) * 2.0 * n * n          # int8 (or fp64) multiply-add ops per SNP
+    rot_ops = (n_planes if i8 else 1) * 2.0 * n * (n + g_cols)   # int8 (or fp64) multiply-add ops per SNP
     cmp_flops = 2.0 * n * 10 * (c0 + 2)                       # compression: n x kCq x (c0+2) FP64 FMAs per SNP
     stages = {
         "rotation": {"ms": rot_ms, "achieved": rot_ops * m_loc / (max(rot_ms, 1e-9) * 1e-3) / 1e12,
@@ -685,7 +688,8 @@ def run_ours(args):
                                    f"all-gathered (NCCL) inside the timed step") if world > 1 else "snp-shard x1",
                    "l2": "inputs_larger_than_l2 (genotype block + 8n B/SNP rotated fp64 per step exceed the 126 MB L2)",
                    "reml_engine": "compressed (eigenvalue-space moments)",
-                   "rotation_engine": ("int8-split fused tcgen05" if fused else "int8-split cuBLAS") if i8 else "fp64"},
+                   "rotation_engine": (("int8-split fused tcgen05 + moments (pg_set_moment_fusion)" if moments_fused else
+                                        "int8-split fused tcgen05") if fused else "int8-split cuBLAS") if i8 else "fp64"},
         "e2e": e2e, "e2e_pinned": e2e_pinned,
         "gpu_launches": int(sum(t["convert_launches"] + t["reml_launches"] + t["rotate_launches"] for t in tms)),
         "clocks": clocks, "roofline": roofline, "parity_spot": spot,

@@ -209,10 +209,12 @@ int pg_set_reml_engine(pg_handle* h, int engine);
  * (x.x) in U^T x.  With fusion the PG_ROT_I8TC kernel produces them itself: the linear moments as extra exact int8 tiles
  * against G = U V (V = the compression operand, built once per design), the x^2 moments in its epilogue; rotated genotypes
  * are never written and the compression kernels do not run.  Results agree with the unfused path to rounding (different
- * summation order), and are deterministic.  mode: -1 (default) = where it pays (PG_ROT_AUTO, int8 / level-coded
- * genotypes, n >= 2048, <= 160 compression nodes, extra tiles <= half of the rotation); 0 = never; 1 = wherever the
- * engine allows it (also with PG_ROT_I8TC selected).  Blocks that need the second, eps-weighted rotation pass (unequally
- * spaced levels, missing .bed calls), the FP64 rotation or another engine are compressed as before.
+ * summation order), and are deterministic.  mode: 1 = wherever the engine allows it (PG_ROT_AUTO or PG_ROT_I8TC, int8 /
+ * level-coded / .bed genotypes, the compressed REML engine); 0 = never; -1 (default) = the library's choice, which is
+ * "off" on B200: measured, the fused kernel takes as long as rotation + compression together because the step is
+ * power-capped (profiles/experiments_r02.md) -- fusion saves the rotated-genotype buffers (3 x 2 GiB) and 160 KB of HBM
+ * traffic per SNP, not time.  Blocks that need the second, eps-weighted rotation pass (unequally spaced levels, missing
+ * .bed calls), the FP64 rotation or another engine are compressed as before.
  * pg_probe_rotated is not available after a fused scan.
  */
 int pg_set_moment_fusion(pg_handle* h, int mode);

@@ -155,7 +155,7 @@ struct pg_handle {
     // Moments straight from the fused rotation (rotate_i8_tc2.cuh, FUSE).  Per eigen-system: which x^2 piece / node every
     // eigen-index feeds and the piece ranges of the segments.  Per design: G = U V (one column per COMPRESS node and linear
     // column), its digit planes, scales, column sums and slab offsets.
-    int fuse_mode = -1;   // pg_set_moment_fusion: -1 automatic, 0 never, 1 wherever the engine allows it
+    int fuse_mode = -1;   // pg_set_moment_fusion: 1 = wherever the engine allows it; -1 (default) and 0 = off (see fuse_wanted)
     struct Fused {
         int2* einfo = nullptr;
         tc2::SegRed* segs = nullptr;
@@ -885,19 +885,20 @@ static bool fuse_env_tc2()
 
 // Whether scans of the current design take the linear moments from tiles of G = U V and the x^2 moments from the rotation
 // epilogue (rotate_i8_tc2.cuh) instead of writing the rotated genotypes and compressing them.  The extra tensor work is
-// (COMPRESS nodes x linear columns) / n of the rotation; the compression it replaces costs ~196 / nodes times that (FP64
-// tensor pipe vs int8 tensor pipe), so the automatic mode asks for <= 160 nodes, and for n >= 2048: below that
-// the rotation is a few per cent of the step and the solver decides.
+// (COMPRESS nodes x linear columns) / n of the rotation.  MEASURED (profiles/experiments_r02.md, one B200, n = 10 000):
+// the fused kernel takes as long as rotation + compression together (c0 = 10: 55.0 ms against 42.6 + 11.0 per 100 k SNPs;
+// c0 = 40: 80.1 against 40.8 + 37.8) because the step is power-capped and the tensor pipe, busy for the whole step, pulls
+// the SM clock from 1.69 to 1.57 GHz; end to end it loses the ~1 ms G costs per design.  So fusion is OPT-IN
+// (pg_set_moment_fusion(h, 1) / PG_FUSE_MOMENTS=1): it saves the three 2 GiB rotated-genotype buffers and 160 KB of HBM
+// traffic per SNP, not time, on this board.
 static bool fuse_wanted(const pg_handle* h)
 {
-    if (h->fuse_mode == 0 || !fuse_env_tc2()) return false;
+    if (h->fuse_mode != 1 || !fuse_env_tc2()) return false;
     if (!(h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) || h->overlap) return false;
     if (!h->have_U || h->rotated_inputs || h->fz.nsegs == 0) return false;
-    if (!(h->rotation == PG_ROT_AUTO || (h->fuse_mode == 1 && h->rotation == PG_ROT_I8TC))) return false;
+    if (!(h->rotation == PG_ROT_AUTO || h->rotation == PG_ROT_I8TC)) return false;
     const long long gcols = (long long)h->fz.cnodes * (h->c0 + h->q);
-    if (h->fuse_mode == 1) return gcols <= 4LL * h->n + 4096;
-    static const int n_min = getenv("PG_FUSE_MIN_N") ? atoi(getenv("PG_FUSE_MIN_N")) : 2048;
-    return h->n >= n_min && h->fz.cnodes <= 160 && gcols <= h->n / 2;
+    return gcols <= 4LL * h->n + 4096;   // digit planes of G: 7 (n + 127) bytes per column
 }
 
 // G = U V for the current design, sliced into digit planes like U^T (slice_u_kernel), with its scales, column sums

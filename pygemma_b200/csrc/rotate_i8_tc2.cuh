@@ -60,7 +60,22 @@ constexpr int kEigGroup = PG_TC2_EIG_GROUP;
 #endif
 constexpr int kEpiWarps = PG_TC2_EPI_WARPS;              // 8: one warp per accumulator and lane quarter; 16: two (column halves)
 constexpr int kThreads = 64 + 32 * kEpiWarps;           // TMA warp, MMA warp, epilogue warps
+// FUSE: what the epilogue needs per tile column (scales, interpolation weights, piece / node / slab offsets), staged into
+// shared memory by the epilogue warps WHILE the tile's MMAs run -- read from global memory inside the epilogue, the two
+// dependent L2 latencies per eigenvector cost 11 us per tile (measured: 59 ms instead of 42 per 100 k SNPs)
+struct TileMeta {
+    double lw[kTileEig][kCq];   // interpolation weights of the tile's eigenvectors (rows are 16-byte aligned)
+    double sc[kTileEig];        // fixed-point scale of the column
+    double u1[kTileEig];        // U^T 1 / G^T 1 (level-coded genotypes)
+    int2 ei[kTileEig];          // {piece, kq} / {node, 0} / {_, -1}
+    int goff[kTileEig];         // G tiles: slab offset of the column, -1 padding
+    int chunk_piece[kTileEig / 8];   // piece of an 8-eigenvector chunk when all eight are COMPRESS rows of one piece, else -1
+    int pad[4];
+};
+static_assert(sizeof(TileMeta) % 16 == 0, "TileMeta is copied around in 16-byte aligned shared memory");
+constexpr size_t kMetaBytes = 2 * sizeof(TileMeta);   // double-buffered by tile parity
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + 256;
+constexpr size_t kSmemBytesFused = kSmemBytes + kMetaBytes;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // cute::Sm100MmaPeerBitMask: address of the even CTA of the pair
 
 // S32 accumulate, S8 x S8, K-major, N = 224, M = 256 (pair)
@@ -231,6 +246,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint64_t* tmem_full = bars + 2 * kStages;
     uint64_t* tmem_empty = tmem_full + 1;
     uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 1);
+    TileMeta* meta = (TileMeta*)(smem + (size_t)kStages * kStageBytes + 256);   // FUSE only (kSmemBytesFused)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -342,16 +358,51 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         constexpr int kCPer = (kTileEig / 8) / (kEpiWarps / 8);
         const int c_begin = (part >> 1) * kCPer;
         uint32_t acc_phase = 0;
+        const int etid = (int)threadIdx.x - 64;   // index among the epilogue threads
         for (long long t = cluster_id; t < total_tiles; t += num_clusters) {
             int st, et;
             decode(t, st, et);
-            mbar_wait(tmem_full, acc_phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const bool g_tile = FUSE && et >= a.eig_tiles;          // a tile of G = U V: its values ARE linear moments
             const int eig0 = (g_tile ? et - a.eig_tiles : et) * kTileEig;   // first eigenvector / first column of G
-            const double* sc_tab = g_tile ? a.f.gscale : a.scale;
-            const double* u1_tab = g_tile ? a.f.g1 : a.u1;
-            const int idx_max = g_tile ? a.f.g_tiles * kTileEig - 1 : a.n - 1;
+            const TileMeta& M = meta[acc_phase];
+            if (FUSE) {
+                // stage this tile's column metadata while its MMAs run.  The buffer alternates with the accumulator phase:
+                // no warp can be more than one tile ahead of another (tmem_empty gates the next tile's MMAs).
+                TileMeta& Mw = meta[acc_phase];
+                for (int i = etid; i < kTileEig * kCq; i += 32 * kEpiWarps) {
+                    const int e = eig0 + i / kCq;
+                    (&Mw.lw[0][0])[i] = (!g_tile && e < a.n) ? __ldg(a.f.Lw + (size_t)eig0 * kCq + i) : 0.0;
+                }
+                for (int i = etid; i < kTileEig; i += 32 * kEpiWarps) {
+                    const int e = eig0 + i;
+                    if (g_tile) {
+                        Mw.sc[i] = __ldg(a.f.gscale + e);
+                        Mw.u1[i] = a.info ? __ldg(a.f.g1 + e) : 0.0;
+                        Mw.goff[i] = __ldg(a.f.goff + e);
+                        Mw.ei[i] = make_int2(0, -1);
+                    } else {
+                        Mw.sc[i] = e < a.n ? __ldg(a.scale + e) : 0.0;
+                        Mw.u1[i] = (a.info && e < a.n) ? __ldg(a.u1 + e) : 0.0;
+                        Mw.goff[i] = -1;
+                        Mw.ei[i] = __ldg(a.f.einfo + e);
+                    }
+                }
+                if (etid < kTileEig / 8) {
+                    int cp = -1;
+                    if (!g_tile) {
+                        const int2 e0 = __ldg(a.f.einfo + eig0 + etid * 8);
+                        cp = e0.y > 0 ? e0.x : -1;
+                        for (int j = 1; j < 8; ++j) {
+                            const int2 ej = __ldg(a.f.einfo + eig0 + etid * 8 + j);
+                            if (ej.y <= 0 || ej.x != cp) cp = -1;
+                        }
+                    }
+                    Mw.chunk_piece[etid] = cp;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            }
+            mbar_wait(tmem_full, acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {
                 const long long snp = (long long)st * kClusterSnps + (long long)rank * kCtaSnps + acc * 128 + quarter * 32 + lane;
                 double lv0 = 0.0, ls = 1.0, leps = 0.0;
@@ -376,6 +427,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         for (int k = 0; k < (FUSE ? kCq : 1); ++k) m2[k] = 0.0;
                     }
                 };
+                double* Zs = FUSE ? a.f.Z + (size_t)(snp < a.mb ? snp : 0) * a.f.ldz : nullptr;
 #pragma unroll 1
                 for (int c = c_begin; c < c_begin + kCPer; ++c) {
                     // eight eigenvectors x seven planes = 56 consecutive columns (eigen-major)
@@ -386,14 +438,13 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (FUSE || snp < a.mb) {
                         double* dst = FUSE ? nullptr : a.xr + (size_t)snp * a.ldx + eig0 + c * 8;
-                        double* Zs = FUSE ? a.f.Z + (size_t)(snp < a.mb ? snp : 0) * a.f.ldz : nullptr;
                         if (!FUSE)
                             PG_BOUNDS(snp >= 0 && snp < a.mb && eig0 + c * 8 < a.ldx && (eig0 + c * 8 + 8 <= a.n ? eig0 + c * 8 + 8 <= a.ldx : true),
                                       "rotated-genotype store outside the block");
                         double out[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int e = min(eig0 + c * 8 + j, idx_max);
+                            const int e = min(eig0 + c * 8 + j, a.n - 1);   // (!FUSE)
                             // the digit planes are recombined as 64-bit integers (|plane sum| < 2^31, so hi < 2^48 and
                             // lo < 2^56 never overflow) and converted once each: 2 int -> double conversions per output
                             // instead of 7.  Same bits as the FP64 Horner form of combine_i8_kernel: both are the exact
@@ -406,35 +457,58 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #undef PG_PL
                             const double hi = (double)hi_i, lo = (double)lo_i;
                             const double v = fma(lo, kLoScale, hi);
-                            out[j] = v * __ldg(sc_tab + e);
+                            out[j] = v * (FUSE ? M.sc[c * 8 + j] : __ldg(a.scale + e));
                             if (a.info) {
                                 if (!FUSE && a.accumulate) out[j] = (leps != 0.0) ? fma(leps, out[j], dst[j]) : dst[j];
-                                else out[j] = fma(ls, out[j], lv0 * __ldg(u1_tab + e));
+                                else out[j] = fma(ls, out[j], lv0 * (FUSE ? M.u1[c * 8 + j] : __ldg(a.u1 + e)));
                             }
-                            if (FUSE) {
-                                if (g_tile) {
-                                    const int off = __ldg(a.f.goff + e);
+                        }
+                        if (FUSE) {
+                            if (g_tile) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int off = M.goff[c * 8 + j];
                                     PG_BOUNDS(off < a.f.ldz, "linear-moment store outside the slab");
                                     if (off >= 0 && snp < a.mb) Zs[off] = out[j];
-                                } else {
-                                    const int2 ei = __ldg(a.f.einfo + eig0 + c * 8 + j);   // the same for every lane
+                                }
+                            } else if (M.chunk_piece[c] >= 0) {
+                                // the common case: eight COMPRESS rows of one piece, straight-line code
+                                if (M.chunk_piece[c] != piece) { flush_piece(); piece = M.chunk_piece[c]; }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const double sq = out[j] * out[j];
+                                    const double2* lw2 = reinterpret_cast<const double2*>(&M.lw[c * 8 + j][0]);
+#pragma unroll
+                                    for (int k2 = 0; k2 < (FUSE ? kCq / 2 : 0); ++k2) {
+                                        const double2 w = lw2[k2];
+                                        m2[2 * k2] = fma(w.x, sq, m2[2 * k2]);
+                                        m2[2 * k2 + 1] = fma(w.y, sq, m2[2 * k2 + 1]);
+                                    }
+                                }
+                            } else {
+                                // segment boundaries, isolated eigenvalues, padding: one eigenvector at a time
+#pragma unroll 1
+                                for (int j = 0; j < 8; ++j) {
+                                    double oj = 0.0;   // out[j] without dynamic register indexing
+#pragma unroll
+                                    for (int jj = 0; jj < 8; ++jj) oj = (jj == j) ? out[jj] : oj;
+                                    const int2 ei = M.ei[c * 8 + j];
+                                    const int e = eig0 + c * 8 + j;
                                     if (ei.y > 0) {
                                         if (ei.x != piece) { flush_piece(); piece = ei.x; }
-                                        const double sq = out[j] * out[j];
-                                        const double* lw = a.f.Lw + (size_t)e * kCq;
+                                        const double sq = oj * oj;
 #pragma unroll
-                                        for (int k = 0; k < (FUSE ? kCq : 1); ++k) m2[k] = fma(__ldg(lw + k), sq, m2[k]);
+                                        for (int k = 0; k < (FUSE ? kCq : 1); ++k) m2[k] = fma(M.lw[c * 8 + j][k], sq, m2[k]);
                                     } else if (ei.y == 0 && snp < a.mb) {
                                         // isolated eigenvalue, its own node: x_l w_jl and x_l^2 (compress_copy_kernel)
                                         PG_BOUNDS(a.f.x2row + ei.x < a.f.ldz, "COPY-row moment store outside the slab");
                                         for (int jj = 0; jj < a.f.klin; ++jj)
-                                            Zs[__ldg(a.f.jrow + jj) + ei.x] = out[j] * __ldg(a.f.wy + (size_t)jj * a.f.ldw + e);
-                                        Zs[a.f.x2row + ei.x] = out[j] * out[j];
+                                            Zs[__ldg(a.f.jrow + jj) + ei.x] = oj * __ldg(a.f.wy + (size_t)jj * a.f.ldw + e);
+                                        Zs[a.f.x2row + ei.x] = oj * oj;
                                     }
                                 }
                             }
-                        }
-                        if (!FUSE) {
+                        } else {
                             if (eig0 + c * 8 + 8 <= a.n) {   // rows are 128-byte aligned (ldx % 16 == 0): four 16-byte stores
 #pragma unroll
                                 for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
@@ -525,14 +599,14 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     // per call: the attribute is per device, and a process may hold handles on several devices
     if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(rotate_i8_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(rotate_i8_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(rotate_i8_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+        cudaFuncSetAttribute(rotate_i8_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesFused) != cudaSuccess ||
+        cudaFuncSetAttribute(rotate_i8_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesFused) != cudaSuccess)
         return -4;
     const long long tiles = (long long)a.snp_tiles * (a.eig_tiles + (fuse ? fuse->g_tiles : 0));
     const int clusters = (int)std::min<long long>(tiles, sm_count / 2);
     if (fuse) {
-        if (xsm) rotate_i8_tc2_kernel<true, true><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
-        else rotate_i8_tc2_kernel<false, true><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
+        if (xsm) rotate_i8_tc2_kernel<true, true><<<2 * clusters, kThreads, kSmemBytesFused, stream>>>(mx, mp, mg, a);
+        else rotate_i8_tc2_kernel<false, true><<<2 * clusters, kThreads, kSmemBytesFused, stream>>>(mx, mp, mg, a);
     } else {
         if (xsm) rotate_i8_tc2_kernel<true, false><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
         else rotate_i8_tc2_kernel<false, false><<<2 * clusters, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);

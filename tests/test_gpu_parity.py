@@ -655,3 +655,88 @@ def test_more_traits_than_one_pass_holds():
         one = lmm.pygemma(Y[:, ph], p["X"], p["W"], p["K"])
         for c in COLS:
             assert np.array_equal(frames[ph][c].to_numpy(), one[c].to_numpy(), equal_nan=True), (ph, c)
+
+
+def test_moment_fusion_matches_the_unfused_path_and_the_oracle():
+    """pg_set_moment_fusion(1): the fused tcgen05 rotation produces the eigenvalue-space moments itself -- linear moments
+    as extra exact int8 tiles against G = U V, x^2 moments in its epilogue -- and never writes the rotated genotypes.
+    Same results as the unfused pipeline to rounding (1e-9: only the summation order differs) and the oracle's tolerance,
+    for int8 dosages (direct MN-major operand and the staged copy for n % 16 != 0), a spectrum with a null space and
+    isolated eigenvalues (COPY rows), several blocks with a ragged tail, level-coded float genotypes (affine fix-up in
+    the fused epilogue; a block that needs the eps pass is compressed as before), several traits, grid mode and the LRT
+    columns; fused scans are deterministic and independent of the block a SNP sits in."""
+    from oracle import oracle
+
+    capi = _capi()
+    rng = np.random.default_rng(17)
+    for n, m, c0 in ((1024, 1700, 5), (1000, 777, 3)):
+        U, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        d = np.sort(10.0 ** (rng.random(n) * 1.5 - 1.0))
+        d[: n // 100] = 0.0                              # null space: one COMPRESS node at d = 0
+        d[-3:] *= np.array([3.0, 10.0, 40.0])           # isolated eigenvalues: COPY rows
+        W = np.column_stack([np.ones(n)] + [rng.standard_normal(n) for _ in range(c0 - 1)])
+        u = U @ (np.sqrt(d) * rng.standard_normal(n))
+        y = 0.7 * u / u.std() + 0.7 * rng.standard_normal(n) + 0.05 * W[:, 1:].sum(1)
+        maf = rng.random(m) * 0.45 + 0.05
+        X = ((rng.random((n, m)) < maf).astype(np.int8) + (rng.random((n, m)) < maf).astype(np.int8))
+        idx = np.unique(np.linspace(0, m - 1, 40).astype(np.int64))
+        ref = oracle.scan_rotated(d, U.T @ y, U.T @ W, np.ascontiguousarray((U.T @ X[:, idx].astype(np.float64)).T))
+        with capi.Handle(n, c0) as h:
+            h.set_eigen(U, d)
+            h.set_design(W, y)
+            h.set_options(block_snps=512)   # several blocks, ragged tail
+            assert not h.fusion_info()["fused"]
+            o0 = h.scan(X)
+            assert o0["timing"]["rot_engine"] == capi.PG_ROT_I8TC
+            h.set_moment_fusion(1)
+            info = h.fusion_info()
+            assert info["fused"] and info["g_columns"] > 0 and info["pieces"] > 0
+            o1 = h.scan(X)
+            assert o1["timing"]["rot_engine"] == capi.PG_ROT_I8TC_MOMENTS and o1["timing"]["compress_ms"] < 0.05
+            assert np.array_equal(o0["status"], o1["status"])
+            for c in COLS:
+                assert rel(o1[c], o0[c]).max() < 1e-9, (n, c, float(rel(o1[c], o0[c]).max()))
+            _check(o1, ref, idx=idx, tag=("fused", n))
+            # deterministic, and a SNP's bits do not depend on its block or its position in a tile
+            o1b = h.scan(X)
+            h.set_options(block_snps=0)
+            o1c = h.scan(X[:, 300:1200 if m > 1200 else m])
+            for c in COLS:
+                assert np.array_equal(o1[c], o1b[c], equal_nan=True), c
+                assert np.array_equal(o1[c][300:300 + o1c[c].shape[0]], o1c[c], equal_nan=True), c
+            with pytest.raises(capi.PgError):
+                h.probe_rotated(4)              # a fused scan leaves no rotated genotypes behind
+            # grid mode and the likelihood-ratio columns read the same moments
+            og0 = h.scan(X, grid=True)
+            h.set_moment_fusion(0)
+            og1 = h.scan(X, grid=True)
+            assert np.array_equal(og0["lambda"], og1["lambda"])
+            ol0 = h.scan(X[:, :256], lrt=True)
+            h.set_moment_fusion(1)
+            ol1 = h.scan(X[:, :256], lrt=True)
+            for c in ("D_lrt", "loglik_ml"):
+                assert np.abs(ol1[c] - ol0[c]).max() < 1e-8, c
+            # level-coded float genotypes: standardised in float64 -> affine, fused; float32 -> eps pass, not fused
+            g = X[:, :300].astype(np.float64)
+            sd = g.std(axis=0)
+            sd[sd == 0] = 1.0
+            Xs = (g - g.mean(axis=0)) / sd
+            of = h.scan(np.ascontiguousarray(Xs))
+            assert of["timing"]["rot_engine"] == capi.PG_ROT_I8TC_MOMENTS
+            o32 = h.scan(np.ascontiguousarray(Xs.astype(np.float32)))
+            assert o32["timing"]["rot_engine"] == capi.PG_ROT_I8TC
+            h.set_moment_fusion(0)
+            of0 = h.scan(np.ascontiguousarray(Xs))
+            ok = sd[:300] > 0
+            ok &= g.std(axis=0) > 0
+            for c in COLS:
+                assert rel(of[c][ok], of0[c][ok]).max() < 1e-8, ("affine", c)
+            # several traits share the tiles of G built from [W0, y_0 .. y_{q-1}]
+            Y = np.stack([y, rng.standard_normal(n), 0.3 * y + rng.standard_normal(n)], axis=1)
+            h.set_design(W, Y)
+            om0 = h.scan(X[:, :600])
+            h.set_moment_fusion(1)
+            om1 = h.scan(X[:, :600])
+            assert om1["timing"]["rot_engine"] == capi.PG_ROT_I8TC_MOMENTS and om1["beta"].shape == (3, min(600, m))
+            for c in COLS:
+                assert rel(om1[c], om0[c]).max() < 1e-9, ("multi", c)
