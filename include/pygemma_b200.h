@@ -210,11 +210,12 @@ int pg_set_reml_engine(pg_handle* h, int engine);
  * against G = U V (V = the compression operand, built once per design), the x^2 moments in its epilogue; rotated genotypes
  * are never written and the compression kernels do not run.  Results agree with the unfused path to rounding (different
  * summation order), and are deterministic.  mode: 1 = wherever the engine allows it (PG_ROT_AUTO or PG_ROT_I8TC, int8 /
- * level-coded / .bed genotypes, the compressed REML engine); 0 = never; -1 (default) = the library's choice, which is
- * "off" on B200: measured, the fused kernel takes as long as rotation + compression together because the step is
- * power-capped (profiles/experiments_r02.md) -- fusion saves the rotated-genotype buffers (3 x 2 GiB) and 160 KB of HBM
- * traffic per SNP, not time.  Blocks that need the second, eps-weighted rotation pass (unequally spaced levels, missing
- * .bed calls), the FP64 rotation or another engine are compressed as before.
+ * level-coded / .bed genotypes, the compressed REML engine); 0 = never; -1 (default) = where it was measured to pay on a
+ * power-capped B200 (profiles/experiments_r02.md): PG_ROT_AUTO, n >= 4096, at least 24 linear columns (c0 + traits) and
+ * at most 140 compression nodes (+7 % SNPs/s at c0 = 40 with 131 nodes).  With fewer columns the fused kernel takes as
+ * long as rotation + compression together; with more nodes its extra tiles cost more than the compression.  Blocks that need the second,
+ * eps-weighted rotation pass (unequally spaced levels, missing .bed calls), the FP64 rotation or another engine are
+ * compressed as before.
  * pg_probe_rotated is not available after a fused scan.
  */
 int pg_set_moment_fusion(pg_handle* h, int mode);

@@ -118,16 +118,18 @@ __global__ void build_v_kernel(int n, int klin, const double* __restrict__ Lw, c
     (void)ngroups;
 }
 
-// Fused moments (rotate_i8_tc2.cuh, FUSE): the compact right-hand operand of G = U V.  Column k * klin + j holds
-// L_k(log d_l) w_jl for the rows l of COMPRESS segments (zero on COPY rows); segment s then contributes the n x (kq klin)
-// block  G_s = U[:, l0:l1] . Vc[l0:l1, 0 : kq klin]  (one DGEMM per segment).
+// Fused moments (rotate_i8_tc2.cuh, FUSE): the compact right-hand operand of G = U V.  Column j * kCq + k holds
+// L_k(log d_l) w_jl for the rows l of COMPRESS segments (zero on COPY rows); a segment with kq = kCq nodes contributes the
+// n x (klin kCq) block  G_s = U[:, l0:l1] . Vc[l0:l1, :]  and a one-node segment the columns k = 0 (leading dimension
+// n kCq): one DGEMM per segment.  Column order linear-column-major, node fastest: the eight columns an epilogue thread of
+// the fused rotation holds are then (mostly) eight consecutive nodes of one slab row, i.e. whole 32-byte sectors.
 __global__ void build_vc_kernel(int n, int klin, const double* __restrict__ Lw, const int* __restrict__ seg_kq,
                                 const double* __restrict__ wy, long long ldw, double* __restrict__ Vc)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n) return;
-    const int col = blockIdx.y;            // k * klin + j
-    const int k = col / klin, j = col - k * klin;
+    const int col = blockIdx.y;            // j * kCq + k
+    const int j = col / kCq, k = col - j * kCq;
     Vc[(size_t)col * n + l] = seg_kq[l] > 0 ? Lw[(size_t)l * kCq + k] * wy[(size_t)j * ldw + l] : 0.0;
 }
 

@@ -155,7 +155,7 @@ struct pg_handle {
     // Moments straight from the fused rotation (rotate_i8_tc2.cuh, FUSE).  Per eigen-system: which x^2 piece / node every
     // eigen-index feeds and the piece ranges of the segments.  Per design: G = U V (one column per COMPRESS node and linear
     // column), its digit planes, scales, column sums and slab offsets.
-    int fuse_mode = -1;   // pg_set_moment_fusion: 1 = wherever the engine allows it; -1 (default) and 0 = off (see fuse_wanted)
+    int fuse_mode = -1;   // pg_set_moment_fusion: -1 automatic (fuse_wanted), 0 never, 1 wherever the engine allows it
     struct Fused {
         int2* einfo = nullptr;
         tc2::SegRed* segs = nullptr;
@@ -885,20 +885,24 @@ static bool fuse_env_tc2()
 
 // Whether scans of the current design take the linear moments from tiles of G = U V and the x^2 moments from the rotation
 // epilogue (rotate_i8_tc2.cuh) instead of writing the rotated genotypes and compressing them.  The extra tensor work is
-// (COMPRESS nodes x linear columns) / n of the rotation.  MEASURED (profiles/experiments_r02.md, one B200, n = 10 000):
-// the fused kernel takes as long as rotation + compression together (c0 = 10: 55.0 ms against 42.6 + 11.0 per 100 k SNPs;
-// c0 = 40: 80.1 against 40.8 + 37.8) because the step is power-capped and the tensor pipe, busy for the whole step, pulls
-// the SM clock from 1.69 to 1.57 GHz; end to end it loses the ~1 ms G costs per design.  So fusion is OPT-IN
-// (pg_set_moment_fusion(h, 1) / PG_FUSE_MOMENTS=1): it saves the three 2 GiB rotated-genotype buffers and 160 KB of HBM
-// traffic per SNP, not time, on this board.
+// (COMPRESS nodes x linear columns) / n of the rotation.  MEASURED (profiles/experiments_r02.md, one B200, n = 10 000, 131
+// nodes, per 100 k SNPs): with 11 linear columns (c0 = 10) the fused kernel takes what rotation + compression take together
+// (53.3-53.8 ms against 42.7 + 11.0; the step is power-capped and the tensor pipe, busy for the whole step, pulls the SM clock
+// from 1.67 to 1.57 GHz), and end to end it loses the ~1 ms G costs per design; with 41 linear columns (c0 = 40) it wins 7 %
+// (73.8 ms against 40.6 + 37.5: 1.23 M instead of 1.15 M SNPs/s).  The extra tiles grow with nodes x columns, the compression
+// with the columns only (in groups of 11): at 206 nodes a 32-trait pass (42 columns) LOSES 7 % fused (85.9 ms against
+// 40.2 + 38.7).  So the automatic mode fuses from 24 linear columns on (c0 >= 23, or several traits per pass) when the plan has
+// at most 140 COMPRESS nodes; pg_set_moment_fusion(h, 1) / PG_FUSE_MOMENTS=1 fuses wherever possible.
 static bool fuse_wanted(const pg_handle* h)
 {
-    if (h->fuse_mode != 1 || !fuse_env_tc2()) return false;
+    if (h->fuse_mode == 0 || !fuse_env_tc2()) return false;
     if (!(h->engine == PG_REML_AUTO || h->engine == PG_REML_COMPRESSED) || h->overlap) return false;
     if (!h->have_U || h->rotated_inputs || h->fz.nsegs == 0) return false;
-    if (!(h->rotation == PG_ROT_AUTO || h->rotation == PG_ROT_I8TC)) return false;
-    const long long gcols = (long long)h->fz.cnodes * (h->c0 + h->q);
-    return gcols <= 4LL * h->n + 4096;   // digit planes of G: 7 (n + 127) bytes per column
+    const int klin = h->c0 + h->q;
+    const long long gcols = (long long)h->fz.cnodes * klin;
+    if (h->fuse_mode == 1)
+        return (h->rotation == PG_ROT_AUTO || h->rotation == PG_ROT_I8TC) && gcols <= 4LL * h->n + 4096;
+    return h->rotation == PG_ROT_AUTO && klin >= 24 && h->n >= 4096 && h->fz.cnodes <= 140 && gcols <= h->n;
 }
 
 // G = U V for the current design, sliced into digit planes like U^T (slice_u_kernel), with its scales, column sums
@@ -962,15 +966,17 @@ static int ensure_fused_operand(pg_handle* h)
     int col0 = 0;
     for (const Segment& sg : F.csegs) {
         const int len = sg.l1 - sg.l0, ncs = sg.kq * klin;
-        // G[:, col0 : col0 + ncs] = U[:, l0:l1] . Vc[l0:l1, 0:ncs]   (all column-major, leading dimension n)
+        // G[:, col0 : col0 + ncs] = U[:, l0:l1] . Vc[l0:l1, .]   (column-major; columns (j, k), node k fastest; a one-node
+        // segment takes the k = 0 column of every j: leading dimension n kCq)
+        const int ldb = sg.kq == kCq ? n : n * kCq;
         if (h->u_op_t)
-            CKB(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, n, ncs, len, &one, h->U + (size_t)sg.l0 * n, n, F.vdc + sg.l0, n,
+            CKB(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, n, ncs, len, &one, h->U + (size_t)sg.l0 * n, n, F.vdc + sg.l0, ldb,
                             &zero, F.G + (size_t)col0 * n, n));
         else
-            CKB(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, n, ncs, len, &one, h->U + sg.l0, n, F.vdc + sg.l0, n, &zero,
+            CKB(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, n, ncs, len, &one, h->U + sg.l0, n, F.vdc + sg.l0, ldb, &zero,
                             F.G + (size_t)col0 * n, n));
-        for (int k = 0; k < sg.kq; ++k)
-            for (int j = 0; j < klin; ++j) goff[col0 + k * klin + j] = jrow[j] + sg.kb + k;
+        for (int j = 0; j < klin; ++j)
+            for (int k = 0; k < sg.kq; ++k) goff[col0 + j * sg.kq + k] = jrow[j] + sg.kb + k;
         col0 += ncs;
     }
     CK(cudaMemsetAsync(F.gscale, 0, sizeof(double) * npad_g, h->compute));

@@ -192,7 +192,7 @@ struct Args {
     int n;
     int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors
     int eig_group;              // eigen tiles swept together (L2 residency of the B panels)
-    int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes (default 2, see launch)
+    int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes, bit 2: streaming stores of the rotated block (default: see launch)
     const double* scale;
     double* xr;
     long long ldx;
@@ -421,7 +421,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                             PG_BOUNDS(snp < a.f.ldp, "x^2 partial store outside the piece buffer");
                             double* pp = a.f.P2 + (size_t)piece * kCq * a.f.ldp + snp;
 #pragma unroll
-                            for (int k = 0; k < (FUSE ? kCq : 1); ++k) pp[(size_t)k * a.f.ldp] = m2[k];
+                            for (int k = 0; k < (FUSE ? kCq : 1); ++k) __stcs(pp + (size_t)k * a.f.ldp, m2[k]);   // streaming: the operand tiles own the L2
                         }
 #pragma unroll
                         for (int k = 0; k < (FUSE ? kCq : 1); ++k) m2[k] = 0.0;
@@ -469,7 +469,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                                 for (int j = 0; j < 8; ++j) {
                                     const int off = M.goff[c * 8 + j];
                                     PG_BOUNDS(off < a.f.ldz, "linear-moment store outside the slab");
-                                    if (off >= 0 && snp < a.mb) Zs[off] = out[j];
+                                    if (off >= 0 && snp < a.mb) __stcs(Zs + off, out[j]);
                                 }
                             } else if (M.chunk_piece[c] >= 0) {
                                 // the common case: eight COMPRESS rows of one piece, straight-line code
@@ -503,15 +503,20 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                                         // isolated eigenvalue, its own node: x_l w_jl and x_l^2 (compress_copy_kernel)
                                         PG_BOUNDS(a.f.x2row + ei.x < a.f.ldz, "COPY-row moment store outside the slab");
                                         for (int jj = 0; jj < a.f.klin; ++jj)
-                                            Zs[__ldg(a.f.jrow + jj) + ei.x] = oj * __ldg(a.f.wy + (size_t)jj * a.f.ldw + e);
-                                        Zs[a.f.x2row + ei.x] = oj * oj;
+                                            __stcs(Zs + __ldg(a.f.jrow + jj) + ei.x, oj * __ldg(a.f.wy + (size_t)jj * a.f.ldw + e));
+                                        __stcs(Zs + a.f.x2row + ei.x, oj * oj);
                                     }
                                 }
                             }
                         } else {
                             if (eig0 + c * 8 + 8 <= a.n) {   // rows are 128-byte aligned (ldx % 16 == 0): four 16-byte stores
+                                if (a.hints & 4) {   // streaming stores: the rotated block is read back from HBM anyway
 #pragma unroll
-                                for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
+                                    for (int j = 0; j < 8; j += 2) __stcs(reinterpret_cast<double2*>(dst + j), make_double2(out[j], out[j + 1]));
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(out[j], out[j + 1]);
+                                }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)

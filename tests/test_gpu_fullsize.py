@@ -209,6 +209,18 @@ def test_c5_n10000_c40_grid_vs_oracle(eig10k):
         h.set_design(W, y)
         og = h.scan(X, grid=True)
         ob = h.scan(X[:, :512])   # Brent + Newton at c0 = 40 as well
+        # the same scans with the moments fused into the rotation (pg_set_moment_fusion; the automatic mode takes it at this
+        # covariate count when the spectrum has <= 140 nodes): thousands of eigen + G tiles per launch, every SNP compared
+        unfused = og["timing"]["rot_engine"] == capi.PG_ROT_I8TC
+        h.set_moment_fusion(1)
+        ogf = h.scan(X, grid=True)
+        obf = h.scan(X[:, :512])
+        assert ogf["timing"]["rot_engine"] == capi.PG_ROT_I8TC_MOMENTS and h.fusion_info()["g_columns"] >= 41 * 100
+        if unfused:
+            assert np.array_equal(ogf["lambda"], og["lambda"])
+            for c in COLS:
+                assert rel(ogf[c], og[c]).max() < 1e-8, ("fused grid", c)
+                assert rel(obf[c], ob[c]).max() < (1e-6 if c == "lambda" else 1e-8), ("fused brent", c)
     assert (og["status"] == 0).all()
     assert set(np.unique(og["lambda"])) <= set(10.0 ** np.arange(-5, 6))
     idx = np.unique(np.linspace(0, m - 1, 24).astype(np.int64))
@@ -217,9 +229,11 @@ def test_c5_n10000_c40_grid_vs_oracle(eig10k):
     refg = oracle.scan_rotated(d, yr, wr, xr, grid=True)
     assert np.array_equal(og["lambda"][idx], refg["lambda"])
     _check(og, refg, idx=idx, tag="c5 grid")
+    _check(ogf, refg, idx=idx, tag="c5 grid, moments fused")
     ib = idx[idx < 512]
     refb = oracle.scan_rotated(d, yr, wr, np.ascontiguousarray((U.T @ X[:, ib].astype(np.float64)).T))
     _check(ob, refb, idx=ib, tag="c5 brent")
+    _check(obf, refb, idx=ib, tag="c5 brent, moments fused")
 
 
 def test_c4_n50000_shape_fused_vs_cublas_and_oracle():

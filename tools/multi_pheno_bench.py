@@ -34,7 +34,8 @@ def main():
                 wall = time.time() - t
             tm = o["timing"]
             rows.append({"q": q, "design_ms": design_ms, "design_wall_s": design_wall, "total_ms": tm["total_ms"], "rotate_ms": tm["rotate_ms"],
-                         "reml_ms": tm["reml_ms"], "wall_s": wall,
+                         "reml_ms": tm["reml_ms"], "compress_ms": tm["compress_ms"], "rot_engine": tm["rot_engine"],
+                         "n_nodes": tm["n_nodes"], "wall_s": wall,
                          "snps_per_s": m / (tm["total_ms"] * 1e-3),
                          "tests_per_s": m * q / (tm["total_ms"] * 1e-3),
                          "tests_per_s_wall": m * q / wall,
