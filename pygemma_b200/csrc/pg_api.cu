@@ -824,8 +824,14 @@ static int build_tables(pg_handle* h)
                         h->tabc, R3));
         scatter_tables_kernel<<<kNumTableRows, 128, 0, h->compute>>>(T0, h->tab.NF, R3, h->tabc, h->hscal, h->fixtab, h->itab);
         CK(cudaGetLastError());
-        eliminate_tables_kernel<<<(kNumTableRows + 63) / 64, 64, 0, h->compute>>>(h->c0, h->tab.NF, h->tab2.NF2, h->fixtab, h->itab,
-                                                                                  h->fix2, h->itab2, h->t2work);
+        // one CTA per table lambda; PG_ELIM_SERIAL=1: the one-thread-per-lambda kernel (same bits, 19 ms at c0 = 40)
+        static const bool elim_serial = getenv("PG_ELIM_SERIAL") && atoi(getenv("PG_ELIM_SERIAL")) != 0;
+        if (elim_serial)
+            eliminate_tables_kernel<<<(kNumTableRows + 63) / 64, 64, 0, h->compute>>>(h->c0, h->tab.NF, h->tab2.NF2, h->fixtab,
+                                                                                      h->itab, h->fix2, h->itab2, h->t2work);
+        else
+            eliminate_tables_cta_kernel<<<kNumTableRows, 128, 0, h->compute>>>(h->c0, h->tab.NF, h->tab2.NF2, h->fixtab, h->itab,
+                                                                               h->fix2, h->itab2, h->t2work);
         CK(cudaGetLastError());
         return PG_OK;
     }

@@ -607,7 +607,8 @@ __global__ void pvalue_kernel(const double* __restrict__ F, double* __restrict__
     if (i < m) p[row0 + i] = f_sf_1_pre(F[row0 + i], nu, lnbeta);
 }
 
-// table-2 rows: one thread eliminates the covariate levels of one table lambda (pg_eval.cuh: eliminate_w0y_row)
+// table-2 rows: one thread eliminates the covariate levels of one table lambda (pg_eval.cuh: eliminate_w0y_row).  The serial
+// form; the default is eliminate_tables_cta_kernel below (PG_ELIM_SERIAL=1 selects this one, the cross-check).
 __global__ void eliminate_tables_kernel(int c0, int NF, int NF2, const double* __restrict__ fixtab,
                                         const double* __restrict__ itab, double* __restrict__ fix2,
                                         double* __restrict__ itab2, double* __restrict__ work)
@@ -620,7 +621,70 @@ __global__ void eliminate_tables_kernel(int c0, int NF, int NF2, const double* _
     eliminate_w0y_row(c0, src, work + (size_t)row * 3 * T0, dst);
 }
 
-// single evaluation from compressed moments (one warp): unit probe
+// The same elimination with one CTA per table lambda: inside a level every trailing entry (r, s) is updated from the pivot
+// column alone, so the entries are spread over the threads and the levels are separated by a barrier.  Every entry goes
+// through the expression of eliminate_w0y_row (same operations, same order): the rows are bit-identical to the serial
+// kernel's.  The serial kernel keeps 971 threads busy for ~c0^3 / 6 dependent entry updates each: 19 ms per design at
+// c0 = 40 (n = 10 000), most of an lmm.pygemma call's set-up there; this one takes a fraction of a millisecond.
+__global__ void __launch_bounds__(128) eliminate_tables_cta_kernel(int c0, int NF, int NF2, const double* __restrict__ fixtab,
+                                                                    const double* __restrict__ itab, double* __restrict__ fix2,
+                                                                    double* __restrict__ itab2, double* __restrict__ work_all)
+{
+    const int row = blockIdx.x;
+    const int k0 = c0 + 1, T0 = k0 * (k0 + 1) / 2, Tp = t2_pairs(c0);
+    const double* row0 = (row < kNumFixed) ? fixtab + (size_t)row * NF : itab + (size_t)(row - kNumFixed) * NF;
+    double* out = (row < kNumFixed) ? fix2 + (size_t)row * NF2 : itab2 + (size_t)(row - kNumFixed) * NF2;
+    double* A = work_all + (size_t)row * 3 * T0;
+    double* B = A + T0;
+    double* C = A + 2 * T0;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int q = tid; q < 3 * T0; q += nth) A[q] = row0[q];
+    double trP = row0[3 * T0], trPP = row0[3 * T0 + 1], logdet = 0.0;   // carried by thread 0
+    __syncthreads();
+    if (tid == 0 && c0 >= 1) A[0] = cy_max(A[0], kMinVal);  // pyx:939 / :993
+    for (int i = 1; i <= c0; ++i) {
+        __syncthreads();   // level i - 1 is complete (and the clamp above)
+        const int p = i - 1, pp = tri(p, p);
+        const double app = A[pp], bpp = B[pp], cpp = C[pp];
+        const double inv = 1.0 / app;
+        const double al2 = -inv, al4 = bpp / (app * app);
+        const double alc = (cpp / (app * app)) - ((bpp * bpp) / (app * app * app));
+        if (tid == 0) {
+            trPP = trPP + (bpp / app) * (bpp / app) - 2 * (cpp / app);
+            trP = trP - bpp / app;
+            logdet += log(app);
+            out[3 * p] = al2; out[3 * p + 1] = al4; out[3 * p + 2] = alc;
+        }
+        for (int s = i + tid; s <= c0; s += nth) {
+            const int q = t2_col(c0, p, s), sp = tri(s, p);
+            out[q] = A[sp]; out[Tp + q] = B[sp]; out[2 * Tp + q] = C[sp];
+        }
+        // trailing entries (r, s2), i <= s2 <= r <= c0: a warp per r, lanes over s2
+        for (int r = i + (tid >> 5); r <= c0; r += (nth >> 5))
+            for (int s2 = i + (tid & 31); s2 <= r; s2 += 32) {
+                const int rs = tri(r, s2), rp = tri(r, p), sp = tri(s2, p);
+                const double ar = A[rp], as = A[sp], br = B[rp], bs = B[sp], cr = C[rp], cs = C[sp];
+                const bool clamp = (r == i && s2 == i && i < c0);  // next pivot (i,i); at i == c0 that entry is (x,x)
+                double v = (C[rs] + alc * ar * as) + al2 * (ar * cs + cr * as) + al2 * (br * bs) + al4 * (ar * bs + br * as);
+                if (clamp) v = cy_max(v, kMinVal);
+                C[rs] = v;
+                v = (B[rs] + al4 * ar * as) + al2 * (ar * bs + br * as);
+                if (clamp) v = cy_max(v, kMinVal);
+                B[rs] = v;
+                v = A[rs] + al2 * ar * as;
+                if (clamp) v = cy_max(v, kMinVal);
+                A[rs] = v;
+            }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int f = t2_fin(c0), yy = tri(c0, c0);
+        out[f] = A[yy]; out[f + 1] = B[yy]; out[f + 2] = C[yy];
+        out[f + 3] = trP; out[f + 4] = trPP; out[f + 5] = row0[3 * T0 + 2]; out[f + 6] = logdet;
+        out[f + 7] = row0[3 * T0]; out[f + 8] = row0[3 * T0 + 1];
+    }
+}
+
 template <int NS>
 __global__ void probe_precompute_compressed_kernel(SolveArgs a, double lam, int fixed_t, int full, double* out9)
 {

@@ -740,3 +740,44 @@ def test_moment_fusion_matches_the_unfused_path_and_the_oracle():
             assert om1["timing"]["rot_engine"] == capi.PG_ROT_I8TC_MOMENTS and om1["beta"].shape == (3, min(600, m))
             for c in COLS:
                 assert rel(om1[c], om0[c]).max() < 1e-9, ("multi", c)
+
+
+def test_cta_parallel_table_elimination_is_bit_identical_to_the_serial_kernel(tmp_path):
+    """The table-2 rows (covariate levels eliminated once per table lambda, pyx:1011-1031 restricted to [W0, y]) are built
+    by one CTA per lambda; PG_ELIM_SERIAL=1 selects the one-thread-per-lambda kernel (read once per process, hence the two
+    subprocesses).  Same operations per entry in the same order: every output of a scan (Brent + Newton and grid, c0 = 1,
+    12 and 40) agrees bit for bit."""
+    import subprocess
+    import sys
+
+    from pygemma_b200.synth import make_problem
+
+    capi = _capi()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from pygemma_b200 import _capi\n"
+        "from pygemma_b200.synth import make_problem\n"
+        "out = {}\n"
+        "for c0 in (1, 12, 40):\n"
+        "    p = make_problem(700, 96, c0, seed=40 + c0, m_k=900)\n"
+        "    with _capi.Handle(700, c0) as h:\n"
+        "        h.set_kinship(p['K']); h.set_design(p['W'], p['Y'])\n"
+        "        for grid in (False, True):\n"
+        "            o = h.scan(p['X'], grid=grid)\n"
+        "            for c in ('beta', 'se_beta', 'tau', 'lambda', 'F_wald', 'p_wald'):\n"
+        "                out[f'{c0}_{int(grid)}_{c}'] = o[c]\n"
+        "np.savez(sys.argv[1], **out)\n"
+    )
+    files = {}
+    for serial in ("0", "1"):
+        files[serial] = str(tmp_path / f"elim_{serial}.npz")
+        env = dict(os.environ, PG_ELIM_SERIAL=serial)
+        r = subprocess.run([sys.executable, "-c", code, files[serial]], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+    a, b = np.load(files["0"]), np.load(files["1"])
+    assert sorted(a.files) == sorted(b.files) and len(a.files) == 36
+    for k in a.files:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert capi is not None
