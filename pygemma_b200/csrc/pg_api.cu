@@ -34,6 +34,11 @@ static constexpr size_t kDynSmemOptIn = 16 * 1024;
 
 // SNP-block boundaries of a scan (see scan_impl, "Block boundaries"): plain blocks of `blk`, preceded for host-resident
 // genotypes with automatic blocking by short blocks growing x 1.6 from 1 536 SNPs (multiples of 256).  PG_RAMP=0: none.
+// Pageable host genotypes of at least this size go through the pinned bounce buffers (and are cut into about four blocks so
+// that packing, upload and compute overlap).  16 MB: the driver's pageable 2-D copy runs at ~5-10 GB/s, so the 45 MB of the
+// GD449 shape (449 x 100 000 int8) took 9 ms of an 11 ms call; round 2 started with 64 MB.
+static constexpr size_t kBounceMinBytes = size_t(16) << 20;
+
 static std::vector<long long> plan_blocks(long long m, long long blk, bool host_input, bool fixed_block)
 {
     std::vector<long long> bstart;
@@ -1204,9 +1209,9 @@ static int ensure_workspace(pg_handle* h, long long m, int xdtype, bool host_inp
         blk = std::min<long long>(blk, 32768);
         // keep at least four blocks in flight on large inputs so uploads overlap compute
         if (m >= 4 * 8192) blk = std::min<long long>(blk, std::max<long long>(8192, ((m + 3) / 4 + 255) / 256 * 256));
-        // a host-resident shard that is worth pipelining (>= 64 MB) but shorter than that, e.g. one rank's 12 544 SNPs of a
+        // a host-resident shard that is worth pipelining (>= kBounceMinBytes) but shorter than that, e.g. one rank's 12 544 SNPs of a
         // problem split over 8 GPUs: still about four blocks of whole 512-SNP tiles, so that packing, upload and compute overlap
-        else if (host_input && (size_t)m * n * xdtype_size(xdtype) >= (size_t(64) << 20) && m >= 4 * 2048)
+        else if (host_input && (size_t)m * n * xdtype_size(xdtype) >= kBounceMinBytes && m >= 4 * 2048)
             blk = std::min<long long>(blk, std::max<long long>(2048, ((m + 3) / 4 + 511) / 512 * 512));
         // compressed moments of a block: at most 2 GiB
         const size_t zrow = sizeof(double) * (size_t)(h->k1p - 1 + h->q) * std::max(h->plan.Kcp, 32);
@@ -1531,7 +1536,7 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
     const long long blk = h->blk;
     // worth it for large pageable inputs only; very wide element types would need multi-GB pinned buffers
     const size_t total_bytes = (size_t)m * n * xdtype_size(xdtype), block_bytes = (size_t)blk * n * xdtype_size(xdtype);
-    const bool use_bounce = !on_device && total_bytes >= (size_t(64) << 20) && block_bytes <= (size_t(1) << 30) &&
+    const bool use_bounce = !on_device && total_bytes >= kBounceMinBytes && block_bytes <= (size_t(1) << 30) &&
                             !getenv("PG_NO_BOUNCE") && !host_pointer_is_pinned(X);
     if (use_bounce) {
         const size_t need_b = (size_t)blk * n * xdtype_size(xdtype);
