@@ -192,7 +192,7 @@ struct Args {
     int n;
     int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors
     int eig_group;              // eigen tiles swept together (L2 residency of the B panels)
-    int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes, bit 2: streaming stores of the rotated block (default: see launch)
+    int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes, bit 2: streaming stores of the rotated block, bit 3: 32-byte stores (default: see launch)
     const double* scale;
     double* xr;
     long long ldx;
@@ -510,7 +510,12 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                             }
                         } else {
                             if (eig0 + c * 8 + 8 <= a.n) {   // rows are 128-byte aligned (ldx % 16 == 0): four 16-byte stores
-                                if (a.hints & 4) {   // streaming stores: the rotated block is read back from HBM anyway
+                                if (a.hints & 8) {   // two 32-byte stores (STG.256): half the store instructions / LSU wavefronts
+                                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(out[0]), "d"(out[1]),
+                                                 "d"(out[2]), "d"(out[3]) : "memory");
+                                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "d"(out[4]), "d"(out[5]),
+                                                 "d"(out[6]), "d"(out[7]) : "memory");
+                                } else if (a.hints & 4) {   // streaming stores: the rotated block is read back from HBM anyway
 #pragma unroll
                                     for (int j = 0; j < 8; j += 2) __stcs(reinterpret_cast<double2*>(dst + j), make_double2(out[j], out[j + 1]));
                                 } else {
@@ -599,7 +604,9 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     static const int eg_env = getenv("PG_TC2_EG") ? atoi(getenv("PG_TC2_EG")) : 0;
     a.eig_group = eg_env > 0 ? eg_env : kEigGroup;
     // measured at n = 10 000 per 25 088 SNPs: no hint 10.17 ms, evict_last(B) 10.13, evict_first(A) 10.86, both 10.81
-    static const int hints_env = getenv("PG_TC2_HINTS") ? atoi(getenv("PG_TC2_HINTS")) : 2;
+    // rotated block written with two 32-byte stores per thread and chunk instead of four 16-byte ones (bit 3): 59.1-59.8 ms
+    // per bench step against 60.1-60.6 (three pairs, back to back); streaming stores (bit 2): inside the noise
+    static const int hints_env = getenv("PG_TC2_HINTS") ? atoi(getenv("PG_TC2_HINTS")) : 10;
     a.hints = hints_env;
     // per call: the attribute is per device, and a process may hold handles on several devices
     if (cudaFuncSetAttribute(rotate_i8_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
