@@ -245,6 +245,8 @@ def load_peaks():
 
 NCU_FILES = {  # committed `ncu --set full` summaries (tools/ncu_summary.py), newest first; SNPs per captured launch
     "rotate_i8_tc2": [("ncu_r02_tc2_16384snps.json", 16384), ("ncu_r01_tc2_final_16384snps.json", 16384)],
+    # moments fused into the rotation (c0 = 10, 206 nodes: +23 % tiles; the c5 shape has +54 %): an order of magnitude only
+    "rotate_i8_tc2_kernel<1, 1>": [("ncu_r02_tc2_fused_16384snps.json", 16384)],
     "compress_dmma": [("ncu_r02_reml_8192snps.json", 8192), ("ncu_r01_reml_final_8192snps.json", 8192)],
     "reml_solve": [("ncu_r02_reml_8192snps.json", 8192), ("ncu_r01_reml_final_8192snps.json", 8192)],
     "cutlass": [("ncu_r01_hot_kernels_8192snps.json", 3584)],
@@ -658,7 +660,9 @@ def run_ours(args):
                 "ops": "int8 multiply-add ops counted 2 per MAC" if (dom == "rotation" and i8) else "fp64 flops",
                 "share_of_step": st["ms"] / step_ms}
     per_snp, src = None, None
-    if dom == "rotation" and i8 and fused:
+    if dom == "rotation" and moments_fused:
+        per_snp, src = ncu_traffic("rotate_i8_tc2_kernel<1, 1>")
+    elif dom == "rotation" and i8 and fused:
         per_snp, src = ncu_traffic("rotate_i8_tc2")
     elif dom == "rotation" and i8:
         (a_, s1), (b_, _) = ncu_traffic("cutlass"), ncu_traffic("combine_i8")
