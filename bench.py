@@ -244,7 +244,8 @@ def load_peaks():
 
 
 NCU_FILES = {  # committed `ncu --set full` summaries (tools/ncu_summary.py), newest first; SNPs per captured launch
-    "rotate_i8_tc2": [("ncu_r02_tc2_16384snps.json", 16384), ("ncu_r01_tc2_final_16384snps.json", 16384)],
+    "rotate_i8_tc2": [("ncu_r02_tc2_persist_16384snps.json", 16384), ("ncu_r02_tc2_16384snps.json", 16384),
+                      ("ncu_r01_tc2_final_16384snps.json", 16384)],
     # moments fused into the rotation (c0 = 10, 206 nodes: +23 % tiles; the c5 shape has +54 %): an order of magnitude only
     "rotate_i8_tc2_kernel<1, 1>": [("ncu_r02_tc2_fused_16384snps.json", 16384)],
     "compress_dmma": [("ncu_r02_reml_8192snps.json", 8192), ("ncu_r01_reml_final_8192snps.json", 8192)],

@@ -1776,6 +1776,8 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         CK(cudaEventRecord(t2, h->compute));
         CK(cudaStreamSynchronize(h->compute));
         CK(cudaStreamSynchronize(h->copy));
+        // the rotation pinned its digit planes in the L2 set-aside (rotate_i8_tc2.cuh): hand the lines back
+        if (rotate && tc2::persist_planes() && n_rot_launch > 0) cudaCtxResetPersistingL2Cache();
         if (!on_device) {
             const double* hd = reinterpret_cast<const double*>(h->res_host);
             const int* hi = reinterpret_cast<const int*>(h->res_host + sizeof(double) * ncols * mq);
@@ -1812,7 +1814,8 @@ static int scan_impl(pg_handle* h, const void* X, int xdtype, long long ld, int 
         // per block: compress (dmma / copy), fixed-lambda x rows, fixed-lambda evaluations + solve per phenotype; one
         // p-value launch per scan
         if (compressed)
-            timing->reml_launches = (int32_t)(nblocks * (1 + 2 * q + (h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)) + 1);
+            timing->reml_launches = (int32_t)(nblocks * (1 + 2 * q) + (nblocks - n_fused_blocks) *   // fused blocks: no compression
+                                              ((h->plan.nitems ? 1 : 0) + (h->plan.ncopy ? 1 : 0)) + 1);
         else
             timing->reml_launches = (int32_t)(nblocks * q);
     }

@@ -35,7 +35,7 @@ constexpr int kLoShift = 8 * (kSlices - 3);   // value = (hi + lo 2^-kLoShift) 2
 // U holds nvec vectors of n entries (the n eigenvectors; the columns of G = U V for the fused moments, rotate_i8_tc2.cuh);
 // vector i is at U + i*n when u_cols_contig (column-major), else strided (U + i, stride nvec)
 __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__ U, int u_cols_contig, int n, int npad,
-                                                       int ldk, int8_t* __restrict__ planes /* [kSlices][npad][ldk] */,
+                                                       int ldk, int8_t* __restrict__ planes /* [npad][kSlices][ldk]: the planes of a vector are adjacent rows */,
                                                        int* __restrict__ exps, int nvec)
 {
     const int i = blockIdx.x;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__
     }
     __syncthreads();
     const int e = e_sh;
-    const size_t plane = (size_t)npad * ldk;
+    (void)npad;
     for (int j = threadIdx.x; j < ldk; j += blockDim.x) {
         long long Q = 0;
         if (i < nvec && j < n) Q = llrint(ldexp(u[(size_t)j * stride], 8 * kSlices - e));
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) slice_u_kernel(const double* __restrict__
         }
         dig[0] = (int8_t)Q;  // |Q| <= 65 here
 #pragma unroll
-        for (int t = 0; t < kSlices; ++t) planes[(size_t)t * plane + (size_t)i * ldk + j] = dig[t];
+        for (int t = 0; t < kSlices; ++t) planes[((size_t)i * kSlices + t) * ldk + j] = dig[t];
     }
 }
 
@@ -105,20 +105,21 @@ __global__ void stage_i8_kernel(const int8_t* __restrict__ src, long long ld, in
     }
 }
 
-// P: [g][kSlices*npad] int32 (column-major (kSlices*npad) x mb as cuBLAS writes it).  xr[g*n + i] fp64.
+// P: [g][npad*kSlices] int32 (column-major (npad*kSlices) x mb as cuBLAS writes it; row i*kSlices + t = plane t of
+// eigenvector i).  xr[g*n + i] fp64.
 __global__ void __launch_bounds__(256) combine_i8_kernel(const int32_t* __restrict__ P, const int* __restrict__ exps,
                                                           int n, int npad, long long mb, double* __restrict__ xr, long long ldx)
 {
     const long long g = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || g >= mb) return;
-    const int32_t* p = P + (size_t)g * kSlices * npad + i;
+    const int32_t* p = P + (size_t)g * kSlices * npad + (size_t)i * kSlices;
     // sum_t P_t 256^(kSlices-1-t): planes 0..2 (<= 2^46) and planes 3.. (<= 2^54) separately, then one fp64 sum
     long long hi = 0, lo = 0;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[(size_t)t * npad];
+    for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[t];
 #pragma unroll
-    for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[(size_t)t * npad];
+    for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[t];
     const double v = (double)hi + ldexp((double)lo, -kLoShift);
     xr[(size_t)g * ldx + i] = ldexp(v, exps[i] - 24);
 }
@@ -304,12 +305,12 @@ __global__ void __launch_bounds__(256) combine_i8_affine_kernel(const int32_t* _
     const long long g = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || g >= mb) return;
-    const int32_t* p = P + (size_t)g * kSlices * npad + i;
+    const int32_t* p = P + (size_t)g * kSlices * npad + (size_t)i * kSlices;
     long long hi = 0, lo = 0;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[(size_t)t * npad];
+    for (int t = 0; t < 3; ++t) hi = hi * 256 + (long long)p[t];
 #pragma unroll
-    for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[(size_t)t * npad];
+    for (int t = 3; t < kSlices; ++t) lo = lo * 256 + (long long)p[t];
     const double r = ldexp((double)hi + ldexp((double)lo, -kLoShift), exps[i] - 24);
     const LevelInfo li = info[g];
     double* dst = xr + (size_t)g * ldx + i;

@@ -190,7 +190,8 @@ struct FuseArgs {
 struct Args {
     long long mb;
     int n;
-    int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors
+    int snp_tiles, eig_tiles;   // cluster tiles of 512 SNPs, tiles of 32 eigenvectors (of this launch)
+    int eig_tile0 = 0;          // first eigen tile of this launch (one launch per eigen-tile group when the planes are pinned in L2)
     int eig_group;              // eigen tiles swept together (L2 residency of the B panels)
     int hints;                  // bit 0: evict_first for genotype tiles, bit 1: evict_last for the planes, bit 2: streaming stores of the rotated block, bit 3: 32-byte stores (default: see launch)
     const double* scale;
@@ -279,7 +280,7 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int e0 = g * a.eig_group;
         const int ecount = min(a.eig_group, all_tiles - e0);
         st = (int)(r / ecount);
-        et = e0 + (int)(r % ecount);
+        et = a.eig_tile0 + e0 + (int)(r % ecount);
     };
 
     if (warp == 0) {
@@ -546,14 +547,29 @@ rotate_i8_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
 }
 
+// L2 persistence of the digit planes (see launch).  Measured on the default bench command (tools/run_r2_s34.sh, back to back):
+// groups of 16 eigen tiles (36 MB of planes) in a 40 MB set-aside 58.5-58.6 ms per step against 58.8-58.9 without, groups of
+// 24 in 56-64 MB 58.7-59.9, groups of 32-40 in 80-100 MB 62 (too little L2 left for the streaming genotype tiles); DRAM reads of
+// the rotation 3.5 GB per 16 384 SNPs instead of 10.5 (ncu).  PG_TC2_PERSIST=0 / 1 overrides the default.
+constexpr int kPersistDefault = 1;
+constexpr int kPersistMB = 40;      // L2 set-aside requested for the plane group
+constexpr int kPersistGroup = 16;   // eigen tiles per launch
+constexpr int kPersistMinWaves = 8; // a launch must hold this many waves of cluster tiles, else one launch over all tiles
+inline bool persist_planes()
+{
+    static const int v = getenv("PG_TC2_PERSIST") ? atoi(getenv("PG_TC2_PERSIST")) : kPersistDefault;
+    return v != 0;
+}
+
 // xsm != nullptr: the caller's sample-major int8 block (element (sample j, SNP g) at xsm[j*ld_sm + g]) is used directly
 // as an MN-major operand; otherwise x8 (SNP-major, staged) is the K-major operand.
 inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long x8_rows, const int8_t* planes, int npad,
                   int ldk, int n, long long mb, const double* scale, double* xr, long long ldx,
                   const int8_t* xsm = nullptr, long long ld_sm = 0, const LevelInfo* info = nullptr,
                   const double* u1 = nullptr, int accumulate = 0, const FuseArgs* fuse = nullptr,
-                  const int8_t* planes_g = nullptr)
+                  const int8_t* planes_g = nullptr, int* n_launched = nullptr)
 {
+    if (n_launched) *n_launched = 1;
     tc::EncodeTiledFn enc = tc::encode_tiled_fn();
     if (!enc) return -1;
     if (fuse && (accumulate || !planes_g)) return -6;
@@ -576,19 +592,19 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
             return -2;
     }
     {
-        // (sample, plane, eigenvector): a box of 16 eigenvectors x 7 planes lands eigen-major, 112 rows of 128 B
+        // (sample, plane, eigenvector) over the [npad][kSlices][ldk] plane array: a box of 16 eigenvectors x 7 planes lands
+        // eigen-major, 112 rows of 128 B
         cuuint64_t dims[3] = {(cuuint64_t)ldk, (cuuint64_t)kSlices, (cuuint64_t)npad};
-        cuuint64_t strides[2] = {(cuuint64_t)ldk * (cuuint64_t)npad, (cuuint64_t)ldk};
+        cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)kSlices * (cuuint64_t)ldk};   // planes of an eigenvector are adjacent rows
         cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)kSlices, (cuuint32_t)(kTileEig / 2)};
         cuuint32_t es[3] = {1, 1, 1};
         if (enc(&mp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return -3;
         mg = mp;
-        if (fuse) {   // the digit planes of G: [kSlices][32 g_tiles][ldk]
+        if (fuse) {   // the digit planes of G: [32 g_tiles][kSlices][ldk]
             const int npad_g = fuse->g_tiles * kTileEig;
             dims[2] = (cuuint64_t)npad_g;
-            strides[0] = (cuuint64_t)ldk * (cuuint64_t)npad_g;
             if (enc(&mg, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes_g, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return -3;
@@ -614,6 +630,53 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
         cudaFuncSetAttribute(rotate_i8_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesFused) != cudaSuccess ||
         cudaFuncSetAttribute(rotate_i8_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesFused) != cudaSuccess)
         return -4;
+    // L2-resident digit planes (VERDICT r1 task 4): one launch per group of eigen tiles with the group's planes -- one contiguous
+    // range of the [npad][kSlices][ldk] array -- pinned in the L2 set-aside by an access-policy window (it applies to the TMA
+    // loads), so that only the genotype tiles stream through the rest of the L2.  In a single launch a wave of 74 K-deep cluster
+    // tiles touches more operand bytes than the L2 keeps and every wave re-reads its planes from HBM (profiles/l2_probe_r02_dram.txt).
+    // Only when every launch still holds kPersistMinWaves waves of tiles: short blocks (the ramp of host-resident input, one
+    // rank's shard of a problem split over 8 GPUs) and large n (a group of planes no longer fits) keep the single launch.
+    if (persist_planes() && !fuse) {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        static const int mb_env = getenv("PG_TC2_PERSIST_MB") ? atoi(getenv("PG_TC2_PERSIST_MB")) : kPersistMB;
+        const size_t setaside = std::min<size_t>((size_t)max_persist, (size_t)mb_env << 20);
+        if (setaside > 0 && max_window > 0) {
+            const size_t tile_bytes = (size_t)kTileEig * kSlices * ldk;
+            static const int g_env = getenv("PG_TC2_PERSIST_EG") ? atoi(getenv("PG_TC2_PERSIST_EG")) : kPersistGroup;
+            const int g = (int)std::min<size_t>({(size_t)std::max(g_env, 1), setaside / tile_bytes, (size_t)max_window / tile_bytes});
+            const int all = a.eig_tiles;
+            int rc = 0;
+            if (g >= 1 && (long long)a.snp_tiles * g >= (long long)kPersistMinWaves * (sm_count / 2)) {
+              cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);
+              for (int e0 = 0; e0 < all && rc == 0; e0 += g) {
+                const int cnt = std::min(g, all - e0);
+                cudaStreamAttrValue v;
+                memset(&v, 0, sizeof v);
+                const size_t first_row = (size_t)e0 * kTileEig, rows = std::min<size_t>((size_t)cnt * kTileEig, (size_t)npad - first_row);
+                v.accessPolicyWindow.base_ptr = (void*)(planes + first_row * kSlices * ldk);
+                v.accessPolicyWindow.num_bytes = rows * kSlices * ldk;
+                v.accessPolicyWindow.hitRatio = 1.0f;
+                v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) { rc = -7; break; }
+                a.eig_tile0 = e0; a.eig_tiles = cnt; a.eig_group = cnt;
+                const long long tiles_g = (long long)a.snp_tiles * cnt;
+                const int clusters_g = (int)std::min<long long>(tiles_g, sm_count / 2);
+                if (xsm) rotate_i8_tc2_kernel<true, false><<<2 * clusters_g, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
+                else rotate_i8_tc2_kernel<false, false><<<2 * clusters_g, kThreads, kSmemBytes, stream>>>(mx, mp, mg, a);
+                if (cudaGetLastError() != cudaSuccess) rc = -5;
+              }
+              if (n_launched) *n_launched = (all + g - 1) / g;
+              cudaStreamAttrValue off;
+              memset(&off, 0, sizeof off);
+              cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &off);   // num_bytes = 0: no window
+              return rc;
+            }
+        }
+    }
     const long long tiles = (long long)a.snp_tiles * (a.eig_tiles + (fuse ? fuse->g_tiles : 0));
     const int clusters = (int)std::min<long long>(tiles, sm_count / 2);
     if (fuse) {

@@ -305,7 +305,7 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)ldk, (cuuint64_t)kSlices, (cuuint64_t)npad};
-        cuuint64_t strides[2] = {(cuuint64_t)ldk * (cuuint64_t)npad, (cuuint64_t)ldk};
+        cuuint64_t strides[2] = {(cuuint64_t)ldk, (cuuint64_t)kSlices * (cuuint64_t)ldk};   // planes of an eigenvector are adjacent rows
         cuuint32_t box[3] = {(cuuint32_t)kStageK, (cuuint32_t)kSlices, (cuuint32_t)(kTileEig / 2)};
         cuuint32_t es[3] = {1, 1, 1};
         if (enc(&mp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

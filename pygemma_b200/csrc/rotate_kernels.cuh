@@ -31,7 +31,7 @@ struct RotWorkspace {
     // int8-split state
     bool planes_valid = false;
     int n = 0, npad = 0, ldk = 0;
-    int8_t* planes = nullptr;  // [8][npad][ldk]
+    int8_t* planes = nullptr;  // [npad][kSlices][ldk]: the digit planes of an eigenvector are adjacent rows
     int* exps = nullptr;       // [n]
     int8_t* x8 = nullptr;      // [cap_snps][ldk]
     long long cap_snps = 0;
@@ -177,7 +177,7 @@ inline int rot_prepare_i8(RotWorkspace* w, cudaStream_t stream, const double* U,
 // args.Z is the block's moment buffer; planes_g shares the row pitch ldk of the eigenvector planes.
 struct FuseLaunch {
     tc2::FuseArgs args;
-    const int8_t* planes_g = nullptr;     // [kSlices][32 g_tiles][ldk]
+    const int8_t* planes_g = nullptr;     // [32 g_tiles][kSlices][ldk]
     const tc2::SegRed* segs = nullptr;    // x^2 reduction: one entry per COMPRESS segment
     int nsegs = 0;
 };
@@ -362,8 +362,12 @@ inline int rot_run(RotWorkspace* w, cublasHandle_t blas, cudaStream_t stream, cu
             if (tc_cluster == 4)
                 return tc4::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
                                    direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, accumulate);
-            return tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
-                               direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, accumulate);
+            int launched = 1;
+            const int rl = tc2::launch(stream, sms, w->x8, w->cap_snps, w->planes, w->npad, w->ldk, n, mb, w->scale, xr, ldx,
+                                       direct ? (const int8_t*)src : nullptr, ld, affine, w->u1, accumulate, nullptr, nullptr,
+                                       &launched);
+            (*n_launch) += launched - 1;   // one launch per eigen-tile group when the planes are pinned in the L2
+            return rl;
         };
         int r = tc_launch(0);
         if (r == 0 && affine && need_eps) {
