@@ -244,7 +244,7 @@ def load_peaks():
 
 
 NCU_FILES = {  # committed `ncu --set full` summaries (tools/ncu_summary.py), newest first; SNPs per captured launch
-    "rotate_i8_tc2": [("ncu_r02_tc2_persist_16384snps.json", 16384), ("ncu_r02_tc2_16384snps.json", 16384),
+    "rotate_i8_tc2": [("ncu_r02_tc2_persist_25088snps.json", 25088), ("ncu_r02_tc2_16384snps.json", 16384),
                       ("ncu_r01_tc2_final_16384snps.json", 16384)],
     # moments fused into the rotation (c0 = 10, 206 nodes: +23 % tiles; the c5 shape has +54 %): an order of magnitude only
     "rotate_i8_tc2_kernel<1, 1>": [("ncu_r02_tc2_fused_16384snps.json", 16384)],
@@ -673,7 +673,7 @@ def run_ours(args):
     elif dom == "solve":
         per_snp, src = ncu_traffic("reml_solve")
     roofline["traffic"] = per_snp * res_tm["block_snps"] if (per_snp and n == 10000) else None
-    roofline["traffic_note"] = (f"dram__bytes_read+write of the stage's kernels per SNP block (ncu --set full at n=10000, profiles/{src}); "
+    roofline["traffic_note"] = (f"dram__bytes_read+write of the stage's kernels per SNP block (ncu at n=10000, profiles/{src}); "
                                 "algorithmic HBM bytes per SNP for the fused rotation: n int8 in + 8n fp64 out (+ the digit planes "
                                 "once per eigen-tile group)")
     roofline["algorithmic_bytes_per_launch"] = (9.0 * n) * res_tm["block_snps"] if dom == "rotation" else None
