@@ -120,4 +120,47 @@ inline void build_compress_plan(const double* d, int n, CompressPlan* P)
     P->Kc = (int)P->nodes.size();
 }
 
+// ---- moments straight from the fused rotation (rotate_i8_tc2.cuh, FUSE) ----------------------------------------------
+// The epilogue of an eigen tile squares the rotated values and accumulates, per thread, the x^2 moments of the
+// `piece_eig` eigenvectors it holds: one partial sum ("piece") per (piece_eig-aligned chunk, COMPRESS segment).  A segment's
+// node k is the sum of its pieces in eigen order (moments_reduce_kernel); COPY rows go straight to their node.
+struct FusedRow {
+    int id;   // COMPRESS row: piece index; COPY row: node
+    int kq;   // COMPRESS row: nodes of its segment (1 or kCq); COPY row: 0; padding beyond n: -1
+};
+struct FusedSeg {
+    int pb, pe;   // piece range of the segment
+    int kb, kq;   // first node, node count
+};
+struct FusedPlan {
+    std::vector<FusedRow> rows;    // [n rounded up to tile_eig]
+    std::vector<FusedSeg> segs;    // the COMPRESS segments, eigen order
+    std::vector<Segment> csegs;
+    int npieces = 0, cnodes = 0;   // cnodes: nodes of COMPRESS segments (columns of G = U V per linear column)
+};
+
+inline void build_fused_plan(const CompressPlan& P, int tile_eig, int piece_eig, FusedPlan* F)
+{
+    const int padded = (P.n + tile_eig - 1) / tile_eig * tile_eig;
+    F->rows.assign(padded, FusedRow{0, -1});
+    F->segs.clear(); F->csegs.clear();
+    F->npieces = 0; F->cnodes = 0;
+    for (const Segment& sg : P.segs) {
+        if (sg.type == kSegCompress) {
+            FusedSeg sr{F->npieces, 0, sg.kb, sg.kq};
+            int last = -1;
+            for (int l = sg.l0; l < sg.l1; ++l) {
+                if (l / piece_eig != last) { last = l / piece_eig; ++F->npieces; }
+                F->rows[l] = FusedRow{F->npieces - 1, sg.kq};
+            }
+            sr.pe = F->npieces;
+            F->segs.push_back(sr);
+            F->csegs.push_back(sg);
+            F->cnodes += sg.kq;
+        } else {
+            for (int l = sg.l0; l < sg.l1; ++l) F->rows[l] = FusedRow{sg.kb + (l - sg.l0), 0};
+        }
+    }
+}
+
 }  // namespace pg

@@ -532,33 +532,17 @@ static int upload_plan(pg_handle* h, const std::vector<double>& d_sorted)
     {
         // fused moments: x^2 piece (COMPRESS rows) or node (COPY rows) of every eigen-index, piece ranges per segment
         pg_handle::Fused& F = h->fz;
-        const int e32 = (n + tc2::kTileEig - 1) / tc2::kTileEig * tc2::kTileEig;
-        std::vector<int2> einfo(e32, make_int2(0, -1));
-        std::vector<tc2::SegRed> segred;
-        F.csegs.clear();
-        F.npieces = 0; F.cnodes = 0;
-        for (const Segment& sg : H.segs) {
-            if (sg.type == kSegCompress) {
-                tc2::SegRed sr{F.npieces, 0, sg.kb, sg.kq};
-                int last = -1;
-                for (int l = sg.l0; l < sg.l1; ++l) {
-                    if (l / tc2::kPieceEig != last) { last = l / tc2::kPieceEig; ++F.npieces; }
-                    einfo[l] = make_int2(F.npieces - 1, sg.kq);
-                }
-                sr.pe = F.npieces;
-                segred.push_back(sr);
-                F.csegs.push_back(sg);
-                F.cnodes += sg.kq;
-            } else {
-                for (int l = sg.l0; l < sg.l1; ++l) einfo[l] = make_int2(sg.kb + (l - sg.l0), 0);
-            }
-        }
-        F.nsegs = (int)segred.size();
-        CK(cudaMalloc(&F.einfo, sizeof(int2) * e32));
-        CK(cudaMemcpy(F.einfo, einfo.data(), sizeof(int2) * e32, cudaMemcpyHostToDevice));
+        FusedPlan fp;
+        build_fused_plan(H, tc2::kTileEig, tc2::kPieceEig, &fp);
+        static_assert(sizeof(FusedRow) == sizeof(int2) && sizeof(FusedSeg) == sizeof(tc2::SegRed), "plain int records");
+        F.csegs = fp.csegs;
+        F.npieces = fp.npieces; F.cnodes = fp.cnodes;
+        F.nsegs = (int)fp.segs.size();
+        CK(cudaMalloc(&F.einfo, sizeof(int2) * fp.rows.size()));
+        CK(cudaMemcpy(F.einfo, fp.rows.data(), sizeof(int2) * fp.rows.size(), cudaMemcpyHostToDevice));
         if (F.nsegs) {
             CK(cudaMalloc(&F.segs, sizeof(tc2::SegRed) * F.nsegs));
-            CK(cudaMemcpy(F.segs, segred.data(), sizeof(tc2::SegRed) * F.nsegs, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(F.segs, fp.segs.data(), sizeof(tc2::SegRed) * F.nsegs, cudaMemcpyHostToDevice));
         }
         F.valid = false;
     }

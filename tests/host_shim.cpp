@@ -210,6 +210,61 @@ int pgh_plan_nodes(int n, const double* d_sorted)
     return P.Kc;
 }
 
+// The bookkeeping of the fused rotation's x^2 moments (compress_plan.h: build_fused_plan) replayed on the host: every
+// eigen-index adds L_k a_l to the piece its row names, a segment's nodes are the sums of its pieces in order, COPY rows
+// write their node.  Returns max |z_fused - z_direct| / max |z_direct| against the plain definition of the compressed
+// moments; *npieces, *cnodes report the plan's sizes.  Also checks the structure the kernel relies on (a piece never
+// spans two piece_eig chunks or two segments; pieces of a segment are consecutive): -1 on violation.
+double pgh_fused_plan_check(int n, const double* d_sorted, const double* a, int tile_eig, int piece_eig, int* npieces,
+                            int* cnodes)
+{
+    CompressPlan P;
+    build_compress_plan(d_sorted, n, &P);
+    FusedPlan F;
+    build_fused_plan(P, tile_eig, piece_eig, &F);
+    if (npieces) *npieces = F.npieces;
+    if (cnodes) *cnodes = F.cnodes;
+    if ((int)F.rows.size() % tile_eig != 0 || (int)F.rows.size() < n) return -1.0;
+    for (size_t l = n; l < F.rows.size(); ++l)
+        if (F.rows[l].kq != -1) return -1.0;
+    std::vector<double> z(P.Kc, 0.0), zf(P.Kc, 0.0);
+    for (const Segment& s : P.segs)
+        for (int l = s.l0; l < s.l1; ++l) {
+            if (s.type == kSegCopy) z[s.kb + (l - s.l0)] += a[l];
+            else for (int q = 0; q < s.kq; ++q) z[s.kb + q] += P.Lw[(size_t)l * kCq + q] * a[l];
+        }
+    std::vector<double> part((size_t)std::max(F.npieces, 1) * kCq, 0.0);
+    std::vector<int> piece_chunk(std::max(F.npieces, 1), -1), piece_seg(std::max(F.npieces, 1), -1);
+    for (int l = 0; l < n; ++l) {
+        const FusedRow r = F.rows[l];
+        if (r.kq > 0) {
+            if (r.id < 0 || r.id >= F.npieces) return -1.0;
+            if (piece_chunk[r.id] >= 0 && piece_chunk[r.id] != l / piece_eig) return -1.0;
+            if (piece_seg[r.id] >= 0 && piece_seg[r.id] != P.seg_of[l]) return -1.0;
+            piece_chunk[r.id] = l / piece_eig; piece_seg[r.id] = P.seg_of[l];
+            for (int k = 0; k < kCq; ++k) part[(size_t)r.id * kCq + k] += P.Lw[(size_t)l * kCq + k] * a[l];
+        } else if (r.kq == 0) {
+            if (r.id < 0 || r.id >= P.Kc) return -1.0;
+            zf[r.id] = a[l];
+        } else {
+            return -1.0;
+        }
+    }
+    int expect_pb = 0, nodes = 0;
+    for (const FusedSeg& sr : F.segs) {
+        if (sr.pb != expect_pb || sr.pe <= sr.pb) return -1.0;
+        expect_pb = sr.pe;
+        nodes += sr.kq;
+        for (int p = sr.pb; p < sr.pe; ++p)
+            for (int k = 0; k < sr.kq; ++k) zf[sr.kb + k] += part[(size_t)p * kCq + k];
+    }
+    if (expect_pb != F.npieces || nodes != F.cnodes) return -1.0;
+    double worst = 0.0, scale = 0.0;
+    for (int q = 0; q < P.Kc; ++q) scale = std::max(scale, fabs(z[q]));
+    for (int q = 0; q < P.Kc; ++q) worst = std::max(worst, fabs(zf[q] - z[q]));
+    return scale > 0.0 ? worst / scale : worst;
+}
+
 // worst |compressed - direct| / sum_l |a_l| h_l^p over a lambda sweep, for a_l given (sorted order)
 double pgh_compress_error(int n, const double* d_sorted, const double* a, int power)
 {

@@ -37,6 +37,8 @@ def lib():
     L.pgh_interp_error.argtypes = [ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_double, ctypes.c_int]
     L.pgh_plan_nodes.restype = ctypes.c_int
     L.pgh_plan_nodes.argtypes = [ctypes.c_int, _dp]
+    L.pgh_fused_plan_check.restype = ctypes.c_double
+    L.pgh_fused_plan_check.argtypes = [ctypes.c_int, _dp, _dp, ctypes.c_int, ctypes.c_int, _ip, _ip]
     L.pgh_compress_error.restype = ctypes.c_double
     L.pgh_compress_error.argtypes = [ctypes.c_int, _dp, _dp, ctypes.c_int]
     L.pgh_scan_compressed.restype = None

@@ -251,6 +251,30 @@ def test_compression_error_bound():
                 assert e < (5e-14 if p == 3 else 2e-15), (name, p, e)
 
 
+def test_fused_moment_plan_reproduces_the_compressed_moments():
+    """compress_plan.h: build_fused_plan -- the bookkeeping of the x^2 moments the fused rotation forms in its epilogue (one
+    partial sum per 16-eigenvector chunk and COMPRESS segment, reduced per segment in eigen order; COPY rows to their node).
+    Replayed on the host it must give the compressed moments of their definition, on every kind of spectrum, and keep the
+    structure the kernel relies on (checked inside the shim: -1 on violation)."""
+    import ctypes
+
+    rng = np.random.default_rng(9)
+    L = hostshim.lib()
+    for n in (449, 1500, 2048):
+        for name, d in _spectra(rng, n).items():
+            d = np.sort(np.maximum(d, 0.0))
+            a = np.ascontiguousarray(rng.standard_normal(n) ** 2)
+            for tile, piece in ((32, 16), (32, 32)):
+                npieces, cnodes = ctypes.c_int32(0), ctypes.c_int32(0)
+                e = L.pgh_fused_plan_check(n, hostshim._p(d), hostshim._p(a), tile, piece, ctypes.byref(npieces),
+                                           ctypes.byref(cnodes))
+                assert 0.0 <= e < 1e-13, (n, name, tile, piece, e)
+                kc = L.pgh_plan_nodes(n, hostshim._p(d))
+                assert cnodes.value <= kc
+                # at most one piece per chunk and segment: chunks + segment boundaries bound the count
+                assert npieces.value <= (n + piece - 1) // piece + kc, (n, name, npieces.value)
+
+
 @pytest.mark.parametrize("path", SCANS, ids=[os.path.basename(p)[5:-4] for p in SCANS])
 def test_compressed_scan_matches_ref64(path):
     g = np.load(path)
