@@ -650,7 +650,11 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
             const int all = a.eig_tiles;
             int rc = 0;
             if (g >= 1 && (long long)a.snp_tiles * g >= (long long)kPersistMinWaves * (sm_count / 2)) {
-              cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);
+              static size_t configured[64] = {0};   // per device: the limit is set once (a benign race between host threads)
+              if (dev < 0 || dev >= 64 || configured[dev] != setaside) {
+                  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);
+                  if (dev >= 0 && dev < 64) configured[dev] = setaside;
+              }
               for (int e0 = 0; e0 < all && rc == 0; e0 += g) {
                 const int cnt = std::min(g, all - e0);
                 cudaStreamAttrValue v;
