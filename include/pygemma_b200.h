@@ -297,6 +297,14 @@ int pg_probe_f_sf(pg_handle* h, const double* F_host, double nu, int64_t k, doub
 /* rotated genotypes of the last SNP block pg_scan processed: copies min(count, block) * n doubles
  * (SNP-major) and reports the global index of the block's first SNP in *row0 (nullable) */
 int pg_probe_rotated(pg_handle* h, double* xr_host, int64_t count, int64_t* row0);
+/*
+ * Host-only probe: how many launches the fused rotation of one block of mb SNPs takes at n samples on a device with the
+ * given L2 persisting set-aside / access-policy window limits (bytes) and SM count, and (*group_tiles, nullable) the eigen
+ * tiles per launch -- 0 and one launch when the block is too short (fewer than 8 waves of cluster tiles per launch) or a
+ * group of digit planes does not fit the set-aside (large n).  See INTEGRATION.md, "L2 set-aside".
+ */
+int pg_probe_rotation_launches(int n, int64_t mb, int64_t setaside_bytes, int64_t max_window_bytes, int sm_count,
+                               int32_t* group_tiles);
 /* The SNP-block boundaries pg_scan uses for m SNPs when one block holds at most `blk` SNPs (pure host arithmetic, needs
  * no device): host_input != 0 -> the geometric ramp of short first blocks that lets packing / upload of block b+1 hide
  * under the compute of block b; on-device input and a caller-fixed block size (pg_set_options) -> plain blocks.

@@ -27,6 +27,7 @@ SYMBOLS = [
     "pg_abi_version", "pg_rotation_planes", "pg_device_count", "pg_last_error", "pg_create", "pg_destroy", "pg_set_kinship",
     "pg_set_eigen", "pg_set_eigen_device", "pg_get_eigen_device", "pg_copy_eigen", "pg_set_design", "pg_set_design_multi", "pg_set_stream", "pg_set_options",
     "pg_set_reml_engine", "pg_set_scan_mode", "pg_grm", "pg_set_bed_options", "pg_set_moment_fusion", "pg_probe_fusion",
+    "pg_probe_rotation_launches",
     "pg_scan", "pg_scan_device", "pg_scan_lrt", "pg_null_model",
     "pg_multi_create", "pg_multi_destroy", "pg_multi_last_error", "pg_multi_count", "pg_multi_handle", "pg_multi_set_kinship",
     "pg_multi_set_eigen", "pg_multi_set_design", "pg_multi_scan", "pg_probe_precompute", "pg_probe_f_sf", "pg_probe_rotated",
@@ -85,6 +86,7 @@ def load():
     L.pg_set_reml_engine.argtypes = [vp, i32]
     L.pg_set_scan_mode.argtypes = [vp, i32]
     L.pg_set_moment_fusion.argtypes = [vp, i32]
+    L.pg_probe_rotation_launches.argtypes = [i32, i64, i64, i64, i32, ctypes.POINTER(i32)]
     L.pg_probe_fusion.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_float)]
     L.pg_set_bed_options.argtypes = [vp, i32, i32]
     L.pg_grm.argtypes = [vp, vp, i32, i64, i32, i64, vp, i32, vp, ctypes.POINTER(ctypes.c_float),

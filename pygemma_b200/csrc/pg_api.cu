@@ -1001,6 +1001,20 @@ extern "C" int pg_set_moment_fusion(pg_handle* h, int mode)
     return PG_OK;
 }
 
+extern "C" int pg_probe_rotation_launches(int n, int64_t mb, int64_t setaside_bytes, int64_t max_window_bytes, int sm_count,
+                                          int32_t* group_tiles)
+{
+    if (n < 1 || mb < 0 || setaside_bytes < 0 || max_window_bytes < 0 || sm_count < 2) return PG_ERR_ARG;
+    const int ldk = (n + 127) / 128 * 128, eig_tiles = (n + tc2::kTileEig - 1) / tc2::kTileEig;
+    const int snp_tiles = (int)((mb + tc2::kClusterSnps - 1) / tc2::kClusterSnps);
+    const size_t setaside = std::min<size_t>((size_t)setaside_bytes, (size_t)tc2::kPersistMB << 20);
+    const int g = tc2::persist_planes()
+                      ? tc2::persist_group_tiles(snp_tiles, ldk, setaside, (size_t)max_window_bytes, sm_count, tc2::kPersistGroup)
+                      : 0;
+    if (group_tiles) *group_tiles = g;
+    return g > 0 ? (eig_tiles + g - 1) / g : 1;
+}
+
 extern "C" int pg_probe_fusion(pg_handle* h, int32_t* fused, int32_t* g_columns, int32_t* pieces, float* build_ms)
 {
     if (!h) return PG_ERR_ARG;

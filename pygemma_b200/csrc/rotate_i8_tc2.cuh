@@ -561,6 +561,17 @@ inline bool persist_planes()
     return v != 0;
 }
 
+// Eigen tiles per launch when the digit planes are pinned in the L2 set-aside, 0 = one launch over all tiles (host arithmetic;
+// pg_probe_rotation_launches exposes it to the CPU tests).  ldk: row pitch of the planes; setaside / max_window: bytes.
+inline int persist_group_tiles(int snp_tiles, int ldk, size_t setaside, size_t max_window, int sm_count, int want)
+{
+    if (setaside == 0 || max_window == 0 || want < 1) return 0;
+    const size_t tile_bytes = (size_t)kTileEig * kSlices * (size_t)ldk;
+    const int g = (int)std::min<size_t>({(size_t)want, setaside / tile_bytes, max_window / tile_bytes});
+    if (g < 1 || (long long)snp_tiles * g < (long long)kPersistMinWaves * (sm_count / 2)) return 0;
+    return g;
+}
+
 // xsm != nullptr: the caller's sample-major int8 block (element (sample j, SNP g) at xsm[j*ld_sm + g]) is used directly
 // as an MN-major operand; otherwise x8 (SNP-major, staged) is the K-major operand.
 inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long x8_rows, const int8_t* planes, int npad,
@@ -643,13 +654,12 @@ inline int launch(cudaStream_t stream, int sm_count, const int8_t* x8, long long
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
         static const int mb_env = getenv("PG_TC2_PERSIST_MB") ? atoi(getenv("PG_TC2_PERSIST_MB")) : kPersistMB;
         const size_t setaside = std::min<size_t>((size_t)max_persist, (size_t)mb_env << 20);
-        if (setaside > 0 && max_window > 0) {
-            const size_t tile_bytes = (size_t)kTileEig * kSlices * ldk;
+        {
             static const int g_env = getenv("PG_TC2_PERSIST_EG") ? atoi(getenv("PG_TC2_PERSIST_EG")) : kPersistGroup;
-            const int g = (int)std::min<size_t>({(size_t)std::max(g_env, 1), setaside / tile_bytes, (size_t)max_window / tile_bytes});
+            const int g = persist_group_tiles(a.snp_tiles, ldk, setaside, (size_t)std::max(max_window, 0), sm_count, g_env);
             const int all = a.eig_tiles;
             int rc = 0;
-            if (g >= 1 && (long long)a.snp_tiles * g >= (long long)kPersistMinWaves * (sm_count / 2)) {
+            if (g >= 1) {
               static size_t configured[64] = {0};   // per device: the limit is set once (a benign race between host threads)
               if (dev < 0 || dev >= 64 || configured[dev] != setaside) {
                   cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);

@@ -93,3 +93,33 @@ def test_block_plan_covers_every_snp_once(lib):
                 assert all(x % 256 == 0 for x in b[:-1]) or blk % 256, (m, blk, b)
     assert _capi.block_plan(0, 1024) == []
     assert lib.pg_probe_block_plan(-1, 1024, 1, 0, None, 0) == -1
+
+
+def test_rotation_launch_plan_of_the_l2_pinned_planes(lib):
+    """pg_probe_rotation_launches (host arithmetic of rotate_i8_tc2.cuh: persist_group_tiles): the bench's 25 088-SNP block at
+    n = 10 000 takes one launch per 16 eigen tiles (36 MB of planes in the 40 MB set-aside); short blocks -- the ramp of
+    host-resident input, one rank's shard of a problem split over 8 GPUs -- and n = 50 000, where not even one wave-filling
+    group of planes fits, keep the single launch; so does a device without a persisting set-aside."""
+    import ctypes
+
+    B200 = dict(setaside=82903040, window=134217728, sms=148)   # cudaDevAttrMaxPersistingL2CacheSize / ...WindowSize on the pool
+
+    def plan(n, mb, **kw):
+        d = dict(B200, **kw)
+        g = ctypes.c_int32(-1)
+        k = lib.pg_probe_rotation_launches(n, mb, d["setaside"], d["window"], d["sms"], ctypes.byref(g))
+        return k, g.value
+
+    if os.environ.get("PG_TC2_PERSIST") == "0":
+        assert plan(10000, 25088) == (1, 0)
+        return
+    assert plan(10000, 25088) == (20, 16)          # 313 eigen tiles in groups of 16
+    assert plan(10000, 100000)[1] == 16
+    assert plan(10000, 12544) == (1, 0)            # 25 SNP tiles x 16 < 8 waves of 74 clusters
+    assert plan(10000, 1536) == (1, 0)
+    assert plan(50000, 5120) == (1, 0)             # 11.2 MB per eigen tile: 3 tiles per 40 MB, far below 8 waves
+    assert plan(10000, 25088, setaside=0) == (1, 0)
+    assert plan(10000, 25088, window=1 << 20) == (1, 0)
+    k, g = plan(4096, 65536)                       # small n: more tiles fit, the group stays at 16
+    assert g == 16 and k == (4096 // 32 + 15) // 16
+    assert lib.pg_probe_rotation_launches(0, 10, 1, 1, 148, None) < 0
